@@ -1,0 +1,184 @@
+"""Generate golden fixtures from the UNMODIFIED reference (run in the build container only).
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+Imports /root/reference/{config,models,tools_for_model,tools_for_loss}.py through the shim of
+SURVEY.md appendix A (stub matplotlib / asteroid, cfg.DEVICE='cpu', cfg.window='hann'), runs
+the reference DCCRN forward + loss + backward (and Adam steps) on seeded inputs and stores
+the results.  /root/reference does not exist on the GPU box; the fixtures travel instead.
+"""
+import contextlib
+import io
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("SEFD_REFERENCE", "/root/reference")
+
+
+def import_reference():
+    sys.path.insert(0, REF)
+    for n in ["matplotlib", "matplotlib.pylab", "asteroid", "asteroid.losses", "asteroid_filterbanks"]:
+        sys.modules[n] = types.ModuleType(n)
+
+    class _Stub:
+        def __init__(self, *a, **k):
+            pass
+
+        def to(self, *a, **k):
+            return self
+
+    sys.modules["asteroid.losses"].SingleSrcPMSQE = _Stub
+    sys.modules["asteroid.losses"].PITLossWrapper = _Stub
+    sys.modules["asteroid_filterbanks"].STFTFB = _Stub
+    sys.modules["asteroid_filterbanks"].Encoder = _Stub
+    sys.modules["asteroid_filterbanks"].transforms = None
+    with contextlib.redirect_stdout(io.StringIO()):
+        import config as cfg
+    cfg.DEVICE, cfg.window = "cpu", "hann"
+    cfg.loss, cfg.lstm, cfg.skip_type, cfg.perceptual = "SI-SNR", "complex", True, False
+    import models
+    import tools_for_loss
+    return cfg, models, tools_for_loss
+
+
+def batch(B, L, seed=1234, amp=0.1):
+    g = torch.Generator().manual_seed(seed)
+    noisy = (torch.rand(B, L, generator=g) * 2 - 1) * amp
+    clean = (torch.rand(B, L, generator=g) * 2 - 1) * amp
+    return noisy, clean
+
+
+def speechlike(B, L, seed=7):
+    """Target correlated with the input (realistic SI-SNR range, exercises alpha != 0)."""
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(L, dtype=torch.float32) / 16000.0
+    clean = torch.stack([0.2 * torch.sin(2 * np.pi * (200.0 + 150.0 * b + 300.0 * t) * t) *
+                         (0.5 + 0.5 * torch.sin(2 * np.pi * 3.0 * t + b)) for b in range(B)])
+    noisy = clean + 0.05 * torch.randn(B, L, generator=g)
+    return noisy, clean
+
+
+def main():
+    cfg, models, tfl = import_reference()
+    torch.set_num_threads(8)
+    out = {}
+
+    # ---- 0. init-stream pin: per-key sum / abs-sum of the seed-0 state dict -------------
+    torch.manual_seed(0)
+    m = models.DCCRN(masking_mode="C")
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    keys = list(sd0.keys())
+    out["init_keys"] = np.array(keys)
+    out["init_sum"] = np.array([float(sd0[k].double().sum()) for k in keys])
+    out["init_abs"] = np.array([float(sd0[k].double().abs().sum()) for k in keys])
+    out["n_params"] = np.array(sum(p.numel() for p in m.parameters()))
+
+    # ---- 1. small case, all mask modes x all losses ------------------------------------
+    B, L = 2, 4000
+    for inputs_name, (noisy, clean) in {"rand": batch(B, L), "speech": speechlike(B, L)}.items():
+        out[f"small_{inputs_name}_noisy"] = noisy.numpy()
+        out[f"small_{inputs_name}_clean"] = clean.numpy()
+        for mode in ["C", "E", "R"]:
+            torch.manual_seed(0)
+            m = models.DCCRN(masking_mode=mode).train()
+            for loss_name in (["SI-SNR", "SDR", "SI-SDR", "MSE"] if mode == "C" else ["SI-SNR"]):
+                cfg.loss = loss_name
+                m.load_state_dict(sd0)
+                m.zero_grad()
+                o_r, o_i, wav = m(noisy, clean)
+                loss = m.loss(wav, clean)
+                loss.backward()
+                tag = f"small_{inputs_name}_{mode}_{loss_name}"
+                out[tag + "_loss"] = np.array(loss.item())
+                if loss_name == "SI-SNR":
+                    out[tag + "_wav"] = wav.detach().numpy()
+                    out[tag + "_out_real"] = o_r.detach().numpy()
+                    out[tag + "_out_imag"] = o_i.detach().numpy()
+                names = [n for n, _ in m.named_parameters()]
+                out[tag + "_gnorm"] = np.array([float(p.grad.double().norm()) for _, p in m.named_parameters()])
+                out["param_names"] = np.array(names)
+                # full gradients of the small tensors + a strided sample of the big ones
+                for n, p in m.named_parameters():
+                    g = p.grad.detach().reshape(-1)
+                    if loss_name == "SI-SNR" and mode == "C" and inputs_name == "speech":
+                        out[tag + "_grad::" + n] = (g if g.numel() <= 4096 else g[:: g.numel() // 2048][:2048]).numpy()
+            cfg.loss = "SI-SNR"
+        # BN running stats after one train forward (mode C, last loop left them updated once per call)
+    torch.manual_seed(0)
+    m = models.DCCRN(masking_mode="C").train()
+    m.load_state_dict(sd0)
+    noisy, clean = speechlike(B, L)
+    m(noisy, clean)
+    for k, v in m.state_dict().items():
+        if "running" in k:
+            out["small_speech_bn::" + k] = v.numpy()
+
+    # eval-mode forward (running stats) for the validation path
+    m.eval()
+    with torch.no_grad():
+        _, _, wav = m(noisy, clean)
+    out["small_speech_C_eval_wav"] = wav.numpy()
+
+    # ---- 2. three Adam steps on the small speech case -----------------------------------
+    cfg.loss = "SI-SNR"
+    torch.manual_seed(0)
+    m = models.DCCRN(masking_mode="C").train()
+    m.load_state_dict(sd0)
+    opt = torch.optim.Adam(m.parameters(), lr=cfg.learning_rate)
+    losses = []
+    for _ in range(3):
+        _, _, wav = m(noisy, clean)
+        loss = m.loss(wav, clean)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    out["adam3_losses"] = np.array(losses)
+    out["adam3_param_sum"] = np.array([float(p.double().sum()) for p in m.parameters()])
+    out["adam3_param_abs"] = np.array([float(p.double().abs().sum()) for p in m.parameters()])
+
+    # ---- 3. full-length case (SURVEY §4 known answer) -----------------------------------
+    torch.manual_seed(0)
+    m = models.DCCRN(masking_mode="C").train()
+    noisy, clean = batch(2, 48000)
+    _, _, wav = m(noisy, clean)
+    loss = m.loss(wav, clean)
+    loss.backward()
+    out["full_loss"] = np.array(loss.item())
+    out["full_wav_head"] = wav.detach()[:, :2048].numpy()
+    out["full_wav_rms"] = np.array(float(wav.double().pow(2).mean().sqrt()))
+    out["full_wav_sum"] = np.array(float(wav.double().sum()))
+    out["full_gnorm_total"] = np.array(float(torch.sqrt(sum(p.grad.double().pow(2).sum() for p in m.parameters()))))
+    out["full_gnorm"] = np.array([float(p.grad.double().norm()) for p in m.parameters()])
+
+    # ---- 4. loss known answers (tools_for_loss.py:57-74 doctest, numpy seed 0) ---------
+    np.random.seed(0)
+    ref = np.random.randn(100)
+    tr = torch.from_numpy(ref)[None]
+    out["si_sdr_doc_inputs"] = ref
+    out["si_sdr_doc_expected"] = np.array([-25.127672346460717, 0.481070445785553, 6.3704606032577304, 6.3704606032577304])
+    out["si_sdr_ref_values"] = np.array([
+        float(tfl.si_sdr(tr, torch.from_numpy(np.flip(ref).copy())[None])),
+        float(tfl.si_sdr(tr, tr + torch.from_numpy(np.flip(ref).copy())[None])),
+        float(tfl.si_sdr(tr, tr + 0.5)),
+        float(tfl.si_sdr(tr, tr * 2 + 1)),
+    ])
+    a, b = batch(4, 1000, seed=5)
+    out["loss_pair_a"], out["loss_pair_b"] = a.numpy(), b.numpy()
+    out["loss_ref_si_snr"] = np.array(float(tfl.si_snr(a, b)))
+    out["loss_ref_sdr"] = np.array(float(tfl.sdr(a, b)))
+    out["loss_ref_si_sdr"] = np.array(float(tfl.si_sdr(a, b)))
+
+    np.savez_compressed(os.path.join(HERE, "dccrn_golden.npz"), **out)
+    sz = os.path.getsize(os.path.join(HERE, "dccrn_golden.npz"))
+    print(f"wrote dccrn_golden.npz ({sz/1e3:.1f} kB), {len(out)} arrays; full_loss={out['full_loss']}, "
+          f"n_params={out['n_params']}")
+
+
+if __name__ == "__main__":
+    main()
