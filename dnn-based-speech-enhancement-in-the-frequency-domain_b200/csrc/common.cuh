@@ -1,0 +1,84 @@
+// Shared helpers for the sefd CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define SEFD_MAX_TAPS 12
+
+// ---- error plumbing (never throws across the C ABI) ---------------------------------
+void sefd_set_error(const char* fmt, ...);
+int sefd_check_launch(const char* what);   // returns 0 or negative code, records message
+
+#define SEFD_REQUIRE(cond, ...)                       \
+    do {                                              \
+        if (!(cond)) {                                \
+            sefd_set_error(__VA_ARGS__);              \
+            return -1;                                \
+        }                                             \
+    } while (0)
+
+#define SEFD_TRY(expr)                 \
+    do {                               \
+        int _rc = (expr);              \
+        if (_rc != 0) return _rc;      \
+    } while (0)
+
+// ---- tensor views (strides in floats) -----------------------------------------------
+// Activations on the path are channels-last: element (b, f, t, c) at p[b*sB + f*sF + t*sT + c].
+struct TapSrc {
+    const float* p;
+    long long sB, sF, sT;
+    int C;
+};
+struct TapDst {
+    float* p;
+    long long sB, sF, sT;
+    int N;
+};
+
+// out[b, j*fo_mul+fo_off, t, n] (+)= bias[n] + sum_tap sum_k A[b, j*fi_mul+df[tap], t+dt[tap], k] * W[wslab[tap]][k][n]
+// with A = concat_k(a[0], a[1]); n split over o[0], o[1]; source coords outside [0,Fin)x[0,Tin) read as 0.
+struct TapGemmParams {
+    TapSrc a[2];
+    TapDst o[2];
+    const float* W;      // [slab][K][N], n contiguous
+    long long wJ;        // extra weight offset per j (weights that vary with the output row)
+    const float* bias;   // [N] or nullptr
+    long long bJ;        // extra bias offset per j
+    double* stats;       // [2][N] (sum, sum of squares over all written outputs) or nullptr
+    int B, J, Tout;
+    int Fin, Tin;
+    int fi_mul, fo_mul, fo_off;
+    int ntaps;
+    int df[SEFD_MAX_TAPS], dt[SEFD_MAX_TAPS], wslab[SEFD_MAX_TAPS];
+    int accum[2];
+};
+
+// dW[wslab[tap]][k][n] += sum_{b,j,t} A[b, j*a_mul+a_off[tap], t+dt[tap], k] * G[b, j*g_mul+g_off[tap], t, n]
+struct WgradParams {
+    TapSrc a[2];
+    TapSrc g;            // C field = N
+    float* dW;           // [slab][K][N]; accumulated with atomics (caller zeroes)
+    int B, J, Tg;        // t runs over [0,Tg)
+    int Fa, Ta, Fg;
+    int a_mul, g_mul;
+    int ntaps;
+    int a_off[SEFD_MAX_TAPS], g_off[SEFD_MAX_TAPS], dt[SEFD_MAX_TAPS], wslab[SEFD_MAX_TAPS];
+    int rows_per_cta;    // (b,j) rows handled by one CTA
+};
+
+int sefd_tapgemm_simt(const TapGemmParams& p, cudaStream_t st);
+int sefd_wgrad_simt(const WgradParams& p, cudaStream_t st);
+
+// ---- small device helpers ------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}

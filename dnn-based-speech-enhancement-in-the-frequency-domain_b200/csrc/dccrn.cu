@@ -1,0 +1,750 @@
+// DCCRN train-step orchestration: parameter layout, workspace carving, forward and backward
+// sequencing of the kernels.  Mirrors DCCRN.forward (models.py:176-284) and the autograd graph the
+// reference gets from torch; see DESIGN.md for the dataflow and SURVEY.md appendix B for the
+// backward obligations.
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "dccrn.cuh"
+#include "taps.cuh"
+
+namespace {
+
+constexpr int NL = 6;            // encoder / decoder depth (config.py:50 dccrn_kernel_num)
+constexpr int NBIN = 257, HOP = 100;
+constexpr int RNN_H = 128, G4 = 512;
+constexpr float BN_EPS = 1e-5f, BN_MOM = 0.1f;
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct ParamInfo {
+    std::string name;
+    long long offset, numel;
+    int ndim;
+    long long shape[4];
+};
+
+struct ConvLayer {
+    int Cin, Cout;          // real channel counts (Cin includes the skip half for decoders)
+    int Fin, Fout;
+    long long wr, br, wi, bi, gamma, beta, alpha;   // param offsets (gamma < 0: no BN/PReLU)
+    long long rmean, rvar;                           // bn buffer offsets
+    // workspace offsets (floats)
+    size_t y, z, Wf, Wt, bias, stats /*doubles*/, save, dz;
+};
+
+}  // namespace
+
+struct sefd_plan {
+    int B, L, T, mask_mode;
+    int ch[NL + 1], Fe[NL + 1];
+    ConvLayer enc[NL], dec[NL];
+    // LSTM parameter offsets [layer][lstm]
+    long long w_ih[2][2], w_hh[2][2], b_ih[2][2], b_hh[2][2], w_tr[2], b_tr[2];
+    std::vector<ParamInfo> params, buffers;
+    long long n_param_floats, n_buffer_floats;
+    // workspace (float offsets unless noted)
+    size_t ws_bytes;
+    size_t spec, raw_wav, dots /*double*/, stats_all /*double*/, stats_all_n;
+    size_t Gt[2], Hh[2], Cc[2], X1, X2, U;
+    size_t Wih0p, Wih0T, Wih1p, Wih1T, Whh[2], bsum[2], Wtrp, WtrT, btrp;
+    size_t dU, dY, dWs, dbs, red /*double*/, dX, dH, dG, dzd[NL];
+    size_t dY_floats, dWs_floats;
+};
+
+namespace {
+
+void add_param(sefd_plan* P, const std::string& name, long long& cursor, long long* off, std::initializer_list<long long> shape) {
+    ParamInfo pi;
+    pi.name = name;
+    pi.ndim = (int)shape.size();
+    pi.numel = 1;
+    int i = 0;
+    for (long long s : shape) {
+        pi.shape[i++] = s;
+        pi.numel *= s;
+    }
+    for (; i < 4; ++i) pi.shape[i] = 1;
+    pi.offset = cursor;
+    *off = cursor;
+    cursor += (pi.numel + 3) / 4 * 4;
+    P->params.push_back(pi);
+}
+
+void add_buffer(sefd_plan* P, const std::string& name, long long& cursor, long long* off, long long n) {
+    ParamInfo pi;
+    pi.name = name;
+    pi.ndim = 1;
+    pi.numel = n;
+    pi.shape[0] = n;
+    pi.shape[1] = pi.shape[2] = pi.shape[3] = 1;
+    pi.offset = cursor;
+    *off = cursor;
+    cursor += (n + 3) / 4 * 4;
+    P->buffers.push_back(pi);
+}
+
+struct Carver {
+    size_t cur = 0;   // bytes
+    size_t floats(size_t n) {
+        cur = align_up(cur, 256);
+        size_t o = cur / 4;
+        cur += n * 4;
+        return o;
+    }
+    size_t doubles(size_t n) {
+        cur = align_up(cur, 256);
+        size_t o = cur / 8;
+        cur += n * 8;
+        return o;
+    }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode) {
+    if (B <= 0 || L <= 0 || L % HOP != 0) {
+        sefd_set_error("plan: need B > 0 and L a positive multiple of %d (got B=%d L=%d)", HOP, B, L);
+        return nullptr;
+    }
+    if (mask_mode < SEFD_MASK_E || mask_mode > SEFD_MASK_R) {
+        sefd_set_error("plan: masking mode %d unsupported (E=1, C=2, R=3)", mask_mode);
+        return nullptr;
+    }
+    sefd_plan* P = new sefd_plan();
+    P->B = B;
+    P->L = L;
+    P->T = L / HOP + 3;
+    P->mask_mode = mask_mode;
+    const int kn[NL + 1] = {2, 32, 64, 128, 256, 256, 256};
+    for (int i = 0; i <= NL; ++i) {
+        P->ch[i] = kn[i];
+        P->Fe[i] = 256 >> i;
+    }
+    long long pc = 0, bc = 0;
+    for (int i = 0; i < NL; ++i) {
+        ConvLayer& c = P->enc[i];
+        c.Cin = kn[i];
+        c.Cout = kn[i + 1];
+        c.Fin = P->Fe[i];
+        c.Fout = P->Fe[i + 1];
+        const std::string pre = "encoder." + std::to_string(i);
+        add_param(P, pre + ".0.real_conv.weight", pc, &c.wr, {c.Cout / 2, c.Cin / 2, 5, 2});
+        add_param(P, pre + ".0.real_conv.bias", pc, &c.br, {c.Cout / 2});
+        add_param(P, pre + ".0.imag_conv.weight", pc, &c.wi, {c.Cout / 2, c.Cin / 2, 5, 2});
+        add_param(P, pre + ".0.imag_conv.bias", pc, &c.bi, {c.Cout / 2});
+        add_param(P, pre + ".1.weight", pc, &c.gamma, {c.Cout});
+        add_param(P, pre + ".1.bias", pc, &c.beta, {c.Cout});
+        add_param(P, pre + ".2.weight", pc, &c.alpha, {1});
+        add_buffer(P, pre + ".1.running_mean", bc, &c.rmean, c.Cout);
+        add_buffer(P, pre + ".1.running_var", bc, &c.rvar, c.Cout);
+    }
+    for (int j = 0; j < NL; ++j) {
+        ConvLayer& c = P->dec[j];
+        const int idx = NL - j;
+        c.Cin = 2 * kn[idx];
+        c.Cout = kn[idx - 1];
+        c.Fin = P->Fe[idx];
+        c.Fout = 2 * c.Fin;
+        const std::string pre = "decoder." + std::to_string(j);
+        add_param(P, pre + ".0.real_conv.weight", pc, &c.wr, {c.Cin / 2, c.Cout / 2, 5, 2});
+        add_param(P, pre + ".0.real_conv.bias", pc, &c.br, {c.Cout / 2});
+        add_param(P, pre + ".0.imag_conv.weight", pc, &c.wi, {c.Cin / 2, c.Cout / 2, 5, 2});
+        add_param(P, pre + ".0.imag_conv.bias", pc, &c.bi, {c.Cout / 2});
+        if (j != NL - 1) {
+            add_param(P, pre + ".1.weight", pc, &c.gamma, {c.Cout});
+            add_param(P, pre + ".1.bias", pc, &c.beta, {c.Cout});
+            add_param(P, pre + ".2.weight", pc, &c.alpha, {1});
+            add_buffer(P, pre + ".1.running_mean", bc, &c.rmean, c.Cout);
+            add_buffer(P, pre + ".1.running_var", bc, &c.rvar, c.Cout);
+        } else {
+            c.gamma = c.beta = c.alpha = c.rmean = c.rvar = -1;
+        }
+    }
+    for (int l = 0; l < 2; ++l) {
+        const long long I = l == 0 ? 512 : 128;
+        const char* part[2] = {"real", "imag"};
+        for (int p = 0; p < 2; ++p) {
+            const std::string pre = "enhance." + std::to_string(l) + "." + part[p] + "_lstm.";
+            add_param(P, pre + "weight_ih_l0", pc, &P->w_ih[l][p], {G4, I});
+            add_param(P, pre + "weight_hh_l0", pc, &P->w_hh[l][p], {G4, RNN_H});
+            add_param(P, pre + "bias_ih_l0", pc, &P->b_ih[l][p], {G4});
+            add_param(P, pre + "bias_hh_l0", pc, &P->b_hh[l][p], {G4});
+        }
+        if (l == 1) {
+            const char* tr[2] = {"r", "i"};
+            for (int q = 0; q < 2; ++q) {
+                const std::string pre = "enhance.1." + std::string(tr[q]) + "_trans.";
+                add_param(P, pre + "weight", pc, &P->w_tr[q], {512, RNN_H});
+                add_param(P, pre + "bias", pc, &P->b_tr[q], {512});
+            }
+        }
+    }
+    P->n_param_floats = pc;
+    P->n_buffer_floats = bc;
+
+    // ---- workspace ----
+    const size_t Bz = B, T = P->T;
+    Carver w;
+    P->spec = w.floats(Bz * NBIN * T * 2);
+    P->raw_wav = w.floats(Bz * L);
+    P->dots = w.doubles(Bz * 8 + 8);
+    size_t nstat = 0;
+    for (int i = 0; i < NL; ++i) nstat += 2 * P->enc[i].Cout;
+    for (int j = 0; j < NL - 1; ++j) nstat += 2 * P->dec[j].Cout;
+    P->stats_all = w.doubles(nstat);
+    P->stats_all_n = nstat;
+    size_t sc = P->stats_all;
+    size_t max_y = 0, max_w = 0;
+    for (int i = 0; i < NL; ++i) {
+        ConvLayer& c = P->enc[i];
+        const size_t n = Bz * c.Fout * T * c.Cout;
+        c.y = w.floats(n);
+        c.z = w.floats(n);
+        c.dz = w.floats(n);
+        c.Wf = w.floats(10ull * c.Cin * c.Cout);
+        c.Wt = w.floats(10ull * c.Cin * c.Cout);
+        c.bias = w.floats(c.Cout);
+        c.save = w.floats(2 * c.Cout);
+        c.stats = sc;
+        sc += 2 * c.Cout;
+        if (n > max_y) max_y = n;
+        if (10ull * c.Cin * c.Cout > max_w) max_w = 10ull * c.Cin * c.Cout;
+    }
+    for (int j = 0; j < NL; ++j) {
+        ConvLayer& c = P->dec[j];
+        const size_t ny = Bz * c.Fout * (T + 1) * c.Cout, nz = Bz * c.Fout * T * c.Cout;
+        c.y = w.floats(ny);
+        c.z = j != NL - 1 ? w.floats(nz) : 0;
+        c.dz = j != NL - 1 ? w.floats(nz) : 0;
+        c.Wf = w.floats(10ull * c.Cin * c.Cout);
+        c.Wt = w.floats(10ull * c.Cin * c.Cout);
+        c.bias = w.floats(c.Cout);
+        c.save = w.floats(2 * c.Cout + 4);
+        if (j != NL - 1) {
+            c.stats = sc;
+            sc += 2 * c.Cout;
+        }
+        if (ny > max_y) max_y = ny;
+        if (10ull * c.Cin * c.Cout > max_w) max_w = 10ull * c.Cin * c.Cout;
+    }
+    for (int l = 0; l < 2; ++l) {
+        P->Gt[l] = w.floats(2 * 2 * Bz * T * G4);
+        P->Hh[l] = w.floats(2 * 2 * Bz * T * RNN_H);
+        P->Cc[l] = w.floats(2 * 2 * Bz * T * RNN_H);
+        P->Whh[l] = w.floats(2 * G4 * RNN_H);
+        P->bsum[l] = w.floats(2 * G4);
+    }
+    P->X1 = w.floats(2 * Bz * T * RNN_H);
+    P->X2 = w.floats(2 * Bz * T * RNN_H);
+    P->U = w.floats(Bz * 4 * T * 256);
+    P->Wih0p = w.floats(2ull * 4 * 128 * G4);     // [p][d][c][n]
+    P->Wih0T = w.floats(4ull * 2 * G4 * 128);     // [d][p*512+n][c]
+    P->Wih1p = w.floats(2ull * 128 * G4);         // [p][k][n]
+    P->Wih1T = w.floats(2ull * G4 * 128);         // [p*512+n][k]
+    P->Wtrp = w.floats(2ull * 4 * 128 * 128);     // [q][d][k][c]
+    P->WtrT = w.floats(2ull * 4 * 128 * 128);     // [q][d][c][k]
+    P->btrp = w.floats(2ull * 4 * 128);           // [q][d][c]
+    // backward scratch
+    P->dU = w.floats(Bz * 4 * T * 256);
+    P->dY_floats = max_y;
+    P->dY = w.floats(max_y);
+    if (max_w < 4ull * 128 * G4) max_w = 4ull * 128 * G4;
+    P->dWs_floats = max_w;
+    P->dWs = w.floats(max_w);
+    P->dbs = w.floats(1024);
+    P->red = w.doubles(2 * 512 + 8);
+    P->dX = w.floats(2 * Bz * T * RNN_H);
+    P->dH = w.floats(2 * 2 * Bz * T * RNN_H);
+    P->dG = w.floats(2 * 2 * Bz * T * G4);
+    P->ws_bytes = align_up(w.cur, 256);
+    return P;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing (once per forward; the packed operands are reused by the backward)
+// ------------------------------------------------------------------------------------------------
+static int pack_weights(const sefd_plan* P, const float* prm, float* ws, cudaStream_t st) {
+    for (int e = 0; e < 2 * NL; ++e) {
+        const ConvLayer& c = e < NL ? P->enc[e] : P->dec[e - NL];
+        CconvPackParams pp;
+        pp.wr = prm + c.wr; pp.wi = prm + c.wi; pp.br = prm + c.br; pp.bi = prm + c.bi;
+        pp.Ci2 = c.Cin / 2; pp.Co2 = c.Cout / 2;
+        pp.transposed = e >= NL; pp.two_src = e >= NL;
+        pp.Wf = ws + c.Wf; pp.Wt = ws + c.Wt; pp.bias = ws + c.bias;
+        SEFD_TRY(sefd_pack_cconv(pp, st));
+    }
+    for (int p = 0; p < 2; ++p) {
+        // layer 0: W_ih [n][c*4+d] -> Wih0p[p][d][c][n] and Wih0T[d][p*512+n][c]
+        SEFD_TRY(sefd_permute3(prm + P->w_ih[0][p], ws + P->Wih0p + (size_t)p * 4 * 128 * G4, 4, 128, G4, 1, 4, 512, 0, st));
+        for (int d = 0; d < 4; ++d)
+            SEFD_TRY(sefd_permute3(prm + P->w_ih[0][p] + d, ws + P->Wih0T + ((size_t)d * 2 + p) * G4 * 128, 1, G4, 128,
+                                   0, 512, 4, 0, st));
+        // layer 1: W_ih [n][k] -> Wih1p[p][k][n]; Wih1T[p*512+n][k] (plain copy)
+        SEFD_TRY(sefd_permute3(prm + P->w_ih[1][p], ws + P->Wih1p + (size_t)p * 128 * G4, 1, 128, G4, 0, 1, 128, 0, st));
+        SEFD_TRY(sefd_permute3(prm + P->w_ih[1][p], ws + P->Wih1T + (size_t)p * G4 * 128, 1, 1, G4 * 128, 0, 0, 1, 0, st));
+        for (int l = 0; l < 2; ++l) {
+            SEFD_TRY(sefd_permute3(prm + P->w_hh[l][p], ws + P->Whh[l] + (size_t)p * G4 * RNN_H, 1, 1, G4 * RNN_H, 0, 0, 1, 0, st));
+            SEFD_TRY(sefd_add2(prm + P->b_ih[l][p], prm + P->b_hh[l][p], ws + P->bsum[l] + (size_t)p * G4, G4, st));
+        }
+    }
+    for (int q = 0; q < 2; ++q) {
+        // W_tr [c*4+d][k] -> Wtrp[q][d][k][c] ; WtrT[q][d][c][k] ; b_tr[c*4+d] -> btrp[q][d][c]
+        SEFD_TRY(sefd_permute3(prm + P->w_tr[q], ws + P->Wtrp + (size_t)q * 4 * 128 * 128, 4, 128, 128, 128, 1, 512, 0, st));
+        SEFD_TRY(sefd_permute3(prm + P->w_tr[q], ws + P->WtrT + (size_t)q * 4 * 128 * 128, 4, 128, 128, 128, 512, 1, 0, st));
+        SEFD_TRY(sefd_permute3(prm + P->b_tr[q], ws + P->btrp + (size_t)q * 4 * 128, 1, 4, 128, 0, 1, 4, 0, st));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const float* noisy, const float* target,
+                      int train, float* out_real, float* out_imag, float* out_wav, void* wsv, size_t ws_bytes,
+                      cudaStream_t st) {
+    SEFD_REQUIRE(ws_bytes >= P->ws_bytes, "forward: workspace too small (%zu < %zu)", ws_bytes, P->ws_bytes);
+    SEFD_REQUIRE(((uintptr_t)wsv & 255) == 0 && ((uintptr_t)prm & 15) == 0, "forward: workspace/params misaligned");
+    float* ws = (float*)wsv;
+    double* wsd = (double*)wsv;
+    const int B = P->B, T = P->T, L = P->L;
+    cudaMemsetAsync(wsd + P->stats_all, 0, sizeof(double) * P->stats_all_n, st);
+    SEFD_TRY(pack_weights(P, prm, ws, st));
+    SEFD_TRY(sefd_stft_launch(noisy, ws + P->spec, B, L, T, st));
+
+    auto bn = [&](const ConvLayer& c, int Ty, int tshift) -> int {
+        BnPreluFwdParams b;
+        memset(&b, 0, sizeof(b));
+        b.y = ws + c.y; b.z = ws + c.z;
+        b.BF = B * c.Fout; b.Ty = Ty; b.T = T; b.tshift = tshift; b.C = c.Cout;
+        b.stats = wsd + c.stats; b.n_stat = (double)B * c.Fout * Ty;
+        b.gamma = prm + c.gamma; b.beta = prm + c.beta; b.alpha = prm + c.alpha;
+        b.save = ws + c.save;
+        b.running_mean = bnbuf ? bnbuf + c.rmean : nullptr;
+        b.running_var = bnbuf ? bnbuf + c.rvar : nullptr;
+        b.momentum = BN_MOM; b.eps = BN_EPS;
+        b.use_running = !train;
+        if (!train) SEFD_REQUIRE(bnbuf != nullptr, "forward: eval mode needs the BN running statistics");
+        return sefd_bn_prelu_fwd(b, st);
+    };
+
+    // ---- encoder ----
+    for (int i = 0; i < NL; ++i) {
+        const ConvLayer& c = P->enc[i];
+        TapGemmParams g;
+        memset(&g, 0, sizeof(g));
+        if (i == 0) {
+            g.a[0].p = ws + P->spec + (size_t)T * 2;   // DC bin dropped (models.py:184)
+            g.a[0].sT = 2; g.a[0].sF = (long long)T * 2; g.a[0].sB = (long long)NBIN * T * 2; g.a[0].C = 2;
+        } else {
+            g.a[0] = src4(ws + P->enc[i - 1].z, c.Fin, T, c.Cin, c.Cin);
+        }
+        g.a[1] = no_src();
+        g.o[0] = dst4(ws + c.y, c.Fout, T, c.Cout, c.Cout);
+        g.o[1] = no_dst();
+        g.W = ws + c.Wf; g.bias = ws + c.bias;
+        g.stats = train ? wsd + c.stats : nullptr;
+        g.B = B; g.J = c.Fout; g.Tout = T; g.Fin = c.Fin; g.Tin = T;
+        conv_taps_down(g, -1);
+        SEFD_TRY(sefd_tapgemm_simt(g, st));
+        SEFD_TRY(bn(c, T, 0));
+    }
+
+    // ---- complex LSTM x2 (tools_for_model.py:162-177) ----
+    const size_t rowsz = (size_t)T * G4;
+    for (int l = 0; l < 2; ++l) {
+        for (int p = 0; p < 2; ++p)
+            for (int q = 0; q < 2; ++q) {
+                TapGemmParams g;
+                memset(&g, 0, sizeof(g));
+                if (l == 0) {
+                    g.a[0] = src4(ws + P->enc[NL - 1].z + q * 128, 4, T, 256, 128);
+                    g.ntaps = 4;
+                    for (int d = 0; d < 4; ++d) { g.df[d] = d; g.dt[d] = 0; g.wslab[d] = d; }
+                    g.Fin = 4;
+                    g.W = ws + P->Wih0p + (size_t)p * 4 * 128 * G4;
+                } else {
+                    g.a[0] = src4(ws + P->X1 + (size_t)q * B * T * RNN_H, 1, T, RNN_H, RNN_H);
+                    g.ntaps = 1;
+                    g.Fin = 1;
+                    g.W = ws + P->Wih1p + (size_t)p * 128 * G4;
+                }
+                g.a[1] = no_src();
+                g.o[0] = dst4(ws + P->Gt[l] + ((size_t)p * 2 + q) * B * rowsz, 1, T, G4, G4);
+                g.o[1] = no_dst();
+                g.bias = ws + P->bsum[l] + (size_t)p * G4;
+                g.B = B; g.J = 1; g.Tout = T; g.Tin = T;
+                g.fi_mul = 0; g.fo_mul = 1; g.fo_off = 0;
+                SEFD_TRY(sefd_tapgemm_simt(g, st));
+            }
+        LstmFwdParams lp;
+        lp.Whh = ws + P->Whh[l]; lp.G = ws + P->Gt[l]; lp.Hh = ws + P->Hh[l]; lp.Cc = ws + P->Cc[l];
+        lp.rows = 2 * B; lp.T = T;
+        SEFD_TRY(sefd_lstm_fwd_launch(lp, st));
+        SEFD_TRY(sefd_clstm_combine(ws + P->Hh[l], ws + (l == 0 ? P->X1 : P->X2), (long long)B * T * RNN_H, st));
+    }
+    // projection r_trans / i_trans (Linear 128 -> 512), output feature c*4+d -> U[b][d][t][q*128+c]
+    for (int q = 0; q < 2; ++q) {
+        TapGemmParams g;
+        memset(&g, 0, sizeof(g));
+        g.a[0] = src4(ws + P->X2 + (size_t)q * B * T * RNN_H, 1, T, RNN_H, RNN_H);
+        g.a[1] = no_src();
+        g.o[0] = dst4(ws + P->U + q * 128, 4, T, 256, 128);
+        g.o[1] = no_dst();
+        g.W = ws + P->Wtrp + (size_t)q * 4 * 128 * 128; g.wJ = 128 * 128;
+        g.bias = ws + P->btrp + (size_t)q * 4 * 128; g.bJ = 128;
+        g.B = B; g.J = 4; g.Tout = T; g.Fin = 1; g.Tin = T;
+        g.fi_mul = 0; g.fo_mul = 1; g.fo_off = 0;
+        g.ntaps = 1;
+        SEFD_TRY(sefd_tapgemm_simt(g, st));
+    }
+
+    // ---- decoder (models.py:222-226): convT on complex_cat(out, skip), BN over T+1 frames, drop frame 0 ----
+    for (int j = 0; j < NL; ++j) {
+        const ConvLayer& c = P->dec[j];
+        const int Ch = c.Cin / 2;
+        const float* in0 = j == 0 ? ws + P->U : ws + P->dec[j - 1].z;
+        const float* in1 = ws + P->enc[NL - 1 - j].z;
+        for (int ph = 0; ph < 2; ++ph) {
+            TapGemmParams g;
+            memset(&g, 0, sizeof(g));
+            g.a[0] = src4(in0, c.Fin, T, Ch, Ch);
+            g.a[1] = src4(in1, c.Fin, T, Ch, Ch);
+            g.o[0] = dst4(ws + c.y, c.Fout, T + 1, c.Cout, c.Cout);
+            g.o[1] = no_dst();
+            g.W = ws + c.Wf; g.bias = ws + c.bias;
+            g.stats = (train && j != NL - 1) ? wsd + c.stats : nullptr;
+            g.B = B; g.J = c.Fin; g.Tout = T + 1; g.Fin = c.Fin; g.Tin = T;
+            conv_taps_up(g, ph, 0);
+            SEFD_TRY(sefd_tapgemm_simt(g, st));
+        }
+        if (j != NL - 1) SEFD_TRY(bn(c, T + 1, 1));
+    }
+
+    // ---- mask, ISTFT, clamp ----
+    const ConvLayer& last = P->dec[NL - 1];
+    MaskIstftParams m;
+    memset(&m, 0, sizeof(m));
+    m.spec = ws + P->spec;
+    m.mask = ws + last.y;
+    m.mT = 2; m.mF = (long long)(T + 1) * 2; m.mB = (long long)256 * (T + 1) * 2;
+    m.m_tshift = 1;
+    m.mode = P->mask_mode;
+    m.B = B; m.L = L; m.T = T;
+    m.out_real = out_real; m.out_imag = out_imag; m.out_wav = out_wav;
+    m.raw_wav = ws + P->raw_wav;
+    m.target = target; m.dots = wsd + P->dots;
+    return sefd_mask_istft_launch(m, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, float* grads, void* wsv,
+                       size_t ws_bytes, cudaStream_t st) {
+    SEFD_REQUIRE(ws_bytes >= P->ws_bytes, "backward: workspace too small");
+    float* ws = (float*)wsv;
+    double* wsd = (double*)wsv;
+    const int B = P->B, T = P->T, L = P->L;
+    float* dY = ws + P->dY;
+    float* dWs = ws + P->dWs;
+
+    auto bn_bwd = [&](const ConvLayer& c, int Ty, int tshift) -> int {
+        BnPreluBwdParams b;
+        memset(&b, 0, sizeof(b));
+        b.y = ws + c.y; b.dz = ws + c.dz; b.dy = dY;
+        b.BF = B * c.Fout; b.Ty = Ty; b.T = T; b.tshift = tshift; b.C = c.Cout;
+        b.n_stat = (double)B * c.Fout * Ty;
+        b.gamma = prm + c.gamma; b.beta = prm + c.beta; b.alpha = prm + c.alpha; b.save = ws + c.save;
+        b.red = wsd + P->red;
+        b.dgamma = grads + c.gamma; b.dbeta = grads + c.beta; b.dalpha = grads + c.alpha;
+        return sefd_bn_prelu_bwd(b, st);
+    };
+    auto fold = [&](const ConvLayer& c, bool dec, const float* dbias) -> int {
+        CconvFoldParams f;
+        f.dWf = dWs; f.dbias = dbias;
+        f.Ci2 = c.Cin / 2; f.Co2 = c.Cout / 2; f.transposed = dec; f.two_src = dec;
+        f.dwr = grads + c.wr; f.dwi = grads + c.wi; f.dbr = grads + c.br; f.dbi = grads + c.bi;
+        return sefd_fold_cconv(f, st);
+    };
+
+    // ---- ISTFT^T and mask Jacobian -> d(mask) laid out like dec[5].y ----
+    const ConvLayer& last = P->dec[NL - 1];
+    {
+        MaskIstftBwdParams m;
+        memset(&m, 0, sizeof(m));
+        m.dwav = dwav; m.raw_wav = ws + P->raw_wav; m.spec = ws + P->spec; m.mask = ws + last.y; m.dmask = dY;
+        m.mT = 2; m.mF = (long long)(T + 1) * 2; m.mB = (long long)256 * (T + 1) * 2;
+        m.m_tshift = 1; m.mode = P->mask_mode; m.B = B; m.L = L; m.T = T;
+        SEFD_TRY(sefd_mask_istft_bwd_launch(m, st));
+    }
+
+    // ---- decoder backward ----
+    for (int j = NL - 1; j >= 0; --j) {
+        const ConvLayer& c = P->dec[j];
+        const int Ch = c.Cin / 2;
+        const float* in0 = j == 0 ? ws + P->U : ws + P->dec[j - 1].z;
+        const float* in1 = ws + P->enc[NL - 1 - j].z;
+        const float* dbias = nullptr;
+        if (j != NL - 1) {
+            SEFD_TRY(bn_bwd(c, T + 1, 1));
+        } else {
+            SEFD_TRY(sefd_colsum2(dY, 1, 0, (long long)B * c.Fout * (T + 1), c.Cout, c.Cout, wsd + P->red, ws + P->dbs, st));
+            dbias = ws + P->dbs;
+        }
+        // weight gradient
+        cudaMemsetAsync(dWs, 0, sizeof(float) * 10 * c.Cin * c.Cout, st);
+        WgradParams wg;
+        memset(&wg, 0, sizeof(wg));
+        wg.a[0] = src4(in0, c.Fin, T, Ch, Ch);
+        wg.a[1] = src4(in1, c.Fin, T, Ch, Ch);
+        wg.g = src4(dY, c.Fout, T + 1, c.Cout, c.Cout);
+        wg.dW = dWs;
+        wg.B = B; wg.J = c.Fin; wg.Tg = T + 1; wg.Fa = c.Fin; wg.Ta = T; wg.Fg = c.Fout;
+        wg.a_mul = 1; wg.g_mul = 2; wg.ntaps = 10;
+        for (int kf = 0; kf < 5; ++kf)
+            for (int kt = 0; kt < 2; ++kt) {
+                const int i = kf * 2 + kt;
+                wg.a_off[i] = 0; wg.g_off[i] = kf - 2; wg.dt[i] = -kt; wg.wslab[i] = i;
+            }
+        SEFD_TRY(sefd_wgrad_simt(wg, st));
+        SEFD_TRY(fold(c, true, dbias));
+        // data gradient: d(in0) and d(skip)
+        TapGemmParams g;
+        memset(&g, 0, sizeof(g));
+        g.a[0] = src4(dY, c.Fout, T + 1, c.Cout, c.Cout);
+        g.a[1] = no_src();
+        g.o[0] = dst4(j == 0 ? ws + P->dU : ws + P->dec[j - 1].dz, c.Fin, T, Ch, Ch);
+        g.o[1] = dst4(ws + P->enc[NL - 1 - j].dz, c.Fin, T, Ch, Ch);
+        g.W = ws + c.Wt;
+        g.B = B; g.J = c.Fin; g.Tout = T; g.Fin = c.Fout; g.Tin = T + 1;
+        conv_taps_down(g, +1);
+        SEFD_TRY(sefd_tapgemm_simt(g, st));
+    }
+
+    // ---- projection backward ----
+    const long long nX = (long long)B * T * RNN_H;
+    for (int q = 0; q < 2; ++q) {
+        TapGemmParams g;
+        memset(&g, 0, sizeof(g));
+        g.a[0] = src4(ws + P->dU + q * 128, 4, T, 256, 128);
+        g.a[1] = no_src();
+        g.o[0] = dst4(ws + P->dX + (size_t)q * nX, 1, T, RNN_H, RNN_H);
+        g.o[1] = no_dst();
+        g.W = ws + P->WtrT + (size_t)q * 4 * 128 * 128;
+        g.B = B; g.J = 1; g.Tout = T; g.Fin = 4; g.Tin = T;
+        g.fi_mul = 0; g.fo_mul = 1;
+        g.ntaps = 4;
+        for (int d = 0; d < 4; ++d) { g.df[d] = d; g.dt[d] = 0; g.wslab[d] = d; }
+        SEFD_TRY(sefd_tapgemm_simt(g, st));
+        // dW_tr[c*4+d][k] = sum dU[b][d][t][q*128+c] * X2[q][b][t][k]
+        cudaMemsetAsync(dWs, 0, sizeof(float) * 4 * 128 * 128, st);
+        WgradParams wg;
+        memset(&wg, 0, sizeof(wg));
+        wg.a[0] = src4(ws + P->X2 + (size_t)q * nX, 1, T, RNN_H, RNN_H);
+        wg.a[1] = no_src();
+        wg.g = src4(ws + P->dU + q * 128, 4, T, 256, 128);
+        wg.dW = dWs;
+        wg.B = B; wg.J = 1; wg.Tg = T; wg.Fa = 1; wg.Ta = T; wg.Fg = 4;
+        wg.a_mul = 0; wg.g_mul = 0; wg.ntaps = 4;
+        for (int d = 0; d < 4; ++d) { wg.a_off[d] = 0; wg.g_off[d] = d; wg.dt[d] = 0; wg.wslab[d] = d; }
+        SEFD_TRY(sefd_wgrad_simt(wg, st));
+        // dWs[d][k][c] -> grads[c][d][k]
+        SEFD_TRY(sefd_permute3(dWs, grads + P->w_tr[q], 128, 4, 128, 1, 128 * 128, 128, 0, st));
+    }
+    // db_tr[q][c*4+d] = sum_{b,t} dU[b][d][t][q*128+c]
+    for (int d = 0; d < 4; ++d)
+        SEFD_TRY(sefd_colsum2(ws + P->dU + (size_t)d * T * 256, B, (long long)4 * T * 256, T, 256, 256,
+                              wsd + P->red, ws + P->dbs + d * 256, st));
+    for (int q = 0; q < 2; ++q)   // dbs[d][q*128+c] -> grads[c*4+d]
+        SEFD_TRY(sefd_permute3(ws + P->dbs + q * 128, grads + P->b_tr[q], 1, 128, 4, 0, 1, 256, 0, st));
+
+    // ---- LSTM backward (layer 1 then layer 0) ----
+    for (int l = 1; l >= 0; --l) {
+        SEFD_TRY(sefd_clstm_combine_bwd(ws + P->dX, ws + P->dH, nX, st));
+        LstmBwdParams lb;
+        lb.Whh = ws + P->Whh[l]; lb.G = ws + P->Gt[l]; lb.Cc = ws + P->Cc[l]; lb.dH = ws + P->dH; lb.dG = ws + P->dG;
+        lb.rows = 2 * B; lb.T = T;
+        SEFD_TRY(sefd_lstm_bwd_launch(lb, st));
+        const size_t lstm_sz = (size_t)2 * B * T * G4;     // one LSTM's dG
+        // data gradient into the layer input
+        for (int q = 0; q < 2; ++q) {
+            TapGemmParams g;
+            memset(&g, 0, sizeof(g));
+            g.a[0] = src4(ws + P->dG + (size_t)q * B * T * G4, 1, T, G4, G4);
+            g.a[1] = src4(ws + P->dG + lstm_sz + (size_t)q * B * T * G4, 1, T, G4, G4);
+            g.o[1] = no_dst();
+            g.B = B; g.Tout = T; g.Fin = 1; g.Tin = T;
+            g.fi_mul = 0; g.fo_mul = 1; g.ntaps = 1;
+            if (l == 1) {
+                g.o[0] = dst4(ws + P->dX + (size_t)q * nX, 1, T, RNN_H, RNN_H);
+                g.W = ws + P->Wih1T; g.J = 1;
+            } else {
+                g.o[0] = dst4(ws + P->enc[NL - 1].dz + q * 128, 4, T, 256, 128);
+                g.accum[0] = 1;                                   // the skip gradient from decoder 0 is already there
+                g.W = ws + P->Wih0T; g.wJ = (long long)2 * G4 * 128; g.J = 4;
+            }
+            SEFD_TRY(sefd_tapgemm_simt(g, st));
+        }
+        // weight gradients
+        for (int p = 0; p < 2; ++p) {
+            const float* dGp = ws + P->dG + (size_t)p * lstm_sz;
+            // W_hh: dW[n][k] = sum_{rows, t>=1} dG[t][n] h[t-1][k]
+            cudaMemsetAsync(dWs, 0, sizeof(float) * 128 * G4, st);
+            WgradParams wg;
+            memset(&wg, 0, sizeof(wg));
+            wg.a[0] = src4(ws + P->Hh[l] + (size_t)p * 2 * B * T * RNN_H, 1, T, RNN_H, RNN_H);
+            wg.a[1] = no_src();
+            wg.g = src4(dGp, 1, T, G4, G4);
+            wg.dW = dWs;
+            wg.B = 2 * B; wg.J = 1; wg.Tg = T; wg.Fa = 1; wg.Ta = T; wg.Fg = 1;
+            wg.ntaps = 1; wg.dt[0] = -1;
+            SEFD_TRY(sefd_wgrad_simt(wg, st));
+            SEFD_TRY(sefd_permute3(dWs, grads + P->w_hh[l][p], G4, 1, 128, 1, 0, G4, 0, st));   // [k][n] -> [n][k]
+            // W_ih
+            if (l == 1) {
+                cudaMemsetAsync(dWs, 0, sizeof(float) * 128 * G4, st);
+                wg.a[0] = src4(ws + P->X1, 1, T, RNN_H, RNN_H);      // [q][B] rows are contiguous = 2B rows
+                wg.dt[0] = 0;
+                SEFD_TRY(sefd_wgrad_simt(wg, st));
+                SEFD_TRY(sefd_permute3(dWs, grads + P->w_ih[1][p], G4, 1, 128, 1, 0, G4, 0, st));
+            } else {
+                cudaMemsetAsync(dWs, 0, sizeof(float) * 4 * 128 * G4, st);
+                for (int q = 0; q < 2; ++q) {
+                    WgradParams w0;
+                    memset(&w0, 0, sizeof(w0));
+                    w0.a[0] = src4(ws + P->enc[NL - 1].z + q * 128, 4, T, 256, 128);
+                    w0.a[1] = no_src();
+                    w0.g = src4(dGp + (size_t)q * B * T * G4, 1, T, G4, G4);
+                    w0.dW = dWs;
+                    w0.B = B; w0.J = 1; w0.Tg = T; w0.Fa = 4; w0.Ta = T; w0.Fg = 1;
+                    w0.a_mul = 0; w0.g_mul = 0; w0.ntaps = 4;
+                    for (int d = 0; d < 4; ++d) { w0.a_off[d] = d; w0.g_off[d] = 0; w0.dt[d] = 0; w0.wslab[d] = d; }
+                    SEFD_TRY(sefd_wgrad_simt(w0, st));
+                }
+                // dWs[d][c][n] -> grads[n][c][d]
+                SEFD_TRY(sefd_permute3(dWs, grads + P->w_ih[0][p], G4, 128, 4, 1, G4, (long long)128 * G4, 0, st));
+            }
+            // biases: both get sum over rows and time of dG
+            SEFD_TRY(sefd_colsum2(dGp, 1, 0, (long long)2 * B * T, G4, G4, wsd + P->red, grads + P->b_ih[l][p], st));
+            SEFD_TRY(sefd_permute3(grads + P->b_ih[l][p], grads + P->b_hh[l][p], 1, 1, G4, 0, 0, 1, 0, st));
+        }
+    }
+
+    // ---- encoder backward ----
+    for (int i = NL - 1; i >= 0; --i) {
+        const ConvLayer& c = P->enc[i];
+        SEFD_TRY(bn_bwd(c, T, 0));
+        cudaMemsetAsync(dWs, 0, sizeof(float) * 10 * c.Cin * c.Cout, st);
+        WgradParams wg;
+        memset(&wg, 0, sizeof(wg));
+        if (i == 0) {
+            wg.a[0].p = ws + P->spec + (size_t)T * 2;
+            wg.a[0].sT = 2; wg.a[0].sF = (long long)T * 2; wg.a[0].sB = (long long)NBIN * T * 2; wg.a[0].C = 2;
+        } else {
+            wg.a[0] = src4(ws + P->enc[i - 1].z, c.Fin, T, c.Cin, c.Cin);
+        }
+        wg.a[1] = no_src();
+        wg.g = src4(dY, c.Fout, T, c.Cout, c.Cout);
+        wg.dW = dWs;
+        wg.B = B; wg.J = c.Fout; wg.Tg = T; wg.Fa = c.Fin; wg.Ta = T; wg.Fg = c.Fout;
+        wg.a_mul = 2; wg.g_mul = 1; wg.ntaps = 10;
+        for (int kf = 0; kf < 5; ++kf)
+            for (int kt = 0; kt < 2; ++kt) {
+                const int k = kf * 2 + kt;
+                wg.a_off[k] = kf - 2; wg.g_off[k] = 0; wg.dt[k] = kt - 1; wg.wslab[k] = k;
+            }
+        SEFD_TRY(sefd_wgrad_simt(wg, st));
+        SEFD_TRY(fold(c, false, nullptr));
+        if (i > 0) {
+            for (int ph = 0; ph < 2; ++ph) {
+                TapGemmParams g;
+                memset(&g, 0, sizeof(g));
+                g.a[0] = src4(dY, c.Fout, T, c.Cout, c.Cout);
+                g.a[1] = no_src();
+                g.o[0] = dst4(ws + P->enc[i - 1].dz, c.Fin, T, c.Cin, c.Cin);
+                g.o[1] = no_dst();
+                g.accum[0] = 1;                                   // skip gradient already stored by the decoder
+                g.W = ws + c.Wt;
+                g.B = B; g.J = c.Fout; g.Tout = T; g.Fin = c.Fout; g.Tin = T;
+                conv_taps_up(g, ph, 1);
+                SEFD_TRY(sefd_tapgemm_simt(g, st));
+            }
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan accessors of the C ABI (they need the struct definition, so they live here)
+// ------------------------------------------------------------------------------------------------
+#include "../../include/sefd.h"
+
+extern "C" {
+
+void sefd_dccrn_plan_destroy(sefd_plan* plan) { delete plan; }
+size_t sefd_dccrn_workspace_bytes(const sefd_plan* plan) { return plan ? plan->ws_bytes : 0; }
+long long sefd_dccrn_param_floats(const sefd_plan* plan) { return plan ? plan->n_param_floats : 0; }
+long long sefd_dccrn_buffer_floats(const sefd_plan* plan) { return plan ? plan->n_buffer_floats : 0; }
+int sefd_dccrn_num_params(const sefd_plan* plan) { return plan ? (int)plan->params.size() : 0; }
+int sefd_dccrn_num_buffers(const sefd_plan* plan) { return plan ? (int)plan->buffers.size() : 0; }
+
+int sefd_dccrn_entry_info(const sefd_plan* plan, int kind, int idx, char* name, int name_cap, long long* offset,
+                          long long* numel, int* ndim, long long shape[4]) {
+    SEFD_REQUIRE(plan != nullptr, "entry_info: null plan");
+    const std::vector<ParamInfo>& v = kind == 0 ? plan->params : plan->buffers;
+    SEFD_REQUIRE(idx >= 0 && idx < (int)v.size(), "entry_info: index %d out of range", idx);
+    const ParamInfo& pi = v[idx];
+    SEFD_REQUIRE((int)pi.name.size() < name_cap, "entry_info: name buffer too small");
+    strcpy(name, pi.name.c_str());
+    *offset = pi.offset;
+    *numel = pi.numel;
+    *ndim = pi.ndim;
+    for (int i = 0; i < 4; ++i) shape[i] = pi.shape[i];
+    return 0;
+}
+
+int sefd_dccrn_tensor_info(const sefd_plan* P, const char* name, long long* off, int* ndim, long long shape[4]) {
+    SEFD_REQUIRE(P != nullptr && name != nullptr, "tensor_info: null argument");
+    const long long B = P->B, T = P->T;
+    auto set = [&](size_t o, long long a, long long b, long long c, long long d) {
+        *off = (long long)o; *ndim = 4; shape[0] = a; shape[1] = b; shape[2] = c; shape[3] = d;
+        return 0;
+    };
+    const std::string n(name);
+    if (n == "spec") return set(P->spec, B, NBIN, T, 2);
+    if (n == "raw_wav") return set(P->raw_wav, 1, 1, B, P->L);
+    if (n == "X1") return set(P->X1, 2, B, T, RNN_H);
+    if (n == "X2") return set(P->X2, 2, B, T, RNN_H);
+    if (n == "dX") return set(P->dX, 2, B, T, RNN_H);
+    if (n == "U") return set(P->U, B, 4, T, 256);
+    if (n == "dU") return set(P->dU, B, 4, T, 256);
+    if (n.size() >= 6 && (n.compare(0, 3, "enc") == 0 || n.compare(0, 3, "dec") == 0)) {
+        const bool dec = n[0] == 'd';
+        const int i = n[3] - '0';
+        SEFD_REQUIRE(i >= 0 && i < NL && n[4] == '.', "tensor_info: bad name %s", name);
+        const ConvLayer& c = dec ? P->dec[i] : P->enc[i];
+        const std::string f = n.substr(5);
+        if (f == "y") return set(c.y, B, c.Fout, dec ? T + 1 : T, c.Cout);
+        if (f == "z" && !(dec && i == NL - 1)) return set(c.z, B, c.Fout, T, c.Cout);
+        if (f == "dz" && !(dec && i == NL - 1)) return set(c.dz, B, c.Fout, T, c.Cout);
+    }
+    if (n.size() == 7 && n.compare(0, 4, "lstm") == 0 && n[5] == '.') {
+        const int l = n[4] - '0';
+        SEFD_REQUIRE(l == 0 || l == 1, "tensor_info: bad name %s", name);
+        if (n[6] == 'G') return set(P->Gt[l], 2, 2 * B, T, G4);
+        if (n[6] == 'H') return set(P->Hh[l], 2, 2 * B, T, RNN_H);
+        if (n[6] == 'C') return set(P->Cc[l], 2, 2 * B, T, RNN_H);
+    }
+    sefd_set_error("tensor_info: unknown tensor '%s'", name);
+    return -1;
+}
+
+int sefd_dccrn_loss(const sefd_plan* P, const float* out_wav, const float* target, int kind, int reuse_dots,
+                    float* loss, float* coef, void* ws, void* stream) {
+    SEFD_REQUIRE(P && out_wav && target && loss && coef && ws, "dccrn_loss: null argument");
+    double* wsd = (double*)ws;
+    return sefd_loss_fwd_launch(out_wav, target, P->B, P->L, kind, wsd + P->dots, reuse_dots, loss, coef,
+                                (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,13 @@
+#pragma once
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "lstm.cuh"
+#include "stft.cuh"
+
+struct sefd_plan;
+sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode);
+int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const float* noisy, const float* target,
+                      int train, float* out_real, float* out_imag, float* out_wav, void* ws, size_t ws_bytes,
+                      cudaStream_t st);
+int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, float* grads, void* ws,
+                       size_t ws_bytes, cudaStream_t st);

@@ -1,0 +1,57 @@
+#pragma once
+#include "common.cuh"
+
+struct BnPreluFwdParams {
+    const float* y;        // [BF][Ty][C] raw conv output
+    float* z;              // [BF][T][C]  z[bf,t] = prelu(bn(y[bf, t+tshift]))
+    int BF, Ty, T, tshift, C;
+    const double* stats;   // [2][C] sum / sum of squares over the n_stat elements of y (train mode)
+    double n_stat;
+    const float *gamma, *beta, *alpha;
+    float* save;           // [2][C] batch mean, inv-std (written by block 0 in train mode)
+    float *running_mean, *running_var;   // updated in train mode when non-null; read when use_running
+    float momentum, eps;
+    int use_running;       // eval mode
+};
+
+struct BnPreluBwdParams {
+    const float* y;        // [BF][Ty][C]
+    const float* dz;       // [BF][T][C]
+    float* dy;             // [BF][Ty][C]
+    int BF, Ty, T, tshift, C;
+    double n_stat;
+    const float *gamma, *beta, *alpha, *save;
+    double* red;           // [2C+1] scratch
+    float *dgamma, *dbeta, *dalpha;
+};
+
+struct CconvPackParams {
+    const float *wr, *wi, *br, *bi;
+    int Ci2, Co2;          // complex channel counts (half of the real channel counts)
+    int transposed;        // 0: Conv2d weight [Co2][Ci2][5][2]; 1: ConvTranspose2d weight [Ci2][Co2][5][2]
+    int two_src;           // K ordering for the skip-concat input
+    float* Wf;             // [10][K][N]
+    float* Wt;             // [10][N][K]
+    float* bias;           // [N]
+};
+
+struct CconvFoldParams {
+    const float* dWf;      // [10][K][N] block-real weight gradient
+    const float* dbias;    // [N] block-real bias gradient or nullptr (-> zeros)
+    int Ci2, Co2, transposed, two_src;
+    float *dwr, *dwi, *dbr, *dbi;
+};
+
+int sefd_bn_prelu_fwd(const BnPreluFwdParams& p, cudaStream_t st);
+int sefd_bn_prelu_bwd(const BnPreluBwdParams& p, cudaStream_t st);
+int sefd_pack_cconv(const CconvPackParams& p, cudaStream_t st);
+int sefd_fold_cconv(const CconvFoldParams& p, cudaStream_t st);
+int sefd_permute3(const float* src, float* dst, int na, int nb, int nc, long long sa, long long sb, long long sc,
+                  int accumulate, cudaStream_t st);
+int sefd_add2(const float* a, const float* b, float* o, long long n, cudaStream_t st);
+int sefd_colsum2(const float* x, int nO, long long sO, long long nI, long long sI, int C, double* scratch, float* out,
+                 cudaStream_t st);
+int sefd_clstm_combine(const float* H, float* X, long long n, cudaStream_t st);
+int sefd_clstm_combine_bwd(const float* dX, float* dH, long long n, cudaStream_t st);
+int sefd_adam(float* w, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+              int step, float gscale, cudaStream_t st);

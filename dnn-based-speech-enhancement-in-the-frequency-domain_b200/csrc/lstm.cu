@@ -1,0 +1,227 @@
+// Recurrent part of the complex LSTM (tools_for_model.py:141-181; nn.LSTM, H = 128, gate order i,f,g,o).
+// The four passes of NavieComplexLSTM (real/imag LSTM x real/imag input) are two LSTMs run on the
+// batch-concatenated rows [real inputs ; imag inputs]; the input projections x W_ih^T + b are computed for
+// all time steps by the tap-GEMM beforehand, so these kernels only do the T sequential steps.
+//
+// One CTA (512 threads) owns R rows of one LSTM for the whole sequence.  W_hh (512 x 128 fp32 = 256 KB)
+// does not fit in shared memory, so every thread keeps half of its weight row in registers and the other
+// half in shared memory (128 KB); h / gate exchange goes through shared memory with two barriers a step.
+#include "lstm.cuh"
+
+namespace {
+
+constexpr int H = 128, G4 = 512, KR = 64;   // KR weights per thread live in registers, H-KR in smem
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <int R>
+__global__ void __launch_bounds__(512, 1) lstm_fwd_kernel(const LstmFwdParams p) {
+    extern __shared__ __align__(16) float sm[];
+    float* Ws = sm;                    // [H-KR][512]
+    float* hs = Ws + (H - KR) * G4;    // [R][H]
+    float* gs = hs + R * H;            // [R][512]
+    const int g = threadIdx.x, lstm = blockIdx.y, row0 = blockIdx.x * R;
+    const float* W = p.Whh + ((size_t)lstm * G4 + g) * H;
+    float wreg[KR];
+#pragma unroll
+    for (int k = 0; k < KR; ++k) wreg[k] = W[k];
+    for (int k = 0; k < H - KR; ++k) Ws[k * G4 + g] = W[KR + k];
+    for (int i = g; i < R * H; i += 512) hs[i] = 0.f;
+
+    const int cr = g >> 7, cj = g & 127;
+    float* Gr[R];
+    bool valid[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        valid[r] = row0 + r < p.rows;
+        Gr[r] = p.G + ((size_t)lstm * p.rows + (valid[r] ? row0 + r : 0)) * p.T * G4;
+    }
+    const bool cvalid = cr < R && row0 + cr < p.rows;
+    const size_t hbase = ((size_t)lstm * p.rows + (cvalid ? row0 + cr : 0)) * p.T * H + cj;
+    float c = 0.f;
+    float pre[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) pre[r] = valid[r] ? Gr[r][g] : 0.f;
+    const int gate = g >> 7;
+    __syncthreads();
+
+    for (int t = 0; t < p.T; ++t) {
+        float acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = pre[r];
+        if (t + 1 < p.T) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) pre[r] = valid[r] ? Gr[r][(size_t)(t + 1) * G4 + g] : 0.f;
+        }
+#pragma unroll
+        for (int k4 = 0; k4 < KR / 4; ++k4) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float4 h4 = *reinterpret_cast<const float4*>(&hs[r * H + 4 * k4]);
+                acc[r] = fmaf(wreg[4 * k4 + 0], h4.x, acc[r]);
+                acc[r] = fmaf(wreg[4 * k4 + 1], h4.y, acc[r]);
+                acc[r] = fmaf(wreg[4 * k4 + 2], h4.z, acc[r]);
+                acc[r] = fmaf(wreg[4 * k4 + 3], h4.w, acc[r]);
+            }
+        }
+#pragma unroll 4
+        for (int k4 = 0; k4 < (H - KR) / 4; ++k4) {
+            const float w0 = Ws[(4 * k4 + 0) * G4 + g], w1 = Ws[(4 * k4 + 1) * G4 + g];
+            const float w2 = Ws[(4 * k4 + 2) * G4 + g], w3 = Ws[(4 * k4 + 3) * G4 + g];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float4 h4 = *reinterpret_cast<const float4*>(&hs[r * H + KR + 4 * k4]);
+                acc[r] = fmaf(w0, h4.x, acc[r]);
+                acc[r] = fmaf(w1, h4.y, acc[r]);
+                acc[r] = fmaf(w2, h4.z, acc[r]);
+                acc[r] = fmaf(w3, h4.w, acc[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float a = gate == 2 ? tanhf(acc[r]) : sigmoidf_(acc[r]);
+            gs[r * G4 + g] = a;
+            if (valid[r]) Gr[r][(size_t)t * G4 + g] = a;
+        }
+        __syncthreads();
+        if (cr < R) {
+            const float ig = gs[cr * G4 + cj], fg = gs[cr * G4 + H + cj];
+            const float gg = gs[cr * G4 + 2 * H + cj], og = gs[cr * G4 + 3 * H + cj];
+            c = fmaf(fg, c, ig * gg);
+            const float h = og * tanhf(c);
+            hs[cr * H + cj] = h;
+            if (cvalid) {
+                p.Hh[hbase + (size_t)t * H] = h;
+                p.Cc[hbase + (size_t)t * H] = c;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(512, 1) lstm_bwd_kernel(const LstmBwdParams p) {
+    extern __shared__ __align__(16) float sm[];
+    float* Ws = sm;                     // [H-KR... as gate index][512 threads]
+    float* dgs = Ws + (H - KR) * G4;    // [R][512]
+    float* part = dgs + R * G4;         // [4][R][H]
+    const int tid = threadIdx.x, lstm = blockIdx.y, row0 = blockIdx.x * R;
+    const int q = tid >> 7, k = tid & 127;          // mat-vec role: gate block q, hidden unit k
+    const int cr = q, cj = k;                       // cell role: row cr, hidden unit cj
+    const float* W = p.Whh + (size_t)lstm * G4 * H;
+    float wreg[KR];
+#pragma unroll
+    for (int gg = 0; gg < KR; ++gg) wreg[gg] = W[(size_t)(q * H + gg) * H + k];
+    for (int gg = 0; gg < H - KR; ++gg) Ws[gg * G4 + tid] = W[(size_t)(q * H + KR + gg) * H + k];
+
+    const bool cvalid = cr < R && row0 + cr < p.rows;
+    const size_t row = (size_t)lstm * p.rows + (cvalid ? row0 + cr : 0);
+    const float* Gp = p.G + row * p.T * G4 + cj;
+    const float* Cp = p.Cc + row * p.T * H + cj;
+    const float* dHp = p.dH + row * p.T * H + cj;
+    float* dGp = p.dG + row * p.T * G4 + cj;
+
+    float dc_next = 0.f, dh_rec = 0.f;
+    // software prefetch of the next step's operands
+    float n_i = 0.f, n_f = 0.f, n_g = 0.f, n_o = 0.f, n_cprev = 0.f, n_dh = 0.f, c_t = 0.f;
+    if (cvalid) {
+        const int t = p.T - 1;
+        n_i = Gp[(size_t)t * G4]; n_f = Gp[(size_t)t * G4 + H]; n_g = Gp[(size_t)t * G4 + 2 * H]; n_o = Gp[(size_t)t * G4 + 3 * H];
+        c_t = Cp[(size_t)t * H];
+        n_cprev = t > 0 ? Cp[(size_t)(t - 1) * H] : 0.f;
+        n_dh = dHp[(size_t)t * H];
+    }
+    __syncthreads();
+
+    for (int t = p.T - 1; t >= 0; --t) {
+        if (cr < R) {
+            const float ig = n_i, fg = n_f, gg = n_g, og = n_o, cprev = n_cprev, dho = n_dh;
+            const float ct = c_t;
+            c_t = cprev;
+            if (cvalid && t > 0) {
+                const int u = t - 1;
+                n_i = Gp[(size_t)u * G4]; n_f = Gp[(size_t)u * G4 + H]; n_g = Gp[(size_t)u * G4 + 2 * H]; n_o = Gp[(size_t)u * G4 + 3 * H];
+                n_cprev = u > 0 ? Cp[(size_t)(u - 1) * H] : 0.f;
+                n_dh = dHp[(size_t)u * H];
+            }
+            const float dh = dho + dh_rec;
+            const float tc = tanhf(ct);
+            const float dc = fmaf(dh * og, 1.f - tc * tc, dc_next);
+            const float dpi = dc * gg * ig * (1.f - ig);
+            const float dpf = dc * cprev * fg * (1.f - fg);
+            const float dpg = dc * ig * (1.f - gg * gg);
+            const float dpo = dh * tc * og * (1.f - og);
+            dc_next = dc * fg;
+            dgs[cr * G4 + cj] = dpi;
+            dgs[cr * G4 + H + cj] = dpf;
+            dgs[cr * G4 + 2 * H + cj] = dpg;
+            dgs[cr * G4 + 3 * H + cj] = dpo;
+            if (cvalid) {
+                dGp[(size_t)t * G4] = dpi; dGp[(size_t)t * G4 + H] = dpf;
+                dGp[(size_t)t * G4 + 2 * H] = dpg; dGp[(size_t)t * G4 + 3 * H] = dpo;
+            }
+        }
+        __syncthreads();
+        float acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = 0.f;
+#pragma unroll
+        for (int g4 = 0; g4 < KR / 4; ++g4) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float4 d4 = *reinterpret_cast<const float4*>(&dgs[r * G4 + q * H + 4 * g4]);
+                acc[r] = fmaf(wreg[4 * g4 + 0], d4.x, acc[r]);
+                acc[r] = fmaf(wreg[4 * g4 + 1], d4.y, acc[r]);
+                acc[r] = fmaf(wreg[4 * g4 + 2], d4.z, acc[r]);
+                acc[r] = fmaf(wreg[4 * g4 + 3], d4.w, acc[r]);
+            }
+        }
+#pragma unroll 4
+        for (int g4 = 0; g4 < (H - KR) / 4; ++g4) {
+            const float w0 = Ws[(4 * g4 + 0) * G4 + tid], w1 = Ws[(4 * g4 + 1) * G4 + tid];
+            const float w2 = Ws[(4 * g4 + 2) * G4 + tid], w3 = Ws[(4 * g4 + 3) * G4 + tid];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float4 d4 = *reinterpret_cast<const float4*>(&dgs[r * G4 + q * H + KR + 4 * g4]);
+                acc[r] = fmaf(w0, d4.x, acc[r]);
+                acc[r] = fmaf(w1, d4.y, acc[r]);
+                acc[r] = fmaf(w2, d4.z, acc[r]);
+                acc[r] = fmaf(w3, d4.w, acc[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) part[(q * R + r) * H + k] = acc[r];
+        __syncthreads();
+        if (cr < R)
+            dh_rec = part[(0 * R + cr) * H + cj] + part[(1 * R + cr) * H + cj] + part[(2 * R + cr) * H + cj] +
+                     part[(3 * R + cr) * H + cj];
+    }
+}
+
+constexpr int LSTM_R = 4;
+
+}  // namespace
+
+int sefd_lstm_fwd_launch(const LstmFwdParams& p, cudaStream_t st) {
+    const size_t smem = sizeof(float) * ((H - KR) * G4 + LSTM_R * H + LSTM_R * G4);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(lstm_fwd_kernel<LSTM_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    dim3 grid((p.rows + LSTM_R - 1) / LSTM_R, 2);
+    lstm_fwd_kernel<LSTM_R><<<grid, 512, smem, st>>>(p);
+    return sefd_check_launch("lstm_fwd");
+}
+
+int sefd_lstm_bwd_launch(const LstmBwdParams& p, cudaStream_t st) {
+    const size_t smem = sizeof(float) * ((H - KR) * G4 + LSTM_R * G4 + 4 * LSTM_R * H);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(lstm_bwd_kernel<LSTM_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    dim3 grid((p.rows + LSTM_R - 1) / LSTM_R, 2);
+    lstm_bwd_kernel<LSTM_R><<<grid, 512, smem, st>>>(p);
+    return sefd_check_launch("lstm_bwd");
+}

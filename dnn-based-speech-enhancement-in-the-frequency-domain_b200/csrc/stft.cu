@@ -1,0 +1,570 @@
+// STFT, mask + ISTFT (+ clamp + loss dot products) and its adjoint, for win 400 / hop 100 / N 512.
+//
+// Reference semantics reproduced (file:line relative to the reference checkout):
+//  * ConvSTFT  (tools_for_model.py:54-61): zero-pad 300|300, frames of 400 x periodic Hann, zero-padded at
+//    the END to 512, rFFT  ->  (sum x w cos, -sum x w sin).
+//  * ConviSTFT (tools_for_model.py:90-112): synthesis with pinv of the truncated basis (NOT irfft). Closed form
+//    used here (derivation in DESIGN.md, checked to 1e-14 against numpy pinv):
+//        y[n] = Re sum_{k=0}^{256} S[k] e^{+2 pi i k n/512},  n < 400
+//        frame[n] = w[n]/256 * ( y[n] - P_{n mod 2}/456 ),  P_q = sum_{n = q mod 2} y[n]
+//    overlap-add, divide by coff = sum of 4 shifted w^2 + 1e-8, trim 300|300.
+//  * DC mask bin is zero (models.py:255-256), mask modes C/E/R (models.py:258-276), clamp (models.py:282).
+// Two real frames share one complex 512-point FFT (fft512.cuh).
+#include "fft512.cuh"
+#include "stft.cuh"
+
+namespace {
+
+constexpr int WIN = 400, HOP = 100, NFFT = 512, NBIN = 257, PAD = 300;
+constexpr float INV_HALF_N = 1.0f / 256.0f, INV_PAR = 1.0f / 456.0f;   // N/2 and N/2 + win/2
+
+__device__ __forceinline__ void init_tables(float2* tw, float* win, float* coff) {
+    for (int j = threadIdx.x; j < NFFT; j += blockDim.x) {
+        float s, c;
+        sincospif(2.0f * j / NFFT, &s, &c);
+        tw[j] = make_float2(c, -s);
+    }
+    for (int n = threadIdx.x; n < WIN; n += blockDim.x) win[n] = 0.5f - 0.5f * cospif(2.0f * n / WIN);
+    if (coff) {
+        __syncthreads();
+        for (int m = threadIdx.x; m < HOP; m += blockDim.x) {
+            float a = 0.f;
+            for (int r = 0; r < WIN / HOP; ++r) a += win[m + HOP * r] * win[m + HOP * r];
+            coff[m] = a + 1e-8f;
+        }
+    }
+}
+
+// sums over the even-n and odd-n samples of one 64-thread group; thread parity == sample parity.
+// scratch: 4 floats per group.
+__device__ __forceinline__ float2 group_parity_sums(float a, float b, float* scratch, int tid64) {
+    // reduce across lanes of equal parity inside the warp
+#pragma unroll
+    for (int o = 16; o >= 2; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    // lanes 0 (even) and 1 (odd) of each of the two warps hold partials
+    const int lane = tid64 & 31, w = tid64 >> 5;
+    __syncthreads();
+    if (lane < 2) {
+        scratch[(w * 2 + lane) * 2 + 0] = a;
+        scratch[(w * 2 + lane) * 2 + 1] = b;
+    }
+    __syncthreads();
+    const int par = tid64 & 1;
+    return make_float2(scratch[(0 * 2 + par) * 2 + 0] + scratch[(1 * 2 + par) * 2 + 0],
+                       scratch[(0 * 2 + par) * 2 + 1] + scratch[(1 * 2 + par) * 2 + 1]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// STFT forward: wav [B][L] -> spec [B][257][T][2]
+// ------------------------------------------------------------------------------------------------
+constexpr int SF = 16;                                  // frames per CTA
+constexpr int SEG = (SF - 1) * HOP + WIN;               // 1900 samples
+
+struct StftSmem {
+    float2 fft[4][NFFT];
+    float2 tw[NFFT];
+    float2 out[NBIN][SF];
+    float win[WIN];
+    float seg[SEG];
+    float scratch[4][8];
+    float coff[HOP];
+};
+
+__global__ void __launch_bounds__(256) stft_fwd_kernel(const float* __restrict__ wav, float* __restrict__ spec,
+                                                       int B, int L, int T) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StftSmem& S = *reinterpret_cast<StftSmem*>(smem_raw);
+    const int b = blockIdx.y, t0 = blockIdx.x * SF;
+    const int tid = threadIdx.x, g = tid >> 6, tid64 = tid & 63;
+    init_tables(S.tw, S.win, nullptr);
+    const float* w = wav + (long long)b * L;
+    for (int i = tid; i < SEG; i += 256) {
+        const int n = t0 * HOP + i - PAD;
+        S.seg[i] = (n >= 0 && n < L) ? __ldg(w + n) : 0.f;
+    }
+    __syncthreads();
+    for (int r = 0; r < SF / 8; ++r) {
+        const int fa = 8 * r + 2 * g;                   // local frame index of the pair (fa, fa+1)
+        float2* s = S.fft[g];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int n = tid64 + 64 * i;
+            float2 v = make_float2(0.f, 0.f);
+            if (n < WIN) v = make_float2(S.win[n] * S.seg[fa * HOP + n], S.win[n] * S.seg[(fa + 1) * HOP + n]);
+            s[n] = v;
+        }
+        __syncthreads();
+        fft512_cta<false>(s, S.tw, tid64);
+        // unpack the two real transforms: XA = (Z[k] + conj Z[N-k])/2, XB = (Z[k] - conj Z[N-k])/(2i)
+        for (int k = tid64; k <= 256; k += 64) {
+            const float2 z = s[k], zc = s[(NFFT - k) & (NFFT - 1)];
+            S.out[k][fa] = make_float2(0.5f * (z.x + zc.x), 0.5f * (z.y - zc.y));
+            S.out[k][fa + 1] = make_float2(0.5f * (z.y + zc.y), -0.5f * (z.x - zc.x));
+        }
+        __syncthreads();
+    }
+    float2* o = reinterpret_cast<float2*>(spec) + (long long)b * NBIN * T;
+    for (int e = tid; e < NBIN * SF; e += 256) {
+        const int k = e / SF, f = e % SF;
+        if (t0 + f < T) o[(long long)k * T + t0 + f] = S.out[k][f];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// mask apply + ISTFT + clamp (+ <est,tgt>, <tgt,tgt>, <est,est>)
+// ------------------------------------------------------------------------------------------------
+constexpr int IF = 32;                  // frames per CTA
+constexpr int IHB = IF - 3;             // hop blocks of output produced per CTA (29)
+constexpr int OLA = (IF + 3) * HOP;     // 3500
+
+struct IstftSmem {
+    float2 fft[4][NFFT];
+    float2 tw[NFFT];
+    float win[WIN];
+    float coff[HOP];
+    float fr[8][WIN];
+    float ola[OLA];
+    float scratch[4][8];
+    float red[3][8];
+};
+
+__device__ __forceinline__ float2 apply_mask(int mode, float2 x, float2 m) {
+    if (mode == SEFD_MASK_C) return make_float2(x.x * m.x - x.y * m.y, x.x * m.y + x.y * m.x);
+    if (mode == SEFD_MASK_R) return make_float2(x.x * m.x, x.y * m.y);
+    if (mode == SEFD_MASK_E) {
+        const float smag = sqrtf(x.x * x.x + x.y * x.y + 1e-8f);
+        const float sph = atan2f(x.y, x.x);
+        const float mm = sqrtf(m.x * m.x + m.y * m.y);
+        const float rp = m.x / (mm + 1e-8f), ip = m.y / (mm + 1e-8f);
+        const float ph = sph + atan2f(ip, rp);
+        const float em = tanhf(mm) * smag;
+        float sn, cs;
+        sincosf(ph, &sn, &cs);
+        return make_float2(em * cs, em * sn);
+    }
+    return x;   // SEFD_MASK_NONE: plain ISTFT of `spec`
+}
+
+__global__ void __launch_bounds__(256) mask_istft_fwd_kernel(const MaskIstftParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    IstftSmem& S = *reinterpret_cast<IstftSmem*>(smem_raw);
+    const int b = blockIdx.y, c = blockIdx.x;
+    const int tid = threadIdx.x, g = tid >> 6, tid64 = tid & 63;
+    const int f0 = IHB * c;                                  // first frame held by this CTA
+    const int T = p.T, L = p.L;
+    init_tables(S.tw, S.win, S.coff);
+    for (int i = tid; i < OLA; i += 256) S.ola[i] = 0.f;
+    const float2* X = reinterpret_cast<const float2*>(p.spec) + (long long)b * NBIN * T;
+    __syncthreads();
+
+    for (int r = 0; r < IF / 8; ++r) {
+        const int la = 8 * r + 2 * g;                        // local frame pair (la, la+1)
+        const int ta = f0 + la, tb = ta + 1;
+        float2* s = S.fft[g];
+        const bool va = ta < T, vb = tb < T;
+        // ownership for the spectrum outputs: frames [f0+3, f0+3+IHB) plus frames 0..2 in the first CTA
+        const bool oa = va && (la >= 3 ? la < 3 + IHB : c == 0);
+        const bool ob = vb && (la + 1 >= 3 ? la + 1 < 3 + IHB : c == 0);
+        for (int k = tid64; k <= 256; k += 64) {
+            float2 sa = make_float2(0.f, 0.f), sb = sa;
+            if (va) {
+                const float2 x = __ldg(X + (long long)k * T + ta);
+                float2 m = make_float2(0.f, 0.f);
+                if (p.mode != SEFD_MASK_NONE && k >= 1)
+                    m = __ldg(reinterpret_cast<const float2*>(p.mask + b * p.mB + (long long)(k - 1) * p.mF +
+                                                              (long long)(ta + p.m_tshift) * p.mT));
+                sa = (p.mode != SEFD_MASK_NONE && k == 0) ? make_float2(0.f, 0.f) : apply_mask(p.mode, x, m);
+            }
+            if (vb) {
+                const float2 x = __ldg(X + (long long)k * T + tb);
+                float2 m = make_float2(0.f, 0.f);
+                if (p.mode != SEFD_MASK_NONE && k >= 1)
+                    m = __ldg(reinterpret_cast<const float2*>(p.mask + b * p.mB + (long long)(k - 1) * p.mF +
+                                                              (long long)(tb + p.m_tshift) * p.mT));
+                sb = (p.mode != SEFD_MASK_NONE && k == 0) ? make_float2(0.f, 0.f) : apply_mask(p.mode, x, m);
+            }
+            if (p.out_real) {
+                const long long o = ((long long)b * NBIN + k) * T;
+                if (oa) { p.out_real[o + ta] = sa.x; p.out_imag[o + ta] = sa.y; }
+                if (ob) { p.out_real[o + tb] = sb.x; p.out_imag[o + tb] = sb.y; }
+            }
+            // Hermitian parts of the one-sided spectra, packed A + iB
+            if (k == 0 || k == 256) {
+                s[k] = make_float2(sa.x, sb.x);
+            } else {
+                s[k] = make_float2(0.5f * (sa.x - sb.y), 0.5f * (sa.y + sb.x));
+                s[NFFT - k] = make_float2(0.5f * (sa.x + sb.y), 0.5f * (sb.x - sa.y));
+            }
+        }
+        __syncthreads();
+        fft512_cta<true>(s, S.tw, tid64);
+        float ea = 0.f, eb = 0.f;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const int n = tid64 + 64 * i;
+            if (n < WIN) { ea += s[n].x; eb += s[n].y; }
+        }
+        const float2 par = group_parity_sums(ea, eb, S.scratch[g], tid64);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const int n = tid64 + 64 * i;
+            if (n < WIN) {
+                const float wn = S.win[n] * INV_HALF_N;
+                S.fr[2 * g][n] = wn * (s[n].x - par.x * INV_PAR);
+                S.fr[2 * g + 1][n] = wn * (s[n].y - par.y * INV_PAR);
+            }
+        }
+        __syncthreads();
+        // overlap-add of the 8 frames of this round (fixed order -> deterministic)
+        const int base = 8 * r * HOP;
+        for (int q = tid; q < 7 * HOP + WIN; q += 256) {
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int n = q - j * HOP;
+                if (n >= 0 && n < WIN) a += S.fr[j][n];
+            }
+            S.ola[base + q] += a;
+        }
+        __syncthreads();
+    }
+
+    // finalize hop blocks [3, 3+IHB): sample index n = f0*HOP + q - PAD
+    float d12 = 0.f, d22 = 0.f, d11 = 0.f;
+    for (int q = PAD + tid; q < PAD + IHB * HOP; q += 256) {
+        const int n = f0 * HOP + q - PAD;
+        if (n < L) {
+            const float raw = S.ola[q] / S.coff[q % HOP];
+            const float v = fminf(fmaxf(raw, -1.f), 1.f);
+            const long long o = (long long)b * L + n;
+            p.out_wav[o] = v;
+            if (p.raw_wav) p.raw_wav[o] = raw;
+            if (p.target) {
+                const float tg = __ldg(p.target + o);
+                d12 += v * tg; d22 += tg * tg; d11 += v * v;
+            }
+        }
+    }
+    if (p.target) {
+        d12 = warp_sum(d12); d22 = warp_sum(d22); d11 = warp_sum(d11);
+        if ((tid & 31) == 0) { S.red[0][tid >> 5] = d12; S.red[1][tid >> 5] = d22; S.red[2][tid >> 5] = d11; }
+        __syncthreads();
+        if (tid < 3) {
+            float a = 0.f;
+            for (int i = 0; i < 8; ++i) a += S.red[tid][i];
+            atomicAdd(p.dots + b * 8 + tid, (double)a);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// adjoint: d wav -> d mask   (ISTFT^T, then the mask-apply Jacobian; no gradient to the noisy spectrum)
+// ------------------------------------------------------------------------------------------------
+struct IstftBwdSmem {
+    float2 fft[4][NFFT];
+    float2 tw[NFFT];
+    float2 out[NBIN][SF];
+    float win[WIN];
+    float coff[HOP];
+    float seg[SEG];
+    float scratch[4][8];
+};
+
+__device__ __forceinline__ float2 mask_bwd(int mode, float2 x, float2 m, float2 ds) {
+    if (mode == SEFD_MASK_C) return make_float2(x.x * ds.x + x.y * ds.y, -x.y * ds.x + x.x * ds.y);
+    if (mode == SEFD_MASK_R) return make_float2(x.x * ds.x, x.y * ds.y);
+    if (mode == SEFD_MASK_E) {
+        const float smag = sqrtf(x.x * x.x + x.y * x.y + 1e-8f);
+        const float sph = atan2f(x.y, x.x);
+        const float mm = sqrtf(m.x * m.x + m.y * m.y);
+        const float den = mm + 1e-8f;
+        const float rp = m.x / den, ip = m.y / den;
+        const float ph = sph + atan2f(ip, rp);
+        const float th = tanhf(mm);
+        const float em = th * smag;
+        float sn, cs;
+        sincosf(ph, &sn, &cs);
+        const float d_em = ds.x * cs + ds.y * sn;
+        const float d_ph = em * (-ds.x * sn + ds.y * cs);
+        float d_mm = d_em * smag * (1.f - th * th);
+        const float r2 = rp * rp + ip * ip;
+        float d_ip = 0.f, d_rp = 0.f;
+        if (r2 > 0.f) { d_ip = rp / r2 * d_ph; d_rp = -ip / r2 * d_ph; }
+        float dmx = d_rp / den, dmy = d_ip / den;
+        d_mm += -(d_rp * m.x + d_ip * m.y) / (den * den);
+        if (mm > 0.f) { dmx += d_mm * m.x / mm; dmy += d_mm * m.y / mm; }
+        return make_float2(dmx, dmy);
+    }
+    return ds;   // NONE: gradient with respect to the spectrum itself
+}
+
+__global__ void __launch_bounds__(256) mask_istft_bwd_kernel(const MaskIstftBwdParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    IstftBwdSmem& S = *reinterpret_cast<IstftBwdSmem*>(smem_raw);
+    const int b = blockIdx.y, t0 = blockIdx.x * SF;
+    const int tid = threadIdx.x, g = tid >> 6, tid64 = tid & 63;
+    const int T = p.T, L = p.L;
+    init_tables(S.tw, S.win, S.coff);
+    for (int i = tid; i < SEG; i += 256) {
+        const int P = t0 * HOP + i, n = P - PAD;
+        float v = 0.f;
+        if (n >= 0 && n < L) {
+            const long long o = (long long)b * L + n;
+            v = __ldg(p.dwav + o);
+            if (p.raw_wav) {
+                const float raw = __ldg(p.raw_wav + o);
+                if (!(raw >= -1.f && raw <= 1.f)) v = 0.f;
+            }
+            v /= S.coff[P % HOP];
+        }
+        S.seg[i] = v;
+    }
+    __syncthreads();
+    for (int r = 0; r < SF / 8; ++r) {
+        const int fa = 8 * r + 2 * g;
+        float2* s = S.fft[g];
+        float ga[7], gb[7];
+        float ea = 0.f, eb = 0.f;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const int n = tid64 + 64 * i;
+            ga[i] = gb[i] = 0.f;
+            if (n < WIN) {
+                const float wn = S.win[n] * INV_HALF_N;
+                ga[i] = wn * S.seg[fa * HOP + n];
+                gb[i] = wn * S.seg[(fa + 1) * HOP + n];
+                ea += ga[i]; eb += gb[i];
+            }
+        }
+        const float2 par = group_parity_sums(ea, eb, S.scratch[g], tid64);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int n = tid64 + 64 * i;
+            float2 v = make_float2(0.f, 0.f);
+            if (i < 7 && n < WIN) v = make_float2(ga[i] - par.x * INV_PAR, gb[i] - par.y * INV_PAR);
+            s[n] = v;
+        }
+        __syncthreads();
+        fft512_cta<false>(s, S.tw, tid64);
+        for (int k = tid64; k <= 256; k += 64) {
+            const float2 z = s[k], zc = s[(NFFT - k) & (NFFT - 1)];
+            S.out[k][fa] = make_float2(0.5f * (z.x + zc.x), 0.5f * (z.y - zc.y));
+            S.out[k][fa + 1] = make_float2(0.5f * (z.y + zc.y), -0.5f * (z.x - zc.x));
+        }
+        __syncthreads();
+    }
+    const float2* X = reinterpret_cast<const float2*>(p.spec) + (long long)b * NBIN * T;
+    const int k_lo = (p.mode == SEFD_MASK_NONE) ? 0 : 1;
+    for (int e = tid; e < NBIN * SF; e += 256) {
+        const int k = e / SF, f = e % SF, t = t0 + f;
+        if (t >= T || k < k_lo) continue;
+        const float2 ds = S.out[k][f];
+        float2 x = make_float2(0.f, 0.f), m = x;
+        if (p.mode != SEFD_MASK_NONE) {
+            x = __ldg(X + (long long)k * T + t);
+            if (p.mode == SEFD_MASK_E)
+                m = __ldg(reinterpret_cast<const float2*>(p.mask + b * p.mB + (long long)(k - 1) * p.mF +
+                                                          (long long)(t + p.m_tshift) * p.mT));
+        }
+        const float2 dm = mask_bwd(p.mode, x, m, ds);
+        *reinterpret_cast<float2*>(p.dmask + b * p.mB + (long long)(k - k_lo) * p.mF +
+                                   (long long)(t + p.m_tshift) * p.mT) = dm;
+    }
+    // frames in front of the shift (the decoder's dropped look-ahead frame) get zero gradient
+    if (blockIdx.x == 0 && p.m_tshift > 0) {
+        for (int e = tid; e < (NBIN - k_lo) * p.m_tshift; e += 256) {
+            const int k = e / p.m_tshift, t = e % p.m_tshift;
+            *reinterpret_cast<float2*>(p.dmask + b * p.mB + (long long)k * p.mF + (long long)t * p.mT) =
+                make_float2(0.f, 0.f);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// losses (tools_for_loss.py:29-94; selection models.py:315-323).  dots[b][8] (double):
+//   0 <E,G>  1 <G,G>  2 <E,E>  3 sum res^2  4 sum res*G      res = E - c_b G
+// coef[b][2]: d loss / d E[b,n] = coef[b][0] * E[b,n] + coef[b][1] * G[b,n]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) loss_dots_kernel(const float* __restrict__ E, const float* __restrict__ G,
+                                                        int L, double* dots) {
+    __shared__ float red[3][8];
+    const int b = blockIdx.y;
+    const float* e = E + (long long)b * L;
+    const float* g = G + (long long)b * L;
+    float d12 = 0.f, d22 = 0.f, d11 = 0.f;
+    for (int n = blockIdx.x * 256 + threadIdx.x; n < L; n += gridDim.x * 256) {
+        const float a = e[n], c = g[n];
+        d12 += a * c; d22 += c * c; d11 += a * a;
+    }
+    d12 = warp_sum(d12); d22 = warp_sum(d22); d11 = warp_sum(d11);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = d12; red[1][threadIdx.x >> 5] = d22; red[2][threadIdx.x >> 5] = d11; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float a = 0.f;
+        for (int i = 0; i < 8; ++i) a += red[threadIdx.x][i];
+        atomicAdd(dots + b * 8 + threadIdx.x, (double)a);
+    }
+}
+
+__device__ __forceinline__ double loss_scale(int kind, const double* d) {
+    const double eps = 1e-8;
+    if (kind == SEFD_LOSS_SISNR) return d[0] / (d[1] + eps);
+    if (kind == SEFD_LOSS_SISDR) return d[0] / d[1] + eps;
+    return 1.0;
+}
+
+__global__ void __launch_bounds__(256) loss_resid_kernel(const float* __restrict__ E, const float* __restrict__ G,
+                                                         int L, int kind, double* dots) {
+    __shared__ float red[2][8];
+    const int b = blockIdx.y;
+    const float* e = E + (long long)b * L;
+    const float* g = G + (long long)b * L;
+    const float c = (float)loss_scale(kind, dots + b * 8);
+    float rr = 0.f, rg = 0.f;
+    for (int n = blockIdx.x * 256 + threadIdx.x; n < L; n += gridDim.x * 256) {
+        const float gg = g[n];
+        const float r = e[n] - c * gg;
+        rr += r * r; rg += r * gg;
+    }
+    rr = warp_sum(rr); rg = warp_sum(rg);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = rr; red[1][threadIdx.x >> 5] = rg; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        float a = 0.f;
+        for (int i = 0; i < 8; ++i) a += red[threadIdx.x][i];
+        atomicAdd(dots + b * 8 + 3 + threadIdx.x, (double)a);
+    }
+}
+
+__global__ void loss_finalize_kernel(const double* dots, int B, int L, int kind, float* loss, float* coef) {
+    // single CTA; B is small (<= a few hundred)
+    __shared__ double acc[256];
+    const double eps = 1e-8, kappa = 10.0 / log(10.0);
+    double local = 0.0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const double* d = dots + b * 8;
+        const double s12 = d[0], s22 = d[1], rr = d[3], rg = d[4];
+        double term = 0.0, cA = 0.0, cB = 0.0;
+        if (kind == SEFD_LOSS_MSE) {
+            term = rr / ((double)B * L);
+            cA = 2.0 / ((double)B * L);
+            cB = -cA;
+        } else if (kind == SEFD_LOSS_SDR) {
+            term = -kappa * log(s22 * s22 / (rr * rr + eps)) / B;
+            cA = 4.0 * kappa * rr / (B * (rr * rr + eps));
+            cB = -cA;
+        } else if (kind == SEFD_LOSS_SISNR) {
+            const double al = s12 / (s22 + eps);
+            const double tt = al * al * s22;
+            const double r = tt / (rr + eps) + eps;
+            term = -kappa * log(r) / B;
+            const double pre = kappa / (B * r);
+            cA = pre * 2.0 * tt / ((rr + eps) * (rr + eps));
+            cB = -pre * (2.0 * al * s22 / ((s22 + eps) * (rr + eps)) +
+                         2.0 * tt * (al + rg / (s22 + eps)) / ((rr + eps) * (rr + eps)));
+        } else {   // SI-SDR: needs the batch mean of the ratios first
+            const double a = s12 / s22 + eps;
+            term = (a * a * s22 / rr + eps) / B;
+        }
+        local += term;
+        if (kind != SEFD_LOSS_SISDR) { coef[2 * b] = (float)cA; coef[2 * b + 1] = (float)cB; }
+    }
+    acc[threadIdx.x] = local;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) acc[threadIdx.x] += acc[threadIdx.x + o];
+        __syncthreads();
+    }
+    const double total = acc[0];
+    if (kind == SEFD_LOSS_SISDR) {
+        const double R = total;
+        for (int b = threadIdx.x; b < B; b += blockDim.x) {
+            const double* d = dots + b * 8;
+            const double s12 = d[0], s22 = d[1], nn = d[3], ng = d[4];
+            const double a = s12 / s22 + eps, pp = a * a * s22;
+            const double pre = kappa / ((R + eps) * B);
+            coef[2 * b] = (float)(pre * 2.0 * pp / (nn * nn));
+            coef[2 * b + 1] = (float)(-pre * (2.0 * a / nn + 2.0 * pp * a / (nn * nn) + 2.0 * pp * ng / (nn * nn * s22)));
+        }
+        if (threadIdx.x == 0) loss[0] = (float)(-kappa * log(R + eps));
+    } else if (threadIdx.x == 0) {
+        loss[0] = (float)total;
+    }
+}
+
+__global__ void loss_bwd_kernel(const float* __restrict__ E, const float* __restrict__ G, const float* __restrict__ coef,
+                                const float* __restrict__ gout, float* __restrict__ dE, int B, int L) {
+    const float go = gout ? gout[0] : 1.f;
+    const long long total = (long long)B * L;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / L);
+        dE[i] = go * (coef[2 * b] * E[i] + coef[2 * b + 1] * G[i]);
+    }
+}
+
+}  // namespace
+
+int sefd_stft_launch(const float* wav, float* spec, int B, int L, int T, cudaStream_t st) {
+    SEFD_REQUIRE(L % HOP == 0 && T == L / HOP + 3, "stft: L=%d must be a multiple of %d and T=%d == L/hop+3", L, HOP, T);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(stft_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StftSmem));
+        attr = true;
+    }
+    dim3 grid((T + SF - 1) / SF, B);
+    stft_fwd_kernel<<<grid, 256, sizeof(StftSmem), st>>>(wav, spec, B, L, T);
+    return sefd_check_launch("stft_fwd");
+}
+
+int sefd_mask_istft_launch(const MaskIstftParams& p, cudaStream_t st) {
+    SEFD_REQUIRE(p.L % HOP == 0 && p.T == p.L / HOP + 3, "istft: L=%d / T=%d inconsistent", p.L, p.T);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(mask_istft_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IstftSmem));
+        attr = true;
+    }
+    if (p.target) cudaMemsetAsync(p.dots, 0, sizeof(double) * 8 * p.B, st);
+    const int chunks = (p.L / HOP + IHB - 1) / IHB;
+    dim3 grid(chunks, p.B);
+    mask_istft_fwd_kernel<<<grid, 256, sizeof(IstftSmem), st>>>(p);
+    return sefd_check_launch("mask_istft_fwd");
+}
+
+int sefd_mask_istft_bwd_launch(const MaskIstftBwdParams& p, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(mask_istft_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IstftBwdSmem));
+        attr = true;
+    }
+    dim3 grid((p.T + SF - 1) / SF, p.B);
+    mask_istft_bwd_kernel<<<grid, 256, sizeof(IstftBwdSmem), st>>>(p);
+    return sefd_check_launch("mask_istft_bwd");
+}
+
+int sefd_loss_fwd_launch(const float* est, const float* tgt, int B, int L, int kind, double* dots, int dots_ready,
+                         float* loss, float* coef, cudaStream_t st) {
+    SEFD_REQUIRE(kind >= 0 && kind <= 3, "loss: unknown kind %d", kind);
+    dim3 grid(8, B);
+    if (!dots_ready) {
+        cudaMemsetAsync(dots, 0, sizeof(double) * 8 * B, st);
+        loss_dots_kernel<<<grid, 256, 0, st>>>(est, tgt, L, dots);
+        SEFD_TRY(sefd_check_launch("loss_dots"));
+    }
+    cudaMemset2DAsync(dots + 3, 8 * sizeof(double), 0, 2 * sizeof(double), B, st);
+    loss_resid_kernel<<<grid, 256, 0, st>>>(est, tgt, L, kind, dots);
+    SEFD_TRY(sefd_check_launch("loss_resid"));
+    loss_finalize_kernel<<<1, 256, 0, st>>>(dots, B, L, kind, loss, coef);
+    return sefd_check_launch("loss_finalize");
+}
+
+int sefd_loss_bwd_launch(const float* est, const float* tgt, const float* coef, const float* gout, float* dest,
+                         int B, int L, cudaStream_t st) {
+    long long n = (long long)B * L;
+    int g = (int)((n + 255) / 256);
+    if (g > 148 * 8) g = 148 * 8;
+    loss_bwd_kernel<<<g, 256, 0, st>>>(est, tgt, coef, gout, dest, B, L);
+    return sefd_check_launch("loss_bwd");
+}

@@ -1,0 +1,39 @@
+#pragma once
+#include "common.cuh"
+
+enum { SEFD_MASK_NONE = 0, SEFD_MASK_E = 1, SEFD_MASK_C = 2, SEFD_MASK_R = 3 };
+enum { SEFD_LOSS_MSE = 0, SEFD_LOSS_SDR = 1, SEFD_LOSS_SISNR = 2, SEFD_LOSS_SISDR = 3 };
+
+struct MaskIstftParams {
+    const float* spec;       // [B][257][T][2] noisy spectrum (or the spectrum itself for SEFD_MASK_NONE)
+    const float* mask;       // element (b, k-1, t + m_tshift) at mask + b*mB + (k-1)*mF + (t+m_tshift)*mT, 2 floats
+    long long mB, mF, mT;
+    int m_tshift;
+    int mode;
+    int B, L, T;
+    float *out_real, *out_imag;   // [B][257][T] or nullptr
+    float* out_wav;               // [B][L] clamped
+    float* raw_wav;               // [B][L] before the clamp (kept for the backward) or nullptr
+    const float* target;          // [B][L] or nullptr
+    double* dots;                 // [B][8]
+};
+
+struct MaskIstftBwdParams {
+    const float* dwav;       // [B][L]
+    const float* raw_wav;    // [B][L] or nullptr (no clamp gating)
+    const float* spec;       // [B][257][T][2]
+    const float* mask;       // as above (only read for mode E)
+    float* dmask;            // same addressing as mask
+    long long mB, mF, mT;
+    int m_tshift;
+    int mode;
+    int B, L, T;
+};
+
+int sefd_stft_launch(const float* wav, float* spec, int B, int L, int T, cudaStream_t st);
+int sefd_mask_istft_launch(const MaskIstftParams& p, cudaStream_t st);
+int sefd_mask_istft_bwd_launch(const MaskIstftBwdParams& p, cudaStream_t st);
+int sefd_loss_fwd_launch(const float* est, const float* tgt, int B, int L, int kind, double* dots, int dots_ready,
+                         float* loss, float* coef, cudaStream_t st);
+int sefd_loss_bwd_launch(const float* est, const float* tgt, const float* coef, const float* gout, float* dest,
+                         int B, int L, cudaStream_t st);

@@ -1,0 +1,238 @@
+"""Thin torch-tensor wrappers over the op-level C ABI (include/sefd.h).
+
+PyTorch is used for device memory, the current stream and autograd plumbing only; every FLOP below
+runs in libsefd.so.  Tensors must be CUDA float32; there is no CPU path.
+"""
+import torch
+
+from . import _lib
+
+MODES = {"E": 1, "C": 2, "R": 3}
+LOSSES = {"MSE": 0, "SDR": 1, "SI-SNR": 2, "SI-SDR": 3}
+
+
+def _req(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("sefd: tensors must live on a CUDA device (no CPU fallback on this path)")
+        if t.dtype != torch.float32 and t.dtype != torch.float64:
+            raise RuntimeError(f"sefd: expected float32 tensor, got {t.dtype}")
+        if not t.is_contiguous():
+            raise RuntimeError("sefd: tensors must be contiguous")
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def frames(L):
+    if L % 100:
+        raise ValueError(f"waveform length {L} must be a multiple of the hop (100)")
+    return L // 100 + 3
+
+
+# ---- STFT / ISTFT -------------------------------------------------------------------------------
+def stft(wav):
+    """ConvSTFT 'complex' (tools_for_model.py:54-61): wav [B,L] -> spec [B,257,T,2]."""
+    wav = wav.contiguous()
+    _req(wav)
+    B, L = wav.shape
+    spec = torch.empty(B, 257, frames(L), 2, device=wav.device, dtype=torch.float32)
+    _lib.check(_lib.load().sefd_stft_forward(ptr(wav), ptr(spec), B, L, stream()), "stft_forward")
+    return spec
+
+
+def istft(spec, L):
+    spec = spec.contiguous()
+    _req(spec)
+    B = spec.shape[0]
+    assert spec.shape[1:] == (257, frames(L), 2)
+    wav = torch.empty(B, L, device=spec.device, dtype=torch.float32)
+    _lib.check(_lib.load().sefd_istft_forward(ptr(spec), ptr(wav), B, L, stream()), "istft_forward")
+    return wav
+
+
+def istft_backward(dwav):
+    dwav = dwav.contiguous()
+    _req(dwav)
+    B, L = dwav.shape
+    dspec = torch.empty(B, 257, frames(L), 2, device=dwav.device, dtype=torch.float32)
+    _lib.check(_lib.load().sefd_istft_backward(ptr(dwav), ptr(dspec), B, L, stream()), "istft_backward")
+    return dspec
+
+
+def mask_istft(spec, mask, mode, L, want_spec=True):
+    """models.py:253-282. spec [B,257,T,2], mask [B,256,T,2] -> (out_real, out_imag, out_wav, raw_wav)."""
+    _req(spec, mask)
+    B, T = spec.shape[0], frames(L)
+    dev = spec.device
+    o_r = torch.empty(B, 257, T, device=dev) if want_spec else None
+    o_i = torch.empty(B, 257, T, device=dev) if want_spec else None
+    wav = torch.empty(B, L, device=dev)
+    raw = torch.empty(B, L, device=dev)
+    _lib.check(_lib.load().sefd_mask_istft_forward(ptr(spec), ptr(mask), MODES[mode], B, L, ptr(o_r), ptr(o_i),
+                                                   ptr(wav), ptr(raw), stream()), "mask_istft_forward")
+    return o_r, o_i, wav, raw
+
+
+def mask_istft_backward(dwav, raw, spec, mask, mode):
+    _req(dwav, raw, spec, mask)
+    B, L = dwav.shape
+    dmask = torch.empty_like(mask)
+    _lib.check(_lib.load().sefd_mask_istft_backward(ptr(dwav), ptr(raw), ptr(spec), ptr(mask), MODES[mode], B, L,
+                                                    ptr(dmask), stream()), "mask_istft_backward")
+    return dmask
+
+
+# ---- losses -------------------------------------------------------------------------------------
+class _Loss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, est, tgt, kind):
+        est, tgt = est.contiguous(), tgt.contiguous()
+        _req(est, tgt)
+        B, L = est.shape
+        scratch = torch.empty(8 * B, device=est.device, dtype=torch.float64)
+        loss = torch.empty(1, device=est.device)
+        coef = torch.empty(2 * B, device=est.device)
+        _lib.check(_lib.load().sefd_loss_forward(ptr(est), ptr(tgt), B, L, kind, ptr(scratch), ptr(loss), ptr(coef),
+                                                 stream()), "loss_forward")
+        ctx.save_for_backward(est, tgt, coef)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        est, tgt, coef = ctx.saved_tensors
+        B, L = est.shape
+        gout = gout.contiguous().float()
+        d = torch.empty_like(est)
+        _lib.check(_lib.load().sefd_loss_backward(ptr(est), ptr(tgt), ptr(coef), ptr(gout), ptr(d), B, L, stream()),
+                   "loss_backward")
+        return d, None, None
+
+
+def loss(est, tgt, name):
+    """DCCRN.loss non-perceptual branch (models.py:315-323): returns the value that is minimised."""
+    return _Loss.apply(est, tgt, LOSSES[name])
+
+
+# ---- complex conv / convT (channels-last) ---------------------------------------------------------
+def _cconv_ws(Cin, Cout, dev):
+    n = _lib.load().sefd_cconv_workspace_bytes(Cin, Cout)
+    return torch.empty((n + 255) // 256 * 256, device=dev, dtype=torch.uint8)
+
+
+def cconv2d_forward(x, wr, br, wi, bi):
+    """x [B,F,T,Cin] -> y [B,F/2,T,Cout] (ComplexConv2d, tools_for_model.py:243-269)."""
+    _req(x, wr, br, wi, bi)
+    B, F, T, Cin = x.shape
+    Cout = 2 * wr.shape[0]
+    y = torch.empty(B, F // 2, T, Cout, device=x.device)
+    ws = _cconv_ws(Cin, Cout, x.device)
+    _lib.check(_lib.load().sefd_cconv2d_forward(ptr(x), ptr(wr), ptr(br), ptr(wi), ptr(bi), ptr(y), B, F, T, Cin, Cout,
+                                                ptr(ws), stream()), "cconv2d_forward")
+    return y
+
+
+def cconv2d_backward(x, wr, wi, dy, need_dx=True):
+    _req(x, wr, wi, dy)
+    B, F, T, Cin = x.shape
+    Cout = dy.shape[-1]
+    dx = torch.empty_like(x) if need_dx else None
+    if need_dx:
+        dx.zero_()
+    dwr, dwi = torch.empty_like(wr), torch.empty_like(wi)
+    dbr = torch.empty(Cout // 2, device=x.device)
+    dbi = torch.empty(Cout // 2, device=x.device)
+    ws = _cconv_ws(Cin, Cout, x.device)
+    _lib.check(_lib.load().sefd_cconv2d_backward(ptr(x), ptr(wr), ptr(wi), ptr(dy), ptr(dx), ptr(dwr), ptr(dbr),
+                                                 ptr(dwi), ptr(dbi), B, F, T, Cin, Cout, ptr(ws), stream()),
+               "cconv2d_backward")
+    return dx, dwr, dbr, dwi, dbi
+
+
+def cconvT2d_forward(x0, x1, wr, br, wi, bi):
+    """x0, x1 [B,F,T,Cin/2] (x1 = skip) -> y [B,2F,T+1,Cout] (ComplexConvTranspose2d on complex_cat)."""
+    _req(x0, x1, wr, br, wi, bi)
+    B, F, T, Ch = x0.shape
+    Cin, Cout = 2 * Ch, 2 * wr.shape[1]
+    y = torch.empty(B, 2 * F, T + 1, Cout, device=x0.device)
+    ws = _cconv_ws(Cin, Cout, x0.device)
+    _lib.check(_lib.load().sefd_cconvT2d_forward(ptr(x0), ptr(x1), ptr(wr), ptr(br), ptr(wi), ptr(bi), ptr(y), B, F, T,
+                                                 Cin, Cout, ptr(ws), stream()), "cconvT2d_forward")
+    return y
+
+
+def cconvT2d_backward(x0, x1, wr, wi, dy):
+    _req(x0, x1, wr, wi, dy)
+    B, F, T, Ch = x0.shape
+    Cin, Cout = 2 * Ch, dy.shape[-1]
+    dx0, dx1 = torch.empty_like(x0), torch.empty_like(x1)
+    dwr, dwi = torch.empty_like(wr), torch.empty_like(wi)
+    dbr = torch.empty(Cout // 2, device=x0.device)
+    dbi = torch.empty(Cout // 2, device=x0.device)
+    ws = _cconv_ws(Cin, Cout, x0.device)
+    _lib.check(_lib.load().sefd_cconvT2d_backward(ptr(x0), ptr(x1), ptr(wr), ptr(wi), ptr(dy), ptr(dx0), ptr(dx1),
+                                                  ptr(dwr), ptr(dbr), ptr(dwi), ptr(dbi), B, F, T, Cin, Cout, ptr(ws),
+                                                  stream()), "cconvT2d_backward")
+    return dx0, dx1, dwr, dbr, dwi, dbi
+
+
+# ---- BatchNorm + PReLU ------------------------------------------------------------------------
+def bn_prelu_forward(y, gamma, beta, alpha, running_mean=None, running_var=None):
+    """y [rows, C] -> (z, save[2,C])  (nn.BatchNorm2d train mode + nn.PReLU, models.py:76-78)."""
+    _req(y, gamma, beta, alpha, running_mean, running_var)
+    rows, Cc = y.shape
+    z = torch.empty_like(y)
+    save = torch.empty(2, Cc, device=y.device)
+    scratch = torch.empty(2 * Cc + 1, device=y.device, dtype=torch.float64)
+    _lib.check(_lib.load().sefd_bn_prelu_forward(ptr(y), ptr(z), rows, Cc, ptr(gamma), ptr(beta), ptr(alpha), ptr(save),
+                                                 ptr(running_mean), ptr(running_var), ptr(scratch), stream()),
+               "bn_prelu_forward")
+    return z, save
+
+
+def bn_prelu_backward(y, dz, gamma, beta, alpha, save):
+    _req(y, dz, gamma, beta, alpha, save)
+    rows, Cc = y.shape
+    dy = torch.empty_like(y)
+    dg, db = torch.empty_like(gamma), torch.empty_like(beta)
+    da = torch.empty_like(alpha)
+    scratch = torch.empty(2 * Cc + 1, device=y.device, dtype=torch.float64)
+    _lib.check(_lib.load().sefd_bn_prelu_backward(ptr(y), ptr(dz), ptr(dy), rows, Cc, ptr(gamma), ptr(beta), ptr(alpha),
+                                                  ptr(save), ptr(dg), ptr(db), ptr(da), ptr(scratch), stream()),
+               "bn_prelu_backward")
+    return dy, dg, db, da
+
+
+# ---- LSTM recurrence ------------------------------------------------------------------------------
+def lstm_forward(w_hh, pregates):
+    """w_hh [2,512,128]; pregates [2,rows,T,512] (consumed: overwritten with the activated gates)."""
+    _req(w_hh, pregates)
+    _, rows, T, _ = pregates.shape
+    h = torch.empty(2, rows, T, 128, device=w_hh.device)
+    c = torch.empty(2, rows, T, 128, device=w_hh.device)
+    _lib.check(_lib.load().sefd_lstm_forward(ptr(w_hh), ptr(pregates), ptr(h), ptr(c), rows, T, stream()),
+               "lstm_forward")
+    return h, c
+
+
+def lstm_backward(w_hh, gates, c, dh):
+    _req(w_hh, gates, c, dh)
+    _, rows, T, _ = gates.shape
+    dg = torch.empty_like(gates)
+    _lib.check(_lib.load().sefd_lstm_backward(ptr(w_hh), ptr(gates), ptr(c), ptr(dh), ptr(dg), rows, T, stream()),
+               "lstm_backward")
+    return dg
+
+
+# ---- Adam -------------------------------------------------------------------------------------------
+def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, gscale=1.0):
+    _req(params, grads, exp_avg, exp_avg_sq)
+    _lib.check(_lib.load().sefd_adam_step(ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq), params.numel(), lr,
+                                          betas[0], betas[1], eps, step, gscale, stream()), "adam_step")

@@ -1,0 +1,33 @@
+"""Drop-in for the loss functions of the reference's tools_for_loss.py that sit on the DCCRN path
+(`from tools_for_loss import sdr, si_sdr, si_snr, get_array_lms_loss, get_array_pmsqe_loss`, models.py:9).
+The arithmetic runs in libsefd.so (csrc/stft.cu loss kernels); argument order and sign conventions follow
+tools_for_loss.py:29-94."""
+from sefd import ops as _ops
+
+
+def l2_norm(s1, s2):
+    raise NotImplementedError("l2_norm is folded into the sefd loss kernels")
+
+
+def si_snr(s1, s2, eps=1e-8):
+    """tools_for_loss.py:36-44: s1 = estimate, s2 = target; returns the batch-mean SI-SNR in dB."""
+    return -_ops.loss(s1, s2, "SI-SNR")
+
+
+def sdr(s1, s2, eps=1e-8):
+    """tools_for_loss.py:29-33: s1 = target, s2 = estimate."""
+    return -_ops.loss(s2, s1, "SDR")
+
+
+def si_sdr(reference, estimation, eps=1e-8):
+    """tools_for_loss.py:47-94."""
+    return -_ops.loss(estimation, reference, "SI-SDR")
+
+
+def get_array_lms_loss(clean_array, est_array):
+    raise NotImplementedError("sefd: LMS perceptual loss is not built yet (SURVEY.md §8(f) rank 3)")
+
+
+def get_array_pmsqe_loss(clean_array, est_array):
+    raise NotImplementedError("sefd: PMSQE perceptual loss is not built yet (SURVEY.md §8 a12; its arithmetic lives "
+                              "in the un-vendored asteroid package: parity unpinned)")

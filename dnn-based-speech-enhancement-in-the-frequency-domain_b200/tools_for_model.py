@@ -1,0 +1,212 @@
+"""Drop-in for the on-path part of the reference's tools_for_model.py (`import tools_for_model as tools`,
+trainer.py:7): the same class names, constructor arguments and tensor conventions ([B, C, F, T], real half
+of the channels first), computed by libsefd.so.  Layout changes between the reference's NCHW tensors and
+the library's channels-last tensors are the only thing torch does here.
+
+Built: ConvSTFT, ConviSTFT ('complex' feature type, tools_for_model.py:36-112), ComplexConv2d and
+ComplexConvTranspose2d in the DCCRN configuration (tools_for_model.py:199-338), complex_cat, Bar.
+Anything else raises NotImplementedError (there is no PyTorch fallback).
+"""
+import sys
+import time
+
+import torch
+import torch.nn as nn
+
+from sefd import dccrn as _d
+from sefd import ops as _ops
+
+
+def _check_stft(win_len, win_inc, fft_len, win_type, feature_type):
+    if (win_len, win_inc, fft_len) != (400, 100, 512) or win_type not in ("hanning", "hann") or feature_type != "complex":
+        raise NotImplementedError("sefd STFT kernels are built for win 400 / hop 100 / fft 512 / Hann / 'complex'")
+
+
+class ConvSTFT(nn.Module):
+    """tools_for_model.py:36-68.  forward(inputs [B, L] or [B, 1, L]) -> [B, 514, T] (real rows then imag rows)."""
+
+    def __init__(self, win_len, win_inc, fft_len=None, win_type="hamming", feature_type="real", fix=True):
+        super().__init__()
+        _check_stft(win_len, win_inc, fft_len, win_type, feature_type)
+        self.register_buffer("weight", _d.STFTBuffers(win_len, fft_len, inverse=False).weight)
+        self.feature_type, self.stride, self.win_len, self.dim = feature_type, win_inc, win_len, fft_len
+
+    def forward(self, inputs):
+        if inputs.dim() == 3:
+            inputs = inputs.squeeze(1)
+        spec = _ops.stft(inputs.float())                                  # [B, 257, T, 2]
+        return torch.cat([spec[..., 0], spec[..., 1]], 1)
+
+
+class _ISTFT(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec, L):
+        return _ops.istft(spec, L)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _ops.istft_backward(g), None
+
+
+class ConviSTFT(nn.Module):
+    """tools_for_model.py:71-112.  forward(inputs [B, 514, T]) -> [B, 1, L]."""
+
+    def __init__(self, win_len, win_inc, fft_len=None, win_type="hamming", feature_type="real", fix=True):
+        super().__init__()
+        _check_stft(win_len, win_inc, fft_len, win_type, feature_type)
+        b = _d.STFTBuffers(win_len, fft_len, inverse=True)
+        self.register_buffer("weight", b.weight)
+        self.register_buffer("window", b.window)
+        self.register_buffer("enframe", b.enframe)
+        self.feature_type, self.win_type, self.win_len, self.stride, self.dim = feature_type, win_type, win_len, win_inc, fft_len
+
+    def forward(self, inputs, phase=None):
+        if phase is not None:
+            raise NotImplementedError("sefd ConviSTFT: magnitude/phase input is not on the built path")
+        B, _, T = inputs.shape
+        spec = torch.stack([inputs[:, :257], inputs[:, 257:]], -1).contiguous()
+        return _ISTFT.apply(spec, (T - 3) * 100).unsqueeze(1)
+
+
+def complex_cat(inputs, axis):
+    """tools_for_model.py:184-193 (pure data movement)."""
+    real, imag = [], []
+    for data in inputs:
+        r, i = torch.chunk(data, 2, axis)
+        real.append(r)
+        imag.append(i)
+    return torch.cat(real + imag, axis)
+
+
+def _to_cl(x):      # [B, C, F, T] -> [B, F, T, C]
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def _from_cl(x):    # [B, F, T, C] -> [B, C, F, T]
+    return x.permute(0, 3, 1, 2)
+
+
+class _CConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, wr, br, wi, bi):
+        xc = _to_cl(x.float())
+        ctx.save_for_backward(xc, wr, wi)
+        return _from_cl(_ops.cconv2d_forward(xc, wr.contiguous(), br.contiguous(), wi.contiguous(), bi.contiguous()))
+
+    @staticmethod
+    def backward(ctx, g):
+        xc, wr, wi = ctx.saved_tensors
+        dx, dwr, dbr, dwi, dbi = _ops.cconv2d_backward(xc, wr.contiguous(), wi.contiguous(), _to_cl(g))
+        return _from_cl(dx), dwr, dbr, dwi, dbi
+
+
+class _CConvT(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, wr, br, wi, bi):
+        # split the already complex_cat'ed input into the library's two sources [r0 | i0], [r1 | i1]
+        B, C, F, T = x.shape
+        h = C // 4
+        r, i = x[:, : C // 2], x[:, C // 2:]
+        x0 = _to_cl(torch.cat([r[:, :h], i[:, :h]], 1).float())
+        x1 = _to_cl(torch.cat([r[:, h:], i[:, h:]], 1).float())
+        ctx.save_for_backward(x0, x1, wr, wi)
+        return _from_cl(_ops.cconvT2d_forward(x0, x1, wr.contiguous(), br.contiguous(), wi.contiguous(), bi.contiguous()))
+
+    @staticmethod
+    def backward(ctx, g):
+        x0, x1, wr, wi = ctx.saved_tensors
+        dx0, dx1, dwr, dbr, dwi, dbi = _ops.cconvT2d_backward(x0, x1, wr.contiguous(), wi.contiguous(), _to_cl(g))
+        d0, d1 = _from_cl(dx0), _from_cl(dx1)
+        h = d0.shape[1] // 2
+        dx = torch.cat([d0[:, :h], d1[:, :h], d0[:, h:], d1[:, h:]], 1)
+        return dx, dwr, dbr, dwi, dbi
+
+
+def _dccrn_geometry(kernel_size, stride, padding, extra_ok):
+    if tuple(kernel_size) != (5, 2) or tuple(stride) != (2, 1) or not extra_ok:
+        raise NotImplementedError("sefd complex conv kernels are built for kernel (5,2), stride (2,1), "
+                                  "padding (2,1|0) [+ output_padding (1,0)] as used by DCCRN")
+
+
+class ComplexConv2d(nn.Module):
+    """tools_for_model.py:199-269 in the DCCRN geometry (causal: one zero frame on the left of T)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=(1, 1), stride=(1, 1), padding=(0, 0), dilation=1,
+                 groups=1, causal=True, complex_axis=1):
+        super().__init__()
+        _dccrn_geometry(kernel_size, stride, padding,
+                        tuple(padding) == (2, 1) and causal and dilation == 1 and groups == 1 and complex_axis == 1)
+        p = _d.ComplexConvParams(in_channels, out_channels, transposed=False)
+        self.real_conv, self.imag_conv = p.real_conv, p.imag_conv
+
+    def forward(self, inputs):
+        return _CConv.apply(inputs, self.real_conv.weight, self.real_conv.bias, self.imag_conv.weight, self.imag_conv.bias)
+
+
+class ComplexConvTranspose2d(nn.Module):
+    """tools_for_model.py:272-338 in the DCCRN geometry; output has T+1 frames like the reference."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=(1, 1), stride=(1, 1), padding=(0, 0),
+                 output_padding=(0, 0), causal=False, complex_axis=1, groups=1):
+        super().__init__()
+        _dccrn_geometry(kernel_size, stride, padding,
+                        tuple(padding) == (2, 0) and tuple(output_padding) == (1, 0) and groups == 1
+                        and complex_axis == 1 and in_channels % 4 == 0)
+        p = _d.ComplexConvParams(in_channels, out_channels, transposed=True)
+        self.real_conv, self.imag_conv = p.real_conv, p.imag_conv
+
+    def forward(self, inputs):
+        return _CConvT.apply(inputs, self.real_conv.weight, self.real_conv.bias, self.imag_conv.weight, self.imag_conv.bias)
+
+
+class Bar(object):
+    """Progress iterator used by the reference trainer loops (`for inputs, targets in tools.Bar(loader)`,
+    trainer.py:23).  Own implementation: prints count, rate and ETA on one line."""
+
+    def __init__(self, dataloader, width=30, out=sys.stdout):
+        self.it = iter(dataloader)
+        try:
+            self.total = len(dataloader)
+        except TypeError:
+            self.total = None
+        self.n, self.t0, self.width, self.out = 0, time.time(), width, out
+
+    def __len__(self):
+        return self.total if self.total is not None else 0
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        try:
+            item = next(self.it)
+        except StopIteration:
+            if self.n:
+                self.out.write("\n")
+            raise
+        self.n += 1
+        el = time.time() - self.t0
+        if self.total:
+            done = int(self.width * self.n / self.total)
+            eta = el / self.n * (self.total - self.n)
+            self.out.write(f"\r[{'=' * done}{' ' * (self.width - done)}] {self.n}/{self.total} "
+                           f"{el:6.1f}s eta {eta:6.1f}s")
+        else:
+            self.out.write(f"\r{self.n} it {el:6.1f}s")
+        self.out.flush()
+        return item
+
+
+def _fullsubnet_only(name):
+    def f(*a, **k):
+        raise NotImplementedError(f"sefd: tools_for_model.{name} belongs to the FullSubNet path, which is not built "
+                                  "yet (SURVEY.md §8 a14)")
+    f.__name__ = name
+    return f
+
+
+stft = _fullsubnet_only("stft")
+istft = _fullsubnet_only("istft")
+mag_phase = _fullsubnet_only("mag_phase")
+build_complex_ideal_ratio_mask = _fullsubnet_only("build_complex_ideal_ratio_mask")
+decompress_cIRM = _fullsubnet_only("decompress_cIRM")

@@ -1,0 +1,127 @@
+/* sefd — C ABI of the B200-native DCCRN speech-enhancement train-step path (libsefd.so).
+ *
+ * Every entry point replaces one piece of the reference's PyTorch path (file:line are relative
+ * to the reference checkout).  Conventions:
+ *   - all pointers are DEVICE pointers to fp32 unless stated; buffers are caller-owned
+ *     (the Python host passes torch CUDA tensors' data_ptr()); the library allocates nothing
+ *     on the device;
+ *   - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it;
+ *   - return value 0 = success, negative = failure with the message in sefd_last_error();
+ *     nothing throws across the ABI; there is no CPU fallback;
+ *   - activations are channels-last: element (b, f, t, c) of a [B][F][T][C] tensor is contiguous in c;
+ *   - STFT geometry is the reference default win 400 / hop 100 / fft 512 / periodic Hann
+ *     (config.py:55-61); waveform length L must be a multiple of 100 and T = L/100 + 3 frames.
+ */
+#ifndef SEFD_H
+#define SEFD_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sefd_plan sefd_plan;
+
+/* masking modes (config.py:27, models.py:258-276) and losses (config.py:23, models.py:315-323) */
+enum { SEFD_MODE_E = 1, SEFD_MODE_C = 2, SEFD_MODE_R = 3 };
+enum { SEFD_MSE = 0, SEFD_SDR = 1, SEFD_SI_SNR = 2, SEFD_SI_SDR = 3 };
+
+int sefd_abi_version(void);
+const char* sefd_last_error(void);
+
+/* ---- op level ------------------------------------------------------------------------------- */
+
+/* ConvSTFT.forward, 'complex' (tools_for_model.py:54-61).  wav [B][L] -> spec [B][257][T][2] (re, im). */
+int sefd_stft_forward(const float* wav, float* spec, int B, int L, void* stream);
+
+/* ConviSTFT.forward (tools_for_model.py:90-112) of spec [B][257][T][2] -> wav [B][L] (no clamp). */
+int sefd_istft_forward(const float* spec, float* wav, int B, int L, void* stream);
+/* its adjoint: dwav [B][L] -> dspec [B][257][T][2] */
+int sefd_istft_backward(const float* dwav, float* dspec, int B, int L, void* stream);
+
+/* mask apply + ISTFT + clamp (models.py:253-282).  mask [B][256][T][2] holds (re, im) for bins 1..256
+ * (the DC mask is zero, models.py:255-256).  out_real/out_imag [B][257][T] may be NULL. raw_wav [B][L]
+ * (pre-clamp, needed by the backward) may be NULL. */
+int sefd_mask_istft_forward(const float* spec, const float* mask, int mode, int B, int L, float* out_real,
+                            float* out_imag, float* out_wav, float* raw_wav, void* stream);
+int sefd_mask_istft_backward(const float* dwav, const float* raw_wav, const float* spec, const float* mask, int mode,
+                             int B, int L, float* dmask, void* stream);
+
+/* DCCRN.loss, non-perceptual branch (models.py:315-323; tools_for_loss.py:29-94).
+ * scratch: 8*B doubles; coef: 2*B floats (kept for the backward); loss: 1 float. */
+int sefd_loss_forward(const float* est, const float* target, int B, int L, int kind, double* scratch, float* loss,
+                      float* coef, void* stream);
+/* d_est[b][n] = gout * (coef[b][0]*est + coef[b][1]*target); gout (1 float, device) may be NULL (= 1). */
+int sefd_loss_backward(const float* est, const float* target, const float* coef, const float* gout, float* d_est,
+                       int B, int L, void* stream);
+
+/* ComplexConv2d (tools_for_model.py:199-269: kernel (5,2), stride (2,1), pad (2,0), causal pad 1) and
+ * ComplexConvTranspose2d (tools_for_model.py:272-338: + output_padding (1,0)); channels-last tensors.
+ *   conv : x [B][F][T][Cin]          -> y [B][F/2][T][Cout]
+ *   convT: x0,x1 [B][F][T][Cin/2]    -> y [B][2F][T+1][Cout]   (x1 = skip tensor of complex_cat, may be NULL
+ *                                                                  when Cin/2 is the whole input)
+ * wr, wi, br, bi are the reference's real_conv / imag_conv parameters in their own layouts.
+ * ws: sefd_cconv_workspace_bytes(Cin, Cout) bytes of scratch (holds the packed block-real operand). */
+size_t sefd_cconv_workspace_bytes(int Cin, int Cout);
+int sefd_cconv2d_forward(const float* x, const float* wr, const float* br, const float* wi, const float* bi, float* y,
+                         int B, int F, int T, int Cin, int Cout, void* ws, void* stream);
+int sefd_cconv2d_backward(const float* x, const float* wr, const float* wi, const float* dy, float* dx, float* dwr,
+                          float* dbr, float* dwi, float* dbi, int B, int F, int T, int Cin, int Cout, void* ws,
+                          void* stream);
+int sefd_cconvT2d_forward(const float* x0, const float* x1, const float* wr, const float* br, const float* wi,
+                          const float* bi, float* y, int B, int F, int T, int Cin, int Cout, void* ws, void* stream);
+int sefd_cconvT2d_backward(const float* x0, const float* x1, const float* wr, const float* wi, const float* dy,
+                           float* dx0, float* dx1, float* dwr, float* dbr, float* dwi, float* dbi, int B, int F, int T,
+                           int Cin, int Cout, void* ws, void* stream);
+
+/* nn.BatchNorm2d (train mode) + nn.PReLU (models.py:76-78) on y [rows][C]; z [rows][C].
+ * save [2][C] (mean, inv-std); running_* may be NULL; scratch: (2*C+1) doubles. */
+int sefd_bn_prelu_forward(const float* y, float* z, long long rows, int C, const float* gamma, const float* beta,
+                          const float* alpha, float* save, float* running_mean, float* running_var, double* scratch,
+                          void* stream);
+int sefd_bn_prelu_backward(const float* y, const float* dz, float* dy, long long rows, int C, const float* gamma,
+                           const float* beta, const float* alpha, const float* save, float* dgamma, float* dbeta,
+                           float* dalpha, double* scratch, void* stream);
+
+/* recurrent part of two nn.LSTM(H=128) run side by side (tools_for_model.py:147-150,167-170):
+ * gates [2][rows][T][512] holds x W_ih^T + b_ih + b_hh on entry and the activated gates on exit. */
+int sefd_lstm_forward(const float* w_hh, float* gates, float* h, float* c, int rows, int T, void* stream);
+int sefd_lstm_backward(const float* w_hh, const float* gates, const float* c, const float* dh, float* dgates, int rows,
+                       int T, void* stream);
+
+/* torch.optim.Adam, defaults of train_interface.py:59 (no weight decay, no amsgrad); step counts from 1.
+ * grads are multiplied by gscale first (1/world_size after an allreduce-sum). */
+int sefd_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                   float beta1, float beta2, float eps, int step, float gscale, void* stream);
+
+/* ---- model level: DCCRN.forward / autograd backward (models.py:176-284) ---------------------- */
+sefd_plan* sefd_dccrn_plan_create(int B, int L, int masking_mode);
+void sefd_dccrn_plan_destroy(sefd_plan* plan);
+size_t sefd_dccrn_workspace_bytes(const sefd_plan* plan);
+long long sefd_dccrn_param_floats(const sefd_plan* plan);    /* size of the flat parameter / gradient buffer */
+long long sefd_dccrn_buffer_floats(const sefd_plan* plan);   /* size of the flat BN running-stat buffer */
+int sefd_dccrn_num_params(const sefd_plan* plan);
+int sefd_dccrn_num_buffers(const sefd_plan* plan);
+/* idx-th parameter (kind 0) or BN buffer (kind 1): reference state_dict key, offset into the flat buffer, shape */
+int sefd_dccrn_entry_info(const sefd_plan* plan, int kind, int idx, char* name, int name_cap, long long* offset,
+                          long long* numel, int* ndim, long long shape[4]);
+/* named intermediate in the workspace (tests / debugging): "spec", "enc3.y", "enc3.z", "dec0.y", "U", ... */
+int sefd_dccrn_tensor_info(const sefd_plan* plan, const char* name, long long* offset_floats, int* ndim,
+                           long long shape[4]);
+
+/* params: flat parameter buffer; bn_buffers: flat running stats (updated in train mode; read in eval mode);
+ * noisy [B][L]; target [B][L] or NULL (when given, the loss dot products are accumulated on the fly);
+ * out_real/out_imag [B][257][T] (may be NULL), out_wav [B][L]. */
+int sefd_dccrn_forward(const sefd_plan* plan, const float* params, float* bn_buffers, const float* noisy,
+                       const float* target, int train, float* out_real, float* out_imag, float* out_wav, void* ws,
+                       size_t ws_bytes, void* stream);
+/* d_wav [B][L] -> grads (flat, same layout as params; every entry is overwritten) */
+int sefd_dccrn_backward(const sefd_plan* plan, const float* params, const float* d_wav, float* grads, void* ws,
+                        size_t ws_bytes, void* stream);
+/* loss on the plan's own outputs, reusing dot products gathered by the forward epilogue when `target` was given */
+int sefd_dccrn_loss(const sefd_plan* plan, const float* out_wav, const float* target, int kind, int reuse_dots,
+                    float* loss, float* coef, void* ws, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,78 @@
+"""CPU-only checks of the drop-in boundary: libsefd.so loads, exports every symbol include/sefd.h declares,
+the parameter layout equals the reference's named_parameters(), and the drop-in module reproduces the
+reference's initial values for a torch seed.  No compute entry point is called (there is no GPU here)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import PKG, ROOT
+from sefd import _lib
+from sefd import dccrn as D
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "sefd.h")).read()
+    declared = set(re.findall(r"\b(sefd_[a-zA-Z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/sefd.h but not exported by libsefd.so"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.sefd_abi_version() == 1
+
+
+def test_plan_layout_matches_reference_named_parameters(golden):
+    plan = D.Plan(2, 4000, "C")
+    names = [n for n, _, _, _ in plan.params]
+    assert names == [str(n) for n in golden["param_names"]]
+    assert sum(n for _, _, n, _ in plan.params) == int(golden["n_params"]) == 3671053
+    offs = [o for _, o, _, _ in plan.params]
+    assert all(o % 4 == 0 for o in offs) and offs == sorted(offs)
+    assert plan.T == 43 and plan.ws_bytes > 0
+    assert [n for n, _, _, _ in plan.buffers][:2] == ["encoder.0.1.running_mean", "encoder.0.1.running_var"]
+
+
+def test_plan_rejects_bad_geometry():
+    with pytest.raises(RuntimeError, match="multiple of 100"):
+        D.Plan(2, 4050, "C")
+    lib = _lib.load()
+    assert lib.sefd_dccrn_plan_create(2, 4000, 7) is None
+    assert b"masking mode" in lib.sefd_last_error()
+
+
+def test_dropin_init_matches_reference_rng_stream(golden):
+    import models
+    torch.manual_seed(0)
+    m = models.DCCRN(masking_mode="C")
+    sd = m.state_dict()
+    keys = [str(k) for k in golden["init_keys"]]
+    assert list(sd.keys()) == keys
+    for k, s, a in zip(keys, golden["init_sum"], golden["init_abs"]):
+        v = sd[k].double()
+        assert abs(float(v.sum()) - s) <= 1e-6 * max(1.0, abs(a)), k
+        assert abs(float(v.abs().sum()) - a) <= 1e-6 * max(1.0, abs(a)), k
+
+
+def test_dropin_refuses_cpu_and_unbuilt_configs():
+    import models
+    m = models.DCCRN(masking_mode="C")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 4000))
+    with pytest.raises(NotImplementedError):
+        models.DCCRN(masking_mode="Direct(None make)")
+    with pytest.raises(NotImplementedError):
+        models.CRN()
+    with pytest.raises(NotImplementedError):
+        models.FullSubNet()
+
+
+def test_fft_index_algebra_on_host(tmp_path):
+    src = os.path.join(PKG, "csrc", "fft512_host_test.cpp")
+    exe = str(tmp_path / "fft_test")
+    subprocess.check_call(["g++", "-O2", "-o", exe, src])
+    out = subprocess.check_output([exe]).decode()
+    assert "max abs err" in out

@@ -1,0 +1,228 @@
+"""GPU parity of the DCCRN path through the drop-in `models.DCCRN` (which calls the C ABI): every
+intermediate, the enhanced waveform, the loss and every parameter gradient against the CPU oracle and the
+golden fixtures generated from the unmodified reference (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import dccrn_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+REPORT = os.path.join(ROOT, "gpurun_out", "model_report.txt")
+
+
+def _report(line):
+    os.makedirs(os.path.dirname(REPORT), exist_ok=True)
+    with open(REPORT, "a") as f:
+        f.write(line + "\n")
+
+
+def _err(got, ref):
+    got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    return float((got - ref).abs().max()), float(ref.abs().max())
+
+
+def _build(mode, sd0):
+    import models
+    m = models.DCCRN(masking_mode=mode)
+    m.load_state_dict(sd0)
+    return m.to(DEV).train()
+
+
+@pytest.fixture(scope="module")
+def sd0():
+    return O.init_state(0)
+
+
+def _cl(x):     # oracle [B,C,F,T] -> library channels-last [B,F,T,C]
+    return x.permute(0, 2, 3, 1)
+
+
+@pytest.mark.parametrize("mode", ["C", "E", "R"])
+def test_small_forward_backward_every_tensor(golden, sd0, mode):
+    import models
+    noisy = torch.from_numpy(golden["small_speech_noisy"])
+    clean = torch.from_numpy(golden["small_speech_clean"])
+    tr = O.OracleTrainer(sd0, masking_mode=mode, loss="SI-SNR")
+    taps = {}
+    loss_ref, wav_ref = tr.forward_backward(noisy, clean, taps)
+
+    m = _build(mode, sd0)
+    models.cfg.loss = "SI-SNR"
+    o_r, o_i, wav = m(noisy.to(DEV), clean.to(DEV))
+    loss = m.loss(wav, clean.to(DEV))
+    loss.backward()
+    plan = m._get_engine().plan(*noisy.shape)
+    B, T = noisy.shape[0], plan.T
+
+    failures = []
+
+    def chk(name, got, ref, atol_rel, rtol=1e-4):
+        e, s = _err(got, ref)
+        g64, r64 = got.detach().double().cpu(), ref.detach().double().cpu()
+        ok = bool(((g64 - r64).abs() <= atol_rel * s + rtol * r64.abs()).all())
+        _report(f"[{mode}] {name:34s} max|err|={e:.3e}  max|ref|={s:.3e}  {'ok' if ok else 'FAIL'}")
+        if not ok:
+            failures.append(name)
+
+    spec = plan.tensor("spec")
+    chk("spec", torch.cat([spec[..., 0], spec[..., 1]], 1), taps["spec"], 2e-6)
+    for i in range(6):
+        chk(f"enc{i}.y", plan.tensor(f"enc{i}.y"), _cl(taps[f"enc{i}_conv"]), 2e-6)
+        chk(f"enc{i}.z", plan.tensor(f"enc{i}.z"), _cl(taps[f"enc{i}"]), 2e-6)
+    # LSTM: X1/X2 are [part][B][T][128]; oracle taps are [T,B,128] (layer 0) / [T,B,512] after projection
+    X1 = plan.tensor("X1")
+    chk("lstm0 real", X1[0], taps["lstm0_r"].permute(1, 0, 2), 5e-6)
+    chk("lstm0 imag", X1[1], taps["lstm0_i"].permute(1, 0, 2), 5e-6)
+    U = plan.tensor("U")                                               # [B,4,T,256]; feature c*4+d
+    u_ref_r = taps["lstm1_r"].reshape(T, B, 128, 4).permute(1, 3, 0, 2)
+    u_ref_i = taps["lstm1_i"].reshape(T, B, 128, 4).permute(1, 3, 0, 2)
+    chk("lstm1+proj real", U[..., :128], u_ref_r, 5e-6)
+    chk("lstm1+proj imag", U[..., 128:], u_ref_i, 5e-6)
+    for j in range(6):
+        chk(f"dec{j}.y", plan.tensor(f"dec{j}.y"), _cl(taps[f"dec{j}_conv"]), 5e-6)
+        if j < 5:
+            chk(f"dec{j}.z", plan.tensor(f"dec{j}.z"), _cl(taps[f"dec{j}"]), 5e-6)
+    chk("out_wav", wav, wav_ref, 2e-5)
+    chk("out_real", o_r, torch.from_numpy(golden[f"small_speech_{mode}_SI-SNR_out_real"]), 2e-5)
+    chk("out_imag", o_i, torch.from_numpy(golden[f"small_speech_{mode}_SI-SNR_out_imag"]), 2e-5)
+    chk("wav vs golden", wav, torch.from_numpy(golden[f"small_speech_{mode}_SI-SNR_wav"]), 2e-5)
+    _report(f"[{mode}] loss got {float(loss):.6f} oracle {float(loss_ref):.6f} golden "
+            f"{float(golden[f'small_speech_{mode}_SI-SNR_loss']):.6f}")
+    if abs(float(loss) - float(loss_ref)) > 2e-4 * abs(float(loss_ref)) + 1e-4:
+        failures.append("loss")
+
+    # gradients of every parameter vs the oracle's autograd (relative to each tensor's own scale, with a
+    # floor for the conv biases in front of a BatchNorm whose true gradient is exactly zero)
+    grads = tr.grads()
+    gmax = max(float(g.abs().max()) for g in grads.values())
+    for name, p in m.named_parameters():
+        ref = grads[name]
+        if name.endswith("_conv.bias") and not name.startswith("decoder.5."):
+            ok = float(p.grad.abs().max()) <= 1e-4 * gmax
+            _report(f"[{mode}] grad {name:40s} (zero by BN) max|got|={float(p.grad.abs().max()):.3e} {'ok' if ok else 'FAIL'}")
+        else:
+            e, s = _err(p.grad, ref)
+            ok = e <= 2e-3 * s + 1e-6 * gmax
+            _report(f"[{mode}] grad {name:40s} max|err|={e:.3e} max|ref|={s:.3e} {'ok' if ok else 'FAIL'}")
+        if not ok:
+            failures.append("grad " + name)
+    # BN running statistics after one train-mode forward
+    for k, v in m.state_dict().items():
+        if "running" in k:
+            ref = tr.sd[k]
+            e, s = _err(v, ref)
+            if e > 1e-4 * s + 1e-6:
+                failures.append(k)
+                _report(f"[{mode}] {k} max|err|={e:.3e} FAIL")
+    assert int(m.encoder[0][1].num_batches_tracked) == 1
+    assert not failures, failures
+
+
+def test_losses_through_dropin(golden, sd0):
+    import models
+    noisy = torch.from_numpy(golden["small_rand_noisy"]).to(DEV)
+    clean = torch.from_numpy(golden["small_rand_clean"]).to(DEV)
+    m = _build("C", sd0)
+    names = [str(n) for n in golden["param_names"]]
+    for loss_name in ["SI-SNR", "SDR", "SI-SDR", "MSE"]:
+        models.cfg.loss = loss_name
+        m.zero_grad()
+        _, _, wav = m(noisy, clean)
+        loss = m.loss(wav, clean)
+        loss.backward()
+        ref = float(golden[f"small_rand_C_{loss_name}_loss"])
+        assert float(loss) == pytest.approx(ref, rel=2e-4, abs=2e-5), loss_name
+        gn = np.array([float(dict(m.named_parameters())[n].grad.double().norm()) for n in names])
+        refn = golden[f"small_rand_C_{loss_name}_gnorm"]
+        keep = [i for i, n in enumerate(names) if not (n.endswith("_conv.bias") and not n.startswith("decoder.5."))]
+        np.testing.assert_allclose(gn[keep], refn[keep], rtol=5e-3, atol=1e-5 * float(refn.max()))
+    models.cfg.loss = "SI-SNR"
+
+
+def test_eval_forward_and_state_dict_round_trip(golden, sd0):
+    import models
+    noisy = torch.from_numpy(golden["small_speech_noisy"]).to(DEV)
+    clean = torch.from_numpy(golden["small_speech_clean"]).to(DEV)
+    m = _build("C", sd0)
+    m(noisy, clean)                                   # one train forward updates the running statistics
+    m.eval()
+    with torch.no_grad():
+        _, _, wav = m(noisy)
+    np.testing.assert_allclose(wav.cpu().numpy(), golden["small_speech_C_eval_wav"], atol=2e-5)
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    m2 = models.DCCRN(masking_mode="C")
+    m2.load_state_dict(sd)
+    m2 = m2.to(DEV).eval()
+    with torch.no_grad():
+        _, _, wav2 = m2(noisy)
+    assert torch.equal(wav, wav2)
+
+
+def test_three_adam_steps_with_reference_optimizer(golden, sd0):
+    """The reference's own loop body (trainer.py:27-37) with torch.optim.Adam driving the drop-in."""
+    import models
+    models.cfg.loss = "SI-SNR"
+    noisy = torch.from_numpy(golden["small_speech_noisy"]).to(DEV)
+    clean = torch.from_numpy(golden["small_speech_clean"]).to(DEV)
+    m = _build("C", sd0)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    losses = []
+    for _ in range(3):
+        _, _, wav = m(noisy, clean)
+        loss = m.loss(wav, clean)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    np.testing.assert_allclose(losses, golden["adam3_losses"], rtol=2e-3, atol=2e-3)
+
+
+def test_full_length_known_answer(golden, sd0):
+    """B=2, 3 s @ 16 kHz, seeds of SURVEY.md §4: loss 43.71657562, waveform RMSE < 1e-4 (north star)."""
+    import models
+    models.cfg.loss = "SI-SNR"
+    noisy, clean = O.synthetic_batch(2)
+    m = _build("C", sd0)
+    _, _, wav = m(noisy.to(DEV), clean.to(DEV))
+    loss = m.loss(wav, clean.to(DEV))
+    loss.backward()
+    assert float(loss) == pytest.approx(43.71657562, rel=2e-5)
+    head = torch.from_numpy(golden["full_wav_head"])
+    rmse = float((wav[:, :2048].cpu() - head).pow(2).mean().sqrt())
+    _report(f"[full] loss {float(loss):.6f} wav RMSE vs reference {rmse:.3e}")
+    assert rmse < 1e-4
+    assert float(wav.double().pow(2).mean().sqrt()) == pytest.approx(float(golden["full_wav_rms"]), rel=1e-4)
+    names = [str(n) for n in golden["param_names"]]
+    gn = np.array([float(dict(m.named_parameters())[n].grad.double().norm()) for n in names])
+    keep = [i for i, n in enumerate(names) if not (n.endswith("_conv.bias") and not n.startswith("decoder.5."))]
+    np.testing.assert_allclose(gn[keep], golden["full_gnorm"][keep], rtol=5e-3,
+                               atol=1e-5 * float(golden["full_gnorm"].max()))
+
+
+def test_batch32_properties():
+    """BASELINE config 2 size (B=32, 3 s): properties that do not need the oracle -
+    per-utterance independence of the eval-mode forward and finiteness of all gradients."""
+    import models
+    models.cfg.loss = "SI-SNR"
+    torch.manual_seed(0)
+    m = models.DCCRN(masking_mode="C").to(DEV)
+    noisy, clean = O.synthetic_batch(32)
+    noisy, clean = noisy.to(DEV), clean.to(DEV)
+    m.train()
+    _, _, wav = m(noisy, clean)
+    loss = m.loss(wav, clean)
+    loss.backward()
+    assert torch.isfinite(loss)
+    for n, p in m.named_parameters():
+        assert torch.isfinite(p.grad).all(), n
+    m.eval()
+    with torch.no_grad():
+        _, _, w32 = m(noisy)
+        _, _, w2 = m(noisy[5:7].contiguous())
+    assert float((w32[5:7] - w2).abs().max()) < 1e-5     # utterances are independent in eval mode

@@ -1,0 +1,259 @@
+"""GPU parity of every op-level C entry point against the CPU oracle (oracle/dccrn_oracle.py) on the same
+seeded inputs.  Tolerances are absolute/relative fp32 figures written next to each check."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dccrn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _close(got, ref, atol, rtol=0.0, name=""):
+    got = got.detach().double().cpu()
+    ref = ref.detach().double().cpu()
+    assert got.shape == ref.shape, (name, got.shape, ref.shape)
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    worst = float((err - tol).max())
+    assert worst <= 0, f"{name}: max|err|={float(err.max()):.3e} (ref max {float(ref.abs().max()):.3e}), tol {atol}+{rtol}*|ref|"
+
+
+@pytest.fixture(scope="module")
+def bases():
+    k_a, k_s, w = O.stft_bases()
+    return (torch.from_numpy(k_a).float(), torch.from_numpy(k_s).float(), torch.from_numpy(w).float())
+
+
+def _spec_to_ref(spec):          # [B,257,T,2] -> [B,514,T]
+    return torch.cat([spec[..., 0], spec[..., 1]], 1)
+
+
+def _ref_to_spec(ref):           # [B,514,T] -> [B,257,T,2]
+    return torch.stack([ref[:, :257], ref[:, 257:]], -1).contiguous()
+
+
+@pytest.mark.parametrize("B,L", [(1, 100), (2, 4000), (3, 48000)])
+def test_stft_matches_conv_stft(bases, B, L):
+    from sefd import ops
+    g = torch.Generator().manual_seed(3)
+    wav = torch.randn(B, L, generator=g)
+    ref = O.conv_stft(wav, bases[0])
+    got = _spec_to_ref(ops.stft(wav.to(DEV)))
+    _close(got, ref, atol=2e-4, rtol=1e-5, name="stft")           # |X| up to ~60 on N(0,1) input
+
+
+@pytest.mark.parametrize("B,L", [(1, 100), (2, 4000), (2, 48000)])
+def test_istft_matches_conv_istft_on_arbitrary_spectra(bases, B, L):
+    """Off-manifold spectra (incl. imaginary DC/Nyquist) exercise the pinv synthesis, not plain irfft."""
+    from sefd import ops
+    T = L // 100 + 3
+    g = torch.Generator().manual_seed(4)
+    spec = torch.randn(B, 514, T, generator=g)
+    ref = O.conv_istft(spec, bases[1], bases[2])
+    got = ops.istft(_ref_to_spec(spec).to(DEV), L)
+    _close(got, ref, atol=2e-5, rtol=1e-5, name="istft")
+
+
+def test_istft_adjoint_matches_autograd(bases):
+    from sefd import ops
+    B, L = 2, 4000
+    T = L // 100 + 3
+    g = torch.Generator().manual_seed(5)
+    spec = torch.randn(B, 514, T, generator=g, requires_grad=True)
+    dwav = torch.randn(B, L, generator=g)
+    O.conv_istft(spec, bases[1], bases[2]).backward(dwav)
+    got = _spec_to_ref(ops.istft_backward(dwav.to(DEV)))
+    _close(got, spec.grad, atol=2e-6, rtol=1e-5, name="istft^T")
+
+
+def test_stft_istft_round_trip_full_size():
+    """Size-independent property at the benchmark size: ISTFT(STFT(x)) == x (B=32, 3 s)."""
+    from sefd import ops
+    g = torch.Generator().manual_seed(6)
+    wav = (torch.rand(32, 48000, generator=g) * 2 - 1).to(DEV)
+    back = ops.istft(ops.stft(wav), 48000)
+    _close(back, wav, atol=5e-6, name="round trip")
+
+
+@pytest.mark.parametrize("mode", ["C", "E", "R"])
+def test_mask_istft_forward_backward(bases, mode):
+    from sefd import ops
+    B, L = 2, 4000
+    T = L // 100 + 3
+    g = torch.Generator().manual_seed(7)
+    wav = torch.randn(B, L, generator=g) * 0.3
+    mask = (torch.randn(B, 256, T, 2, generator=g)).requires_grad_(True)
+    specs = O.conv_stft(wav, bases[0])
+    real, imag = specs[:, :257], specs[:, 257:]
+    mr = torch.nn.functional.pad(mask[..., 0], [0, 0, 1, 0])
+    mi = torch.nn.functional.pad(mask[..., 1], [0, 0, 1, 0])
+    if mode == "C":
+        o_r, o_i = real * mr - imag * mi, real * mi + imag * mr
+    elif mode == "R":
+        o_r, o_i = real * mr, imag * mi
+    else:
+        smag = torch.sqrt(real ** 2 + imag ** 2 + 1e-8)
+        sph = torch.atan2(imag, real)
+        mm = (mr ** 2 + mi ** 2) ** 0.5
+        ph = sph + torch.atan2(mi / (mm + 1e-8), mr / (mm + 1e-8))
+        em = torch.tanh(mm) * smag
+        o_r, o_i = em * torch.cos(ph), em * torch.sin(ph)
+    raw = O.conv_istft(torch.cat([o_r, o_i], 1), bases[1], bases[2])
+    out = torch.clamp(raw, -1, 1)
+    dwav = torch.randn(B, L, generator=g)
+    out.backward(dwav)
+
+    spec_d = ops.stft(wav.to(DEV))
+    mask_d = mask.detach().to(DEV).contiguous()
+    g_r, g_i, g_wav, g_raw = ops.mask_istft(spec_d, mask_d, mode, L)
+    _close(g_r, o_r, atol=3e-5, rtol=1e-5, name="out_real")
+    _close(g_i, o_i, atol=3e-5, rtol=1e-5, name="out_imag")
+    _close(g_wav, out, atol=5e-6, rtol=1e-5, name="out_wav")
+    assert float((raw.abs() > 1).float().mean()) > 0.001, "test should exercise the clamp"
+    dmask = ops.mask_istft_backward(dwav.to(DEV), g_raw, spec_d, mask_d, mode)
+    _close(dmask, mask.grad, atol=2e-5, rtol=2e-4, name="dmask")
+
+
+@pytest.mark.parametrize("name", ["MSE", "SDR", "SI-SNR", "SI-SDR"])
+def test_losses_forward_backward(name, golden):
+    from sefd import ops
+    a = torch.from_numpy(golden["loss_pair_a"])
+    b = torch.from_numpy(golden["loss_pair_b"])
+    for est, tgt in [(a, b), (b + 0.05 * a, b)]:          # uncorrelated pair and a ~26 dB pair
+        e = est.clone().requires_grad_(True)
+        ref = O.dccrn_loss(e.double(), tgt.double(), name)
+        ref.backward()
+        ed = est.to(DEV).requires_grad_(True)
+        got = ops.loss(ed, tgt.to(DEV), name)
+        got.backward()
+        assert float(got) == pytest.approx(float(ref), rel=2e-6, abs=1e-7)
+        _close(ed.grad, e.grad, atol=1e-7 * float(e.grad.abs().max()) + 1e-12, rtol=2e-5, name=name + " grad")
+    if name == "SI-SNR":
+        assert float(-ops.loss(a.to(DEV), b.to(DEV), name)) == pytest.approx(float(golden["loss_ref_si_snr"]), rel=1e-5)
+
+
+def _nchw(x):     # channels-last [B,F,T,C] -> reference [B,C,F,T]
+    return x.permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("B,F,T,Cin,Cout", [(2, 16, 43, 2, 32), (1, 8, 130, 64, 128), (2, 4, 21, 256, 256)])
+def test_complex_conv2d_forward_backward(B, F, T, Cin, Cout):
+    from sefd import ops
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(B, F, T, Cin, generator=g)
+    wr = (torch.randn(Cout // 2, Cin // 2, 5, 2, generator=g) * 0.05)
+    wi = (torch.randn(Cout // 2, Cin // 2, 5, 2, generator=g) * 0.05)
+    br, bi = torch.randn(Cout // 2, generator=g), torch.randn(Cout // 2, generator=g)
+    leaves = [t.clone().requires_grad_(True) for t in (x, wr, br, wi, bi)]
+    y = O.complex_conv2d(_nchw(leaves[0]), *leaves[1:])
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    yd = ops.cconv2d_forward(x.to(DEV), wr.to(DEV), br.to(DEV), wi.to(DEV), bi.to(DEV))
+    _close(_nchw(yd), y, atol=1e-5 * (Cin ** 0.5), rtol=1e-5, name="conv fwd")
+    dyc = dy.permute(0, 2, 3, 1).contiguous().to(DEV)
+    dx, dwr, dbr, dwi, dbi = ops.cconv2d_backward(x.to(DEV), wr.to(DEV), wi.to(DEV), dyc)
+    _close(dx, leaves[0].grad, atol=2e-5 * (Cout ** 0.5), rtol=1e-5, name="conv dx")
+    scale = float(leaves[1].grad.abs().max())
+    _close(dwr, leaves[1].grad, atol=2e-5 * scale, rtol=1e-4, name="conv dWr")
+    _close(dwi, leaves[3].grad, atol=2e-5 * scale, rtol=1e-4, name="conv dWi")
+    _close(dbr, leaves[2].grad, atol=2e-5 * float(leaves[2].grad.abs().max()), rtol=1e-4, name="conv dbr")
+    _close(dbi, leaves[4].grad, atol=2e-5 * float(leaves[4].grad.abs().max()), rtol=1e-4, name="conv dbi")
+
+
+@pytest.mark.parametrize("B,F,T,Cin,Cout", [(2, 8, 43, 64, 2), (1, 4, 130, 512, 256), (2, 16, 21, 128, 32)])
+def test_complex_conv_transpose2d_forward_backward(B, F, T, Cin, Cout):
+    from sefd import ops
+    g = torch.Generator().manual_seed(9)
+    Ch = Cin // 2
+    x0 = torch.randn(B, F, T, Ch, generator=g)
+    x1 = torch.randn(B, F, T, Ch, generator=g)
+    wr = (torch.randn(Cin // 2, Cout // 2, 5, 2, generator=g) * 0.05)
+    wi = (torch.randn(Cin // 2, Cout // 2, 5, 2, generator=g) * 0.05)
+    br, bi = torch.randn(Cout // 2, generator=g), torch.randn(Cout // 2, generator=g)
+    leaves = [t.clone().requires_grad_(True) for t in (x0, x1, wr, br, wi, bi)]
+    xin = O.complex_cat(_nchw(leaves[0]), _nchw(leaves[1]))
+    y = O.complex_conv_transpose2d(xin, *leaves[2:])                  # [B, Cout, 2F, T+1]
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    dev = [t.to(DEV) for t in (x0, x1, wr, br, wi, bi)]
+    yd = ops.cconvT2d_forward(*dev)
+    _close(_nchw(yd), y, atol=1e-5 * (Cin ** 0.5), rtol=1e-5, name="convT fwd")
+    dyc = dy.permute(0, 2, 3, 1).contiguous().to(DEV)
+    dx0, dx1, dwr, dbr, dwi, dbi = ops.cconvT2d_backward(dev[0], dev[1], dev[2], dev[4], dyc)
+    _close(dx0, leaves[0].grad, atol=2e-5 * (Cout ** 0.5), rtol=1e-5, name="convT dx0")
+    _close(dx1, leaves[1].grad, atol=2e-5 * (Cout ** 0.5), rtol=1e-5, name="convT dx1")
+    scale = float(leaves[2].grad.abs().max())
+    _close(dwr, leaves[2].grad, atol=2e-5 * scale, rtol=1e-4, name="convT dWr")
+    _close(dwi, leaves[4].grad, atol=2e-5 * scale, rtol=1e-4, name="convT dWi")
+    _close(dbr, leaves[3].grad, atol=2e-5 * float(leaves[3].grad.abs().max()), rtol=1e-4, name="convT dbr")
+    _close(dbi, leaves[5].grad, atol=2e-5 * float(leaves[5].grad.abs().max()), rtol=1e-4, name="convT dbi")
+
+
+@pytest.mark.parametrize("rows,C", [(5000, 32), (3001, 256)])
+def test_bn_prelu_forward_backward(rows, C):
+    from sefd import ops
+    g = torch.Generator().manual_seed(10)
+    y = torch.randn(rows, C, generator=g) * 2 + 0.5
+    gamma = torch.rand(C, generator=g) + 0.5
+    beta = torch.randn(C, generator=g) * 0.3
+    alpha = torch.tensor([0.25])
+    leaves = [t.clone().requires_grad_(True) for t in (y, gamma, beta, alpha)]
+    y4 = leaves[0].t().reshape(1, C, rows, 1)
+    z, mean, var = O.batch_norm_train(y4, leaves[1], leaves[2])
+    z = O.prelu(z, leaves[3])
+    dz = torch.randn(rows, C, generator=g)
+    z.backward(dz.t().reshape(1, C, rows, 1))
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    zd, save = ops.bn_prelu_forward(y.to(DEV), gamma.to(DEV), beta.to(DEV), alpha.to(DEV), rm, rv)
+    _close(zd, z.reshape(C, rows).t(), atol=3e-6, rtol=1e-5, name="bn fwd")
+    _close(save[0], mean, atol=1e-6, name="bn mean")
+    _close(rm, 0.1 * mean, atol=1e-6, name="running mean")
+    _close(rv, 0.9 + 0.1 * var * rows / (rows - 1), atol=1e-5, name="running var")
+    dy, dg, db, da = ops.bn_prelu_backward(y.to(DEV), dz.to(DEV), gamma.to(DEV), beta.to(DEV), alpha.to(DEV), save)
+    _close(dy, leaves[0].grad, atol=3e-6, rtol=1e-4, name="bn dy")
+    _close(dg, leaves[1].grad, atol=2e-5 * float(leaves[1].grad.abs().max()), rtol=1e-4, name="bn dgamma")
+    _close(db, leaves[2].grad, atol=2e-5 * float(leaves[2].grad.abs().max()), rtol=1e-4, name="bn dbeta")
+    _close(da, leaves[3].grad, atol=0, rtol=1e-4, name="prelu dalpha")
+
+
+@pytest.mark.parametrize("rows,T", [(4, 7), (6, 43), (64, 483)])
+def test_lstm_recurrence_forward_backward(rows, T):
+    from sefd import ops
+    g = torch.Generator().manual_seed(11)
+    k = 1 / 128 ** 0.5
+    w_hh = (torch.rand(2, 512, 128, generator=g) * 2 - 1) * k
+    pre = torch.randn(2, rows, T, 512, generator=g)
+    wl = w_hh.clone().requires_grad_(True)
+    pl = pre.clone().requires_grad_(True)
+    hs = []
+    for p in range(2):
+        # drive the oracle's LSTM with identity input weights so that x W_ih^T + b == pre
+        x = pl[p].permute(1, 0, 2)                                    # [T, rows, 512]
+        hs.append(O.lstm_seq(x, torch.eye(512), wl[p], torch.zeros(512), torch.zeros(512)).permute(1, 0, 2))
+    h_ref = torch.stack(hs)
+    dh = torch.randn(h_ref.shape, generator=g)
+    h_ref.backward(dh)
+    gates = pre.clone().to(DEV)
+    h, c = ops.lstm_forward(w_hh.to(DEV), gates)
+    _close(h, h_ref, atol=2e-6 * T ** 0.5, rtol=1e-5, name="lstm h")
+    dg = ops.lstm_backward(w_hh.to(DEV), gates, c, dh.to(DEV))
+    _close(dg, pl.grad, atol=2e-6 * T ** 0.5 * float(pl.grad.abs().max()), rtol=2e-4, name="lstm dpre")
+
+
+def test_adam_matches_torch_optim():
+    from sefd import ops
+    g = torch.Generator().manual_seed(12)
+    w = torch.randn(10007, generator=g)
+    ref = w.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    wd = w.clone().to(DEV)
+    m, v = torch.zeros_like(wd), torch.zeros_like(wd)
+    for step in range(1, 6):
+        grad = torch.randn(10007, generator=g) * 10 ** float(torch.randint(-6, 2, (1,), generator=g))
+        ref.grad = grad.clone()
+        opt.step()
+        ops.adam_step(wd, grad.to(DEV), m, v, step)
+        _close(wd, ref, atol=2e-7, rtol=1e-6, name=f"adam step {step}")
