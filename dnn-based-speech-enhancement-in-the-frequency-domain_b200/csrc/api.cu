@@ -18,7 +18,10 @@ void sefd_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static long long g_launches = 0;
+
 int sefd_check_launch(const char* what) {
+    ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         sefd_set_error("%s: %s", what, cudaGetErrorString(e));
@@ -32,6 +35,7 @@ struct PlanView;
 extern "C" {
 
 int sefd_abi_version(void) { return 1; }
+long long sefd_launch_count(void) { return g_launches; }
 const char* sefd_last_error(void) { return g_err; }
 
 static_assert((int)SEFD_MODE_E == (int)SEFD_MASK_E && (int)SEFD_MODE_C == (int)SEFD_MASK_C && (int)SEFD_MODE_R == (int)SEFD_MASK_R, "mode enums");

@@ -2,6 +2,7 @@
 // packing of the complex conv weights into the block-real GEMM operand (and folding the
 // block-real weight gradient back), complex-LSTM output combination, fused Adam.
 #include "elementwise.cuh"
+#include "prof.cuh"
 
 namespace {
 
@@ -352,12 +353,14 @@ inline int grid_for(long long n, int block = 256, int cap = 148 * 16) {
 
 int sefd_bn_prelu_fwd(const BnPreluFwdParams& p, cudaStream_t st) {
     SEFD_REQUIRE(p.C % 4 == 0 && p.C <= MAXC, "bn_prelu_fwd: C=%d unsupported", p.C);
+    SefdProfScope prof(SEFD_PROF_BN, 0, 8.0 * p.BF * (double)p.T * p.C, st);
     bn_prelu_fwd_kernel<<<grid_for((long long)p.BF * p.T * (p.C / 4)), 256, 0, st>>>(p);
     return sefd_check_launch("bn_prelu_fwd");
 }
 
 int sefd_bn_prelu_bwd(const BnPreluBwdParams& p, cudaStream_t st) {
     SEFD_REQUIRE(p.C % 4 == 0 && p.C <= MAXC && 256 % (p.C / 4) == 0, "bn_prelu_bwd: C=%d unsupported", p.C);
+    SefdProfScope prof(SEFD_PROF_BN, 0, 4.0 * p.BF * p.C * (2.0 * p.T + 2.0 * p.T + p.Ty), st);
     cudaMemsetAsync(p.red, 0, sizeof(double) * (2 * p.C + 1), st);
     const int lanes = 256 / (p.C / 4);
     long long g = ((long long)p.BF * p.T + lanes - 1) / lanes;
@@ -369,22 +372,26 @@ int sefd_bn_prelu_bwd(const BnPreluBwdParams& p, cudaStream_t st) {
 }
 
 int sefd_pack_cconv(const CconvPackParams& p, cudaStream_t st) {
+    SefdProfScope prof(SEFD_PROF_MISC, 0, 0, st);
     pack_cconv_kernel<<<grid_for(40ll * p.Ci2 * p.Co2), 256, 0, st>>>(p);
     return sefd_check_launch("pack_cconv");
 }
 
 int sefd_fold_cconv(const CconvFoldParams& p, cudaStream_t st) {
+    SefdProfScope prof(SEFD_PROF_MISC, 0, 0, st);
     fold_cconv_kernel<<<grid_for(10ll * p.Ci2 * p.Co2), 256, 0, st>>>(p);
     return sefd_check_launch("fold_cconv");
 }
 
 int sefd_permute3(const float* src, float* dst, int na, int nb, int nc, long long sa, long long sb, long long sc,
                   int accumulate, cudaStream_t st) {
+    SefdProfScope prof(SEFD_PROF_MISC, 0, 0, st);
     permute3_kernel<<<grid_for((long long)na * nb * nc), 256, 0, st>>>(src, dst, na, nb, nc, sa, sb, sc, accumulate);
     return sefd_check_launch("permute3");
 }
 
 int sefd_add2(const float* a, const float* b, float* o, long long n, cudaStream_t st) {
+    SefdProfScope prof(SEFD_PROF_MISC, 0, 0, st);
     add2_kernel<<<grid_for(n), 256, 0, st>>>(a, b, o, n);
     return sefd_check_launch("add2");
 }
@@ -392,6 +399,7 @@ int sefd_add2(const float* a, const float* b, float* o, long long n, cudaStream_
 int sefd_colsum2(const float* x, int nO, long long sO, long long nI, long long sI, int C, double* scratch, float* out,
                  cudaStream_t st) {
     SEFD_REQUIRE(C >= 1 && C <= 512, "colsum: C=%d unsupported", C);
+    SefdProfScope prof(SEFD_PROF_MISC, 0, 0, st);
     cudaMemsetAsync(scratch, 0, sizeof(double) * C, st);
     const int block = C > 256 ? 512 : 256;
     const int lanes = block / C;
@@ -404,11 +412,13 @@ int sefd_colsum2(const float* x, int nO, long long sO, long long nI, long long s
 }
 
 int sefd_clstm_combine(const float* H, float* X, long long n, cudaStream_t st) {
+    SefdProfScope prof(SEFD_PROF_MISC, 0, 0, st);
     clstm_combine_kernel<<<grid_for(n), 256, 0, st>>>(H, X, n);
     return sefd_check_launch("clstm_combine");
 }
 
 int sefd_clstm_combine_bwd(const float* dX, float* dH, long long n, cudaStream_t st) {
+    SefdProfScope prof(SEFD_PROF_MISC, 0, 0, st);
     clstm_combine_bwd_kernel<<<grid_for(n), 256, 0, st>>>(dX, dH, n);
     return sefd_check_launch("clstm_combine_bwd");
 }
@@ -417,6 +427,7 @@ int sefd_adam(float* w, const float* g, float* m, float* v, long long n, float l
               int step, float gscale, cudaStream_t st) {
     const double bc1 = 1.0 - pow((double)b1, (double)step);
     const double bc2 = 1.0 - pow((double)b2, (double)step);
+    SefdProfScope prof(SEFD_PROF_MISC, 0, 0, st);
     adam_kernel<<<grid_for(n), 256, 0, st>>>(w, g, m, v, n, lr, b1, b2, eps, (float)bc1, (float)sqrt(bc2), gscale);
     return sefd_check_launch("adam");
 }

@@ -7,6 +7,7 @@
 // does not fit in shared memory, so every thread keeps half of its weight row in registers and the other
 // half in shared memory (128 KB); h / gate exchange goes through shared memory with two barriers a step.
 #include "lstm.cuh"
+#include "prof.cuh"
 
 namespace {
 
@@ -210,6 +211,7 @@ int sefd_lstm_fwd_launch(const LstmFwdParams& p, cudaStream_t st) {
         attr = true;
     }
     dim3 grid((p.rows + LSTM_R - 1) / LSTM_R, 2);
+    SefdProfScope prof(SEFD_PROF_LSTM, 4.0 * p.rows * p.T * 512.0 * 128.0, 4.0 * 2 * p.rows * p.T * (2 * 512.0 + 256.0), st);
     lstm_fwd_kernel<LSTM_R><<<grid, 512, smem, st>>>(p);
     return sefd_check_launch("lstm_fwd");
 }
@@ -222,6 +224,7 @@ int sefd_lstm_bwd_launch(const LstmBwdParams& p, cudaStream_t st) {
         attr = true;
     }
     dim3 grid((p.rows + LSTM_R - 1) / LSTM_R, 2);
+    SefdProfScope prof(SEFD_PROF_LSTM, 4.0 * p.rows * p.T * 512.0 * 128.0, 4.0 * 2 * p.rows * p.T * (2 * 512.0 + 384.0), st);
     lstm_bwd_kernel<LSTM_R><<<grid, 512, smem, st>>>(p);
     return sefd_check_launch("lstm_bwd");
 }

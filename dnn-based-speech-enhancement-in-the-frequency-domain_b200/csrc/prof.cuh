@@ -1,0 +1,29 @@
+// Optional per-kernel-category device timing with CUDA events on the launching stream (used by bench.py for
+// the roofline figures; off by default, costs nothing when off).
+#pragma once
+#include <cuda_runtime.h>
+
+enum SefdProfCat {
+    SEFD_PROF_TAPGEMM = 0,   // conv / convT / linear forward and data gradients
+    SEFD_PROF_WGRAD = 1,     // weight gradients
+    SEFD_PROF_BN = 2,        // BatchNorm + PReLU forward / backward passes
+    SEFD_PROF_LSTM = 3,      // recurrent kernels
+    SEFD_PROF_STFT = 4,      // STFT, mask + ISTFT and its adjoint, loss passes
+    SEFD_PROF_MISC = 5,      // weight packing / folding, small reductions, Adam
+    SEFD_PROF_NCAT = 6
+};
+
+bool sefd_prof_on();
+void sefd_prof_push(int cat, double flops, double bytes, cudaStream_t st, bool begin);
+
+struct SefdProfScope {
+    int cat;
+    cudaStream_t st;
+    bool on;
+    SefdProfScope(int c, double flops, double bytes, cudaStream_t s) : cat(c), st(s), on(sefd_prof_on()) {
+        if (on) sefd_prof_push(cat, flops, bytes, st, true);
+    }
+    ~SefdProfScope() {
+        if (on) sefd_prof_push(cat, 0, 0, st, false);
+    }
+};

@@ -12,6 +12,7 @@
 // Two real frames share one complex 512-point FFT (fft512.cuh).
 #include "fft512.cuh"
 #include "stft.cuh"
+#include "prof.cuh"
 
 namespace {
 
@@ -33,6 +34,7 @@ __device__ __forceinline__ void init_tables(float2* tw, float* win, float* coff)
             coff[m] = a + 1e-8f;
         }
     }
+    __syncthreads();   // tables are read by every thread right after this returns
 }
 
 // sums over the even-n and odd-n samples of one 64-thread group; thread parity == sample parity.
@@ -515,6 +517,7 @@ int sefd_stft_launch(const float* wav, float* spec, int B, int L, int T, cudaStr
         attr = true;
     }
     dim3 grid((T + SF - 1) / SF, B);
+    SefdProfScope prof(SEFD_PROF_STFT, 0, 4.0 * B * L + 8.0 * B * NBIN * T, st);
     stft_fwd_kernel<<<grid, 256, sizeof(StftSmem), st>>>(wav, spec, B, L, T);
     return sefd_check_launch("stft_fwd");
 }
@@ -529,6 +532,8 @@ int sefd_mask_istft_launch(const MaskIstftParams& p, cudaStream_t st) {
     if (p.target) cudaMemsetAsync(p.dots, 0, sizeof(double) * 8 * p.B, st);
     const int chunks = (p.L / HOP + IHB - 1) / IHB;
     dim3 grid(chunks, p.B);
+    SefdProfScope prof(SEFD_PROF_STFT, 0, 8.0 * p.B * NBIN * p.T * (p.mode != SEFD_MASK_NONE ? 2 : 1) +
+                       4.0 * p.B * p.L * (p.target ? 3 : 2) + (p.out_real ? 8.0 * p.B * NBIN * p.T : 0.0), st);
     mask_istft_fwd_kernel<<<grid, 256, sizeof(IstftSmem), st>>>(p);
     return sefd_check_launch("mask_istft_fwd");
 }
@@ -540,6 +545,7 @@ int sefd_mask_istft_bwd_launch(const MaskIstftBwdParams& p, cudaStream_t st) {
         attr = true;
     }
     dim3 grid((p.T + SF - 1) / SF, p.B);
+    SefdProfScope prof(SEFD_PROF_STFT, 0, 8.0 * p.B * NBIN * p.T * 2 + 8.0 * p.B * p.L, st);
     mask_istft_bwd_kernel<<<grid, 256, sizeof(IstftBwdSmem), st>>>(p);
     return sefd_check_launch("mask_istft_bwd");
 }
@@ -548,6 +554,7 @@ int sefd_loss_fwd_launch(const float* est, const float* tgt, int B, int L, int k
                          float* loss, float* coef, cudaStream_t st) {
     SEFD_REQUIRE(kind >= 0 && kind <= 3, "loss: unknown kind %d", kind);
     dim3 grid(8, B);
+    SefdProfScope prof(SEFD_PROF_STFT, 0, 8.0 * B * L * (dots_ready ? 1 : 2), st);
     if (!dots_ready) {
         cudaMemsetAsync(dots, 0, sizeof(double) * 8 * B, st);
         loss_dots_kernel<<<grid, 256, 0, st>>>(est, tgt, L, dots);
@@ -565,6 +572,7 @@ int sefd_loss_bwd_launch(const float* est, const float* tgt, const float* coef, 
     long long n = (long long)B * L;
     int g = (int)((n + 255) / 256);
     if (g > 148 * 8) g = 148 * 8;
+    SefdProfScope prof(SEFD_PROF_STFT, 0, 12.0 * B * L, st);
     loss_bwd_kernel<<<g, 256, 0, st>>>(est, tgt, coef, gout, dest, B, L);
     return sefd_check_launch("loss_bwd");
 }

@@ -5,6 +5,7 @@
 // channels-last activation directly.  This is the reference-precision engine; the tensor-core
 // (tcgen05, TF32) engine in tapgemm_tc.cu implements the same contract for the wide layers.
 #include "common.cuh"
+#include "prof.cuh"
 
 namespace {
 
@@ -286,6 +287,9 @@ int sefd_tapgemm_simt(const TapGemmParams& p, cudaStream_t st) {
     const long long gx = ttiles * p.B * p.J;
     SEFD_REQUIRE(gx < (1ll << 31), "tapgemm: grid too large");
     dim3 grid((unsigned)gx, (unsigned)((N + BN - 1) / BN));
+    const double K = p.a[0].C + p.a[1].C, pos = (double)p.B * p.J * p.Tout;
+    SefdProfScope prof(SEFD_PROF_TAPGEMM, 2.0 * pos * N * K * p.ntaps,
+                       4.0 * ((double)p.B * p.J * (p.fi_mul > 1 ? p.fi_mul : 1) * p.Tin * K + pos * N), st);
     tapgemm_simt_kernel<<<grid, NT, 0, st>>>(p);
     return sefd_check_launch("tapgemm_simt");
 }
@@ -303,6 +307,10 @@ int sefd_wgrad_simt(const WgradParams& p_in, cudaStream_t st) {
     splits = (rows + p.rows_per_cta - 1) / p.rows_per_cta;
     SEFD_REQUIRE(splits <= 65535, "wgrad: too many splits");
     dim3 grid(tiles, p.ntaps, splits);
+    const double pos = (double)p.B * p.J * p.Tg;
+    SefdProfScope prof(SEFD_PROF_WGRAD, 2.0 * pos * K * N * p.ntaps,
+                       4.0 * ((double)p.B * p.J * (p.a_mul > 1 ? p.a_mul : 1) * p.Ta * K +
+                              (double)p.B * p.J * (p.g_mul > 1 ? p.g_mul : 1) * p.Tg * N), st);
     wgrad_simt_kernel<<<grid, 256, 0, st>>>(p);
     return sefd_check_launch("wgrad_simt");
 }

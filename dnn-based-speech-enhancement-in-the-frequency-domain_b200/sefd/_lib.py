@@ -44,6 +44,10 @@ SIGNATURES = {
     "sefd_dccrn_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sefd_dccrn_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sefd_dccrn_loss": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "sefd_launch_count": (_ll, []),
+    "sefd_prof_enable": (_i, [_i]),
+    "sefd_prof_reset": (_i, []),
+    "sefd_prof_get": (_i, [_i, C.POINTER(C.c_double), C.POINTER(_ll), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
 _lib = None

@@ -1,0 +1,103 @@
+"""Autograd-free train step over the C ABI: forward (+loss sums in the epilogue) -> loss -> backward ->
+[one NCCL all-reduce of the flat gradient buffer] -> fused Adam.  Equivalent to the body of the reference's
+trainer.model_train loop (trainer.py:27-37) with torch.optim.Adam(lr) (train_interface.py:59).
+
+Data-parallel semantics: utterances are sharded by batch, weights replicated, BatchNorm uses
+per-rank statistics (standard DDP), gradients are summed over ranks and scaled by 1/world inside Adam.
+"""
+import torch
+
+from . import _lib
+from .ops import LOSSES, ptr, stream
+
+
+class TrainStep:
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, loss="SI-SNR", process_group=None):
+        self.model = model
+        self.engine = model._get_engine()
+        self.engine.sync()
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.kind = LOSSES[loss]
+        self.exp_avg = torch.zeros_like(self.engine.flat)
+        self.exp_avg_sq = torch.zeros_like(self.engine.flat)
+        self.steps = 0
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self._bufs = {}
+
+    def _scratch(self, B, L, dev):
+        key = (B, L)
+        if key not in self._bufs:
+            self._bufs[key] = dict(
+                wav=torch.empty(B, L, device=dev), dwav=torch.empty(B, L, device=dev),
+                loss=torch.empty(1, device=dev), coef=torch.empty(2 * B, device=dev))
+        return self._bufs[key]
+
+    def forward_backward(self, noisy, clean):
+        """Fills engine.flat_grad with this rank's gradient; returns the loss tensor (1 element, device)."""
+        lib = _lib.load()
+        eng = self.engine
+        eng.sync()
+        B, L = noisy.shape
+        plan = eng.plan(B, L)
+        ws = plan.workspace(noisy.device)
+        s = self._scratch(B, L, noisy.device)
+        st = stream()
+        plan.generation += 1
+        _lib.check(lib.sefd_dccrn_forward(plan.handle, ptr(eng.flat), ptr(eng.flat_buf), ptr(noisy), ptr(clean), 1,
+                                          None, None, ptr(s["wav"]), ptr(ws), plan.ws_bytes, st), "dccrn_forward")
+        _lib.check(lib.sefd_dccrn_loss(plan.handle, ptr(s["wav"]), ptr(clean), self.kind, 1, ptr(s["loss"]),
+                                       ptr(s["coef"]), ptr(ws), st), "dccrn_loss")
+        _lib.check(lib.sefd_loss_backward(ptr(s["wav"]), ptr(clean), ptr(s["coef"]), None, ptr(s["dwav"]), B, L, st),
+                   "loss_backward")
+        _lib.check(lib.sefd_dccrn_backward(plan.handle, ptr(eng.flat), ptr(s["dwav"]), ptr(eng.flat_grad), ptr(ws),
+                                           plan.ws_bytes, st), "dccrn_backward")
+        return s["loss"]
+
+    def step(self, noisy, clean):
+        loss = self.forward_backward(noisy, clean)
+        eng = self.engine
+        if self.world > 1:
+            torch.distributed.all_reduce(eng.flat_grad, group=self.pg)     # single flat 14.7 MB buffer
+        self.steps += 1
+        _lib.check(_lib.load().sefd_adam_step(ptr(eng.flat), ptr(eng.flat_grad), ptr(self.exp_avg),
+                                              ptr(self.exp_avg_sq), eng.flat.numel(), self.lr, self.betas[0],
+                                              self.betas[1], self.eps, self.steps, 1.0 / self.world, stream()),
+                   "adam_step")
+        return loss
+
+
+class FlatAdam:
+    """Optimizer-shaped wrapper (zero_grad / step) that can stand where train_interface.py:59 builds
+    torch.optim.Adam(model.parameters(), lr): after loss.backward() the gradients already sit in the model's flat
+    gradient buffer, so step() is [all-reduce over ranks] + one fused Adam kernel.  One backward per step, like
+    the reference loop (trainer.py:35-37)."""
+
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, process_group=None):
+        self.model, self.lr, self.betas, self.eps, self.pg = model, lr, betas, eps, process_group
+        self.engine = model._get_engine()
+        self.engine.sync()
+        self.exp_avg = torch.zeros_like(self.engine.flat)
+        self.exp_avg_sq = torch.zeros_like(self.engine.flat)
+        self.steps = 0
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.model.parameters():
+            p.grad = None
+
+    def step(self):
+        eng = self.engine
+        if eng.flat.data_ptr() != self.exp_avg.data_ptr() and eng.flat.numel() != self.exp_avg.numel():
+            raise RuntimeError("FlatAdam: the model's parameter layout changed")
+        if self.world > 1:
+            torch.distributed.all_reduce(eng.flat_grad, group=self.pg)
+        self.steps += 1
+        _lib.check(_lib.load().sefd_adam_step(ptr(eng.flat), ptr(eng.flat_grad), ptr(self.exp_avg),
+                                              ptr(self.exp_avg_sq), eng.flat.numel(), self.lr, self.betas[0],
+                                              self.betas[1], self.eps, self.steps, 1.0 / self.world, stream()),
+                   "adam_step")

@@ -121,6 +121,15 @@ int sefd_dccrn_backward(const sefd_plan* plan, const float* params, const float*
 int sefd_dccrn_loss(const sefd_plan* plan, const float* out_wav, const float* target, int kind, int reuse_dots,
                     float* loss, float* coef, void* ws, void* stream);
 
+/* ---- measurement support (bench.py): CUDA-event timing per kernel category on the launching stream.
+ * categories: 0 tap-GEMM (conv/convT/linear fwd + dgrad), 1 weight gradients, 2 BN+PReLU passes,
+ * 3 LSTM recurrence, 4 STFT/ISTFT/loss, 5 packing/reductions/Adam.  flops/bytes are the ALGORITHMIC figures
+ * of the recorded launches (DESIGN.md states the formulas). */
+long long sefd_launch_count(void);   /* kernels launched by this library since load */
+int sefd_prof_enable(int on);
+int sefd_prof_reset(void);
+int sefd_prof_get(int category, double* ms, long long* launches, double* flops, double* bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,8 +84,8 @@ def test_mask_istft_forward_backward(bases, mode):
     B, L = 2, 4000
     T = L // 100 + 3
     g = torch.Generator().manual_seed(7)
-    wav = torch.randn(B, L, generator=g) * 0.3
-    mask = (torch.randn(B, 256, T, 2, generator=g)).requires_grad_(True)
+    wav = torch.randn(B, L, generator=g)
+    mask = (torch.randn(B, 256, T, 2, generator=g) * 1.5).requires_grad_(True)
     specs = O.conv_stft(wav, bases[0])
     real, imag = specs[:, :257], specs[:, 257:]
     mr = torch.nn.functional.pad(mask[..., 0], [0, 0, 1, 0])
@@ -130,7 +130,7 @@ def test_losses_forward_backward(name, golden):
         got = ops.loss(ed, tgt.to(DEV), name)
         got.backward()
         assert float(got) == pytest.approx(float(ref), rel=2e-6, abs=1e-7)
-        _close(ed.grad, e.grad, atol=1e-7 * float(e.grad.abs().max()) + 1e-12, rtol=2e-5, name=name + " grad")
+        _close(ed.grad, e.grad, atol=3e-6 * float(e.grad.abs().max()), rtol=2e-5, name=name + " grad")
     if name == "SI-SNR":
         assert float(-ops.loss(a.to(DEV), b.to(DEV), name)) == pytest.approx(float(golden["loss_ref_si_snr"]), rel=1e-5)
 
