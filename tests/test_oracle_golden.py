@@ -121,3 +121,16 @@ def test_full_length_known_answer(golden, sd0):
     names = [str(n) for n in golden["param_names"]]
     gn = np.array([float(tr.sd[n].grad.double().norm()) for n in names])
     np.testing.assert_allclose(gn, golden["full_gnorm"], rtol=5e-3, atol=1e-5 * float(golden["full_gnorm"].max()))
+
+
+def test_fused_lstm_equals_explicit_loop():
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(37, 5, 128, generator=g, requires_grad=True)
+    w = [torch.randn(512, 128, generator=g) * 0.1, torch.randn(512, 128, generator=g) * 0.1,
+         torch.randn(512, generator=g) * 0.1, torch.randn(512, generator=g) * 0.1]
+    a = O.lstm_seq(x, *w)
+    b = O.lstm_fused(x, *w)
+    np.testing.assert_allclose(a.detach().numpy(), b.detach().numpy(), atol=2e-6)
+    ga, = torch.autograd.grad(a.sum(), x)
+    gb, = torch.autograd.grad(b.sum(), x)
+    np.testing.assert_allclose(ga.numpy(), gb.numpy(), atol=2e-5)
