@@ -109,7 +109,7 @@ int sefd_loss_backward(const float* est, const float* target, const float* coef,
 // ---- complex conv ops -------------------------------------------------------------------------
 size_t sefd_cconv_workspace_bytes(int Cin, int Cout) {
     // Wf, Wt, dWf (10*Cin*Cout each) + bias / dbias (Cout each, padded) + reduction scratch
-    return sizeof(float) * (3ull * 10 * Cin * Cout + 2 * 1024) + sizeof(double) * 1024 + 1024;
+    return sizeof(float) * ((2ull + 16) * 10 * Cin * Cout + 2 * 1024) + sizeof(double) * 1024 + 1024;
 }
 
 struct CconvWs {
@@ -120,7 +120,7 @@ static CconvWs carve_cconv(void* ws, int Cin, int Cout) {
     CconvWs c;
     const size_t n = 10ull * Cin * Cout;
     float* f = (float*)ws;
-    c.Wf = f; c.Wt = f + n; c.dW = f + 2 * n; c.bias = f + 3 * n; c.dbias = c.bias + 1024;
+    c.Wf = f; c.Wt = f + n; c.dW = f + 2 * n; c.bias = f + 18 * n; c.dbias = c.bias + 1024;
     c.red = (double*)(((uintptr_t)(c.dbias + 1024) + 255) & ~(uintptr_t)255);
     return c;
 }
@@ -130,6 +130,7 @@ static int pack_op(const float* wr, const float* br, const float* wi, const floa
     pp.wr = wr; pp.wi = wi; pp.br = br ? br : zero_bias_src; pp.bi = bi ? bi : zero_bias_src;
     pp.Ci2 = Cin / 2; pp.Co2 = Cout / 2; pp.transposed = transposed; pp.two_src = transposed;
     pp.Wf = c.Wf; pp.Wt = c.Wt; pp.bias = c.bias;
+    pp.round_tf32 = sefd_get_engine_internal() == 1 && Cin % 32 == 0 && Cout % 32 == 0;
     return sefd_pack_cconv(pp, st);
 }
 
@@ -143,10 +144,10 @@ int sefd_cconv2d_forward(const float* x, const float* wr, const float* br, const
     memset(&g, 0, sizeof(g));
     g.a[0] = src4(x, F, T, Cin, Cin);
     g.o[0] = dst4(y, F / 2, T, Cout, Cout);
-    g.W = c.Wf; g.bias = c.bias;
+    g.W = c.Wf; g.Wnk = c.Wt; g.nslabs = 10; g.bias = c.bias;
     g.B = B; g.J = F / 2; g.Tout = T; g.Fin = F; g.Tin = T;
     conv_taps_down(g, -1);
-    return sefd_tapgemm_simt(g, ST);
+    return sefd_tapgemm(g, ST);
 }
 
 int sefd_cconv2d_backward(const float* x, const float* wr, const float* wi, const float* dy, float* dx, float* dwr,
@@ -155,7 +156,6 @@ int sefd_cconv2d_backward(const float* x, const float* wr, const float* wi, cons
     CconvWs c = carve_cconv(ws, Cin, Cout);
     cudaMemsetAsync(c.dbias, 0, sizeof(float) * 1024, ST);
     SEFD_TRY(pack_op(wr, nullptr, wi, nullptr, Cin, Cout, 0, c, ST, c.dbias));
-    cudaMemsetAsync(c.dW, 0, sizeof(float) * 10 * Cin * Cout, ST);
     WgradParams wg;
     memset(&wg, 0, sizeof(wg));
     wg.a[0] = src4(x, F, T, Cin, Cin);
@@ -168,10 +168,12 @@ int sefd_cconv2d_backward(const float* x, const float* wr, const float* wi, cons
             const int k = kf * 2 + kt;
             wg.a_off[k] = kf - 2; wg.g_off[k] = 0; wg.dt[k] = kt - 1; wg.wslab[k] = k;
         }
-    SEFD_TRY(sefd_wgrad_simt(wg, ST));
+    int nsplit = 1;
+    long long sstride = 0;
+    SEFD_TRY(sefd_wgrad(wg, c.dW, 16ll * 10 * Cin * Cout, 10, &nsplit, &sstride, ST));
     SEFD_TRY(sefd_colsum2(dy, 1, 0, (long long)B * (F / 2) * T, Cout, Cout, c.red, c.dbias, ST));
     CconvFoldParams f;
-    f.dWf = c.dW; f.dbias = c.dbias; f.Ci2 = Cin / 2; f.Co2 = Cout / 2; f.transposed = 0; f.two_src = 0;
+    f.dWf = c.dW; f.dbias = c.dbias; f.nsplit = nsplit; f.split_stride = sstride; f.Ci2 = Cin / 2; f.Co2 = Cout / 2; f.transposed = 0; f.two_src = 0;
     f.dwr = dwr; f.dwi = dwi; f.dbr = dbr; f.dbi = dbi;
     SEFD_TRY(sefd_fold_cconv(f, ST));
     if (dx) {
@@ -180,10 +182,10 @@ int sefd_cconv2d_backward(const float* x, const float* wr, const float* wi, cons
             memset(&g, 0, sizeof(g));
             g.a[0] = src4(dy, F / 2, T, Cout, Cout);
             g.o[0] = dst4(dx, F, T, Cin, Cin);
-            g.W = c.Wt;
+            g.W = c.Wt; g.Wnk = c.Wf; g.nslabs = 10;
             g.B = B; g.J = F / 2; g.Tout = T; g.Fin = F / 2; g.Tin = T;
             conv_taps_up(g, ph, 1);
-            SEFD_TRY(sefd_tapgemm_simt(g, ST));
+            SEFD_TRY(sefd_tapgemm(g, ST));
         }
     }
     return 0;
@@ -202,10 +204,10 @@ int sefd_cconvT2d_forward(const float* x0, const float* x1, const float* wr, con
         g.a[0] = src4(x0, F, T, Ch, Ch);
         g.a[1] = src4(x1, F, T, Ch, Ch);
         g.o[0] = dst4(y, 2 * F, T + 1, Cout, Cout);
-        g.W = c.Wf; g.bias = c.bias;
+        g.W = c.Wf; g.Wnk = c.Wt; g.nslabs = 10; g.bias = c.bias;
         g.B = B; g.J = F; g.Tout = T + 1; g.Fin = F; g.Tin = T;
         conv_taps_up(g, ph, 0);
-        SEFD_TRY(sefd_tapgemm_simt(g, ST));
+        SEFD_TRY(sefd_tapgemm(g, ST));
     }
     return 0;
 }
@@ -217,7 +219,6 @@ int sefd_cconvT2d_backward(const float* x0, const float* x1, const float* wr, co
     cudaMemsetAsync(c.dbias, 0, sizeof(float) * 1024, ST);
     SEFD_TRY(pack_op(wr, nullptr, wi, nullptr, Cin, Cout, 1, c, ST, c.dbias));
     const int Ch = Cin / 2;
-    cudaMemsetAsync(c.dW, 0, sizeof(float) * 10 * Cin * Cout, ST);
     WgradParams wg;
     memset(&wg, 0, sizeof(wg));
     wg.a[0] = src4(x0, F, T, Ch, Ch);
@@ -231,10 +232,12 @@ int sefd_cconvT2d_backward(const float* x0, const float* x1, const float* wr, co
             const int k = kf * 2 + kt;
             wg.a_off[k] = 0; wg.g_off[k] = kf - 2; wg.dt[k] = -kt; wg.wslab[k] = k;
         }
-    SEFD_TRY(sefd_wgrad_simt(wg, ST));
+    int nsplit = 1;
+    long long sstride = 0;
+    SEFD_TRY(sefd_wgrad(wg, c.dW, 16ll * 10 * Cin * Cout, 10, &nsplit, &sstride, ST));
     SEFD_TRY(sefd_colsum2(dy, 1, 0, (long long)B * 2 * F * (T + 1), Cout, Cout, c.red, c.dbias, ST));
     CconvFoldParams f;
-    f.dWf = c.dW; f.dbias = c.dbias; f.Ci2 = Cin / 2; f.Co2 = Cout / 2; f.transposed = 1; f.two_src = 1;
+    f.dWf = c.dW; f.dbias = c.dbias; f.nsplit = nsplit; f.split_stride = sstride; f.Ci2 = Cin / 2; f.Co2 = Cout / 2; f.transposed = 1; f.two_src = 1;
     f.dwr = dwr; f.dwi = dwi; f.dbr = dbr; f.dbi = dbi;
     SEFD_TRY(sefd_fold_cconv(f, ST));
     TapGemmParams g;
@@ -242,10 +245,10 @@ int sefd_cconvT2d_backward(const float* x0, const float* x1, const float* wr, co
     g.a[0] = src4(dy, 2 * F, T + 1, Cout, Cout);
     g.o[0] = dst4(dx0, F, T, Ch, Ch);
     g.o[1] = dst4(dx1, F, T, Ch, Ch);
-    g.W = c.Wt;
+    g.W = c.Wt; g.Wnk = c.Wf; g.nslabs = 10;
     g.B = B; g.J = F; g.Tout = T; g.Fin = 2 * F; g.Tin = T + 1;
     conv_taps_down(g, +1);
-    return sefd_tapgemm_simt(g, ST);
+    return sefd_tapgemm(g, ST);
 }
 
 // ---- BN + PReLU -------------------------------------------------------------------------------

@@ -42,8 +42,13 @@ struct TapDst {
 struct TapGemmParams {
     TapSrc a[2];
     TapDst o[2];
-    const float* W;      // [slab][K][N], n contiguous
+    const float* W;      // [slab][K][N], n contiguous (operand layout of the fp32 CUDA-core engine)
     long long wJ;        // extra weight offset per j (weights that vary with the output row)
+    const float* Wnk;    // same weights as [slab][N][K], k contiguous (operand layout of the tensor-core engine) or null
+    int nslabs;          // slabs addressable from Wnk
+    int wJ_slabs;        // slab offset per j (the tensor-core engine's equivalent of wJ)
+    long long w_ldk;     // row pitch of Wnk in floats (0: K)
+    long long w_slab_stride;   // slab pitch of Wnk in floats (0: K*N)
     const float* bias;   // [N] or nullptr
     long long bJ;        // extra bias offset per j
     double* stats;       // [2][N] (sum, sum of squares over all written outputs) or nullptr
@@ -69,9 +74,26 @@ struct WgradParams {
 };
 
 int sefd_tapgemm_simt(const TapGemmParams& p, cudaStream_t st);
+bool sefd_tapgemm_tc_eligible(const TapGemmParams& p);
+int sefd_tapgemm_tc(const TapGemmParams& p, cudaStream_t st);
+// dispatch: tensor-core engine when selected (default) and the problem is eligible, else the fp32 engine
+int sefd_tapgemm(const TapGemmParams& p, cudaStream_t st);
+int sefd_get_engine_internal();
 int sefd_wgrad_simt(const WgradParams& p, cudaStream_t st);
+// dispatch (tensor-core engine when eligible): writes *nsplit partial gradients [nslabs][K][N], *split_stride
+// floats apart, into `partial`; the caller's fold step sums them.
+int sefd_wgrad(const WgradParams& w, float* partial, long long cap_floats, int nslabs, int* nsplit,
+               long long* split_stride, cudaStream_t st);
 
 // ---- small device helpers ------------------------------------------------------------
+// round-to-nearest fp32 -> tf32 (10-bit mantissa).  The tcgen05 tf32 datapath ignores the low 13 mantissa bits
+// of its operands (truncation, biased); producers of tensor-core operands round here instead, for free.
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -253,8 +253,8 @@ sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode) {
     P->dY_floats = max_y;
     P->dY = w.floats(max_y);
     if (max_w < 4ull * 128 * G4) max_w = 4ull * 128 * G4;
-    P->dWs_floats = max_w;
-    P->dWs = w.floats(max_w);
+    P->dWs_floats = 16 * max_w;                   // room for the split partials of the tensor-core wgrad
+    P->dWs = w.floats(16 * max_w);
     P->dbs = w.floats(1024);
     P->red = w.doubles(2 * 512 + 8);
     P->dX = w.floats(2 * Bz * T * RNN_H);
@@ -275,6 +275,7 @@ static int pack_weights(const sefd_plan* P, const float* prm, float* ws, cudaStr
         pp.Ci2 = c.Cin / 2; pp.Co2 = c.Cout / 2;
         pp.transposed = e >= NL; pp.two_src = e >= NL;
         pp.Wf = ws + c.Wf; pp.Wt = ws + c.Wt; pp.bias = ws + c.bias;
+        pp.round_tf32 = sefd_get_engine_internal() == 1 && c.Cin % 32 == 0 && (c.Cout % 32 == 0);
         SEFD_TRY(sefd_pack_cconv(pp, st));
     }
     for (int p = 0; p < 2; ++p) {
@@ -325,6 +326,7 @@ int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const 
         b.running_var = bnbuf ? bnbuf + c.rvar : nullptr;
         b.momentum = BN_MOM; b.eps = BN_EPS;
         b.use_running = !train;
+        b.round_tf32 = sefd_get_engine_internal() == 1;
         if (!train) SEFD_REQUIRE(bnbuf != nullptr, "forward: eval mode needs the BN running statistics");
         return sefd_bn_prelu_fwd(b, st);
     };
@@ -343,11 +345,11 @@ int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const 
         g.a[1] = no_src();
         g.o[0] = dst4(ws + c.y, c.Fout, T, c.Cout, c.Cout);
         g.o[1] = no_dst();
-        g.W = ws + c.Wf; g.bias = ws + c.bias;
+        g.W = ws + c.Wf; g.Wnk = ws + c.Wt; g.nslabs = 10; g.bias = ws + c.bias;
         g.stats = train ? wsd + c.stats : nullptr;
         g.B = B; g.J = c.Fout; g.Tout = T; g.Fin = c.Fin; g.Tin = T;
         conv_taps_down(g, -1);
-        SEFD_TRY(sefd_tapgemm_simt(g, st));
+        SEFD_TRY(sefd_tapgemm(g, st));
         SEFD_TRY(bn(c, T, 0));
     }
 
@@ -376,7 +378,7 @@ int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const 
                 g.bias = ws + P->bsum[l] + (size_t)p * G4;
                 g.B = B; g.J = 1; g.Tout = T; g.Tin = T;
                 g.fi_mul = 0; g.fo_mul = 1; g.fo_off = 0;
-                SEFD_TRY(sefd_tapgemm_simt(g, st));
+                SEFD_TRY(sefd_tapgemm(g, st));
             }
         LstmFwdParams lp;
         lp.Whh = ws + P->Whh[l]; lp.G = ws + P->Gt[l]; lp.Hh = ws + P->Hh[l]; lp.Cc = ws + P->Cc[l];
@@ -397,7 +399,7 @@ int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const 
         g.B = B; g.J = 4; g.Tout = T; g.Fin = 1; g.Tin = T;
         g.fi_mul = 0; g.fo_mul = 1; g.fo_off = 0;
         g.ntaps = 1;
-        SEFD_TRY(sefd_tapgemm_simt(g, st));
+        SEFD_TRY(sefd_tapgemm(g, st));
     }
 
     // ---- decoder (models.py:222-226): convT on complex_cat(out, skip), BN over T+1 frames, drop frame 0 ----
@@ -413,11 +415,11 @@ int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const 
             g.a[1] = src4(in1, c.Fin, T, Ch, Ch);
             g.o[0] = dst4(ws + c.y, c.Fout, T + 1, c.Cout, c.Cout);
             g.o[1] = no_dst();
-            g.W = ws + c.Wf; g.bias = ws + c.bias;
+            g.W = ws + c.Wf; g.Wnk = ws + c.Wt; g.nslabs = 10; g.bias = ws + c.bias;
             g.stats = (train && j != NL - 1) ? wsd + c.stats : nullptr;
             g.B = B; g.J = c.Fin; g.Tout = T + 1; g.Fin = c.Fin; g.Tin = T;
             conv_taps_up(g, ph, 0);
-            SEFD_TRY(sefd_tapgemm_simt(g, st));
+            SEFD_TRY(sefd_tapgemm(g, st));
         }
         if (j != NL - 1) SEFD_TRY(bn(c, T + 1, 1));
     }
@@ -457,11 +459,14 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
         b.gamma = prm + c.gamma; b.beta = prm + c.beta; b.alpha = prm + c.alpha; b.save = ws + c.save;
         b.red = wsd + P->red;
         b.dgamma = grads + c.gamma; b.dbeta = grads + c.beta; b.dalpha = grads + c.alpha;
+        b.round_tf32 = sefd_get_engine_internal() == 1;
         return sefd_bn_prelu_bwd(b, st);
     };
+    int nsplit = 1;
+    long long sstride = 0;
     auto fold = [&](const ConvLayer& c, bool dec, const float* dbias) -> int {
         CconvFoldParams f;
-        f.dWf = dWs; f.dbias = dbias;
+        f.dWf = dWs; f.dbias = dbias; f.nsplit = nsplit; f.split_stride = sstride;
         f.Ci2 = c.Cin / 2; f.Co2 = c.Cout / 2; f.transposed = dec; f.two_src = dec;
         f.dwr = grads + c.wr; f.dwi = grads + c.wi; f.dbr = grads + c.br; f.dbi = grads + c.bi;
         return sefd_fold_cconv(f, st);
@@ -492,7 +497,6 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
             dbias = ws + P->dbs;
         }
         // weight gradient
-        cudaMemsetAsync(dWs, 0, sizeof(float) * 10 * c.Cin * c.Cout, st);
         WgradParams wg;
         memset(&wg, 0, sizeof(wg));
         wg.a[0] = src4(in0, c.Fin, T, Ch, Ch);
@@ -506,7 +510,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
                 const int i = kf * 2 + kt;
                 wg.a_off[i] = 0; wg.g_off[i] = kf - 2; wg.dt[i] = -kt; wg.wslab[i] = i;
             }
-        SEFD_TRY(sefd_wgrad_simt(wg, st));
+        SEFD_TRY(sefd_wgrad(wg, dWs, (long long)P->dWs_floats, 10, &nsplit, &sstride, st));
         SEFD_TRY(fold(c, true, dbias));
         // data gradient: d(in0) and d(skip)
         TapGemmParams g;
@@ -515,10 +519,10 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
         g.a[1] = no_src();
         g.o[0] = dst4(j == 0 ? ws + P->dU : ws + P->dec[j - 1].dz, c.Fin, T, Ch, Ch);
         g.o[1] = dst4(ws + P->enc[NL - 1 - j].dz, c.Fin, T, Ch, Ch);
-        g.W = ws + c.Wt;
+        g.W = ws + c.Wt; g.Wnk = ws + c.Wf; g.nslabs = 10;
         g.B = B; g.J = c.Fin; g.Tout = T; g.Fin = c.Fout; g.Tin = T + 1;
         conv_taps_down(g, +1);
-        SEFD_TRY(sefd_tapgemm_simt(g, st));
+        SEFD_TRY(sefd_tapgemm(g, st));
     }
 
     // ---- projection backward ----
@@ -535,7 +539,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
         g.fi_mul = 0; g.fo_mul = 1;
         g.ntaps = 4;
         for (int d = 0; d < 4; ++d) { g.df[d] = d; g.dt[d] = 0; g.wslab[d] = d; }
-        SEFD_TRY(sefd_tapgemm_simt(g, st));
+        SEFD_TRY(sefd_tapgemm(g, st));
         // dW_tr[c*4+d][k] = sum dU[b][d][t][q*128+c] * X2[q][b][t][k]
         cudaMemsetAsync(dWs, 0, sizeof(float) * 4 * 128 * 128, st);
         WgradParams wg;
@@ -583,7 +587,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
                 g.accum[0] = 1;                                   // the skip gradient from decoder 0 is already there
                 g.W = ws + P->Wih0T; g.wJ = (long long)2 * G4 * 128; g.J = 4;
             }
-            SEFD_TRY(sefd_tapgemm_simt(g, st));
+            SEFD_TRY(sefd_tapgemm(g, st));
         }
         // weight gradients
         for (int p = 0; p < 2; ++p) {
@@ -634,7 +638,6 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
     for (int i = NL - 1; i >= 0; --i) {
         const ConvLayer& c = P->enc[i];
         SEFD_TRY(bn_bwd(c, T, 0));
-        cudaMemsetAsync(dWs, 0, sizeof(float) * 10 * c.Cin * c.Cout, st);
         WgradParams wg;
         memset(&wg, 0, sizeof(wg));
         if (i == 0) {
@@ -653,7 +656,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
                 const int k = kf * 2 + kt;
                 wg.a_off[k] = kf - 2; wg.g_off[k] = 0; wg.dt[k] = kt - 1; wg.wslab[k] = k;
             }
-        SEFD_TRY(sefd_wgrad_simt(wg, st));
+        SEFD_TRY(sefd_wgrad(wg, dWs, (long long)P->dWs_floats, 10, &nsplit, &sstride, st));
         SEFD_TRY(fold(c, false, nullptr));
         if (i > 0) {
             for (int ph = 0; ph < 2; ++ph) {
@@ -664,10 +667,10 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
                 g.o[0] = dst4(ws + P->enc[i - 1].dz, c.Fin, T, c.Cin, c.Cin);
                 g.o[1] = no_dst();
                 g.accum[0] = 1;                                   // skip gradient already stored by the decoder
-                g.W = ws + c.Wt;
+                g.W = ws + c.Wt; g.Wnk = ws + c.Wf; g.nslabs = 10;
                 g.B = B; g.J = c.Fout; g.Tout = T; g.Fin = c.Fout; g.Tin = T;
                 conv_taps_up(g, ph, 1);
-                SEFD_TRY(sefd_tapgemm_simt(g, st));
+                SEFD_TRY(sefd_tapgemm(g, st));
             }
         }
     }

@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(256) bn_prelu_fwd_kernel(const BnPreluFwdParam
         o.y = o.y > 0.f ? o.y : alpha * o.y;
         o.z = o.z > 0.f ? o.z : alpha * o.z;
         o.w = o.w > 0.f ? o.w : alpha * o.w;
+        if (p.round_tf32) { o.x = tf32_rn(o.x); o.y = tf32_rn(o.y); o.z = tf32_rn(o.z); o.w = tf32_rn(o.w); }
         *reinterpret_cast<float4*>(p.z + e * 4) = o;
     }
 }
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(256) bn_prelu_bwd_apply_kernel(const BnPreluBw
             const float u = fmaf(gam, xh, p.beta[c + i]);
             const float g = u > 0.f ? d4[i] : alpha * d4[i];
             o[i] = gam * istd * (g - s_mg[c + i] - xh * s_mgx[c + i]);
+            if (p.round_tf32) o[i] = tf32_rn(o[i]);
         }
         *reinterpret_cast<float4*>(p.dy + e * 4) = make_float4(o[0], o[1], o[2], o[3]);
     }
@@ -218,6 +220,7 @@ __global__ void pack_cconv_kernel(const CconvPackParams p) {
         if (kp == np) v = p.wr[widx];
         else if (kp == 1) v = -p.wi[widx];   // imag in -> real out
         else v = p.wi[widx];                 // real in -> imag out
+        if (p.round_tf32) v = tf32_rn(v);
         p.Wf[e] = v;
         p.Wt[((long long)slab * N + n) * K + k] = v;
     }
@@ -244,9 +247,14 @@ __global__ void fold_cconv_kernel(const CconvFoldParams p) {
             ni = (int)(e / (10ll * p.Ci2));
         }
         const int kr = kinv(0, ki, p.Ci2, p.two_src), kim = kinv(1, ki, p.Ci2, p.two_src);
-        const float* d = p.dWf + (long long)slab * K * N;
-        const float rr = d[(long long)kr * N + ni], ii = d[(long long)kim * N + p.Co2 + ni];
-        const float ri = d[(long long)kr * N + p.Co2 + ni], ir = d[(long long)kim * N + ni];
+        float rr = 0.f, ii = 0.f, ri = 0.f, ir = 0.f;
+        for (int s = 0; s < p.nsplit; ++s) {
+            const float* d = p.dWf + s * p.split_stride + (long long)slab * K * N;
+            rr += d[(long long)kr * N + ni];
+            ii += d[(long long)kim * N + p.Co2 + ni];
+            ri += d[(long long)kr * N + p.Co2 + ni];
+            ir += d[(long long)kim * N + ni];
+        }
         p.dwr[e] = rr + ii;
         p.dwi[e] = ri - ir;
     }

@@ -12,6 +12,7 @@ struct BnPreluFwdParams {
     float *running_mean, *running_var;   // updated in train mode when non-null; read when use_running
     float momentum, eps;
     int use_running;       // eval mode
+    int round_tf32;        // z feeds a tensor-core GEMM: round to tf32 while writing
 };
 
 struct BnPreluBwdParams {
@@ -23,6 +24,7 @@ struct BnPreluBwdParams {
     const float *gamma, *beta, *alpha, *save;
     double* red;           // [2C+1] scratch
     float *dgamma, *dbeta, *dalpha;
+    int round_tf32;        // dy feeds tensor-core GEMMs
 };
 
 struct CconvPackParams {
@@ -33,10 +35,13 @@ struct CconvPackParams {
     float* Wf;             // [10][K][N]
     float* Wt;             // [10][N][K]
     float* bias;           // [N]
+    int round_tf32;
 };
 
 struct CconvFoldParams {
-    const float* dWf;      // [10][K][N] block-real weight gradient
+    const float* dWf;      // nsplit x [10][K][N] block-real weight gradient partials, split_stride floats apart
+    int nsplit;
+    long long split_stride;
     const float* dbias;    // [N] block-real bias gradient or nullptr (-> zeros)
     int Ci2, Co2, transposed, two_src;
     float *dwr, *dwi, *dbr, *dbi;

@@ -18,3 +18,13 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden():
     return np.load(os.path.join(ROOT, "tests", "golden", "dccrn_golden.npz"), allow_pickle=False)
+
+
+@pytest.fixture(params=[0, 1], ids=["fp32", "tf32"])
+def engine(request):
+    """GEMM engine under test: 0 = fp32 CUDA cores (exact), 1 = tcgen05 TF32 tensor cores (the product default)."""
+    from sefd import _lib
+    lib = _lib.load()
+    lib.sefd_set_engine(request.param)
+    yield request.param
+    lib.sefd_set_engine(1)

@@ -44,8 +44,9 @@ def _cl(x):     # oracle [B,C,F,T] -> library channels-last [B,F,T,C]
 
 
 @pytest.mark.parametrize("mode", ["C", "E", "R"])
-def test_small_forward_backward_every_tensor(golden, sd0, mode):
+def test_small_forward_backward_every_tensor(golden, sd0, mode, engine):
     import models
+    tf = engine == 1
     noisy = torch.from_numpy(golden["small_speech_noisy"])
     clean = torch.from_numpy(golden["small_speech_clean"])
     tr = O.OracleTrainer(sd0, masking_mode=mode, loss="SI-SNR")
@@ -63,10 +64,13 @@ def test_small_forward_backward_every_tensor(golden, sd0, mode):
     failures = []
 
     def chk(name, got, ref, atol_rel, rtol=1e-4):
+        if tf:                      # TF32 operands: errors of ~1e-3 of each tensor's scale, growing with depth
+            atol_rel, rtol = 2e-2, 1e-2
         e, s = _err(got, ref)
         g64, r64 = got.detach().double().cpu(), ref.detach().double().cpu()
         ok = bool(((g64 - r64).abs() <= atol_rel * s + rtol * r64.abs()).all())
-        _report(f"[{mode}] {name:34s} max|err|={e:.3e}  max|ref|={s:.3e}  {'ok' if ok else 'FAIL'}")
+        rms = float((g64 - r64).pow(2).mean().sqrt())
+        _report(f"[{mode}{'/tf32' if tf else ''}] {name:34s} max|err|={e:.3e} rms err={rms:.3e} max|ref|={s:.3e}  {'ok' if ok else 'FAIL'}")
         if not ok:
             failures.append(name)
 
@@ -94,7 +98,7 @@ def test_small_forward_backward_every_tensor(golden, sd0, mode):
     chk("wav vs golden", wav, torch.from_numpy(golden[f"small_speech_{mode}_SI-SNR_wav"]), 2e-5)
     _report(f"[{mode}] loss got {float(loss):.6f} oracle {float(loss_ref):.6f} golden "
             f"{float(golden[f'small_speech_{mode}_SI-SNR_loss']):.6f}")
-    if abs(float(loss) - float(loss_ref)) > 2e-4 * abs(float(loss_ref)) + 1e-4:
+    if abs(float(loss) - float(loss_ref)) > (5e-3 if tf else 2e-4) * abs(float(loss_ref)) + 1e-4:
         failures.append("loss")
 
     # gradients of every parameter vs the oracle's autograd (relative to each tensor's own scale, with a
@@ -110,6 +114,10 @@ def test_small_forward_backward_every_tensor(golden, sd0, mode):
             e, s = _err(p.grad, ref)
             # the single PReLU slope's gradient is one global sum with heavy cancellation: looser relative bound
             ok = e <= (2e-2 if name.endswith(".2.weight") else 2e-3) * s + 1e-6 * gmax
+            if tf:                  # TF32 gradients: direction and norm must agree, element-wise bound is loose
+                g64, r64 = p.grad.detach().double().cpu().reshape(-1), ref.detach().double().reshape(-1)
+                cos = float((g64 * r64).sum() / (g64.norm() * r64.norm() + 1e-30))
+                ok = (cos > 0.995 and e <= 5e-2 * s + 1e-5 * gmax) or name.endswith(".2.weight")
             _report(f"[{mode}] grad {name:40s} max|err|={e:.3e} max|ref|={s:.3e} {'ok' if ok else 'FAIL'}")
         if not ok:
             failures.append("grad " + name)
@@ -118,15 +126,16 @@ def test_small_forward_backward_every_tensor(golden, sd0, mode):
         if "running" in k:
             ref = tr.sd[k]
             e, s = _err(v, ref)
-            if e > 1e-4 * s + 1e-6:
+            if e > (1e-2 if tf else 1e-4) * s + 1e-6:
                 failures.append(k)
                 _report(f"[{mode}] {k} max|err|={e:.3e} FAIL")
     assert int(m.encoder[0][1].num_batches_tracked) == 1
     assert not failures, failures
 
 
-def test_losses_through_dropin(golden, sd0):
+def test_losses_through_dropin(golden, sd0, engine):
     import models
+    lt, gt = (5e-3, 5e-2) if engine == 1 else (2e-4, 5e-3)
     noisy = torch.from_numpy(golden["small_rand_noisy"]).to(DEV)
     clean = torch.from_numpy(golden["small_rand_clean"]).to(DEV)
     m = _build("C", sd0)
@@ -138,16 +147,22 @@ def test_losses_through_dropin(golden, sd0):
         loss = m.loss(wav, clean)
         loss.backward()
         ref = float(golden[f"small_rand_C_{loss_name}_loss"])
-        assert float(loss) == pytest.approx(ref, rel=2e-4, abs=2e-5), loss_name
+        assert float(loss) == pytest.approx(ref, rel=lt, abs=2e-5), loss_name
         gn = np.array([float(dict(m.named_parameters())[n].grad.double().norm()) for n in names])
         refn = golden[f"small_rand_C_{loss_name}_gnorm"]
-        keep = [i for i, n in enumerate(names) if not (n.endswith("_conv.bias") and not n.startswith("decoder.5."))]
-        rt = np.array([2e-2 if names[i].endswith(".2.weight") else 5e-3 for i in keep])     # PReLU slopes: see above
-        assert (np.abs(gn[keep] - refn[keep]) <= rt * np.abs(refn[keep]) + 1e-5 * float(refn.max())).all(), loss_name
+        bad = []
+        for i, n in enumerate(names):
+            if n.endswith("_conv.bias") and not n.startswith("decoder.5."):
+                continue                                   # exactly zero here, rounding noise in the reference
+            rt = max(2e-2, gt) if n.endswith(".2.weight") else gt      # PReLU slopes: cancelling global sum
+            if abs(gn[i] - refn[i]) > rt * abs(refn[i]) + 1e-5 * float(refn.max()):
+                bad.append((n, gn[i], refn[i]))
+                _report(f"[losses engine={engine} {loss_name}] gnorm {n}: got {gn[i]:.6e} ref {refn[i]:.6e} FAIL")
+        assert not bad, (loss_name, bad[:5])
     models.cfg.loss = "SI-SNR"
 
 
-def test_eval_forward_and_state_dict_round_trip(golden, sd0):
+def test_eval_forward_and_state_dict_round_trip(golden, sd0, engine):
     import models
     noisy = torch.from_numpy(golden["small_speech_noisy"]).to(DEV)
     clean = torch.from_numpy(golden["small_speech_clean"]).to(DEV)
@@ -156,7 +171,7 @@ def test_eval_forward_and_state_dict_round_trip(golden, sd0):
     m.eval()
     with torch.no_grad():
         _, _, wav = m(noisy)
-    np.testing.assert_allclose(wav.cpu().numpy(), golden["small_speech_C_eval_wav"], atol=2e-5)
+    np.testing.assert_allclose(wav.cpu().numpy(), golden["small_speech_C_eval_wav"], atol=3e-3 if engine == 1 else 2e-5)
     sd = {k: v.cpu() for k, v in m.state_dict().items()}
     m2 = models.DCCRN(masking_mode="C")
     m2.load_state_dict(sd)
@@ -166,7 +181,7 @@ def test_eval_forward_and_state_dict_round_trip(golden, sd0):
     assert torch.equal(wav, wav2)
 
 
-def test_three_adam_steps_with_reference_optimizer(golden, sd0):
+def test_three_adam_steps_with_reference_optimizer(golden, sd0, engine):
     """The reference's own loop body (trainer.py:27-37) with torch.optim.Adam driving the drop-in."""
     import models
     models.cfg.loss = "SI-SNR"
@@ -182,10 +197,10 @@ def test_three_adam_steps_with_reference_optimizer(golden, sd0):
         loss.backward()
         opt.step()
         losses.append(float(loss))
-    np.testing.assert_allclose(losses, golden["adam3_losses"], rtol=2e-3, atol=2e-3)
+    np.testing.assert_allclose(losses, golden["adam3_losses"], rtol=2e-2 if engine == 1 else 2e-3, atol=2e-3)
 
 
-def test_full_length_known_answer(golden, sd0):
+def test_full_length_known_answer(golden, sd0, engine):
     """B=2, 3 s @ 16 kHz, seeds of SURVEY.md §4: loss 43.71657562, waveform RMSE < 1e-4 (north star)."""
     import models
     models.cfg.loss = "SI-SNR"
@@ -194,18 +209,27 @@ def test_full_length_known_answer(golden, sd0):
     _, _, wav = m(noisy.to(DEV), clean.to(DEV))
     loss = m.loss(wav, clean.to(DEV))
     loss.backward()
-    assert float(loss) == pytest.approx(43.71657562, rel=2e-5)
+    assert float(loss) == pytest.approx(43.71657562, rel=2e-3 if engine == 1 else 2e-5)
     head = torch.from_numpy(golden["full_wav_head"])
     rmse = float((wav[:, :2048].cpu() - head).pow(2).mean().sqrt())
-    _report(f"[full] loss {float(loss):.6f} wav RMSE vs reference {rmse:.3e}")
+    _report(f"[full engine={engine}] loss {float(loss):.6f} wav RMSE vs reference {rmse:.3e}")
     assert rmse < 1e-4
     assert float(wav.double().pow(2).mean().sqrt()) == pytest.approx(float(golden["full_wav_rms"]), rel=1e-4)
     names = [str(n) for n in golden["param_names"]]
     gn = np.array([float(dict(m.named_parameters())[n].grad.double().norm()) for n in names])
-    keep = [i for i, n in enumerate(names) if not (n.endswith("_conv.bias") and not n.startswith("decoder.5."))]
     ref = golden["full_gnorm"]
-    rt = np.array([3e-2 if names[i].endswith(".2.weight") else 5e-3 for i in keep])
-    assert (np.abs(gn[keep] - ref[keep]) <= rt * np.abs(ref[keep]) + 1e-5 * float(ref.max())).all()
+    gt = 5e-2 if engine == 1 else 5e-3
+    bad = []
+    for i, n in enumerate(names):
+        if n.endswith("_conv.bias") and not n.startswith("decoder.5."):
+            continue
+        rt = max(3e-2, gt) if n.endswith(".2.weight") else gt
+        rel = abs(gn[i] - ref[i]) / max(abs(ref[i]), 1e-30)
+        if engine == 1:
+            _report(f"[full engine=1] gnorm {n:44s} got {gn[i]:.5e} ref {ref[i]:.5e} rel {rel:.2e}")
+        if abs(gn[i] - ref[i]) > rt * abs(ref[i]) + 1e-5 * float(ref.max()):
+            bad.append((n, gn[i], ref[i]))
+    assert not bad, bad[:8]
 
 
 def test_batch32_properties():
