@@ -207,6 +207,8 @@ def main():
         ts.step(noisy, clean)
         torch.cuda.synchronize()
         lib.sefd_prof_enable(0)
+        if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+            lib.sefd_prof_dump(os.path.join(ROOT, "gpurun_out", "launch_profile.csv").encode())
         breakdown = {}
         for c, name in enumerate(CATS):
             t, n, f, b = C.c_double(), C.c_longlong(), C.c_double(), C.c_double()

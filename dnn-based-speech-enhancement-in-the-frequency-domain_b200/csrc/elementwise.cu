@@ -361,6 +361,7 @@ inline int grid_for(long long n, int block = 256, int cap = 148 * 16) {
 
 int sefd_bn_prelu_fwd(const BnPreluFwdParams& p, cudaStream_t st) {
     SEFD_REQUIRE(p.C % 4 == 0 && p.C <= MAXC, "bn_prelu_fwd: C=%d unsupported", p.C);
+    sefd_prof_label("bn_prelu_fwd C%d rows%lld", p.C, (long long)p.BF * p.T);
     SefdProfScope prof(SEFD_PROF_BN, 0, 8.0 * p.BF * (double)p.T * p.C, st);
     bn_prelu_fwd_kernel<<<grid_for((long long)p.BF * p.T * (p.C / 4)), 256, 0, st>>>(p);
     return sefd_check_launch("bn_prelu_fwd");
@@ -368,6 +369,7 @@ int sefd_bn_prelu_fwd(const BnPreluFwdParams& p, cudaStream_t st) {
 
 int sefd_bn_prelu_bwd(const BnPreluBwdParams& p, cudaStream_t st) {
     SEFD_REQUIRE(p.C % 4 == 0 && p.C <= MAXC && 256 % (p.C / 4) == 0, "bn_prelu_bwd: C=%d unsupported", p.C);
+    sefd_prof_label("bn_prelu_bwd C%d rows%lld", p.C, (long long)p.BF * p.T);
     SefdProfScope prof(SEFD_PROF_BN, 0, 4.0 * p.BF * p.C * (2.0 * p.T + 2.0 * p.T + p.Ty), st);
     cudaMemsetAsync(p.red, 0, sizeof(double) * (2 * p.C + 1), st);
     const int lanes = 256 / (p.C / 4);

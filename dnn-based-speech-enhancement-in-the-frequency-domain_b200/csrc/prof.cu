@@ -1,3 +1,6 @@
+#include <stdarg.h>
+#include <stdio.h>
+
 #include <vector>
 
 #include "../../include/sefd.h"
@@ -9,7 +12,9 @@ struct Rec {
     int cat;
     cudaEvent_t e0, e1;
     double flops, bytes;
+    char label[96];
 };
+char g_label[96] = "";
 bool g_on = false;
 std::vector<Rec> g_recs;
 std::vector<cudaEvent_t> g_pool;
@@ -27,12 +32,22 @@ cudaEvent_t get_event() {
 
 bool sefd_prof_on() { return g_on; }
 
+void sefd_prof_label(const char* fmt, ...) {
+    if (!g_on) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_label, sizeof(g_label), fmt, ap);
+    va_end(ap);
+}
+
 void sefd_prof_push(int cat, double flops, double bytes, cudaStream_t st, bool begin) {
     if (begin) {
         Rec r;
         r.cat = cat;
         r.flops = flops;
         r.bytes = bytes;
+        snprintf(r.label, sizeof(r.label), "%s", g_label);
+        g_label[0] = 0;
         r.e0 = get_event();
         r.e1 = get_event();
         cudaEventRecord(r.e0, st);
@@ -60,6 +75,23 @@ int sefd_prof_reset(void) {
         g_pool.push_back(r.e1);
     }
     g_recs.clear();
+    return 0;
+}
+
+int sefd_prof_dump(const char* path) {
+    cudaError_t e = cudaDeviceSynchronize();
+    SEFD_REQUIRE(e == cudaSuccess, "prof_dump: %s", cudaGetErrorString(e));
+    FILE* f = fopen(path, "w");
+    SEFD_REQUIRE(f != nullptr, "prof_dump: cannot open %s", path);
+    fprintf(f, "idx,category,label,ms,gflop,gbyte,tflops,gbs\n");
+    int i = 0;
+    for (const Rec& r : g_recs) {
+        float dt = 0.f;
+        cudaEventElapsedTime(&dt, r.e0, r.e1);
+        fprintf(f, "%d,%d,%s,%.4f,%.3f,%.4f,%.2f,%.1f\n", i++, r.cat, r.label, dt, r.flops / 1e9, r.bytes / 1e9,
+                dt > 0 ? r.flops / 1e9 / dt : 0.0, dt > 0 ? r.bytes / 1e6 / dt : 0.0);
+    }
+    fclose(f);
     return 0;
 }
 

@@ -15,6 +15,7 @@ enum SefdProfCat {
 
 bool sefd_prof_on();
 void sefd_prof_push(int cat, double flops, double bytes, cudaStream_t st, bool begin);
+void sefd_prof_label(const char* fmt, ...);   // label for the NEXT pushed record (ignored when profiling is off)
 
 struct SefdProfScope {
     int cat;

@@ -288,6 +288,7 @@ int sefd_tapgemm_simt(const TapGemmParams& p, cudaStream_t st) {
     SEFD_REQUIRE(gx < (1ll << 31), "tapgemm: grid too large");
     dim3 grid((unsigned)gx, (unsigned)((N + BN - 1) / BN));
     const double K = p.a[0].C + p.a[1].C, pos = (double)p.B * p.J * p.Tout;
+    sefd_prof_label("tapgemm_simt K%d N%d taps%d J%d Tout%d", (int)K, N, p.ntaps, p.J, p.Tout);
     SefdProfScope prof(SEFD_PROF_TAPGEMM, 2.0 * pos * N * K * p.ntaps,
                        4.0 * ((double)p.B * p.J * (p.fi_mul > 1 ? p.fi_mul : 1) * p.Tin * K + pos * N), st);
     tapgemm_simt_kernel<<<grid, NT, 0, st>>>(p);
@@ -308,6 +309,7 @@ int sefd_wgrad_simt(const WgradParams& p_in, cudaStream_t st) {
     SEFD_REQUIRE(splits <= 65535, "wgrad: too many splits");
     dim3 grid(tiles, p.ntaps, splits);
     const double pos = (double)p.B * p.J * p.Tg;
+    sefd_prof_label("wgrad_simt K%d N%d taps%d J%d splits%d", K, N, p.ntaps, p.J, splits);
     SefdProfScope prof(SEFD_PROF_WGRAD, 2.0 * pos * K * N * p.ntaps,
                        4.0 * ((double)p.B * p.J * (p.a_mul > 1 ? p.a_mul : 1) * p.Ta * K +
                               (double)p.B * p.J * (p.g_mul > 1 ? p.g_mul : 1) * p.Tg * N), st);

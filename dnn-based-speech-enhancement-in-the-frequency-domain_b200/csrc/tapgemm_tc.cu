@@ -338,6 +338,7 @@ int sefd_tapgemm_tc(const TapGemmParams& g, cudaStream_t st) {
         SEFD_TRY(make_map(&w, g.Wnk, 3, dims, str, box));
     }
     const double pos = (double)g.B * g.J * g.Tout;
+    sefd_prof_label("tapgemm_tc BN%d K%d N%d taps%d J%d Tout%d tiles%lld", BN, K, N, g.ntaps, g.J, g.Tout, p.total_tiles);
     SefdProfScope prof(SEFD_PROF_TAPGEMM, 2.0 * pos * N * K * g.ntaps,
                        4.0 * ((double)g.B * g.J * (g.fi_mul > 1 ? g.fi_mul : 1) * g.Tin * K + pos * N), st);
     switch (BN) {

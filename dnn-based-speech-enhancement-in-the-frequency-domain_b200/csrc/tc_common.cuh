@@ -62,14 +62,17 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
 //   K-major operand : rows of 128 B (32 fp32 of K), 8-row groups SBO = 1024 B apart, LBO unused
 //   MN-major operand: 128 B = 32 fp32 of M/N per K row, 8 K-rows per swizzle atom (SBO = 1024 B between atoms),
 //                     LBO = distance between successive 32-element M/N chunks
-__device__ __forceinline__ uint64_t make_desc_lbo(uint32_t smem_addr, uint32_t lbo_bytes) {
+__device__ __forceinline__ uint64_t make_desc_full(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);   // start address / 16
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    d |= (uint64_t)(layout_type & 7) << 61;        // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B (tf32 MN-major)
     return d;
+}
+__device__ __forceinline__ uint64_t make_desc_lbo(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return make_desc_full(smem_addr, lbo_bytes, 1024, 2);
 }
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) { return make_desc_lbo(smem_addr, 16); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
@@ -108,12 +111,12 @@ inline EncodeTiledFn get_encode() {
 }
 
 inline int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-             const cuuint32_t* box) {
+                    const cuuint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn enc = get_encode();
     SEFD_REQUIRE(enc != nullptr, "tapgemm_tc: cuTensorMapEncodeTiled is not available from this driver");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box,
-                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SEFD_REQUIRE(r == CUDA_SUCCESS, "tapgemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;

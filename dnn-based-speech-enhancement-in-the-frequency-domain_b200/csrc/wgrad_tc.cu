@@ -2,7 +2,7 @@
 //   dW[slab(tap)][k][n] = sum_{b,j,t} A[b, j*a_mul+a_off[tap], t+dt[tap], k] * G[b, j*g_mul+g_off[tap], t, n]
 // The contraction index is the POSITION (b, j, t); both operands are channels-last, i.e. MN-major for the MMA
 // (the channel index is contiguous, positions are strided).  TMA fetches [32 ch x 32 positions] boxes
-// (128B-swizzled) - 4 per stage for the 128 k-channels of A, BN/32 for G - and one tcgen05.mma consumes 8
+// (128B span / 32B-atom swizzle, the only MN-major layout tcgen05 accepts for tf32) - 4 per stage for the 128 k-channels of A, BN/32 for G - and one tcgen05.mma consumes 8
 // positions.  Work unit = (tap, 128-channel slice of K, BN slice of N, split of the (b,j) rows); every unit
 // writes its own partial tile (no atomics), the fold kernel sums the splits.
 #include <string.h>
@@ -144,8 +144,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                         const uint32_t sa = smem_u32(stages + stage * C::STAGE_BYTES);
 #pragma unroll
                         for (int k8 = 0; k8 < PB / 8; ++k8) {
-                            const uint64_t ad = make_desc_lbo(sa + k8 * 1024, CHB);
-                            const uint64_t bd = make_desc_lbo(sa + C::A_BYTES + k8 * 1024, CHB);
+                            // MN-major tf32: SWIZZLE_128B_BASE32B (layout type 1), LBO = stride between 32-channel
+                            // chunks, SBO = one 4-position swizzle atom (probed on hardware: tools/umma_probe.cu)
+                            const uint64_t ad = make_desc_full(sa + k8 * 1024, CHB, 512, 1);
+                            const uint64_t bd = make_desc_full(sa + C::A_BYTES + k8 * 1024, CHB, 512, 1);
                             tc_mma_tf32(d_tmem, ad, bd, idesc, acc);
                             acc = 1;
                         }
@@ -219,7 +221,7 @@ int make_pos_map(CUtensorMap* m, const TapSrc& s, int F, int T, int B) {
     cuuint64_t str[3] = {(cuuint64_t)s.sT * 4, (cuuint64_t)(s.sF ? s.sF : s.sT * T) * 4,
                          (cuuint64_t)(s.sB ? s.sB : s.sT * T * F) * 4};
     cuuint32_t box[4] = {32, PB, 1, 1};
-    return make_map(m, s.p, 4, dims, str, box);
+    return make_map(m, s.p, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
 }
 
 template <int BN>
@@ -291,6 +293,7 @@ int sefd_wgrad_tc(const WgradParams& w, float* partial, long long cap_floats, in
     else a1 = a0;
     SEFD_TRY(make_pos_map(&g, w.g, w.Fg, w.Tg, w.B));
     const double pos = (double)w.B * w.J * w.Tg;
+    sefd_prof_label("wgrad_tc BN%d K%d N%d taps%d J%d splits%d units%lld", BN, K, N, w.ntaps, w.J, p.splits, p.units);
     SefdProfScope prof(SEFD_PROF_WGRAD, 2.0 * pos * K * N * w.ntaps,
                        4.0 * ((double)w.B * w.J * (w.a_mul > 1 ? w.a_mul : 1) * w.Ta * K +
                               (double)w.B * w.J * (w.g_mul > 1 ? w.g_mul : 1) * w.Tg * N), st);

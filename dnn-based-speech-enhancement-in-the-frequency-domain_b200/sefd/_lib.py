@@ -49,6 +49,7 @@ SIGNATURES = {
     "sefd_launch_count": (_ll, []),
     "sefd_prof_enable": (_i, [_i]),
     "sefd_prof_reset": (_i, []),
+    "sefd_prof_dump": (_i, [C.c_char_p]),
     "sefd_prof_get": (_i, [_i, C.POINTER(C.c_double), C.POINTER(_ll), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 

@@ -133,6 +133,7 @@ long long sefd_launch_count(void);   /* kernels launched by this library since l
 int sefd_prof_enable(int on);
 int sefd_prof_reset(void);
 int sefd_prof_get(int category, double* ms, long long* launches, double* flops, double* bytes);
+int sefd_prof_dump(const char* csv_path);   /* one row per recorded launch */
 
 #ifdef __cplusplus
 }
