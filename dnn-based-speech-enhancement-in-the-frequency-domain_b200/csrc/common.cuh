@@ -79,6 +79,11 @@ int sefd_tapgemm_tc(const TapGemmParams& p, cudaStream_t st);
 // dispatch: tensor-core engine when selected (default) and the problem is eligible, else the fp32 engine
 int sefd_tapgemm(const TapGemmParams& p, cudaStream_t st);
 int sefd_get_engine_internal();
+// dedicated kernels for the 2-channel ends of the network (K = 2 or N = 2 per tap)
+bool sefd_skinny_conv_eligible(const TapGemmParams& p);
+int sefd_skinny_conv(const TapGemmParams& p, cudaStream_t st);
+bool sefd_skinny_wgrad_eligible(const WgradParams& p);
+int sefd_skinny_wgrad(const WgradParams& p, cudaStream_t st);
 int sefd_wgrad_simt(const WgradParams& p, cudaStream_t st);
 // dispatch (tensor-core engine when eligible): writes *nsplit partial gradients [nslabs][K][N], *split_stride
 // floats apart, into `partial`; the caller's fold step sums them.

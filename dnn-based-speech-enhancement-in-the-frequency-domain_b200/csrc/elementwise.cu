@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) bn_prelu_fwd_kernel(const BnPreluFwdParam
 // red layout (double): [0..C) sum g', [C..2C) sum g'*xhat, [2C] d alpha
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bn_prelu_bwd_reduce_kernel(const BnPreluBwdParams p) {
-    __shared__ float s_red[3][256 * 4 / 4][4];   // [which][thread][4]
+    __shared__ double s_red[3][256][4];          // [which][thread][4]; sums cancel heavily -> double throughout
     const int C = p.C, C4 = C >> 2;
     const int lanes = 256 / C4;                  // rows processed per block iteration
     const int c4 = threadIdx.x % C4;
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) bn_prelu_bwd_reduce_kernel(const BnPreluB
         bet[i] = p.beta[c + i];
     }
     const float alpha = p.alpha[0];
-    float sg[4] = {0, 0, 0, 0}, sgx[4] = {0, 0, 0, 0}, sa = 0.f;
+    double sg[4] = {0, 0, 0, 0}, sgx[4] = {0, 0, 0, 0}, sa = 0.0;
     const long long rows = (long long)p.BF * p.T;
     if (rl < lanes) {
         for (long long row = (long long)blockIdx.x * lanes + rl; row < rows; row += (long long)gridDim.x * lanes) {
@@ -101,9 +101,9 @@ __global__ void __launch_bounds__(256) bn_prelu_bwd_reduce_kernel(const BnPreluB
                 const float xh = (y4[i] - mean[i]) * istd[i];
                 const float u = fmaf(gam[i], xh, bet[i]);
                 const float g = u > 0.f ? d4[i] : alpha * d4[i];
-                sg[i] += g;
-                sgx[i] += g * xh;
-                sa += u > 0.f ? 0.f : d4[i] * u;
+                sg[i] += (double)g;
+                sgx[i] += (double)(g * xh);
+                sa += u > 0.f ? 0.0 : (double)(d4[i] * u);
             }
         }
     }
@@ -118,19 +118,19 @@ __global__ void __launch_bounds__(256) bn_prelu_bwd_reduce_kernel(const BnPreluB
     if (threadIdx.x < C4) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            float a = 0.f, b = 0.f;
+            double a = 0.0, b = 0.0;
             for (int l = 0; l < lanes; ++l) {
                 a += s_red[0][l * C4 + threadIdx.x][i];
                 b += s_red[1][l * C4 + threadIdx.x][i];
             }
-            atomicAdd(p.red + threadIdx.x * 4 + i, (double)a);
-            atomicAdd(p.red + C + threadIdx.x * 4 + i, (double)b);
+            atomicAdd(p.red + threadIdx.x * 4 + i, a);
+            atomicAdd(p.red + C + threadIdx.x * 4 + i, b);
         }
     }
     if (threadIdx.x == 0) {
-        float a = 0.f;
+        double a = 0.0;
         for (int l = 0; l < lanes * C4; ++l) a += s_red[2][l][0];
-        atomicAdd(p.red + 2 * C, (double)a);
+        atomicAdd(p.red + 2 * C, a);
     }
 }
 

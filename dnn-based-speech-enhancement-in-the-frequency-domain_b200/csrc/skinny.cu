@@ -1,0 +1,300 @@
+// Kernels for the two-channel ends of the network (encoder 0 reads the 2-channel spectrum, decoder 5 writes the
+// 2-channel mask).  These contractions have K = 2 or N = 2 per tap: no tensor-core shape fits and the work is
+// HBM-bound (intensity ~9 FLOP/B), so they are CUDA-core kernels organised around ONE pass
+// over the wide (32/64-channel) tensor with the 2-channel tensor read at the tap offsets.  Same TapGemmParams /
+// WgradParams contract as the generic engines.
+#include "common.cuh"
+#include "prof.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// T1: K = 2 per tap -> N in {32, 64}   (encoder-0 forward, decoder-5 data gradient)
+// one thread = one output position; the <= 20 input scalars come straight from global (coalesced float2).
+// ---------------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(128) smallk_conv_kernel(const TapGemmParams p) {
+    __shared__ __align__(16) float Ws[SEFD_MAX_TAPS * 2 * N];
+    __shared__ float stg[128 * (N + 1)];
+    __shared__ float s_stat[2 * N];
+    const int tid = threadIdx.x;
+    const int ttiles = (p.Tout + 127) / 128;
+    const int t0 = (blockIdx.x % ttiles) * 128;
+    const int row = blockIdx.x / ttiles;
+    const int b = row / p.J, j = row % p.J;
+    for (int i = tid; i < p.ntaps * 2 * N; i += 128) {
+        const int tap = i / (2 * N), r = i % (2 * N);
+        Ws[i] = p.W[(long long)p.wslab[tap] * 2 * N + r];
+    }
+    __syncthreads();
+    float acc[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) acc[n] = p.bias ? __ldg(p.bias + n) : 0.f;
+    const int t = t0 + tid;
+    for (int tap = 0; tap < p.ntaps; ++tap) {
+        const int fi = j * p.fi_mul + p.df[tap];
+        if (fi < 0 || fi >= p.Fin) continue;
+        const int tin = t + p.dt[tap];
+        float2 x = make_float2(0.f, 0.f);
+        if (tin >= 0 && tin < p.Tin)
+            x = __ldg(reinterpret_cast<const float2*>(p.a[0].p + b * p.a[0].sB + fi * p.a[0].sF + (long long)tin * p.a[0].sT));
+        const float4* w0 = reinterpret_cast<const float4*>(Ws + tap * 2 * N);
+        const float4* w1 = reinterpret_cast<const float4*>(Ws + tap * 2 * N + N);
+#pragma unroll
+        for (int n4 = 0; n4 < N / 4; ++n4) {
+            const float4 a = w0[n4], c = w1[n4];
+            acc[4 * n4 + 0] = fmaf(x.x, a.x, fmaf(x.y, c.x, acc[4 * n4 + 0]));
+            acc[4 * n4 + 1] = fmaf(x.x, a.y, fmaf(x.y, c.y, acc[4 * n4 + 1]));
+            acc[4 * n4 + 2] = fmaf(x.x, a.z, fmaf(x.y, c.z, acc[4 * n4 + 2]));
+            acc[4 * n4 + 3] = fmaf(x.x, a.w, fmaf(x.y, c.w, acc[4 * n4 + 3]));
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < N; ++n) stg[tid * (N + 1) + n] = acc[n];
+    __syncthreads();
+    // coalesced stores: N/4 float4 per row
+    const int fo = j * p.fo_mul + p.fo_off;
+    const int N0 = p.o[0].N;
+    constexpr int Q = N / 4;
+    for (int idx = tid; idx < 128 * Q; idx += 128) {
+        const int r = idx / Q, c4 = (idx % Q) * 4;
+        const int tt = t0 + r;
+        if (tt >= p.Tout) continue;
+        const int d = c4 < N0 ? 0 : 1;
+        const int nn = d ? c4 - N0 : c4;
+        float* dst = p.o[d].p + b * p.o[d].sB + fo * p.o[d].sF + (long long)tt * p.o[d].sT + nn;
+        const float* sp = stg + r * (N + 1) + c4;
+        float4 v = make_float4(sp[0], sp[1], sp[2], sp[3]);
+        if (p.accum[d]) {
+            const float4 o = *reinterpret_cast<const float4*>(dst);
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        }
+        *reinterpret_cast<float4*>(dst) = v;
+    }
+    if (p.stats) {
+        // 128 threads: column c = tid % N, row part = tid / N
+        constexpr int PARTS = 128 / N;
+        const int c = tid % N, part = tid / N;
+        float s1 = 0.f, s2 = 0.f;
+        for (int r = part; r < 128; r += PARTS) {
+            if (t0 + r < p.Tout) {
+                const float x = stg[r * (N + 1) + c];
+                s1 += x;
+                s2 += x * x;
+            }
+        }
+        if (tid < 2 * N) s_stat[tid] = 0.f;
+        __syncthreads();
+        atomicAdd(&s_stat[c], s1);
+        atomicAdd(&s_stat[N + c], s2);
+        __syncthreads();
+        if (tid < N) {
+            atomicAdd(p.stats + tid, (double)s_stat[tid]);
+            atomicAdd(p.stats + N + tid, (double)s_stat[N + tid]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// T3: N = 2   (decoder-5 forward): one thread = one output position, serial dot products over K channels
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) smalln_conv_kernel(const TapGemmParams p) {
+    extern __shared__ __align__(16) float Wsm[];      // [ntaps][K][2]
+    const int tid = threadIdx.x;
+    const int C0 = p.a[0].C, C1 = p.a[1].C, K = C0 + C1;
+    const int ttiles = (p.Tout + 127) / 128;
+    const int t0 = (blockIdx.x % ttiles) * 128;
+    const int row = blockIdx.x / ttiles;
+    const int b = row / p.J, j = row % p.J;
+    for (int i = tid; i < p.ntaps * K * 2; i += 128) {
+        const int tap = i / (K * 2), r = i % (K * 2);
+        Wsm[i] = p.W[(long long)p.wslab[tap] * K * 2 + r];
+    }
+    __syncthreads();
+    const int t = t0 + tid;
+    if (t >= p.Tout) return;
+    float a0 = p.bias ? __ldg(p.bias) : 0.f, a1 = p.bias ? __ldg(p.bias + 1) : 0.f;
+    for (int tap = 0; tap < p.ntaps; ++tap) {
+        const int fi = j * p.fi_mul + p.df[tap];
+        if (fi < 0 || fi >= p.Fin) continue;
+        const int tin = t + p.dt[tap];
+        if (tin < 0 || tin >= p.Tin) continue;
+        const float2* w = reinterpret_cast<const float2*>(Wsm + tap * K * 2);
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int C = s ? C1 : C0;
+            if (!C) continue;
+            const float4* x = reinterpret_cast<const float4*>(p.a[s].p + b * p.a[s].sB + fi * p.a[s].sF + (long long)tin * p.a[s].sT);
+            const float2* ws = w + (s ? C0 : 0);
+#pragma unroll 4
+            for (int k4 = 0; k4 < C / 4; ++k4) {
+                const float4 v = __ldg(x + k4);
+                const float2 w0 = ws[4 * k4], w1 = ws[4 * k4 + 1], w2 = ws[4 * k4 + 2], w3 = ws[4 * k4 + 3];
+                a0 = fmaf(v.x, w0.x, fmaf(v.y, w1.x, fmaf(v.z, w2.x, fmaf(v.w, w3.x, a0))));
+                a1 = fmaf(v.x, w0.y, fmaf(v.y, w1.y, fmaf(v.z, w2.y, fmaf(v.w, w3.y, a1))));
+            }
+        }
+    }
+    const int fo = j * p.fo_mul + p.fo_off;
+    float* dst = p.o[0].p + b * p.o[0].sB + fo * p.o[0].sF + (long long)t * p.o[0].sT;
+    if (p.accum[0]) { a0 += dst[0]; a1 += dst[1]; }
+    *reinterpret_cast<float2*>(dst) = make_float2(a0, a1);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// T2: weight gradient with a 2-channel side.  One pass over the wide tensor (lane = wide channel); the
+// 2-channel tensor's rows are staged in shared memory and read at the tap offsets (broadcast).
+//   wide_is_g = 1 (encoder 0): wide = G[b, j, t, n<32],  small = A[b, j*a_mul+a_off, t+dt, c<2]   -> dW[tap][c][n]
+//   wide_is_g = 0 (decoder 5): wide = A[b, j, u, k<64],  small = G[b, j*g_mul+g_off, u-dt, c<2]   -> dW[tap][k][c]
+// (for the second form the loop variable is the wide tensor's own time u = t + dt)
+// ---------------------------------------------------------------------------------------------------
+constexpr int SW_T = 512;      // max staged time extent (+2 halo)
+
+template <int WIDE>            // number of wide channels handled per lane: WIDE/32
+__global__ void __launch_bounds__(256) smallside_wgrad_kernel(const WgradParams p, int wide_is_g, int rows_per_cta) {
+    constexpr int PER = WIDE / 32;
+    __shared__ float2 srow[10][SW_T + 4];              // small tensor rows per tap (<= 10 taps), index = time + 2
+    __shared__ float sred[SEFD_MAX_TAPS * 2 * WIDE];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const TapSrc& small = wide_is_g ? p.a[0] : p.g;
+    const int Fs = wide_is_g ? p.Fa : p.Fg, Ts = wide_is_g ? p.Ta : p.Tg;
+    const int Tw = wide_is_g ? p.Tg : p.Ta;             // wide tensor time extent
+    float acc[SEFD_MAX_TAPS][2][PER];
+#pragma unroll
+    for (int a = 0; a < SEFD_MAX_TAPS; ++a)
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int q = 0; q < PER; ++q) acc[a][c][q] = 0.f;
+
+    const int rows = p.B * p.J;
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    for (int r = r0; r < r1; ++r) {
+        const int b = r / p.J, j = r % p.J;
+        __syncthreads();
+        // stage the small tensor rows (zero outside the tensor)
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+            const int fs = wide_is_g ? j * p.a_mul + p.a_off[tap] : j * p.g_mul + p.g_off[tap];
+            const bool ok = fs >= 0 && fs < Fs;
+            const float* base = small.p + b * small.sB + (ok ? fs : 0) * small.sF;
+            for (int i = tid; i < Tw + 4; i += 256) {
+                const int ts = i - 2;
+                float2 v = make_float2(0.f, 0.f);
+                if (ok && ts >= 0 && ts < Ts) v = __ldg(reinterpret_cast<const float2*>(base + (long long)ts * small.sT));
+                srow[tap][i] = v;
+            }
+        }
+        __syncthreads();
+        // wide tensor row(s): wide_is_g -> G at (b, j*g_mul+g_off[0]) ; else A sources at (b, j*a_mul + a_off[0])
+        const int fw = wide_is_g ? j * p.g_mul + p.g_off[0] : j * p.a_mul + p.a_off[0];
+        for (int u = warp; u < Tw; u += 8) {
+            float wv[PER];
+            if (wide_is_g) {
+#pragma unroll
+                for (int q = 0; q < PER; ++q)
+                    wv[q] = __ldg(p.g.p + b * p.g.sB + fw * p.g.sF + (long long)u * p.g.sT + lane + 32 * q);
+            } else {
+#pragma unroll
+                for (int q = 0; q < PER; ++q) {
+                    const int k = lane + 32 * q;
+                    wv[q] = k < p.a[0].C ? __ldg(p.a[0].p + b * p.a[0].sB + fw * p.a[0].sF + (long long)u * p.a[0].sT + k)
+                                         : __ldg(p.a[1].p + b * p.a[1].sB + fw * p.a[1].sF + (long long)u * p.a[1].sT + (k - p.a[0].C));
+                }
+            }
+#pragma unroll
+            for (int tap = 0; tap < SEFD_MAX_TAPS; ++tap) {
+                if (tap < p.ntaps) {
+                    // small-tensor time for this tap: A at t+dt when wide is G (t = u); G at u-dt when wide is A
+                    const int ts = wide_is_g ? u + p.dt[tap] : u - p.dt[tap];
+                    const float2 s = srow[tap][ts + 2];
+#pragma unroll
+                    for (int q = 0; q < PER; ++q) {
+                        acc[tap][0][q] = fmaf(s.x, wv[q], acc[tap][0][q]);
+                        acc[tap][1][q] = fmaf(s.y, wv[q], acc[tap][1][q]);
+                    }
+                }
+            }
+        }
+    }
+    // reduce the 8 warps through shared memory, then one atomic per output element and CTA
+    for (int i = tid; i < p.ntaps * 2 * WIDE; i += 256) sred[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int tap = 0; tap < SEFD_MAX_TAPS; ++tap)
+        if (tap < p.ntaps)
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int q = 0; q < PER; ++q) atomicAdd(&sred[(tap * 2 + c) * WIDE + lane + 32 * q], acc[tap][c][q]);
+    __syncthreads();
+    for (int i = tid; i < p.ntaps * 2 * WIDE; i += 256) {
+        const int tap = i / (2 * WIDE), c = (i / WIDE) % 2, w = i % WIDE;
+        // dW[slab][k][n]: encoder 0 -> k = c (2), n = w (WIDE) ; decoder 5 -> k = w (WIDE), n = c (2)
+        const long long off = wide_is_g ? ((long long)p.wslab[tap] * 2 + c) * WIDE + w
+                                        : ((long long)p.wslab[tap] * WIDE + w) * 2 + c;
+        atomicAdd(p.dW + off, sred[i]);
+    }
+}
+
+}  // namespace
+
+bool sefd_skinny_conv_eligible(const TapGemmParams& p) {
+    const int N = p.o[0].N + p.o[1].N, K = p.a[0].C + p.a[1].C;
+    if (p.wJ != 0 || p.bJ != 0) return false;
+    if (K == 2 && p.a[1].C == 0 && (N == 32 || N == 64) && p.o[0].N % 4 == 0 && p.a[0].sT % 2 == 0 && p.a[0].sF % 2 == 0 &&
+        p.a[0].sB % 2 == 0)
+        return true;
+    if (N == 2 && p.o[1].N == 0 && !p.stats && p.a[0].C % 4 == 0 && p.a[1].C % 4 == 0 && K <= 128) return true;
+    return false;
+}
+
+int sefd_skinny_conv(const TapGemmParams& p, cudaStream_t st) {
+    const int N = p.o[0].N + p.o[1].N, K = p.a[0].C + p.a[1].C;
+    const long long blocks = (long long)((p.Tout + 127) / 128) * p.B * p.J;
+    const double pos = (double)p.B * p.J * p.Tout;
+    sefd_prof_label("skinny_conv K%d N%d taps%d J%d Tout%d", K, N, p.ntaps, p.J, p.Tout);
+    SefdProfScope prof(SEFD_PROF_TAPGEMM, 2.0 * pos * N * K * p.ntaps,
+                       4.0 * ((double)p.B * p.J * (p.fi_mul > 1 ? p.fi_mul : 1) * p.Tin * K + pos * N), st);
+    if (K == 2) {
+        if (N == 32) smallk_conv_kernel<32><<<(unsigned)blocks, 128, 0, st>>>(p);
+        else smallk_conv_kernel<64><<<(unsigned)blocks, 128, 0, st>>>(p);
+    } else {
+        smalln_conv_kernel<<<(unsigned)blocks, 128, sizeof(float) * p.ntaps * K * 2, st>>>(p);
+    }
+    return sefd_check_launch("skinny_conv");
+}
+
+bool sefd_skinny_wgrad_eligible(const WgradParams& p) {
+    const int K = p.a[0].C + p.a[1].C, N = p.g.C;
+    if (p.Tg > SW_T || p.Ta > SW_T || p.ntaps > 10) return false;
+    if (K == 2 && p.a[1].C == 0 && N == 32) {          // wide = G: all taps must share the G row and time
+        for (int i = 0; i < p.ntaps; ++i)
+            if (p.g_off[i] != p.g_off[0]) return false;
+        return true;
+    }
+    if (N == 2 && (K == 64 || K == 32) && p.a[0].C % 32 == 0) {   // wide = A: all taps must share the A row
+        for (int i = 0; i < p.ntaps; ++i)
+            if (p.a_off[i] != p.a_off[0]) return false;
+        return true;
+    }
+    return false;
+}
+
+int sefd_skinny_wgrad(const WgradParams& p, cudaStream_t st) {
+    const int K = p.a[0].C + p.a[1].C, N = p.g.C;
+    const int wide_is_g = K == 2;
+    const int rows = p.B * p.J;
+    int ctas = 148 * 2;
+    if (ctas > rows) ctas = rows;
+    const int rpc = (rows + ctas - 1) / ctas;
+    ctas = (rows + rpc - 1) / rpc;
+    const double pos = (double)p.B * p.J * p.Tg;
+    sefd_prof_label("skinny_wgrad K%d N%d taps%d J%d", K, N, p.ntaps, p.J);
+    SefdProfScope prof(SEFD_PROF_WGRAD, 2.0 * pos * K * N * p.ntaps,
+                       4.0 * ((double)p.B * p.J * (p.a_mul > 1 ? p.a_mul : 1) * p.Ta * K +
+                              (double)p.B * p.J * (p.g_mul > 1 ? p.g_mul : 1) * p.Tg * N), st);
+    if (wide_is_g) smallside_wgrad_kernel<32><<<ctas, 256, 0, st>>>(p, 1, rpc);
+    else if (K == 64) smallside_wgrad_kernel<64><<<ctas, 256, 0, st>>>(p, 0, rpc);
+    else smallside_wgrad_kernel<32><<<ctas, 256, 0, st>>>(p, 0, rpc);
+    return sefd_check_launch("skinny_wgrad");
+}

@@ -352,6 +352,7 @@ int sefd_tapgemm_tc(const TapGemmParams& g, cudaStream_t st) {
 static int g_engine = 1;   // 0: fp32 CUDA-core engine everywhere (exact; tests), 1: tcgen05 TF32 where eligible
 
 int sefd_tapgemm(const TapGemmParams& p, cudaStream_t st) {
+    if (sefd_skinny_conv_eligible(p)) return sefd_skinny_conv(p, st);
     if (g_engine == 1 && sefd_tapgemm_tc_eligible(p)) return sefd_tapgemm_tc(p, st);
     return sefd_tapgemm_simt(p, st);
 }

@@ -317,5 +317,6 @@ int sefd_wgrad(const WgradParams& w, float* partial, long long cap_floats, int n
     p.dW = partial;
     *nsplit = 1;
     *split_stride = one;
+    if (sefd_skinny_wgrad_eligible(p)) return sefd_skinny_wgrad(p, st);
     return sefd_wgrad_simt(p, st);
 }

@@ -8,6 +8,7 @@ per-rank statistics (standard DDP), gradients are summed over ranks and scaled b
 import torch
 
 from . import _lib
+from . import dist as _dist
 from .ops import LOSSES, ptr, stream
 
 
@@ -59,12 +60,11 @@ class TrainStep:
     def step(self, noisy, clean):
         loss = self.forward_backward(noisy, clean)
         eng = self.engine
-        if self.world > 1:
-            torch.distributed.all_reduce(eng.flat_grad, group=self.pg)     # single flat 14.7 MB buffer
+        gscale = _dist.allreduce_sum_(eng.flat_grad, self.pg)              # single flat 14.7 MB buffer
         self.steps += 1
         _lib.check(_lib.load().sefd_adam_step(ptr(eng.flat), ptr(eng.flat_grad), ptr(self.exp_avg),
                                               ptr(self.exp_avg_sq), eng.flat.numel(), self.lr, self.betas[0],
-                                              self.betas[1], self.eps, self.steps, 1.0 / self.world, stream()),
+                                              self.betas[1], self.eps, self.steps, gscale, stream()),
                    "adam_step")
         return loss
 
@@ -94,10 +94,9 @@ class FlatAdam:
         eng = self.engine
         if eng.flat.data_ptr() != self.exp_avg.data_ptr() and eng.flat.numel() != self.exp_avg.numel():
             raise RuntimeError("FlatAdam: the model's parameter layout changed")
-        if self.world > 1:
-            torch.distributed.all_reduce(eng.flat_grad, group=self.pg)
+        gscale = _dist.allreduce_sum_(eng.flat_grad, self.pg)
         self.steps += 1
         _lib.check(_lib.load().sefd_adam_step(ptr(eng.flat), ptr(eng.flat_grad), ptr(self.exp_avg),
                                               ptr(self.exp_avg_sq), eng.flat.numel(), self.lr, self.betas[0],
-                                              self.betas[1], self.eps, self.steps, 1.0 / self.world, stream()),
+                                              self.betas[1], self.eps, self.steps, gscale, stream()),
                    "adam_step")

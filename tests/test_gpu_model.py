@@ -105,6 +105,7 @@ def test_small_forward_backward_every_tensor(golden, sd0, mode, engine):
     # floor for the conv biases in front of a BatchNorm whose true gradient is exactly zero)
     grads = tr.grads()
     gmax = max(float(g.abs().max()) for g in grads.values())
+    amax = max(float(g.abs().max()) for k, g in grads.items() if k.endswith(".2.weight"))
     for name, p in m.named_parameters():
         ref = grads[name]
         if name.endswith("_conv.bias") and not name.startswith("decoder.5."):
@@ -114,10 +115,15 @@ def test_small_forward_backward_every_tensor(golden, sd0, mode, engine):
             e, s = _err(p.grad, ref)
             # the single PReLU slope's gradient is one global sum with heavy cancellation: looser relative bound
             ok = e <= (2e-2 if name.endswith(".2.weight") else 2e-3) * s + 1e-6 * gmax
+            cosv = 1.0
             if tf:                  # TF32 gradients: direction and norm must agree, element-wise bound is loose
                 g64, r64 = p.grad.detach().double().cpu().reshape(-1), ref.detach().double().reshape(-1)
-                cos = float((g64 * r64).sum() / (g64.norm() * r64.norm() + 1e-30))
-                ok = (cos > 0.995 and e <= 5e-2 * s + 1e-5 * gmax) or name.endswith(".2.weight")
+                cosv = float((g64 * r64).sum() / (g64.norm() * r64.norm() + 1e-30))
+                nr = float(g64.norm() / (r64.norm() + 1e-30))
+                ok = cosv > 0.99 and abs(nr - 1) < 0.05
+                if name.endswith(".2.weight"):      # one cancelling global sum: TF32 noise does not cancel with it
+                    ok = e <= 2e-2 * amax
+                _report(f"[{mode}/tf32] grad {name:40s} cos={cosv:.5f} |got|/|ref|={nr:.4f}")
             _report(f"[{mode}] grad {name:40s} max|err|={e:.3e} max|ref|={s:.3e} {'ok' if ok else 'FAIL'}")
         if not ok:
             failures.append("grad " + name)
@@ -150,12 +156,14 @@ def test_losses_through_dropin(golden, sd0, engine):
         assert float(loss) == pytest.approx(ref, rel=lt, abs=2e-5), loss_name
         gn = np.array([float(dict(m.named_parameters())[n].grad.double().norm()) for n in names])
         refn = golden[f"small_rand_C_{loss_name}_gnorm"]
+        amaxn = max(refn[i] for i, n in enumerate(names) if n.endswith(".2.weight"))
         bad = []
         for i, n in enumerate(names):
             if n.endswith("_conv.bias") and not n.startswith("decoder.5."):
                 continue                                   # exactly zero here, rounding noise in the reference
             rt = max(2e-2, gt) if n.endswith(".2.weight") else gt      # PReLU slopes: cancelling global sum
-            if abs(gn[i] - refn[i]) > rt * abs(refn[i]) + 1e-5 * float(refn.max()):
+            slack = 2e-2 * amaxn if (engine == 1 and n.endswith(".2.weight")) else 0.0
+            if abs(gn[i] - refn[i]) > rt * abs(refn[i]) + 1e-5 * float(refn.max()) + slack:
                 bad.append((n, gn[i], refn[i]))
                 _report(f"[losses engine={engine} {loss_name}] gnorm {n}: got {gn[i]:.6e} ref {refn[i]:.6e} FAIL")
         assert not bad, (loss_name, bad[:5])
@@ -219,6 +227,7 @@ def test_full_length_known_answer(golden, sd0, engine):
     gn = np.array([float(dict(m.named_parameters())[n].grad.double().norm()) for n in names])
     ref = golden["full_gnorm"]
     gt = 5e-2 if engine == 1 else 5e-3
+    amaxn = max(ref[i] for i, n in enumerate(names) if n.endswith(".2.weight"))
     bad = []
     for i, n in enumerate(names):
         if n.endswith("_conv.bias") and not n.startswith("decoder.5."):
@@ -227,7 +236,8 @@ def test_full_length_known_answer(golden, sd0, engine):
         rel = abs(gn[i] - ref[i]) / max(abs(ref[i]), 1e-30)
         if engine == 1:
             _report(f"[full engine=1] gnorm {n:44s} got {gn[i]:.5e} ref {ref[i]:.5e} rel {rel:.2e}")
-        if abs(gn[i] - ref[i]) > rt * abs(ref[i]) + 1e-5 * float(ref.max()):
+        slack = 2e-2 * amaxn if (engine == 1 and n.endswith(".2.weight")) else 0.0
+        if abs(gn[i] - ref[i]) > rt * abs(ref[i]) + 1e-5 * float(ref.max()) + slack:
             bad.append((n, gn[i], ref[i]))
     assert not bad, bad[:8]
 

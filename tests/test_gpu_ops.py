@@ -158,8 +158,8 @@ def test_complex_conv2d_forward_backward(B, F, T, Cin, Cout, engine):
     dx, dwr, dbr, dwi, dbi = ops.cconv2d_backward(x.to(DEV), wr.to(DEV), wi.to(DEV), dyc)
     _close(dx, leaves[0].grad, atol=tf * 2e-5 * (Cout ** 0.5), rtol=1e-5, name="conv dx")
     scale = float(leaves[1].grad.abs().max())
-    _close(dwr, leaves[1].grad, atol=2e-5 * scale, rtol=1e-4, name="conv dWr")
-    _close(dwi, leaves[3].grad, atol=2e-5 * scale, rtol=1e-4, name="conv dWi")
+    _close(dwr, leaves[1].grad, atol=tf * 2e-5 * scale, rtol=1e-4, name="conv dWr")
+    _close(dwi, leaves[3].grad, atol=tf * 2e-5 * scale, rtol=1e-4, name="conv dWi")
     _close(dbr, leaves[2].grad, atol=2e-5 * float(leaves[2].grad.abs().max()), rtol=1e-4, name="conv dbr")
     _close(dbi, leaves[4].grad, atol=2e-5 * float(leaves[4].grad.abs().max()), rtol=1e-4, name="conv dbi")
 
@@ -188,8 +188,8 @@ def test_complex_conv_transpose2d_forward_backward(B, F, T, Cin, Cout, engine):
     _close(dx0, leaves[0].grad, atol=tf * 2e-5 * (Cout ** 0.5), rtol=1e-5, name="convT dx0")
     _close(dx1, leaves[1].grad, atol=tf * 2e-5 * (Cout ** 0.5), rtol=1e-5, name="convT dx1")
     scale = float(leaves[2].grad.abs().max())
-    _close(dwr, leaves[2].grad, atol=2e-5 * scale, rtol=1e-4, name="convT dWr")
-    _close(dwi, leaves[4].grad, atol=2e-5 * scale, rtol=1e-4, name="convT dWi")
+    _close(dwr, leaves[2].grad, atol=tf * 2e-5 * scale, rtol=1e-4, name="convT dWr")
+    _close(dwi, leaves[4].grad, atol=tf * 2e-5 * scale, rtol=1e-4, name="convT dWi")
     _close(dbr, leaves[3].grad, atol=2e-5 * float(leaves[3].grad.abs().max()), rtol=1e-4, name="convT dbr")
     _close(dbi, leaves[5].grad, atol=2e-5 * float(leaves[5].grad.abs().max()), rtol=1e-4, name="convT dbi")
 
