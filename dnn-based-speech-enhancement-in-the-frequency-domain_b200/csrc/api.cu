@@ -303,7 +303,7 @@ int sefd_lstm_forward(const float* w_hh, float* gates, float* h, float* c, int r
 int sefd_lstm_backward(const float* w_hh, const float* gates, const float* c, const float* dh, float* dgates, int rows,
                        int T, void* stream) {
     LstmBwdParams p;
-    p.Whh = w_hh; p.G = gates; p.Cc = c; p.dH = dh; p.dG = dgates; p.rows = rows; p.T = T;
+    p.Whh = w_hh; p.G = gates; p.Cc = c; p.dH = dh; p.dG = dgates; p.rows = rows; p.T = T; p.round_tf32 = 0;
     return sefd_lstm_bwd_launch(p, ST);
 }
 

@@ -58,6 +58,7 @@ struct TapGemmParams {
     int ntaps;
     int df[SEFD_MAX_TAPS], dt[SEFD_MAX_TAPS], wslab[SEFD_MAX_TAPS];
     int accum[2];
+    int round_out[2];    // round the stored values to tf32 (the destination feeds a tensor-core GEMM)
 };
 
 // dW[wslab[tap]][k][n] += sum_{b,j,t} A[b, j*a_mul+a_off[tap], t+dt[tap], k] * G[b, j*g_mul+g_off[tap], t, n]

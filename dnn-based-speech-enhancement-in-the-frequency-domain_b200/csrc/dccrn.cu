@@ -49,7 +49,7 @@ struct sefd_plan {
     size_t ws_bytes;
     size_t spec, raw_wav, dots /*double*/, stats_all /*double*/, stats_all_n;
     size_t Gt[2], Hh[2], Cc[2], X1, X2, U;
-    size_t Wih0p, Wih0T, Wih1p, Wih1T, Whh[2], bsum[2], Wtrp, WtrT, btrp;
+    size_t Wih0p, Wih0T, Wih0Q, Wih1p, Wih1T, Wih1Q, Whh[2], bsum[2], Wtrp, WtrT, btrp;
     size_t dU, dY, dWs, dbs, red /*double*/, dX, dH, dG, dzd[NL];
     size_t dY_floats, dWs_floats;
 };
@@ -245,6 +245,8 @@ sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode) {
     P->Wih0T = w.floats(4ull * 2 * G4 * 128);     // [d][p*512+n][c]
     P->Wih1p = w.floats(2ull * 128 * G4);         // [p][k][n]
     P->Wih1T = w.floats(2ull * G4 * 128);         // [p*512+n][k]
+    P->Wih0Q = w.floats(4ull * 128 * 2 * G4);     // [d][c][p*512+n]
+    P->Wih1Q = w.floats(128ull * 2 * G4);         // [k][p*512+n]
     P->Wtrp = w.floats(2ull * 4 * 128 * 128);     // [q][d][k][c]
     P->WtrT = w.floats(2ull * 4 * 128 * 128);     // [q][d][c][k]
     P->btrp = w.floats(2ull * 4 * 128);           // [q][d][c]
@@ -278,15 +280,25 @@ static int pack_weights(const sefd_plan* P, const float* prm, float* ws, cudaStr
         pp.round_tf32 = sefd_get_engine_internal() == 1 && c.Cin % 32 == 0 && (c.Cout % 32 == 0);
         SEFD_TRY(sefd_pack_cconv(pp, st));
     }
+    const int tf = sefd_get_engine_internal() == 1;
+    auto perm = [&](const float* src, float* dst, int na, int nb, int nc, long long sa, long long sb, long long sc,
+                    long long da, long long db, long long dc) -> int {
+        Permute3Params q;
+        q.src = src; q.dst = dst; q.na = na; q.nb = nb; q.nc = nc; q.sa = sa; q.sb = sb; q.sc = sc;
+        q.da = da; q.db = db; q.dc = dc; q.accumulate = 0; q.nsplit = 1; q.split_stride = 0; q.round_tf32 = tf;
+        return sefd_permute3p(q, st);
+    };
     for (int p = 0; p < 2; ++p) {
-        // layer 0: W_ih [n][c*4+d] -> Wih0p[p][d][c][n] and Wih0T[d][p*512+n][c]
-        SEFD_TRY(sefd_permute3(prm + P->w_ih[0][p], ws + P->Wih0p + (size_t)p * 4 * 128 * G4, 4, 128, G4, 1, 4, 512, 0, st));
-        for (int d = 0; d < 4; ++d)
-            SEFD_TRY(sefd_permute3(prm + P->w_ih[0][p] + d, ws + P->Wih0T + ((size_t)d * 2 + p) * G4 * 128, 1, G4, 128,
-                                   0, 512, 4, 0, st));
-        // layer 1: W_ih [n][k] -> Wih1p[p][k][n]; Wih1T[p*512+n][k] (plain copy)
-        SEFD_TRY(sefd_permute3(prm + P->w_ih[1][p], ws + P->Wih1p + (size_t)p * 128 * G4, 1, 128, G4, 0, 1, 128, 0, st));
-        SEFD_TRY(sefd_permute3(prm + P->w_ih[1][p], ws + P->Wih1T + (size_t)p * G4 * 128, 1, 1, G4 * 128, 0, 0, 1, 0, st));
+        const float* w0 = prm + P->w_ih[0][p];      // [n][c*4+d]
+        const float* w1 = prm + P->w_ih[1][p];      // [n][k]
+        // layer 0: Wih0p[p][d][c][n], Wih0T[d][p*512+n][c], Wih0Q[d][c][p*512+n]
+        SEFD_TRY(perm(w0, ws + P->Wih0p + (size_t)p * 4 * 128 * G4, 4, 128, G4, 1, 4, 512, 128ll * G4, G4, 1));
+        SEFD_TRY(perm(w0, ws + P->Wih0T + (size_t)p * G4 * 128, 4, G4, 128, 1, 512, 4, 2ll * G4 * 128, 128, 1));
+        SEFD_TRY(perm(w0, ws + P->Wih0Q + (size_t)p * G4, 4, 128, G4, 1, 4, 512, 128ll * 2 * G4, 2ll * G4, 1));
+        // layer 1: Wih1p[p][k][n], Wih1T[p*512+n][k], Wih1Q[k][p*512+n]
+        SEFD_TRY(perm(w1, ws + P->Wih1p + (size_t)p * 128 * G4, 1, 128, G4, 0, 1, 128, 0, G4, 1));
+        SEFD_TRY(perm(w1, ws + P->Wih1T + (size_t)p * G4 * 128, 1, G4, 128, 0, 128, 1, 0, 128, 1));
+        SEFD_TRY(perm(w1, ws + P->Wih1Q + (size_t)p * G4, 1, 128, G4, 0, 1, 128, 0, 2ll * G4, 1));
         for (int l = 0; l < 2; ++l) {
             SEFD_TRY(sefd_permute3(prm + P->w_hh[l][p], ws + P->Whh[l] + (size_t)p * G4 * RNN_H, 1, 1, G4 * RNN_H, 0, 0, 1, 0, st));
             SEFD_TRY(sefd_add2(prm + P->b_ih[l][p], prm + P->b_hh[l][p], ws + P->bsum[l] + (size_t)p * G4, G4, st));
@@ -294,8 +306,9 @@ static int pack_weights(const sefd_plan* P, const float* prm, float* ws, cudaStr
     }
     for (int q = 0; q < 2; ++q) {
         // W_tr [c*4+d][k] -> Wtrp[q][d][k][c] ; WtrT[q][d][c][k] ; b_tr[c*4+d] -> btrp[q][d][c]
-        SEFD_TRY(sefd_permute3(prm + P->w_tr[q], ws + P->Wtrp + (size_t)q * 4 * 128 * 128, 4, 128, 128, 128, 1, 512, 0, st));
-        SEFD_TRY(sefd_permute3(prm + P->w_tr[q], ws + P->WtrT + (size_t)q * 4 * 128 * 128, 4, 128, 128, 128, 512, 1, 0, st));
+        const float* wt = prm + P->w_tr[q];
+        SEFD_TRY(perm(wt, ws + P->Wtrp + (size_t)q * 4 * 128 * 128, 4, 128, 128, 128, 1, 512, 128 * 128, 128, 1));
+        SEFD_TRY(perm(wt, ws + P->WtrT + (size_t)q * 4 * 128 * 128, 4, 128, 128, 128, 512, 1, 128 * 128, 128, 1));
         SEFD_TRY(sefd_permute3(prm + P->b_tr[q], ws + P->btrp + (size_t)q * 4 * 128, 1, 4, 128, 0, 1, 4, 0, st));
     }
     return 0;
@@ -366,11 +379,13 @@ int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const 
                     for (int d = 0; d < 4; ++d) { g.df[d] = d; g.dt[d] = 0; g.wslab[d] = d; }
                     g.Fin = 4;
                     g.W = ws + P->Wih0p + (size_t)p * 4 * 128 * G4;
+                    g.Wnk = ws + P->Wih0T + (size_t)p * G4 * 128; g.nslabs = 4; g.w_slab_stride = 2ll * G4 * 128;
                 } else {
                     g.a[0] = src4(ws + P->X1 + (size_t)q * B * T * RNN_H, 1, T, RNN_H, RNN_H);
                     g.ntaps = 1;
                     g.Fin = 1;
                     g.W = ws + P->Wih1p + (size_t)p * 128 * G4;
+                    g.Wnk = ws + P->Wih1T + (size_t)p * G4 * 128; g.nslabs = 1;
                 }
                 g.a[1] = no_src();
                 g.o[0] = dst4(ws + P->Gt[l] + ((size_t)p * 2 + q) * B * rowsz, 1, T, G4, G4);
@@ -384,7 +399,8 @@ int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const 
         lp.Whh = ws + P->Whh[l]; lp.G = ws + P->Gt[l]; lp.Hh = ws + P->Hh[l]; lp.Cc = ws + P->Cc[l];
         lp.rows = 2 * B; lp.T = T;
         SEFD_TRY(sefd_lstm_fwd_launch(lp, st));
-        SEFD_TRY(sefd_clstm_combine(ws + P->Hh[l], ws + (l == 0 ? P->X1 : P->X2), (long long)B * T * RNN_H, st));
+        SEFD_TRY(sefd_clstm_combine(ws + P->Hh[l], ws + (l == 0 ? P->X1 : P->X2), (long long)B * T * RNN_H,
+                                    sefd_get_engine_internal() == 1, st));
     }
     // projection r_trans / i_trans (Linear 128 -> 512), output feature c*4+d -> U[b][d][t][q*128+c]
     for (int q = 0; q < 2; ++q) {
@@ -395,6 +411,8 @@ int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const 
         g.o[0] = dst4(ws + P->U + q * 128, 4, T, 256, 128);
         g.o[1] = no_dst();
         g.W = ws + P->Wtrp + (size_t)q * 4 * 128 * 128; g.wJ = 128 * 128;
+        g.Wnk = ws + P->WtrT + (size_t)q * 4 * 128 * 128; g.nslabs = 4; g.wJ_slabs = 1;
+        g.round_out[0] = sefd_get_engine_internal() == 1;      // U feeds decoder 0
         g.bias = ws + P->btrp + (size_t)q * 4 * 128; g.bJ = 128;
         g.B = B; g.J = 4; g.Tout = T; g.Fin = 1; g.Tin = T;
         g.fi_mul = 0; g.fo_mul = 1; g.fo_off = 0;
@@ -472,6 +490,16 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
         return sefd_fold_cconv(f, st);
     };
 
+    // sum the wgrad split partials while un-permuting into the reference's parameter layout
+    auto unperm = [&](const float* src, float* dst, int na, int nb, int nc, long long sa, long long sb, long long sc,
+                      int accumulate) -> int {
+        Permute3Params q;
+        q.src = src; q.dst = dst; q.na = na; q.nb = nb; q.nc = nc; q.sa = sa; q.sb = sb; q.sc = sc;
+        q.da = (long long)nb * nc; q.db = nc; q.dc = 1;
+        q.accumulate = accumulate; q.nsplit = nsplit; q.split_stride = sstride; q.round_tf32 = 0;
+        return sefd_permute3p(q, st);
+    };
+
     // ---- ISTFT^T and mask Jacobian -> d(mask) laid out like dec[5].y ----
     const ConvLayer& last = P->dec[NL - 1];
     {
@@ -520,6 +548,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
         g.o[0] = dst4(j == 0 ? ws + P->dU : ws + P->dec[j - 1].dz, c.Fin, T, Ch, Ch);
         g.o[1] = dst4(ws + P->enc[NL - 1 - j].dz, c.Fin, T, Ch, Ch);
         g.W = ws + c.Wt; g.Wnk = ws + c.Wf; g.nslabs = 10;
+        g.round_out[0] = (j == 0) && sefd_get_engine_internal() == 1;      // dU feeds the projection GEMMs
         g.B = B; g.J = c.Fin; g.Tout = T; g.Fin = c.Fout; g.Tin = T + 1;
         conv_taps_down(g, +1);
         SEFD_TRY(sefd_tapgemm(g, st));
@@ -535,13 +564,13 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
         g.o[0] = dst4(ws + P->dX + (size_t)q * nX, 1, T, RNN_H, RNN_H);
         g.o[1] = no_dst();
         g.W = ws + P->WtrT + (size_t)q * 4 * 128 * 128;
+        g.Wnk = ws + P->Wtrp + (size_t)q * 4 * 128 * 128; g.nslabs = 4;
         g.B = B; g.J = 1; g.Tout = T; g.Fin = 4; g.Tin = T;
         g.fi_mul = 0; g.fo_mul = 1;
         g.ntaps = 4;
         for (int d = 0; d < 4; ++d) { g.df[d] = d; g.dt[d] = 0; g.wslab[d] = d; }
         SEFD_TRY(sefd_tapgemm(g, st));
         // dW_tr[c*4+d][k] = sum dU[b][d][t][q*128+c] * X2[q][b][t][k]
-        cudaMemsetAsync(dWs, 0, sizeof(float) * 4 * 128 * 128, st);
         WgradParams wg;
         memset(&wg, 0, sizeof(wg));
         wg.a[0] = src4(ws + P->X2 + (size_t)q * nX, 1, T, RNN_H, RNN_H);
@@ -551,9 +580,9 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
         wg.B = B; wg.J = 1; wg.Tg = T; wg.Fa = 1; wg.Ta = T; wg.Fg = 4;
         wg.a_mul = 0; wg.g_mul = 0; wg.ntaps = 4;
         for (int d = 0; d < 4; ++d) { wg.a_off[d] = 0; wg.g_off[d] = d; wg.dt[d] = 0; wg.wslab[d] = d; }
-        SEFD_TRY(sefd_wgrad_simt(wg, st));
+        SEFD_TRY(sefd_wgrad(wg, dWs, (long long)P->dWs_floats, 4, &nsplit, &sstride, st));
         // dWs[d][k][c] -> grads[c][d][k]
-        SEFD_TRY(sefd_permute3(dWs, grads + P->w_tr[q], 128, 4, 128, 1, 128 * 128, 128, 0, st));
+        SEFD_TRY(unperm(dWs, grads + P->w_tr[q], 128, 4, 128, 1, 128 * 128, 128, 0));
     }
     // db_tr[q][c*4+d] = sum_{b,t} dU[b][d][t][q*128+c]
     for (int d = 0; d < 4; ++d)
@@ -567,7 +596,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
         SEFD_TRY(sefd_clstm_combine_bwd(ws + P->dX, ws + P->dH, nX, st));
         LstmBwdParams lb;
         lb.Whh = ws + P->Whh[l]; lb.G = ws + P->Gt[l]; lb.Cc = ws + P->Cc[l]; lb.dH = ws + P->dH; lb.dG = ws + P->dG;
-        lb.rows = 2 * B; lb.T = T;
+        lb.rows = 2 * B; lb.T = T; lb.round_tf32 = sefd_get_engine_internal() == 1;
         SEFD_TRY(sefd_lstm_bwd_launch(lb, st));
         const size_t lstm_sz = (size_t)2 * B * T * G4;     // one LSTM's dG
         // data gradient into the layer input
@@ -582,10 +611,12 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
             if (l == 1) {
                 g.o[0] = dst4(ws + P->dX + (size_t)q * nX, 1, T, RNN_H, RNN_H);
                 g.W = ws + P->Wih1T; g.J = 1;
+                g.Wnk = ws + P->Wih1Q; g.nslabs = 1;
             } else {
                 g.o[0] = dst4(ws + P->enc[NL - 1].dz + q * 128, 4, T, 256, 128);
                 g.accum[0] = 1;                                   // the skip gradient from decoder 0 is already there
                 g.W = ws + P->Wih0T; g.wJ = (long long)2 * G4 * 128; g.J = 4;
+                g.Wnk = ws + P->Wih0Q; g.nslabs = 4; g.wJ_slabs = 1;
             }
             SEFD_TRY(sefd_tapgemm(g, st));
         }
@@ -593,7 +624,6 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
         for (int p = 0; p < 2; ++p) {
             const float* dGp = ws + P->dG + (size_t)p * lstm_sz;
             // W_hh: dW[n][k] = sum_{rows, t>=1} dG[t][n] h[t-1][k]
-            cudaMemsetAsync(dWs, 0, sizeof(float) * 128 * G4, st);
             WgradParams wg;
             memset(&wg, 0, sizeof(wg));
             wg.a[0] = src4(ws + P->Hh[l] + (size_t)p * 2 * B * T * RNN_H, 1, T, RNN_H, RNN_H);
@@ -602,17 +632,15 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
             wg.dW = dWs;
             wg.B = 2 * B; wg.J = 1; wg.Tg = T; wg.Fa = 1; wg.Ta = T; wg.Fg = 1;
             wg.ntaps = 1; wg.dt[0] = -1;
-            SEFD_TRY(sefd_wgrad_simt(wg, st));
-            SEFD_TRY(sefd_permute3(dWs, grads + P->w_hh[l][p], G4, 1, 128, 1, 0, G4, 0, st));   // [k][n] -> [n][k]
+            SEFD_TRY(sefd_wgrad(wg, dWs, (long long)P->dWs_floats, 1, &nsplit, &sstride, st));
+            SEFD_TRY(unperm(dWs, grads + P->w_hh[l][p], G4, 1, 128, 1, 0, G4, 0));   // [k][n] -> [n][k]
             // W_ih
             if (l == 1) {
-                cudaMemsetAsync(dWs, 0, sizeof(float) * 128 * G4, st);
                 wg.a[0] = src4(ws + P->X1, 1, T, RNN_H, RNN_H);      // [q][B] rows are contiguous = 2B rows
                 wg.dt[0] = 0;
-                SEFD_TRY(sefd_wgrad_simt(wg, st));
-                SEFD_TRY(sefd_permute3(dWs, grads + P->w_ih[1][p], G4, 1, 128, 1, 0, G4, 0, st));
+                SEFD_TRY(sefd_wgrad(wg, dWs, (long long)P->dWs_floats, 1, &nsplit, &sstride, st));
+                SEFD_TRY(unperm(dWs, grads + P->w_ih[1][p], G4, 1, 128, 1, 0, G4, 0));
             } else {
-                cudaMemsetAsync(dWs, 0, sizeof(float) * 4 * 128 * G4, st);
                 for (int q = 0; q < 2; ++q) {
                     WgradParams w0;
                     memset(&w0, 0, sizeof(w0));
@@ -623,10 +651,10 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
                     w0.B = B; w0.J = 1; w0.Tg = T; w0.Fa = 4; w0.Ta = T; w0.Fg = 1;
                     w0.a_mul = 0; w0.g_mul = 0; w0.ntaps = 4;
                     for (int d = 0; d < 4; ++d) { w0.a_off[d] = d; w0.g_off[d] = 0; w0.dt[d] = 0; w0.wslab[d] = d; }
-                    SEFD_TRY(sefd_wgrad_simt(w0, st));
+                    SEFD_TRY(sefd_wgrad(w0, dWs, (long long)P->dWs_floats, 4, &nsplit, &sstride, st));
+                    // dWs[d][c][n] -> grads[n][c][d]   (the second part accumulates onto the first)
+                    SEFD_TRY(unperm(dWs, grads + P->w_ih[0][p], G4, 128, 4, 1, G4, (long long)128 * G4, q));
                 }
-                // dWs[d][c][n] -> grads[n][c][d]
-                SEFD_TRY(sefd_permute3(dWs, grads + P->w_ih[0][p], G4, 128, 4, 1, G4, (long long)128 * G4, 0, st));
             }
             // biases: both get sum over rows and time of dG
             SEFD_TRY(sefd_colsum2(dGp, 1, 0, (long long)2 * B * T, G4, G4, wsd + P->red, grads + P->b_ih[l][p], st));

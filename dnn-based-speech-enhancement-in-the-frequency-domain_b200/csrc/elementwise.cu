@@ -272,16 +272,19 @@ __global__ void fold_cconv_kernel(const CconvFoldParams p) {
 // used for the LSTM / Linear weight (un)permutations, expressed as a 3-d index transpose:
 //   dst[(a*nb + b)*nc + c] = src[a*sa + b*sb + c*sc]
 // ------------------------------------------------------------------------------------
-__global__ void permute3_kernel(const float* __restrict__ src, float* __restrict__ dst, int na, int nb, int nc,
-                                long long sa, long long sb, long long sc, int accumulate) {
-    const long long total = (long long)na * nb * nc;
+__global__ void permute3_kernel(const Permute3Params q) {
+    const long long total = (long long)q.na * q.nb * q.nc;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(e % nc);
-        const int b = (int)((e / nc) % nb);
-        const int a = (int)(e / ((long long)nc * nb));
-        const float v = src[a * sa + b * sb + c * sc];
-        dst[e] = accumulate ? dst[e] + v : v;
+        const int c = (int)(e % q.nc);
+        const int b = (int)((e / q.nc) % q.nb);
+        const int a = (int)(e / ((long long)q.nc * q.nb));
+        const long long so = a * q.sa + b * q.sb + c * q.sc;
+        float v = 0.f;
+        for (int s = 0; s < q.nsplit; ++s) v += q.src[s * q.split_stride + so];
+        if (q.round_tf32) v = tf32_rn(v);
+        float* d = q.dst + a * q.da + b * q.db + c * q.dc;
+        *d = q.accumulate ? *d + v : v;
     }
 }
 
@@ -317,10 +320,12 @@ __global__ void d2f_kernel(const double* s, float* d, int n) {
 //   real = H[0][0] - H[1][1] ;  imag = H[0][1] + H[1][0]      -> X [part][B][T][H]
 // backward: dH[0][0] = dreal, dH[1][1] = -dreal, dH[0][1] = dH[1][0] = dimag  (accumulated into dH)
 // ------------------------------------------------------------------------------------
-__global__ void clstm_combine_kernel(const float* __restrict__ Hh, float* __restrict__ X, long long n) {
+__global__ void clstm_combine_kernel(const float* __restrict__ Hh, float* __restrict__ X, long long n, int round_tf32) {
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-        X[e] = Hh[e] - Hh[3 * n + e];
-        X[n + e] = Hh[n + e] + Hh[2 * n + e];
+        float r = Hh[e] - Hh[3 * n + e], i = Hh[n + e] + Hh[2 * n + e];
+        if (round_tf32) { r = tf32_rn(r); i = tf32_rn(i); }
+        X[e] = r;
+        X[n + e] = i;
     }
 }
 __global__ void clstm_combine_bwd_kernel(const float* __restrict__ dX, float* __restrict__ dH, long long n) {
@@ -393,11 +398,19 @@ int sefd_fold_cconv(const CconvFoldParams& p, cudaStream_t st) {
     return sefd_check_launch("fold_cconv");
 }
 
+int sefd_permute3p(const Permute3Params& q, cudaStream_t st) {
+    SefdProfScope prof(SEFD_PROF_MISC, 0, 0, st);
+    permute3_kernel<<<grid_for((long long)q.na * q.nb * q.nc), 256, 0, st>>>(q);
+    return sefd_check_launch("permute3");
+}
+
 int sefd_permute3(const float* src, float* dst, int na, int nb, int nc, long long sa, long long sb, long long sc,
                   int accumulate, cudaStream_t st) {
-    SefdProfScope prof(SEFD_PROF_MISC, 0, 0, st);
-    permute3_kernel<<<grid_for((long long)na * nb * nc), 256, 0, st>>>(src, dst, na, nb, nc, sa, sb, sc, accumulate);
-    return sefd_check_launch("permute3");
+    Permute3Params q;
+    q.src = src; q.dst = dst; q.na = na; q.nb = nb; q.nc = nc; q.sa = sa; q.sb = sb; q.sc = sc;
+    q.da = (long long)nb * nc; q.db = nc; q.dc = 1;
+    q.accumulate = accumulate; q.nsplit = 1; q.split_stride = 0; q.round_tf32 = 0;
+    return sefd_permute3p(q, st);
 }
 
 int sefd_add2(const float* a, const float* b, float* o, long long n, cudaStream_t st) {
@@ -421,9 +434,9 @@ int sefd_colsum2(const float* x, int nO, long long sO, long long nI, long long s
     return sefd_check_launch("d2f");
 }
 
-int sefd_clstm_combine(const float* H, float* X, long long n, cudaStream_t st) {
+int sefd_clstm_combine(const float* H, float* X, long long n, int round_tf32, cudaStream_t st) {
     SefdProfScope prof(SEFD_PROF_MISC, 0, 0, st);
-    clstm_combine_kernel<<<grid_for(n), 256, 0, st>>>(H, X, n);
+    clstm_combine_kernel<<<grid_for(n), 256, 0, st>>>(H, X, n, round_tf32);
     return sefd_check_launch("clstm_combine");
 }
 

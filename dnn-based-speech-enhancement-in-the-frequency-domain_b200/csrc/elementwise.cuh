@@ -51,12 +51,23 @@ int sefd_bn_prelu_fwd(const BnPreluFwdParams& p, cudaStream_t st);
 int sefd_bn_prelu_bwd(const BnPreluBwdParams& p, cudaStream_t st);
 int sefd_pack_cconv(const CconvPackParams& p, cudaStream_t st);
 int sefd_fold_cconv(const CconvFoldParams& p, cudaStream_t st);
+// dst[a*da + b*db + c*dc] (+)= sum_{s < nsplit} src[s*split_stride + a*sa + b*sb + c*sc]   (optionally tf32-rounded)
+struct Permute3Params {
+    const float* src;
+    float* dst;
+    int na, nb, nc;
+    long long sa, sb, sc, da, db, dc;
+    int accumulate, nsplit;
+    long long split_stride;
+    int round_tf32;
+};
+int sefd_permute3p(const Permute3Params& q, cudaStream_t st);
 int sefd_permute3(const float* src, float* dst, int na, int nb, int nc, long long sa, long long sb, long long sc,
                   int accumulate, cudaStream_t st);
 int sefd_add2(const float* a, const float* b, float* o, long long n, cudaStream_t st);
 int sefd_colsum2(const float* x, int nO, long long sO, long long nI, long long sI, int C, double* scratch, float* out,
                  cudaStream_t st);
-int sefd_clstm_combine(const float* H, float* X, long long n, cudaStream_t st);
+int sefd_clstm_combine(const float* H, float* X, long long n, int round_tf32, cudaStream_t st);
 int sefd_clstm_combine_bwd(const float* dX, float* dH, long long n, cudaStream_t st);
 int sefd_adam(float* w, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
               int step, float gscale, cudaStream_t st);

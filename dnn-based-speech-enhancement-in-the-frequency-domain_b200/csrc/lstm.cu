@@ -11,11 +11,11 @@
 
 namespace {
 
-constexpr int H = 128, G4 = 512, KR = 64;   // KR weights per thread live in registers, H-KR in smem
+constexpr int H = 128, G4 = 512;   // KR of a thread's 128 weights live in registers, H-KR in shared memory
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-template <int R>
+template <int R, int KR>
 __global__ void __launch_bounds__(512, 1) lstm_fwd_kernel(const LstmFwdParams p) {
     extern __shared__ __align__(16) float sm[];
     float* Ws = sm;                    // [H-KR][512]
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(512, 1) lstm_fwd_kernel(const LstmFwdParams p)
     }
 }
 
-template <int R>
+template <int R, int KR>
 __global__ void __launch_bounds__(512, 1) lstm_bwd_kernel(const LstmBwdParams p) {
     extern __shared__ __align__(16) float sm[];
     float* Ws = sm;                     // [H-KR... as gate index][512 threads]
@@ -148,18 +148,23 @@ __global__ void __launch_bounds__(512, 1) lstm_bwd_kernel(const LstmBwdParams p)
             const float dh = dho + dh_rec;
             const float tc = tanhf(ct);
             const float dc = fmaf(dh * og, 1.f - tc * tc, dc_next);
-            const float dpi = dc * gg * ig * (1.f - ig);
-            const float dpf = dc * cprev * fg * (1.f - fg);
-            const float dpg = dc * ig * (1.f - gg * gg);
-            const float dpo = dh * tc * og * (1.f - og);
+            float dpi = dc * gg * ig * (1.f - ig);
+            float dpf = dc * cprev * fg * (1.f - fg);
+            float dpg = dc * ig * (1.f - gg * gg);
+            float dpo = dh * tc * og * (1.f - og);
             dc_next = dc * fg;
             dgs[cr * G4 + cj] = dpi;
             dgs[cr * G4 + H + cj] = dpf;
             dgs[cr * G4 + 2 * H + cj] = dpg;
             dgs[cr * G4 + 3 * H + cj] = dpo;
             if (cvalid) {
-                dGp[(size_t)t * G4] = dpi; dGp[(size_t)t * G4 + H] = dpf;
-                dGp[(size_t)t * G4 + 2 * H] = dpg; dGp[(size_t)t * G4 + 3 * H] = dpo;
+                if (p.round_tf32) {
+                    dGp[(size_t)t * G4] = tf32_rn(dpi); dGp[(size_t)t * G4 + H] = tf32_rn(dpf);
+                    dGp[(size_t)t * G4 + 2 * H] = tf32_rn(dpg); dGp[(size_t)t * G4 + 3 * H] = tf32_rn(dpo);
+                } else {
+                    dGp[(size_t)t * G4] = dpi; dGp[(size_t)t * G4 + H] = dpf;
+                    dGp[(size_t)t * G4 + 2 * H] = dpg; dGp[(size_t)t * G4 + 3 * H] = dpo;
+                }
             }
         }
         __syncthreads();
@@ -199,32 +204,59 @@ __global__ void __launch_bounds__(512, 1) lstm_bwd_kernel(const LstmBwdParams p)
     }
 }
 
-constexpr int LSTM_R = 4;
+// rows per CTA: as few as keeps the grid within one wave of SMs (more CTAs = shorter per-step critical path)
+template <int R, int KR>
+int launch_fwd(const LstmFwdParams& p, cudaStream_t st) {
+    const size_t smem = sizeof(float) * ((H - KR) * G4 + R * H + R * G4);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(lstm_fwd_kernel<R, KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    dim3 grid((p.rows + R - 1) / R, 2);
+    lstm_fwd_kernel<R, KR><<<grid, 512, smem, st>>>(p);
+    return sefd_check_launch("lstm_fwd");
+}
+template <int R, int KR>
+int launch_bwd(const LstmBwdParams& p, cudaStream_t st) {
+    const size_t smem = sizeof(float) * ((H - KR) * G4 + R * G4 + 4 * R * H);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(lstm_bwd_kernel<R, KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    dim3 grid((p.rows + R - 1) / R, 2);
+    lstm_bwd_kernel<R, KR><<<grid, 512, smem, st>>>(p);
+    return sefd_check_launch("lstm_bwd");
+}
+int pick_rows(int rows) {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    if (2 * rows <= sms) return 1;
+    if (rows <= sms) return 2;
+    return 4;
+}
 
 }  // namespace
 
 int sefd_lstm_fwd_launch(const LstmFwdParams& p, cudaStream_t st) {
-    const size_t smem = sizeof(float) * ((H - KR) * G4 + LSTM_R * H + LSTM_R * G4);
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(lstm_fwd_kernel<LSTM_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
-    }
-    dim3 grid((p.rows + LSTM_R - 1) / LSTM_R, 2);
+    const int R = pick_rows(p.rows);
+    sefd_prof_label("lstm_fwd rows%d T%d R%d", p.rows, p.T, R);
     SefdProfScope prof(SEFD_PROF_LSTM, 4.0 * p.rows * p.T * 512.0 * 128.0, 4.0 * 2 * p.rows * p.T * (2 * 512.0 + 256.0), st);
-    lstm_fwd_kernel<LSTM_R><<<grid, 512, smem, st>>>(p);
-    return sefd_check_launch("lstm_fwd");
+    if (R == 1) return launch_fwd<1, 88>(p, st);
+    if (R == 2) return launch_fwd<2, 80>(p, st);
+    return launch_fwd<4, 64>(p, st);
 }
 
 int sefd_lstm_bwd_launch(const LstmBwdParams& p, cudaStream_t st) {
-    const size_t smem = sizeof(float) * ((H - KR) * G4 + LSTM_R * G4 + 4 * LSTM_R * H);
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(lstm_bwd_kernel<LSTM_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
-    }
-    dim3 grid((p.rows + LSTM_R - 1) / LSTM_R, 2);
+    const int R = pick_rows(p.rows);
+    sefd_prof_label("lstm_bwd rows%d T%d R%d", p.rows, p.T, R);
     SefdProfScope prof(SEFD_PROF_LSTM, 4.0 * p.rows * p.T * 512.0 * 128.0, 4.0 * 2 * p.rows * p.T * (2 * 512.0 + 384.0), st);
-    lstm_bwd_kernel<LSTM_R><<<grid, 512, smem, st>>>(p);
-    return sefd_check_launch("lstm_bwd");
+    if (R == 1) return launch_bwd<1, 88>(p, st);
+    if (R == 2) return launch_bwd<2, 80>(p, st);
+    return launch_bwd<4, 64>(p, st);
 }

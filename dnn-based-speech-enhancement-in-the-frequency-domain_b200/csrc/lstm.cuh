@@ -17,6 +17,7 @@ struct LstmBwdParams {
     const float* dH;    // [2][rows][T][128]  gradient arriving at every h_t from above
     float* dG;          // [2][rows][T][512]  gradient w.r.t. the gate pre-activations
     int rows, T;
+    int round_tf32;     // dG feeds tensor-core GEMMs
 };
 int sefd_lstm_fwd_launch(const LstmFwdParams& p, cudaStream_t st);
 int sefd_lstm_bwd_launch(const LstmBwdParams& p, cudaStream_t st);

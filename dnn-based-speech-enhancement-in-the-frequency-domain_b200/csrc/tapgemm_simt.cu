@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(NT) tapgemm_simt_kernel(const TapGemmParams p)
                 const float4 o = *reinterpret_cast<const float4*>(dst);
                 v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
             }
+            if (p.round_out[d]) { v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w); }
             *reinterpret_cast<float4*>(dst) = v;
             s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
             s2[0] += v.x * v.x; s2[1] += v.y * v.y; s2[2] += v.z * v.z; s2[3] += v.w * v.w;

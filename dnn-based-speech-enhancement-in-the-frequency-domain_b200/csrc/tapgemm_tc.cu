@@ -30,7 +30,7 @@ constexpr int NTHREADS = 192;
 
 struct TcParams {
     TapDst o[2];
-    int accum[2];
+    int accum[2], round_out[2];
     const float* bias;
     long long bJ;
     double* stats;
@@ -224,6 +224,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                             const float4 old = *reinterpret_cast<const float4*>(dst);
                             o4.x += old.x; o4.y += old.y; o4.z += old.z; o4.w += old.w;
                         }
+                        if (p.round_out[d]) { o4.x = tf32_rn(o4.x); o4.y = tf32_rn(o4.y); o4.z = tf32_rn(o4.z); o4.w = tf32_rn(o4.w); }
                         *reinterpret_cast<float4*>(dst) = o4;
                     }
                 }
@@ -317,6 +318,7 @@ int sefd_tapgemm_tc(const TapGemmParams& g, cudaStream_t st) {
     TcParams p;
     memset(&p, 0, sizeof(p));
     p.o[0] = g.o[0]; p.o[1] = g.o[1]; p.accum[0] = g.accum[0]; p.accum[1] = g.accum[1];
+    p.round_out[0] = g.round_out[0]; p.round_out[1] = g.round_out[1];
     p.bias = g.bias; p.bJ = g.bJ; p.stats = g.stats;
     p.B = g.B; p.J = g.J; p.Tout = g.Tout; p.Fin = g.Fin;
     p.fi_mul = g.fi_mul; p.fo_mul = g.fo_mul; p.fo_off = g.fo_off;

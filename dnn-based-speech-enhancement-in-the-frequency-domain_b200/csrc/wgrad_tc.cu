@@ -277,7 +277,7 @@ int sefd_wgrad_tc(const WgradParams& w, float* partial, long long cap_floats, in
     long long splits = (2 * 148 + tiles - 1) / tiles;
     if (splits > rows) splits = rows;
     if (splits > cap_floats / one) splits = cap_floats / one;
-    if (splits > 32) splits = 32;
+    if (splits > 64) splits = 64;
     SEFD_REQUIRE(splits >= 1, "wgrad_tc: partial buffer too small");
     p.rows_per_split = (int)((rows + splits - 1) / splits);
     p.splits = (rows + p.rows_per_split - 1) / p.rows_per_split;
