@@ -77,8 +77,8 @@ def test_small_forward_backward_every_tensor(golden, sd0, mode, engine):
     spec = plan.tensor("spec")
     chk("spec", torch.cat([spec[..., 0], spec[..., 1]], 1), taps["spec"], 2e-6)
     for i in range(6):
-        chk(f"enc{i}.y", plan.tensor(f"enc{i}.y"), _cl(taps[f"enc{i}_conv"]), 2e-6)
-        chk(f"enc{i}.z", plan.tensor(f"enc{i}.z"), _cl(taps[f"enc{i}"]), 2e-6)
+        chk(f"enc{i}.y", plan.tensor(f"enc{i}.y"), _cl(taps[f"enc{i}_conv"]), 4e-6)
+        chk(f"enc{i}.z", plan.tensor(f"enc{i}.z"), _cl(taps[f"enc{i}"]), 4e-6)
     # LSTM: X1/X2 are [part][B][T][128]; oracle taps are [T,B,128] (layer 0) / [T,B,512] after projection
     X1 = plan.tensor("X1")
     chk("lstm0 real", X1[0], taps["lstm0_r"].permute(1, 0, 2), 5e-6)
