@@ -14,39 +14,43 @@ namespace {
 
 constexpr int WM = 128, PB = 32, CHB = PB * 32 * 4;   // 4 KB per [32 ch x 32 pos] box
 constexpr int STG_LD = 33, NTHREADS = 192;
+constexpr int MAX_OPS = 10, MAX_GROUPS = 5;
+constexpr int SMEM_BUDGET = 225 * 1024;
+
+// A tap group: per k-step the producer loads nA activation tiles and nG gradient tiles; op i multiplies
+// A slot op_a[i] with G slot op_g[i] into TMEM accumulator i (BN columns each) and ends up in slab op_slab[i].
+struct Group {
+    int nA, nG, nOps;
+    int a_roff[MAX_OPS], a_toff[MAX_OPS];    // A tile: row = j*a_mul + a_roff, time = t0 + a_toff
+    int g_roff[MAX_OPS];                     // G tile: row = j*g_mul + g_roff, time = t0
+    int op_a[MAX_OPS], op_g[MAX_OPS], op_slab[MAX_OPS];
+};
 
 struct WgParams {
     float* out;
     long long split_stride;
-    int B, J, Tg, Fa, Fg, a_mul, g_mul;
-    int ntaps;
-    int a_off[SEFD_MAX_TAPS], g_off[SEFD_MAX_TAPS], dt[SEFD_MAX_TAPS], wslab[SEFD_MAX_TAPS];
+    int B, J, a_mul, g_mul;
     int C0, C1, K, N;
+    int ngroups;
+    Group grp[MAX_GROUPS];
     int m_tiles, n_tiles, splits, rows_per_split, t_blocks;
+    int nstage, stage_bytes;
+    int a_sp;          // spacing of the A slots inside a stage, in 4 KB chunks (= min(4, K/32))
     long long units;
 };
 
-template <int BN>
-struct WCfg {
-    static constexpr int A_BYTES = 4 * CHB;
-    static constexpr int G_BYTES = (BN / 32) * CHB;
-    static constexpr int STAGE_BYTES = A_BYTES + G_BYTES;
-    static constexpr int NSTAGE = BN == 256 ? 3 : (BN == 128 ? 5 : 6);
-    static constexpr int SMEM = NSTAGE * STAGE_BYTES + 2 * WM * STG_LD * 4 + (2 * NSTAGE + 4) * 8 + 16 + 1024;
-};
-
 struct Unit {
-    int tap, m0, n0, r0, r1;
+    int g, m0, n0, r0, r1, split;
 };
 __device__ __forceinline__ Unit decode_unit(const WgParams& p, long long u, int BN) {
     Unit x;
-    const int split = (int)(u % p.splits);
+    x.split = (int)(u % p.splits);
     u /= p.splits;
     x.n0 = (int)(u % p.n_tiles) * BN;
     u /= p.n_tiles;
     x.m0 = (int)(u % p.m_tiles) * WM;
-    x.tap = (int)(u / p.m_tiles);
-    x.r0 = split * p.rows_per_split;
+    x.g = (int)(u / p.m_tiles);
+    x.r0 = x.split * p.rows_per_split;
     const int rows = p.B * p.J;
     x.r1 = x.r0 + p.rows_per_split < rows ? x.r0 + p.rows_per_split : rows;
     return x;
@@ -56,28 +60,26 @@ template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmG, const WgParams p) {
-    using C = WCfg<BN>;
+    constexpr int NG = BN / 32;                 // 32-channel chunks of one G tile
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* stages = smem;
-    float* stg = reinterpret_cast<float*>(smem + C::NSTAGE * C::STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stg + 2 * WM * STG_LD);
+    float* stg = reinterpret_cast<float*>(smem + p.nstage * p.stage_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stg + WM * STG_LD);
     uint64_t* full = bars;
-    uint64_t* empty = bars + C::NSTAGE;
-    uint64_t* tfull = bars + 2 * C::NSTAGE;
-    uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* empty = bars + 8;
+    uint64_t* tfull = bars + 16;
+    uint64_t* tempty = bars + 17;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < C::NSTAGE; ++s) {
+        for (int s = 0; s < p.nstage; ++s) {
             mbar_init(smem_u32(&full[s]), 1);
             mbar_init(smem_u32(&empty[s]), 1);
         }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(smem_u32(&tfull[a]), 1);
-            mbar_init(smem_u32(&tempty[a]), 4);
-        }
+        mbar_init(smem_u32(tfull), 1);
+        mbar_init(smem_u32(tempty), 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -91,120 +93,123 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
+        // ================= TMA producer =================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
                 const Unit x = decode_unit(p, u, BN);
-                const int nA = (p.K - x.m0) / 32 < 4 ? (p.K - x.m0) / 32 : 4;
-                const int dt = p.dt[x.tap];
+                const Group& G = p.grp[x.g];
+                const int nAc = (p.K - x.m0) / 32 < 4 ? (p.K - x.m0) / 32 : 4;   // 32-channel chunks of one A tile
+                const uint32_t bytes = (uint32_t)((G.nA * nAc + G.nG * NG) * CHB);
                 for (int r = x.r0; r < x.r1; ++r) {
                     const int b = r / p.J, j = r % p.J;
-                    const int fa = j * p.a_mul + p.a_off[x.tap], fg = j * p.g_mul + p.g_off[x.tap];
-                    if (fa < 0 || fa >= p.Fa || fg < 0 || fg >= p.Fg) continue;
                     for (int tb = 0; tb < p.t_blocks; ++tb) {
                         mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
                         const uint32_t fb = smem_u32(&full[stage]);
-                        const uint32_t sa = smem_u32(stages + stage * C::STAGE_BYTES);
-                        mbar_expect_tx(fb, (uint32_t)((nA + BN / 32) * CHB));
+                        const uint32_t sa = smem_u32(stages + stage * p.stage_bytes);
+                        mbar_expect_tx(fb, bytes);
                         const int t0 = tb * PB;
-                        for (int i = 0; i < nA; ++i) {
-                            const int kc = x.m0 + 32 * i;
-                            if (kc < p.C0) tma_load_4d(&tmA0, fb, sa + i * CHB, kc, t0 + dt, fa, b);
-                            else tma_load_4d(&tmA1, fb, sa + i * CHB, kc - p.C0, t0 + dt, fa, b);
+                        for (int a = 0; a < G.nA; ++a) {
+                            const int fa = j * p.a_mul + G.a_roff[a], ta = t0 + G.a_toff[a];
+                            for (int i = 0; i < nAc; ++i) {
+                                const int kc = x.m0 + 32 * i;
+                                const uint32_t dst = sa + (uint32_t)((a * p.a_sp + i) * CHB);
+                                if (kc < p.C0) tma_load_4d(&tmA0, fb, dst, kc, ta, fa, b);
+                                else tma_load_4d(&tmA1, fb, dst, kc - p.C0, ta, fa, b);
+                            }
                         }
+                        const uint32_t sg = sa + (uint32_t)(G.nA * p.a_sp * CHB);
+                        for (int g = 0; g < G.nG; ++g) {
+                            const int fg = j * p.g_mul + G.g_roff[g];
 #pragma unroll
-                        for (int i = 0; i < BN / 32; ++i)
-                            tma_load_4d(&tmG, fb, sa + C::A_BYTES + i * CHB, x.n0 + 32 * i, t0, fg, b);
-                        if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
+                            for (int i = 0; i < NG; ++i)
+                                tma_load_4d(&tmG, fb, sg + (uint32_t)((g * NG + i) * CHB), x.n0 + 32 * i, t0, fg, b);
+                        }
+                        if (++stage == p.nstage) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
+        // ================= MMA issuer =================
         if (lane == 0) {
             // D fp32, A/B tf32, both MN-major (bits 15, 16), N = BN, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(WM >> 4) << 24);
-            int stage = 0, abuf = 0;
+            int stage = 0;
             uint32_t phase = 0, aphase = 0;
             for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
                 const Unit x = decode_unit(p, u, BN);
-                mbar_wait(smem_u32(&tempty[abuf]), aphase ^ 1);
+                const Group& G = p.grp[x.g];
+                mbar_wait(smem_u32(tempty), aphase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(abuf * 256);
                 uint32_t acc = 0;
                 for (int r = x.r0; r < x.r1; ++r) {
-                    const int j = r % p.J;
-                    const int fa = j * p.a_mul + p.a_off[x.tap], fg = j * p.g_mul + p.g_off[x.tap];
-                    if (fa < 0 || fa >= p.Fa || fg < 0 || fg >= p.Fg) continue;
                     for (int tb = 0; tb < p.t_blocks; ++tb) {
                         mbar_wait(smem_u32(&full[stage]), phase);
                         tc_fence_after();
-                        const uint32_t sa = smem_u32(stages + stage * C::STAGE_BYTES);
+                        const uint32_t sa = smem_u32(stages + stage * p.stage_bytes);
+                        const uint32_t sg = sa + (uint32_t)(G.nA * p.a_sp * CHB);
+                        for (int o = 0; o < G.nOps; ++o) {
+                            const uint32_t abase = sa + (uint32_t)(G.op_a[o] * p.a_sp * CHB);
+                            const uint32_t gbase = sg + (uint32_t)(G.op_g[o] * NG * CHB);
 #pragma unroll
-                        for (int k8 = 0; k8 < PB / 8; ++k8) {
-                            // MN-major tf32: SWIZZLE_128B_BASE32B (layout type 1), LBO = stride between 32-channel
-                            // chunks, SBO = one 4-position swizzle atom (probed on hardware: tools/umma_probe.cu)
-                            const uint64_t ad = make_desc_full(sa + k8 * 1024, CHB, 512, 1);
-                            const uint64_t bd = make_desc_full(sa + C::A_BYTES + k8 * 1024, CHB, 512, 1);
-                            tc_mma_tf32(d_tmem, ad, bd, idesc, acc);
-                            acc = 1;
+                            for (int k8 = 0; k8 < PB / 8; ++k8) {
+                                // MN-major tf32: SWIZZLE_128B_BASE32B (layout type 1), LBO = stride between 32-channel
+                                // chunks, SBO = one 4-position swizzle atom (probed on hardware: tools/umma_probe.cu)
+                                tc_mma_tf32(tmem_base + (uint32_t)(o * BN), make_desc_full(abase + k8 * 1024, CHB, 512, 1),
+                                            make_desc_full(gbase + k8 * 1024, CHB, 512, 1), idesc, acc);
+                            }
                         }
+                        acc = 1;
                         tc_commit(smem_u32(&empty[stage]));
-                        if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
+                        if (++stage == p.nstage) { stage = 0; phase ^= 1; }
                     }
                 }
-                tc_commit(smem_u32(&tfull[abuf]));
-                if (++abuf == 2) { abuf = 0; aphase ^= 1; }
+                tc_commit(smem_u32(tfull));
+                aphase ^= 1;
             }
         }
     } else {
+        // ================= epilogue: TMEM -> padded smem -> coalesced rows of the partial buffer =================
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const int et = threadIdx.x - 64;
-        int abuf = 0, sb = 0;
         uint32_t aphase = 0;
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit x = decode_unit(p, u, BN);
-            int nk = 0;
-            for (int r = x.r0; r < x.r1; ++r) {
-                const int j = r % p.J;
-                const int fa = j * p.a_mul + p.a_off[x.tap], fg = j * p.g_mul + p.g_off[x.tap];
-                nk += (fa >= 0 && fa < p.Fa && fg >= 0 && fg < p.Fg);
-            }
-            const int split = (int)(u % p.splits);
-            float* obase = p.out + split * p.split_stride + (long long)p.wslab[x.tap] * p.K * p.N + x.n0;
-            mbar_wait(smem_u32(&tfull[abuf]), aphase);
+            const Group& G = p.grp[x.g];
+            mbar_wait(smem_u32(tfull), aphase);
             tc_fence_after();
+            for (int o = 0; o < G.nOps; ++o) {
+                float* obase = p.out + x.split * p.split_stride + (long long)G.op_slab[o] * p.K * p.N + x.n0;
 #pragma unroll 1
-            for (int ch = 0; ch < BN / 32; ++ch) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * 256 + ch * 32), v);
-                if (ch == BN / 32 - 1) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&tempty[abuf]));
-                }
-                float* srow = stg + (sb * WM + row) * STG_LD;
+                for (int ch = 0; ch < NG; ++ch) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(o * BN + ch * 32), v);
+                    asm volatile("bar.sync 1, 128;" ::: "memory");      // previous chunk's readers are done
+                    float* srow = stg + row * STG_LD;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) srow[i] = nk ? v[i] : 0.f;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const float* sbuf = stg + sb * WM * STG_LD;
+                    for (int i = 0; i < 32; ++i) srow[i] = v[i];
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
-                for (int pass = 0; pass < 8; ++pass) {
-                    const int idx = pass * 128 + et;
-                    const int r = idx >> 3, c4 = (idx & 7) * 4;
-                    const int k = x.m0 + r;
-                    if (k < p.K) {
-                        const float* sp = sbuf + r * STG_LD + c4;
-                        *reinterpret_cast<float4*>(obase + (long long)k * p.N + ch * 32 + c4) =
-                            make_float4(sp[0], sp[1], sp[2], sp[3]);
+                    for (int pass = 0; pass < 8; ++pass) {
+                        const int idx = pass * 128 + et;
+                        const int r = idx >> 3, c4 = (idx & 7) * 4;
+                        const int k = x.m0 + r;
+                        if (k < p.K) {
+                            const float* sp = stg + r * STG_LD + c4;
+                            *reinterpret_cast<float4*>(obase + (long long)k * p.N + ch * 32 + c4) =
+                                make_float4(sp[0], sp[1], sp[2], sp[3]);
+                        }
                     }
                 }
-                sb ^= 1;
             }
-            if (++abuf == 2) { abuf = 0; aphase ^= 1; }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(tempty));
+            aphase ^= 1;
         }
     }
 
@@ -225,11 +230,11 @@ int make_pos_map(CUtensorMap* m, const TapSrc& s, int F, int T, int B) {
 }
 
 template <int BN>
-int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& g, const WgParams& p, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, WCfg<BN>::SMEM);
-        attr = true;
+int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& g, const WgParams& p, int smem, cudaStream_t st) {
+    static int cur = 0;
+    if (smem > cur) {
+        cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cur = smem;
     }
     static int sms = 0;
     if (!sms) {
@@ -238,8 +243,47 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& g, c
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const int grid = (int)(p.units < sms ? p.units : sms);
-    wgrad_tc_kernel<BN><<<grid, NTHREADS, WCfg<BN>::SMEM, st>>>(a0, a1, g, p);
+    wgrad_tc_kernel<BN><<<grid, NTHREADS, smem, st>>>(a0, a1, g, p);
     return sefd_check_launch("wgrad_tc");
+}
+
+// Partition the taps into groups that share operand tiles.  Taps with the same A tile (a_off, dt) share an A slot,
+// taps with the same G row share a G slot.  A group is grown tap-by-tap (in kf order) while its accumulators fit
+// TMEM (nOps * BN <= 512 columns) and its stage fits the shared-memory budget.
+int build_groups(const WgradParams& w, int BN, int nAc, WgParams& p) {
+    const int NG = BN / 32;
+    const int max_ops = 512 / BN < MAX_OPS ? 512 / BN : MAX_OPS;
+    const int max_stage = 64 * 1024;
+    p.ngroups = 0;
+    Group cur;
+    memset(&cur, 0, sizeof(cur));
+    auto flush = [&]() {
+        if (cur.nOps) p.grp[p.ngroups++] = cur;
+        memset(&cur, 0, sizeof(cur));
+    };
+    for (int t = 0; t < w.ntaps; ++t) {
+        // find or add slots
+        Group trial = cur;
+        int ia = -1, ig = -1;
+        for (int a = 0; a < trial.nA; ++a)
+            if (trial.a_roff[a] == w.a_off[t] && trial.a_toff[a] == w.dt[t]) ia = a;
+        if (ia < 0) { ia = trial.nA; trial.a_roff[ia] = w.a_off[t]; trial.a_toff[ia] = w.dt[t]; ++trial.nA; }
+        for (int g = 0; g < trial.nG; ++g)
+            if (trial.g_roff[g] == w.g_off[t]) ig = g;
+        if (ig < 0) { ig = trial.nG; trial.g_roff[ig] = w.g_off[t]; ++trial.nG; }
+        trial.op_a[trial.nOps] = ia; trial.op_g[trial.nOps] = ig; trial.op_slab[trial.nOps] = w.wslab[t];
+        ++trial.nOps;
+        const int bytes = (trial.nA * nAc + trial.nG * NG) * CHB;   // A slots are spaced nAc chunks apart
+        if (cur.nOps && (trial.nOps > max_ops || bytes > max_stage)) {
+            flush();
+            --t;            // retry this tap in a fresh group
+            continue;
+        }
+        cur = trial;
+        if (p.ngroups >= MAX_GROUPS) return -1;
+    }
+    flush();
+    return p.ngroups <= MAX_GROUPS ? 0 : -1;
 }
 
 }  // namespace
@@ -262,17 +306,27 @@ int sefd_wgrad_tc(const WgradParams& w, float* partial, long long cap_floats, in
     const int BN = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32));
     WgParams p;
     memset(&p, 0, sizeof(p));
-    p.B = w.B; p.J = w.J; p.Tg = w.Tg; p.Fa = w.Fa; p.Fg = w.Fg; p.a_mul = w.a_mul; p.g_mul = w.g_mul;
-    p.ntaps = w.ntaps;
-    for (int i = 0; i < w.ntaps; ++i) {
-        p.a_off[i] = w.a_off[i]; p.g_off[i] = w.g_off[i]; p.dt[i] = w.dt[i]; p.wslab[i] = w.wslab[i];
-    }
+    p.B = w.B; p.J = w.J; p.a_mul = w.a_mul; p.g_mul = w.g_mul;
     p.C0 = w.a[0].C; p.C1 = w.a[1].C; p.K = K; p.N = N;
     p.m_tiles = (K + WM - 1) / WM;
     p.n_tiles = N / BN;
     p.t_blocks = (w.Tg + PB - 1) / PB;
+    p.a_sp = K / 32 < 4 ? K / 32 : 4;
+    SEFD_REQUIRE(build_groups(w, BN, p.a_sp, p) == 0, "wgrad_tc: tap grouping failed");
+    int stage = 0;
+    for (int g = 0; g < p.ngroups; ++g) {
+        const int b = (p.grp[g].nA * p.a_sp + p.grp[g].nG * (BN / 32)) * CHB + 3 * CHB;   // + slack: the MMA always reads 4 chunks
+        if (b > stage) stage = b;
+    }
+    p.stage_bytes = stage;
+    const int fixed = WM * STG_LD * 4 + 20 * 8 + 16 + 1024;
+    p.nstage = (SMEM_BUDGET - fixed) / stage;
+    if (p.nstage > 8) p.nstage = 8;
+    SEFD_REQUIRE(p.nstage >= 2, "wgrad_tc: stage of %d bytes leaves no room for a pipeline", stage);
+    const int smem = p.nstage * stage + fixed;
+
     const int rows = w.B * w.J;
-    const long long tiles = (long long)w.ntaps * p.m_tiles * p.n_tiles;
+    const long long tiles = (long long)p.ngroups * p.m_tiles * p.n_tiles;
     const long long one = (long long)nslabs * K * N;
     long long splits = (2 * 148 + tiles - 1) / tiles;
     if (splits > rows) splits = rows;
@@ -293,15 +347,16 @@ int sefd_wgrad_tc(const WgradParams& w, float* partial, long long cap_floats, in
     else a1 = a0;
     SEFD_TRY(make_pos_map(&g, w.g, w.Fg, w.Tg, w.B));
     const double pos = (double)w.B * w.J * w.Tg;
-    sefd_prof_label("wgrad_tc BN%d K%d N%d taps%d J%d splits%d units%lld", BN, K, N, w.ntaps, w.J, p.splits, p.units);
+    sefd_prof_label("wgrad_tc BN%d K%d N%d taps%d J%d groups%d stage%dK x%d splits%d units%lld", BN, K, N, w.ntaps, w.J,
+                    p.ngroups, stage / 1024, p.nstage, p.splits, p.units);
     SefdProfScope prof(SEFD_PROF_WGRAD, 2.0 * pos * K * N * w.ntaps,
                        4.0 * ((double)w.B * w.J * (w.a_mul > 1 ? w.a_mul : 1) * w.Ta * K +
                               (double)w.B * w.J * (w.g_mul > 1 ? w.g_mul : 1) * w.Tg * N), st);
     switch (BN) {
-        case 256: return launch<256>(a0, a1, g, p, st);
-        case 128: return launch<128>(a0, a1, g, p, st);
-        case 64: return launch<64>(a0, a1, g, p, st);
-        default: return launch<32>(a0, a1, g, p, st);
+        case 256: return launch<256>(a0, a1, g, p, smem, st);
+        case 128: return launch<128>(a0, a1, g, p, smem, st);
+        case 64: return launch<64>(a0, a1, g, p, smem, st);
+        default: return launch<32>(a0, a1, g, p, smem, st);
     }
 }
 
