@@ -24,7 +24,6 @@ namespace {
 
 constexpr int TM = 128;                 // tile rows = consecutive time positions of one (b, f) row
 constexpr int KB = 32;                  // fp32 channels per k-block = 128 B = swizzle span
-constexpr int A_BYTES = TM * KB * 4;    // 16 KB
 constexpr int STG_LD = 33;
 constexpr int NTHREADS = 192;
 
@@ -36,18 +35,27 @@ struct TcParams {
     double* stats;
     int B, J, Tout, Fin;
     int fi_mul, fo_mul, fo_off;
-    int ntaps;
-    int df[SEFD_MAX_TAPS], dt[SEFD_MAX_TAPS], wslab[SEFD_MAX_TAPS];
+    // work items: one activation tile per item, shared by up to two taps whose time shifts differ by one frame
+    int nitems;
+    int it_df[SEFD_MAX_TAPS], it_dt0[SEFD_MAX_TAPS], it_n[SEFD_MAX_TAPS];
+    int it_slab[SEFD_MAX_TAPS][2], it_roff[SEFD_MAX_TAPS][2];
     int C0, C1, N, wJ_slabs;
     int t_tiles, n_tiles;
     long long total_tiles;
 };
 
+// PAIR: the activation tile holds 136 rows (one extra swizzle atom) so that two taps that differ by one frame read
+// it at row offsets 0 and 1 (the MMA descriptor start address moves by 128 B; swizzling is on absolute address bits -
+// verified on hardware with tools/umma_probe.cu), and the stage carries both taps' weight tiles.
 template <int BN>
 struct Cfg {
+    static constexpr bool PAIR = BN <= 128;
+    static constexpr int A_ROWS = PAIR ? 136 : TM;
+    static constexpr int A_TILE = A_ROWS * KB * 4;
     static constexpr int B_BYTES = BN * KB * 4;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int NSTAGE = BN == 256 ? 3 : (BN == 128 ? 5 : 6);
+    static constexpr int NW = PAIR ? 2 : 1;
+    static constexpr int STAGE_BYTES = A_TILE + NW * B_BYTES;
+    static constexpr int NSTAGE = BN == 256 ? 3 : (BN == 128 ? 3 : (BN == 64 ? 5 : 6));
     static constexpr int STG_BYTES = 2 * TM * STG_LD * 4;
     static constexpr int STAT_BYTES = 2 * BN * 4;
     static constexpr int BAR_BYTES = (2 * NSTAGE + 4) * 8 + 16;
@@ -118,20 +126,21 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             uint32_t phase = 0;
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const TileCoord tc = decode(p, tile, BN);
-                for (int tap = 0; tap < p.ntaps; ++tap) {
-                    const int fi = tc.j * p.fi_mul + p.df[tap];
+                for (int it = 0; it < p.nitems; ++it) {
+                    const int fi = tc.j * p.fi_mul + p.it_df[it];
                     if (fi < 0 || fi >= p.Fin) continue;
-                    const int slab = tc.j * p.wJ_slabs + p.wslab[tap];
-                    const int tin = tc.t0 + p.dt[tap];
+                    const int n = p.it_n[it];
+                    const int tin = tc.t0 + p.it_dt0[it];
                     for (int kb = 0; kb < kblocks; ++kb) {
                         mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
                         const uint32_t fb = smem_u32(&full[stage]);
                         const uint32_t sa = smem_u32(stages + stage * C::STAGE_BYTES);
-                        mbar_expect_tx(fb, C::STAGE_BYTES);
+                        mbar_expect_tx(fb, (uint32_t)(C::A_TILE + n * C::B_BYTES));
                         const int k = kb * KB;
                         if (k < p.C0) tma_load_4d(&tmA0, fb, sa, k, tin, fi, tc.b);
                         else tma_load_4d(&tmA1, fb, sa, k - p.C0, tin, fi, tc.b);
-                        tma_load_3d(&tmW, fb, sa + A_BYTES, k, tc.n0, slab);
+                        for (int w = 0; w < n; ++w)
+                            tma_load_3d(&tmW, fb, sa + C::A_TILE + w * C::B_BYTES, k, tc.n0, tc.j * p.wJ_slabs + p.it_slab[it][w]);
                         if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -150,18 +159,22 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(abuf * 256);
                 uint32_t acc = 0;
-                for (int tap = 0; tap < p.ntaps; ++tap) {
-                    const int fi = tc.j * p.fi_mul + p.df[tap];
+                for (int it = 0; it < p.nitems; ++it) {
+                    const int fi = tc.j * p.fi_mul + p.it_df[it];
                     if (fi < 0 || fi >= p.Fin) continue;
+                    const int n = p.it_n[it];
                     for (int kb = 0; kb < kblocks; ++kb) {
                         mbar_wait(smem_u32(&full[stage]), phase);
                         tc_fence_after();
                         const uint32_t sa = smem_u32(stages + stage * C::STAGE_BYTES);
-                        const uint64_t ad = make_desc(sa), bd = make_desc(sa + A_BYTES);
+                        for (int w = 0; w < n; ++w) {
+                            const uint64_t ad = make_desc(sa + (uint32_t)(p.it_roff[it][w] * 128));
+                            const uint64_t bd = make_desc(sa + C::A_TILE + w * C::B_BYTES);
 #pragma unroll
-                        for (int k8 = 0; k8 < KB / 8; ++k8) {
-                            tc_mma_tf32(d_tmem, ad + 2 * k8, bd + 2 * k8, idesc, acc);   // +32 B per K=8 step
-                            acc = 1;
+                            for (int k8 = 0; k8 < KB / 8; ++k8) {
+                                tc_mma_tf32(d_tmem, ad + 2 * k8, bd + 2 * k8, idesc, acc);   // +32 B per K=8 step
+                                acc = 1;
+                            }
                         }
                         tc_commit(smem_u32(&empty[stage]));
                         if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
@@ -182,8 +195,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const TileCoord tc = decode(p, tile, BN);
             int nk = 0;
-            for (int tap = 0; tap < p.ntaps; ++tap) {
-                const int fi = tc.j * p.fi_mul + p.df[tap];
+            for (int it = 0; it < p.nitems; ++it) {
+                const int fi = tc.j * p.fi_mul + p.it_df[it];
                 nk += (fi >= 0 && fi < p.Fin);
             }
             mbar_wait(smem_u32(&tfull[abuf]), aphase);
@@ -265,11 +278,11 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-int make_act_map(CUtensorMap* m, const TapSrc& s, int F, int T, int B) {
+int make_act_map(CUtensorMap* m, const TapSrc& s, int F, int T, int B, int rows) {
     cuuint64_t dims[4] = {(cuuint64_t)s.C, (cuuint64_t)T, (cuuint64_t)F, (cuuint64_t)B};
     cuuint64_t str[3] = {(cuuint64_t)s.sT * 4, (cuuint64_t)(s.sF ? s.sF : s.sT * T) * 4,
                          (cuuint64_t)(s.sB ? s.sB : s.sT * T * F) * 4};
-    cuuint32_t box[4] = {KB, TM, 1, 1};
+    cuuint32_t box[4] = {KB, (cuuint32_t)rows, 1, 1};
     return make_map(m, s.p, 4, dims, str, box);
 }
 
@@ -322,16 +335,43 @@ int sefd_tapgemm_tc(const TapGemmParams& g, cudaStream_t st) {
     p.bias = g.bias; p.bJ = g.bJ; p.stats = g.stats;
     p.B = g.B; p.J = g.J; p.Tout = g.Tout; p.Fin = g.Fin;
     p.fi_mul = g.fi_mul; p.fo_mul = g.fo_mul; p.fo_off = g.fo_off;
-    p.ntaps = g.ntaps;
-    for (int i = 0; i < g.ntaps; ++i) { p.df[i] = g.df[i]; p.dt[i] = g.dt[i]; p.wslab[i] = g.wslab[i]; }
+    // pair up taps on the same source row whose time shifts differ by one frame (BN <= 128 only)
+    const bool pair = BN <= 128;
+    bool used[SEFD_MAX_TAPS] = {false};
+    p.nitems = 0;
+    for (int i = 0; i < g.ntaps; ++i) {
+        if (used[i]) continue;
+        int it = p.nitems++;
+        p.it_df[it] = g.df[i]; p.it_dt0[it] = g.dt[i]; p.it_n[it] = 1;
+        p.it_slab[it][0] = g.wslab[i]; p.it_roff[it][0] = 0;
+        used[i] = true;
+        if (!pair) continue;
+        for (int j2 = i + 1; j2 < g.ntaps; ++j2) {
+            if (used[j2] || g.df[j2] != g.df[i]) continue;
+            const int d = g.dt[j2] - g.dt[i];
+            if (d == 1 || d == -1) {
+                used[j2] = true;
+                p.it_n[it] = 2;
+                if (d == 1) {
+                    p.it_slab[it][1] = g.wslab[j2]; p.it_roff[it][1] = 1;
+                } else {            // the partner starts one frame earlier: it becomes row offset 0
+                    p.it_dt0[it] = g.dt[j2];
+                    p.it_slab[it][1] = g.wslab[i]; p.it_roff[it][1] = 1;
+                    p.it_slab[it][0] = g.wslab[j2]; p.it_roff[it][0] = 0;
+                }
+                break;
+            }
+        }
+    }
     p.C0 = g.a[0].C; p.C1 = g.a[1].C; p.N = N; p.wJ_slabs = g.wJ_slabs;
     p.t_tiles = (g.Tout + TM - 1) / TM;
     p.n_tiles = N / BN;
     p.total_tiles = (long long)g.B * g.J * p.t_tiles * p.n_tiles;
 
     CUtensorMap a0, a1, w;
-    SEFD_TRY(make_act_map(&a0, g.a[0], g.Fin, g.Tin, g.B));
-    if (g.a[1].C) SEFD_TRY(make_act_map(&a1, g.a[1], g.Fin, g.Tin, g.B));
+    const int arows = pair ? 136 : TM;
+    SEFD_TRY(make_act_map(&a0, g.a[0], g.Fin, g.Tin, g.B, arows));
+    if (g.a[1].C) SEFD_TRY(make_act_map(&a1, g.a[1], g.Fin, g.Tin, g.B, arows));
     else a1 = a0;
     {
         cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)g.nslabs};
@@ -340,7 +380,7 @@ int sefd_tapgemm_tc(const TapGemmParams& g, cudaStream_t st) {
         SEFD_TRY(make_map(&w, g.Wnk, 3, dims, str, box));
     }
     const double pos = (double)g.B * g.J * g.Tout;
-    sefd_prof_label("tapgemm_tc BN%d K%d N%d taps%d J%d Tout%d tiles%lld", BN, K, N, g.ntaps, g.J, g.Tout, p.total_tiles);
+    sefd_prof_label("tapgemm_tc BN%d K%d N%d taps%d items%d J%d Tout%d tiles%lld", BN, K, N, g.ntaps, p.nitems, g.J, g.Tout, p.total_tiles);
     SefdProfScope prof(SEFD_PROF_TAPGEMM, 2.0 * pos * N * K * g.ntaps,
                        4.0 * ((double)g.B * g.J * (g.fi_mul > 1 ? g.fi_mul : 1) * g.Tin * K + pos * N), st);
     switch (BN) {

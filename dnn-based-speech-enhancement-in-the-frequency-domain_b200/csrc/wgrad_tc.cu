@@ -93,41 +93,41 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
-                const Unit x = decode_unit(p, u, BN);
-                const Group& G = p.grp[x.g];
-                const int nAc = (p.K - x.m0) / 32 < 4 ? (p.K - x.m0) / 32 : 4;   // 32-channel chunks of one A tile
-                const uint32_t bytes = (uint32_t)((G.nA * nAc + G.nG * NG) * CHB);
-                for (int r = x.r0; r < x.r1; ++r) {
-                    const int b = r / p.J, j = r % p.J;
-                    for (int tb = 0; tb < p.t_blocks; ++tb) {
-                        mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
-                        const uint32_t fb = smem_u32(&full[stage]);
-                        const uint32_t sa = smem_u32(stages + stage * p.stage_bytes);
-                        mbar_expect_tx(fb, bytes);
-                        const int t0 = tb * PB;
-                        for (int a = 0; a < G.nA; ++a) {
+        // ================= TMA producer: the whole warp issues, one box per lane =================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
+            const Unit x = decode_unit(p, u, BN);
+            const Group& G = p.grp[x.g];
+            const int nAc = (p.K - x.m0) / 32 < 4 ? (p.K - x.m0) / 32 : 4;   // 32-channel chunks of one A tile
+            const int nAb = G.nA * nAc, nGb = G.nG * NG;                     // boxes per k-step
+            const uint32_t bytes = (uint32_t)((nAb + nGb) * CHB);
+            for (int r = x.r0; r < x.r1; ++r) {
+                const int b = r / p.J, j = r % p.J;
+                for (int tb = 0; tb < p.t_blocks; ++tb) {
+                    mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+                    const uint32_t fb = smem_u32(&full[stage]);
+                    const uint32_t sa = smem_u32(stages + stage * p.stage_bytes);
+                    if (lane == 0) mbar_expect_tx(fb, bytes);
+                    __syncwarp();
+                    const int t0 = tb * PB;
+                    for (int op = lane; op < nAb + nGb; op += 32) {
+                        if (op < nAb) {
+                            const int a = op / nAc, i = op % nAc;
                             const int fa = j * p.a_mul + G.a_roff[a], ta = t0 + G.a_toff[a];
-                            for (int i = 0; i < nAc; ++i) {
-                                const int kc = x.m0 + 32 * i;
-                                const uint32_t dst = sa + (uint32_t)((a * p.a_sp + i) * CHB);
-                                if (kc < p.C0) tma_load_4d(&tmA0, fb, dst, kc, ta, fa, b);
-                                else tma_load_4d(&tmA1, fb, dst, kc - p.C0, ta, fa, b);
-                            }
-                        }
-                        const uint32_t sg = sa + (uint32_t)(G.nA * p.a_sp * CHB);
-                        for (int g = 0; g < G.nG; ++g) {
+                            const int kc = x.m0 + 32 * i;
+                            const uint32_t dst = sa + (uint32_t)((a * p.a_sp + i) * CHB);
+                            if (kc < p.C0) tma_load_4d(&tmA0, fb, dst, kc, ta, fa, b);
+                            else tma_load_4d(&tmA1, fb, dst, kc - p.C0, ta, fa, b);
+                        } else {
+                            const int og = op - nAb;
+                            const int g = og / NG, i = og % NG;
                             const int fg = j * p.g_mul + G.g_roff[g];
-#pragma unroll
-                            for (int i = 0; i < NG; ++i)
-                                tma_load_4d(&tmG, fb, sg + (uint32_t)((g * NG + i) * CHB), x.n0 + 32 * i, t0, fg, b);
+                            const uint32_t sg = sa + (uint32_t)(G.nA * p.a_sp * CHB);
+                            tma_load_4d(&tmG, fb, sg + (uint32_t)((g * NG + i) * CHB), x.n0 + 32 * i, t0, fg, b);
                         }
-                        if (++stage == p.nstage) { stage = 0; phase ^= 1; }
                     }
+                    if (++stage == p.nstage) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -159,7 +159,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                                 // MN-major tf32: SWIZZLE_128B_BASE32B (layout type 1), LBO = stride between 32-channel
                                 // chunks, SBO = one 4-position swizzle atom (probed on hardware: tools/umma_probe.cu)
                                 tc_mma_tf32(tmem_base + (uint32_t)(o * BN), make_desc_full(abase + k8 * 1024, CHB, 512, 1),
-                                            make_desc_full(gbase + k8 * 1024, CHB, 512, 1), idesc, acc);
+                                            make_desc_full(gbase + k8 * 1024, CHB, 512, 1), idesc, acc | (uint32_t)(k8 > 0));
                             }
                         }
                         acc = 1;

@@ -47,7 +47,12 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUte
     const uint32_t tmem = tmem_ptr;
     if (threadIdx.x == 0) {
         const uint32_t fb = smem_u32(&bar_full);
-        if (!v.mn_major) {
+        if (v.mn_major == 2) {
+            // K-major A tile of 136 rows (one extra swizzle atom); the MMA starts v.lbo rows into it
+            mbar_expect_tx(fb, 136 * 128 + 64 * 128);
+            tma_load_4d(&tmA, fb, sa, 0, 0, 0, 0);
+            tma_load_4d(&tmB, fb, sb, 0, 0, 0, 0);
+        } else if (!v.mn_major) {
             // K-major: A global [M=128 rows][K=32] -> one box {32 k, 128 rows}; B [N=64][K=32] -> {32, 64}
             mbar_expect_tx(fb, 128 * 128 + 64 * 128);
             tma_load_4d(&tmA, fb, sa, 0, 0, 0, 0);
@@ -60,11 +65,16 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUte
         }
         mbar_wait(fb, 0);
         tc_fence_after();
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (v.a_major_bit << 15) | (v.b_major_bit << 16) |
+        const uint32_t amaj = v.mn_major == 2 ? 0u : v.a_major_bit, bmaj = v.mn_major == 2 ? 0u : v.b_major_bit;
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (amaj << 15) | (bmaj << 16) |
                                ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         for (int k8 = 0; k8 < 4; ++k8) {
-            const uint64_t ad = make_desc_full(sa + k8 * v.kadv, v.lbo, v.sbo, v.layout);
-            const uint64_t bd = make_desc_full(sb + k8 * v.kadv, v.lbo, v.sbo, v.layout);
+            uint64_t ad = make_desc_full(sa + k8 * v.kadv, v.lbo, v.sbo, v.layout);
+            uint64_t bd = make_desc_full(sb + k8 * v.kadv, v.lbo, v.sbo, v.layout);
+            if (v.mn_major == 2) {
+                ad = make_desc_full(sa + v.lbo * 128 + k8 * 32, 16, 1024, 2) | ((uint64_t)(v.a_major_bit & 7) << 49);   // base_offset
+                bd = make_desc_full(sb + k8 * 32, 16, 1024, 2);
+            }
             tc_mma_tf32(tmem, ad, bd, idesc, k8 ? 1u : 0u);
         }
         tc_commit(smem_u32(&bar_done));
@@ -109,6 +119,11 @@ int main() {
     cudaMalloc(&dout, M * N * 4);
     cudaMemcpy(dAk, Akm.data(), M * K * 4, cudaMemcpyHostToDevice); cudaMemcpy(dBk, Bkm.data(), N * K * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(dAm, Amn.data(), M * K * 4, cudaMemcpyHostToDevice); cudaMemcpy(dBm, Bmn.data(), N * K * 4, cudaMemcpyHostToDevice);
+    std::vector<float> A2(136 * K);
+    for (auto& x : A2) x = (float)((rand() % 17) - 8) / 8.0f;
+    float* dA2; cudaMalloc(&dA2, 136 * K * 4); cudaMemcpy(dA2, A2.data(), 136 * K * 4, cudaMemcpyHostToDevice);
+    CUtensorMap mA2;
+    if (make4(&mA2, dA2, K, 136, 32, 136)) return 1;
     CUtensorMap mAk, mBk, mAm, mBm, mAm32, mBm32;
     if (make4(&mAk, dAk, K, M, 32, 128) || make4(&mBk, dBk, K, N, 32, 64) || make4(&mAm, dAm, M, K, 32, 32) || make4(&mBm, dBm, N, K, 32, 32)) return 1;
     if (make4(&mAm32, dAm, M, K, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) || make4(&mBm32, dBm, N, K, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
@@ -122,17 +137,31 @@ int main() {
         {1, 1024, 4096, 1024, 1, 1, 1},
         {1, 4096, 4096, 1024, 1, 1, 1},
         {1, 512, 512, 1024, 1, 1, 1},
+        {2, 0, 1024, 32, 0, 0, 2},          // K-major, 136-row tile, start at row 0 (sanity)
+        {2, 1, 1024, 32, 0, 0, 2},          // start at row 1, base_offset 0
+        {2, 1, 1024, 32, 1, 0, 2},          // start at row 1, base_offset 1
+        {2, 3, 1024, 32, 3, 0, 2},          // start at row 3, base_offset 3
+        {2, 3, 1024, 32, 0, 0, 2},          // start at row 3, base_offset 0
     };
     std::vector<float> got(M * N);
     for (size_t i = 0; i < sizeof(vs) / sizeof(vs[0]); ++i) {
         cudaMemset(dout, 0xff, M * N * 4);
         const Variant& v = vs[i];
-        probe_kernel<<<1, 128, 64 * 1024>>>(v.mn_major ? (v.layout == 1 ? mAm32 : mAm) : mAk, v.mn_major ? (v.layout == 1 ? mBm32 : mBm) : mBk, v, dout);
+        if (v.mn_major == 2) probe_kernel<<<1, 128, 64 * 1024>>>(mA2, mBk, v, dout);
+        else probe_kernel<<<1, 128, 64 * 1024>>>(v.mn_major ? (v.layout == 1 ? mAm32 : mAm) : mAk, v.mn_major ? (v.layout == 1 ? mBm32 : mBm) : mBk, v, dout);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("variant %zu: CUDA error %s\n", i, cudaGetErrorString(e)); return 2; }
         cudaMemcpy(got.data(), dout, M * N * 4, cudaMemcpyDeviceToHost);
         double worst = 0, nz = 0; int bad = 0;
-        for (int j = 0; j < M * N; ++j) { double d = fabs((double)got[j] - D[j]); if (!(d < 1e-3)) ++bad; if (d > worst) worst = d; nz += got[j] != 0; }
+        std::vector<float> Dr(D);
+        if (v.mn_major == 2)
+            for (int m = 0; m < M; ++m)
+                for (int n = 0; n < N; ++n) {
+                    double sacc = 0;
+                    for (int k = 0; k < K; ++k) sacc += (double)A2[(m + v.lbo) * K + k] * B[n * K + k];
+                    Dr[m * N + n] = (float)sacc;
+                }
+        for (int j = 0; j < M * N; ++j) { double d = fabs((double)got[j] - Dr[j]); if (!(d < 1e-3)) ++bad; if (d > worst) worst = d; nz += got[j] != 0; }
         printf("variant %zu mn=%d layout=%u lbo=%u sbo=%u kadv=%u amaj=%u bmaj=%u : bad %d / %d, max err %.3g, nonzero %.0f, D[0..3]= %g %g %g %g (ref %g %g %g %g)\n",
                i, v.mn_major, v.layout, v.lbo, v.sbo, v.kadv, v.a_major_bit, v.b_major_bit, bad, M * N, worst, nz, got[0], got[1], got[2], got[3],
                D[0], D[1], D[2], D[3]);
