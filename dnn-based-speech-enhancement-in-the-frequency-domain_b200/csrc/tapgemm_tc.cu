@@ -3,20 +3,24 @@
 // as TF32, fp32 accumulation in TMEM).
 //
 // Persistent, warp-specialised CTA (192 threads, one per SM):
-//   warp 0      : TMA producer  - per (tap, 32-channel block): one 4-D box [32 ch x 128 t] of the channels-last
-//                 activation (shifted by the tap, zero-filled outside the tensor = conv padding) and one 3-D box
-//                 [32 k x BN n] of the packed weights, 128B-swizzled, completing on a full[] mbarrier
-//   warp 1      : MMA issuer    - 4 x tcgen05.mma (K = 8) per stage into a 128 x BN fp32 accumulator in TMEM,
-//                 tcgen05.commit releases the stage (empty[]) and finally publishes the accumulator (tmem_full[])
+//   warp 0      : TMA producer  - per (work item, group of k-blocks) ONE 5-D box of the channels-last activation
+//                 ([32 ch x 128|136 t x kbs channel blocks], shifted by the tap, zero-filled outside the tensor =
+//                 conv padding) and ONE 4-D box of the packed weights ([32 k x BN n x kbs x 1|2 taps]), all
+//                 128B-swizzled, completing on a full[] mbarrier.  A work item is one source row with one or two
+//                 taps: two taps that differ by one frame share the activation tile (136 rows; the second tap's
+//                 MMA descriptor starts 128 B = one row further).
+//   warp 1      : MMA issuer    - 4 x tcgen05.mma (K = 8) per (tap, k-block) into a 128 x BN fp32 accumulator in
+//                 TMEM; tcgen05.commit releases the stage (empty[]) and publishes the accumulator (tfull[])
 //   warps 2..5  : epilogue      - tcgen05.ld 32 columns at a time, + bias, stage through padded shared memory,
-//                 coalesced 128-byte row stores (optionally += for gradient accumulation) and per-channel
-//                 sum / sum-of-squares for the following BatchNorm; two accumulators (TMEM double buffer) let
-//                 the epilogue of tile i overlap the main loop of tile i+1.
+//                 coalesced 128-byte row stores (optionally += / tf32-rounded) and per-channel sum / sum-of-squares
+//                 for the following BatchNorm; two accumulators (TMEM double buffer) let the epilogue of tile i
+//                 overlap the main loop of tile i+1.
+// (ncu, round 1: with one TMA instruction per 16-24 KB the single producer thread was ~64 % busy issuing and the
+//  small-tile layers sat at a 0.3 ms floor; hence the multi-block boxes.)
 #include <cuda.h>
-
-#include "common.cuh"
 #include <string.h>
 
+#include "common.cuh"
 #include "prof.cuh"
 #include "tc_common.cuh"
 
@@ -26,6 +30,8 @@ constexpr int TM = 128;                 // tile rows = consecutive time position
 constexpr int KB = 32;                  // fp32 channels per k-block = 128 B = swizzle span
 constexpr int STG_LD = 33;
 constexpr int NTHREADS = 192;
+constexpr int MAX_STAGES = 8;
+constexpr int SMEM_BUDGET = 225 * 1024;
 
 struct TcParams {
     TapDst o[2];
@@ -38,28 +44,21 @@ struct TcParams {
     // work items: one activation tile per item, shared by up to two taps whose time shifts differ by one frame
     int nitems;
     int it_df[SEFD_MAX_TAPS], it_dt0[SEFD_MAX_TAPS], it_n[SEFD_MAX_TAPS];
-    int it_slab[SEFD_MAX_TAPS][2], it_roff[SEFD_MAX_TAPS][2];
+    int it_slab_lo[SEFD_MAX_TAPS];                       // first weight slab of the item's box
+    int it_wt[SEFD_MAX_TAPS][2], it_roff[SEFD_MAX_TAPS][2];   // per tap: weight sub-tile (0/1) and activation row offset
     int C0, C1, N, wJ_slabs;
     int t_tiles, n_tiles;
     long long total_tiles;
+    int kbs, nstage, stage_bytes, a_bytes;               // k-blocks per stage, pipeline depth, bytes
 };
 
-// PAIR: the activation tile holds 136 rows (one extra swizzle atom) so that two taps that differ by one frame read
-// it at row offsets 0 and 1 (the MMA descriptor start address moves by 128 B; swizzling is on absolute address bits -
-// verified on hardware with tools/umma_probe.cu), and the stage carries both taps' weight tiles.
 template <int BN>
 struct Cfg {
     static constexpr bool PAIR = BN <= 128;
     static constexpr int A_ROWS = PAIR ? 136 : TM;
     static constexpr int A_TILE = A_ROWS * KB * 4;
     static constexpr int B_BYTES = BN * KB * 4;
-    static constexpr int NW = PAIR ? 2 : 1;
-    static constexpr int STAGE_BYTES = A_TILE + NW * B_BYTES;
-    static constexpr int NSTAGE = BN == 256 ? 3 : (BN == 128 ? 3 : (BN == 64 ? 5 : 6));
-    static constexpr int STG_BYTES = 2 * TM * STG_LD * 4;
-    static constexpr int STAT_BYTES = 2 * BN * 4;
-    static constexpr int BAR_BYTES = (2 * NSTAGE + 4) * 8 + 16;
-    static constexpr int SMEM = NSTAGE * STAGE_BYTES + STG_BYTES + STAT_BYTES + BAR_BYTES + 1024;   // + align slack
+    static constexpr int FIXED = TM * STG_LD * 4 + 2 * BN * 4 + (2 * MAX_STAGES + 4) * 8 + 64;
 };
 
 struct TileCoord {
@@ -79,26 +78,26 @@ __device__ __forceinline__ TileCoord decode(const TcParams& p, long long tile, i
 template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                  const __grid_constant__ CUtensorMap tmW, const TcParams p) {
+                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const TcParams p) {
     using C = Cfg<BN>;
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* stages = smem;
-    float* stg = reinterpret_cast<float*>(smem + C::NSTAGE * C::STAGE_BYTES);
-    float* s_stat = stg + 2 * TM * STG_LD;
+    // declared alignment keeps every derived pointer in the shared address space (LDS/STS/ATOMS, not generic)
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float* stg = reinterpret_cast<float*>(smem + p.nstage * p.stage_bytes);
+    float* s_stat = stg + TM * STG_LD;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + 2 * BN);
     uint64_t* full = bars;
-    uint64_t* empty = bars + C::NSTAGE;
-    uint64_t* tfull = bars + 2 * C::NSTAGE;
+    uint64_t* empty = bars + MAX_STAGES;
+    uint64_t* tfull = bars + 2 * MAX_STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int K = p.C0 + p.C1;
-    const int kblocks = K / KB;
+    const int kgroups = (p.C0 + p.C1) / KB / p.kbs;
+    const int kg0 = p.C0 / KB / p.kbs;          // k-groups that come from source 0
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < C::NSTAGE; ++s) {
+        if (smem_u32(smem) & 1023u) __trap();   // the swizzled tiles need 1024-byte aligned bases
+        for (int s = 0; s < p.nstage; ++s) {
             mbar_init(smem_u32(&full[s]), 1);
             mbar_init(smem_u32(&empty[s]), 1);
         }
@@ -118,6 +117,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t smem_base = smem_u32(smem);
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -131,17 +131,18 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                     if (fi < 0 || fi >= p.Fin) continue;
                     const int n = p.it_n[it];
                     const int tin = tc.t0 + p.it_dt0[it];
-                    for (int kb = 0; kb < kblocks; ++kb) {
+                    const int slab = tc.j * p.wJ_slabs + p.it_slab_lo[it];
+                    const uint32_t bytes = (uint32_t)(p.a_bytes + n * p.kbs * C::B_BYTES);
+                    for (int kg = 0; kg < kgroups; ++kg) {
                         mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
                         const uint32_t fb = smem_u32(&full[stage]);
-                        const uint32_t sa = smem_u32(stages + stage * C::STAGE_BYTES);
-                        mbar_expect_tx(fb, (uint32_t)(C::A_TILE + n * C::B_BYTES));
-                        const int k = kb * KB;
-                        if (k < p.C0) tma_load_4d(&tmA0, fb, sa, k, tin, fi, tc.b);
-                        else tma_load_4d(&tmA1, fb, sa, k - p.C0, tin, fi, tc.b);
-                        for (int w = 0; w < n; ++w)
-                            tma_load_3d(&tmW, fb, sa + C::A_TILE + w * C::B_BYTES, k, tc.n0, tc.j * p.wJ_slabs + p.it_slab[it][w]);
-                        if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
+                        const uint32_t sa = smem_base + (uint32_t)(stage * p.stage_bytes);
+                        mbar_expect_tx(fb, bytes);
+                        if (kg < kg0) tma_load_5d(&tmA0, fb, sa, 0, tin, kg * p.kbs, fi, tc.b);
+                        else tma_load_5d(&tmA1, fb, sa, 0, tin, (kg - kg0) * p.kbs, fi, tc.b);
+                        if (n == 2) tma_load_4d(&tmW2, fb, sa + p.a_bytes, 0, tc.n0, kg * p.kbs, slab);
+                        else tma_load_4d(&tmW1, fb, sa + p.a_bytes, 0, tc.n0, kg * p.kbs, slab);
+                        if (++stage == p.nstage) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -163,21 +164,23 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                     const int fi = tc.j * p.fi_mul + p.it_df[it];
                     if (fi < 0 || fi >= p.Fin) continue;
                     const int n = p.it_n[it];
-                    for (int kb = 0; kb < kblocks; ++kb) {
+                    for (int kg = 0; kg < kgroups; ++kg) {
                         mbar_wait(smem_u32(&full[stage]), phase);
                         tc_fence_after();
-                        const uint32_t sa = smem_u32(stages + stage * C::STAGE_BYTES);
+                        const uint32_t sa = smem_base + (uint32_t)(stage * p.stage_bytes);
                         for (int w = 0; w < n; ++w) {
-                            const uint64_t ad = make_desc(sa + (uint32_t)(p.it_roff[it][w] * 128));
-                            const uint64_t bd = make_desc(sa + C::A_TILE + w * C::B_BYTES);
+                            for (int kb = 0; kb < p.kbs; ++kb) {
+                                const uint64_t ad = make_desc(sa + (uint32_t)(kb * C::A_TILE + p.it_roff[it][w] * 128));
+                                const uint64_t bd = make_desc(sa + (uint32_t)(p.a_bytes + (p.it_wt[it][w] * p.kbs + kb) * C::B_BYTES));
 #pragma unroll
-                            for (int k8 = 0; k8 < KB / 8; ++k8) {
-                                tc_mma_tf32(d_tmem, ad + 2 * k8, bd + 2 * k8, idesc, acc);   // +32 B per K=8 step
-                                acc = 1;
+                                for (int k8 = 0; k8 < KB / 8; ++k8) {
+                                    tc_mma_tf32(d_tmem, ad + 2 * k8, bd + 2 * k8, idesc, acc);   // +32 B per K=8 step
+                                    acc = 1;
+                                }
                             }
                         }
                         tc_commit(smem_u32(&empty[stage]));
-                        if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
+                        if (++stage == p.nstage) { stage = 0; phase ^= 1; }
                     }
                 }
                 tc_commit(smem_u32(&tfull[abuf]));
@@ -189,7 +192,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;
         const int et = threadIdx.x - 64;        // 0..127
-        int abuf = 0, sb = 0;
+        int abuf = 0;
         uint32_t aphase = 0;
         const int N0 = p.o[0].N;
         for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -212,25 +215,26 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                     if (lane == 0) mbar_arrive(smem_u32(&tempty[abuf]));
                 }
                 const int n = tc.n0 + ch * 32;
-                float* srow = stg + (sb * TM + row) * STG_LD;
+                float bv = 0.f;                 // lane i holds bias[n + i]; broadcast below
+                if (p.bias) bv = __ldg(p.bias + p.bJ * tc.j + n + lane);
+                asm volatile("bar.sync 1, 128;" ::: "memory");          // readers of the previous chunk are done
+                float* srow = stg + row * STG_LD;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    float x = nk ? v[i] : 0.f;
-                    if (p.bias) x += __ldg(p.bias + p.bJ * tc.j + n + i);
+                    const float x = (nk ? v[i] : 0.f) + __shfl_sync(0xffffffffu, bv, i);
                     srow[i] = x;
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 const int d = n < N0 ? 0 : 1;
                 const int nn = d ? n - N0 : n;
                 float* obase = p.o[d].p + tc.b * p.o[d].sB + fo * p.o[d].sF + nn;
-                const float* sbuf = stg + sb * TM * STG_LD;
 #pragma unroll
                 for (int pass = 0; pass < 8; ++pass) {
                     const int idx = pass * 128 + et;
                     const int r = idx >> 3, c4 = (idx & 7) * 4;
                     const int t = tc.t0 + r;
                     if (t < p.Tout) {
-                        const float* sp = sbuf + r * STG_LD + c4;
+                        const float* sp = stg + r * STG_LD + c4;
                         float4 o4 = make_float4(sp[0], sp[1], sp[2], sp[3]);
                         float* dst = obase + (long long)t * p.o[d].sT + c4;
                         if (p.accum[d]) {
@@ -248,7 +252,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                     for (int i = 0; i < 32; ++i) {
                         const int r = part * 32 + i;
                         if (tc.t0 + r < p.Tout) {
-                            const float x = sbuf[r * STG_LD + c];
+                            const float x = stg[r * STG_LD + c];
                             s1 += x;
                             s2 += x * x;
                         }
@@ -256,7 +260,6 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                     atomicAdd(&s_stat[ch * 32 + c], s1);
                     atomicAdd(&s_stat[BN + ch * 32 + c], s2);
                 }
-                sb ^= 1;
             }
             if (++abuf == 2) { abuf = 0; aphase ^= 1; }
         }
@@ -277,21 +280,13 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
 }
 
-// ---- host side ---------------------------------------------------------------------------------
-int make_act_map(CUtensorMap* m, const TapSrc& s, int F, int T, int B, int rows) {
-    cuuint64_t dims[4] = {(cuuint64_t)s.C, (cuuint64_t)T, (cuuint64_t)F, (cuuint64_t)B};
-    cuuint64_t str[3] = {(cuuint64_t)s.sT * 4, (cuuint64_t)(s.sF ? s.sF : s.sT * T) * 4,
-                         (cuuint64_t)(s.sB ? s.sB : s.sT * T * F) * 4};
-    cuuint32_t box[4] = {KB, (cuuint32_t)rows, 1, 1};
-    return make_map(m, s.p, 4, dims, str, box);
-}
-
 template <int BN>
-int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const TcParams& p, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(tapgemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM);
-        attr = true;
+int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w1, const CUtensorMap& w2, const TcParams& p,
+           int smem, cudaStream_t st) {
+    static int cur = 0;
+    if (smem > cur) {
+        cudaFuncSetAttribute(tapgemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cur = smem;
     }
     static int sms = 0;
     if (!sms) {
@@ -300,8 +295,51 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, c
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const int grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
-    tapgemm_tc_kernel<BN><<<grid, NTHREADS, Cfg<BN>::SMEM, st>>>(a0, a1, w, p);
+    tapgemm_tc_kernel<BN><<<grid, NTHREADS, smem, st>>>(a0, a1, w1, w2, p);
     return sefd_check_launch("tapgemm_tc");
+}
+
+int make_w_map(CUtensorMap* m, const TapGemmParams& g, int K, int N, int BN, int kbs, int nslab_box) {
+    // packed weights [slab][N][K] seen as (k_inner 32, n, k_block, slab): one box = kbs k-blocks x nslab_box taps
+    cuuint64_t dims[4] = {32, (cuuint64_t)N, (cuuint64_t)(K / 32), (cuuint64_t)g.nslabs};
+    cuuint64_t str[3] = {(cuuint64_t)(g.w_ldk ? g.w_ldk : K) * 4, 128,
+                         (cuuint64_t)(g.w_slab_stride ? g.w_slab_stride : (long long)K * N) * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)BN, (cuuint32_t)kbs, (cuuint32_t)nslab_box};
+    return make_map(m, g.Wnk, 4, dims, str, box);
+}
+
+template <int BN>
+int run(const TapGemmParams& g, TcParams& p, cudaStream_t st) {
+    using C = Cfg<BN>;
+    const int N = p.N, K = p.C0 + p.C1;
+    // k-blocks per stage: as many as keep >= 3 stages in flight
+    int kbs = 4;
+    for (;; kbs >>= 1) {
+        const bool div = (p.C0 / KB) % kbs == 0 && (p.C1 == 0 || (p.C1 / KB) % kbs == 0);
+        const int stage = kbs * (C::A_TILE + (C::PAIR ? 2 : 1) * C::B_BYTES);
+        if (kbs == 1 || (div && (SMEM_BUDGET - C::FIXED) / stage >= 3)) break;
+    }
+    p.kbs = kbs;
+    p.a_bytes = kbs * C::A_TILE;
+    p.stage_bytes = kbs * (C::A_TILE + (C::PAIR ? 2 : 1) * C::B_BYTES);
+    p.nstage = (SMEM_BUDGET - C::FIXED) / p.stage_bytes;
+    if (p.nstage > MAX_STAGES) p.nstage = MAX_STAGES;
+    SEFD_REQUIRE(p.nstage >= 2, "tapgemm_tc: no room for a pipeline (stage %d bytes)", p.stage_bytes);
+    const int smem = p.nstage * p.stage_bytes + C::FIXED;
+
+    CUtensorMap a0, a1, w1, w2;
+    SEFD_TRY(make_act_map5(&a0, g.a[0], g.Fin, g.Tin, g.B, C::A_ROWS, kbs));
+    if (g.a[1].C) SEFD_TRY(make_act_map5(&a1, g.a[1], g.Fin, g.Tin, g.B, C::A_ROWS, kbs));
+    else a1 = a0;
+    SEFD_TRY(make_w_map(&w1, g, K, N, BN, kbs, 1));
+    if (C::PAIR) SEFD_TRY(make_w_map(&w2, g, K, N, BN, kbs, 2));
+    else w2 = w1;
+    const double pos = (double)g.B * g.J * g.Tout;
+    sefd_prof_label("tapgemm_tc BN%d K%d N%d taps%d items%d kbs%d x%d J%d Tout%d tiles%lld", BN, K, N, g.ntaps, p.nitems, kbs,
+                    p.nstage, g.J, g.Tout, p.total_tiles);
+    SefdProfScope prof(SEFD_PROF_TAPGEMM, 2.0 * pos * N * K * g.ntaps,
+                       4.0 * ((double)g.B * g.J * (g.fi_mul > 1 ? g.fi_mul : 1) * g.Tin * K + pos * N), st);
+    return launch<BN>(a0, a1, w1, w2, p, smem, st);
 }
 
 }  // namespace
@@ -326,7 +364,7 @@ bool sefd_tapgemm_tc_eligible(const TapGemmParams& p) {
 
 int sefd_tapgemm_tc(const TapGemmParams& g, cudaStream_t st) {
     SEFD_REQUIRE(sefd_tapgemm_tc_eligible(g), "tapgemm_tc: problem not eligible for the tensor-core engine");
-    const int N = g.o[0].N + g.o[1].N, K = g.a[0].C + g.a[1].C;
+    const int N = g.o[0].N + g.o[1].N;
     const int BN = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32));
     TcParams p;
     memset(&p, 0, sizeof(p));
@@ -335,30 +373,30 @@ int sefd_tapgemm_tc(const TapGemmParams& g, cudaStream_t st) {
     p.bias = g.bias; p.bJ = g.bJ; p.stats = g.stats;
     p.B = g.B; p.J = g.J; p.Tout = g.Tout; p.Fin = g.Fin;
     p.fi_mul = g.fi_mul; p.fo_mul = g.fo_mul; p.fo_off = g.fo_off;
-    // pair up taps on the same source row whose time shifts differ by one frame (BN <= 128 only)
+    // pair up taps on the same source row whose time shifts differ by one frame and whose weight slabs are
+    // adjacent (BN <= 128 only: there the activation traffic dominates)
     const bool pair = BN <= 128;
     bool used[SEFD_MAX_TAPS] = {false};
     p.nitems = 0;
     for (int i = 0; i < g.ntaps; ++i) {
         if (used[i]) continue;
-        int it = p.nitems++;
+        const int it = p.nitems++;
         p.it_df[it] = g.df[i]; p.it_dt0[it] = g.dt[i]; p.it_n[it] = 1;
-        p.it_slab[it][0] = g.wslab[i]; p.it_roff[it][0] = 0;
+        p.it_slab_lo[it] = g.wslab[i]; p.it_wt[it][0] = 0; p.it_roff[it][0] = 0;
         used[i] = true;
         if (!pair) continue;
         for (int j2 = i + 1; j2 < g.ntaps; ++j2) {
             if (used[j2] || g.df[j2] != g.df[i]) continue;
-            const int d = g.dt[j2] - g.dt[i];
-            if (d == 1 || d == -1) {
+            const int d = g.dt[j2] - g.dt[i], ds = g.wslab[j2] - g.wslab[i];
+            if ((d == 1 || d == -1) && (ds == 1 || ds == -1)) {
                 used[j2] = true;
                 p.it_n[it] = 2;
-                if (d == 1) {
-                    p.it_slab[it][1] = g.wslab[j2]; p.it_roff[it][1] = 1;
-                } else {            // the partner starts one frame earlier: it becomes row offset 0
-                    p.it_dt0[it] = g.dt[j2];
-                    p.it_slab[it][1] = g.wslab[i]; p.it_roff[it][1] = 1;
-                    p.it_slab[it][0] = g.wslab[j2]; p.it_roff[it][0] = 0;
-                }
+                p.it_dt0[it] = d == 1 ? g.dt[i] : g.dt[j2];
+                p.it_slab_lo[it] = ds == 1 ? g.wslab[i] : g.wslab[j2];
+                p.it_roff[it][0] = d == 1 ? 0 : 1;          // tap i
+                p.it_roff[it][1] = d == 1 ? 1 : 0;          // tap j2
+                p.it_wt[it][0] = ds == 1 ? 0 : 1;
+                p.it_wt[it][1] = ds == 1 ? 1 : 0;
                 break;
             }
         }
@@ -367,27 +405,11 @@ int sefd_tapgemm_tc(const TapGemmParams& g, cudaStream_t st) {
     p.t_tiles = (g.Tout + TM - 1) / TM;
     p.n_tiles = N / BN;
     p.total_tiles = (long long)g.B * g.J * p.t_tiles * p.n_tiles;
-
-    CUtensorMap a0, a1, w;
-    const int arows = pair ? 136 : TM;
-    SEFD_TRY(make_act_map(&a0, g.a[0], g.Fin, g.Tin, g.B, arows));
-    if (g.a[1].C) SEFD_TRY(make_act_map(&a1, g.a[1], g.Fin, g.Tin, g.B, arows));
-    else a1 = a0;
-    {
-        cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)g.nslabs};
-        cuuint64_t str[2] = {(cuuint64_t)(g.w_ldk ? g.w_ldk : K) * 4, (cuuint64_t)(g.w_slab_stride ? g.w_slab_stride : (long long)K * N) * 4};
-        cuuint32_t box[3] = {KB, (cuuint32_t)BN, 1};
-        SEFD_TRY(make_map(&w, g.Wnk, 3, dims, str, box));
-    }
-    const double pos = (double)g.B * g.J * g.Tout;
-    sefd_prof_label("tapgemm_tc BN%d K%d N%d taps%d items%d J%d Tout%d tiles%lld", BN, K, N, g.ntaps, p.nitems, g.J, g.Tout, p.total_tiles);
-    SefdProfScope prof(SEFD_PROF_TAPGEMM, 2.0 * pos * N * K * g.ntaps,
-                       4.0 * ((double)g.B * g.J * (g.fi_mul > 1 ? g.fi_mul : 1) * g.Tin * K + pos * N), st);
     switch (BN) {
-        case 256: return launch<256>(a0, a1, w, p, st);
-        case 128: return launch<128>(a0, a1, w, p, st);
-        case 64: return launch<64>(a0, a1, w, p, st);
-        default: return launch<32>(a0, a1, w, p, st);
+        case 256: return run<256>(g, p, st);
+        case 128: return run<128>(g, p, st);
+        case 64: return run<64>(g, p, st);
+        default: return run<32>(g, p, st);
     }
 }
 

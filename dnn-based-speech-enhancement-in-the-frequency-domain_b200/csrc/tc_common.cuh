@@ -39,6 +39,12 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -122,5 +128,17 @@ inline int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
     return 0;
 }
 
+
+// Channels-last activation [B][F][T][C] seen as a 5-D tensor (c_inner 32, t, c_block, f, b): one box
+// {32, rows, nblk, 1, 1} lands in shared memory as nblk consecutive [rows x 128 B] swizzled tiles, i.e. one TMA
+// instruction fetches several 32-channel k-blocks (the single issuing thread is otherwise the bottleneck).
+inline int make_act_map5(CUtensorMap* m, const TapSrc& s, int F, int T, int B, int rows, int nblk,
+                         CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+    cuuint64_t dims[5] = {32, (cuuint64_t)T, (cuuint64_t)(s.C / 32), (cuuint64_t)F, (cuuint64_t)B};
+    cuuint64_t str[4] = {(cuuint64_t)s.sT * 4, 128, (cuuint64_t)(s.sF ? s.sF : s.sT * T) * 4,
+                         (cuuint64_t)(s.sB ? s.sB : s.sT * T * F) * 4};
+    cuuint32_t box[5] = {32, (cuuint32_t)rows, (cuuint32_t)nblk, 1, 1};
+    return make_map(m, s.p, 5, dims, str, box, swz);
+}
 
 }  // namespace

@@ -36,6 +36,7 @@ struct WgParams {
     int m_tiles, n_tiles, splits, rows_per_split, t_blocks;
     int nstage, stage_bytes;
     int a_sp;          // spacing of the A slots inside a stage, in 4 KB chunks (= min(4, K/32))
+    int a_box;         // 32-channel blocks fetched by one A TMA instruction (divides a_sp and the source widths)
     long long units;
 };
 
@@ -61,8 +62,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmG, const WgParams p) {
     constexpr int NG = BN / 32;                 // 32-channel chunks of one G tile
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // declared alignment keeps derived pointers in the shared address space (no generic LD/ST in the epilogue)
+    extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* stages = smem;
     float* stg = reinterpret_cast<float*>(smem + p.nstage * p.stage_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(stg + WM * STG_LD);
@@ -74,6 +75,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
+        if (smem_u32(smem) & 1023u) __trap();
         for (int s = 0; s < p.nstage; ++s) {
             mbar_init(smem_u32(&full[s]), 1);
             mbar_init(smem_u32(&empty[s]), 1);
@@ -99,9 +101,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit x = decode_unit(p, u, BN);
             const Group& G = p.grp[x.g];
-            const int nAc = (p.K - x.m0) / 32 < 4 ? (p.K - x.m0) / 32 : 4;   // 32-channel chunks of one A tile
-            const int nAb = G.nA * nAc, nGb = G.nG * NG;                     // boxes per k-step
-            const uint32_t bytes = (uint32_t)((nAb + nGb) * CHB);
+            const int opa = p.a_sp / p.a_box;                                // TMA instructions per A tile
+            const int nAb = G.nA * opa, nGb = G.nG;                          // TMA instructions per k-step
+            const uint32_t bytes = (uint32_t)((G.nA * p.a_sp + G.nG * NG) * CHB);
             for (int r = x.r0; r < x.r1; ++r) {
                 const int b = r / p.J, j = r % p.J;
                 for (int tb = 0; tb < p.t_blocks; ++tb) {
@@ -113,18 +115,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                     const int t0 = tb * PB;
                     for (int op = lane; op < nAb + nGb; op += 32) {
                         if (op < nAb) {
-                            const int a = op / nAc, i = op % nAc;
+                            const int a = op / opa, i = (op % opa) * p.a_box;          // first 32-channel block of this box
                             const int fa = j * p.a_mul + G.a_roff[a], ta = t0 + G.a_toff[a];
                             const int kc = x.m0 + 32 * i;
                             const uint32_t dst = sa + (uint32_t)((a * p.a_sp + i) * CHB);
-                            if (kc < p.C0) tma_load_4d(&tmA0, fb, dst, kc, ta, fa, b);
-                            else tma_load_4d(&tmA1, fb, dst, kc - p.C0, ta, fa, b);
+                            // blocks beyond the tensor (last m-tile of a narrow K) are zero-filled by TMA
+                            if (kc < p.C0) tma_load_5d(&tmA0, fb, dst, 0, ta, kc / 32, fa, b);
+                            else tma_load_5d(&tmA1, fb, dst, 0, ta, (kc - p.C0) / 32, fa, b);
                         } else {
-                            const int og = op - nAb;
-                            const int g = og / NG, i = og % NG;
+                            const int g = op - nAb;
                             const int fg = j * p.g_mul + G.g_roff[g];
                             const uint32_t sg = sa + (uint32_t)(G.nA * p.a_sp * CHB);
-                            tma_load_4d(&tmG, fb, sg + (uint32_t)((g * NG + i) * CHB), x.n0 + 32 * i, t0, fg, b);
+                            tma_load_5d(&tmG, fb, sg + (uint32_t)(g * NG * CHB), 0, t0, x.n0 / 32, fg, b);
                         }
                     }
                     if (++stage == p.nstage) { stage = 0; phase ^= 1; }
@@ -221,12 +223,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     }
 }
 
-int make_pos_map(CUtensorMap* m, const TapSrc& s, int F, int T, int B) {
-    cuuint64_t dims[4] = {(cuuint64_t)s.C, (cuuint64_t)T, (cuuint64_t)F, (cuuint64_t)B};
-    cuuint64_t str[3] = {(cuuint64_t)s.sT * 4, (cuuint64_t)(s.sF ? s.sF : s.sT * T) * 4,
-                         (cuuint64_t)(s.sB ? s.sB : s.sT * T * F) * 4};
-    cuuint32_t box[4] = {32, PB, 1, 1};
-    return make_map(m, s.p, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+int make_pos_map(CUtensorMap* m, const TapSrc& s, int F, int T, int B, int nblk) {
+    return make_act_map5(m, s, F, T, B, PB, nblk, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
 }
 
 template <int BN>
@@ -312,6 +310,10 @@ int sefd_wgrad_tc(const WgradParams& w, float* partial, long long cap_floats, in
     p.n_tiles = N / BN;
     p.t_blocks = (w.Tg + PB - 1) / PB;
     p.a_sp = K / 32 < 4 ? K / 32 : 4;
+    p.a_box = p.a_sp;
+    if (w.a[1].C) {
+        while ((w.a[0].C / 32) % p.a_box || (w.a[1].C / 32) % p.a_box) p.a_box >>= 1;
+    }
     SEFD_REQUIRE(build_groups(w, BN, p.a_sp, p) == 0, "wgrad_tc: tap grouping failed");
     int stage = 0;
     for (int g = 0; g < p.ngroups; ++g) {
@@ -342,10 +344,10 @@ int sefd_wgrad_tc(const WgradParams& w, float* partial, long long cap_floats, in
     *split_stride = one;
 
     CUtensorMap a0, a1, g;
-    SEFD_TRY(make_pos_map(&a0, w.a[0], w.Fa, w.Ta, w.B));
-    if (w.a[1].C) SEFD_TRY(make_pos_map(&a1, w.a[1], w.Fa, w.Ta, w.B));
+    SEFD_TRY(make_pos_map(&a0, w.a[0], w.Fa, w.Ta, w.B, p.a_box));
+    if (w.a[1].C) SEFD_TRY(make_pos_map(&a1, w.a[1], w.Fa, w.Ta, w.B, p.a_box));
     else a1 = a0;
-    SEFD_TRY(make_pos_map(&g, w.g, w.Fg, w.Tg, w.B));
+    SEFD_TRY(make_pos_map(&g, w.g, w.Fg, w.Tg, w.B, BN / 32));
     const double pos = (double)w.B * w.J * w.Tg;
     sefd_prof_label("wgrad_tc BN%d K%d N%d taps%d J%d groups%d stage%dK x%d splits%d units%lld", BN, K, N, w.ntaps, w.J,
                     p.ngroups, stage / 1024, p.nstage, p.splits, p.units);
