@@ -228,6 +228,19 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                 const int d = n < N0 ? 0 : 1;
                 const int nn = d ? n - N0 : n;
                 float* obase = p.o[d].p + tc.b * p.o[d].sB + fo * p.o[d].sF + nn;
+                // gradient accumulation: issue all eight loads of the old values first (independent, one DRAM
+                // latency) instead of a load -> add -> store chain per pass
+                float4 oldv[8];
+                if (p.accum[d]) {
+#pragma unroll
+                    for (int pass = 0; pass < 8; ++pass) {
+                        const int idx = pass * 128 + et;
+                        const int r = idx >> 3, c4 = (idx & 7) * 4;
+                        const int t = tc.t0 + r;
+                        oldv[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (t < p.Tout) oldv[pass] = __ldcg(reinterpret_cast<const float4*>(obase + (long long)t * p.o[d].sT + c4));
+                    }
+                }
 #pragma unroll
                 for (int pass = 0; pass < 8; ++pass) {
                     const int idx = pass * 128 + et;
@@ -236,13 +249,9 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                     if (t < p.Tout) {
                         const float* sp = stg + r * STG_LD + c4;
                         float4 o4 = make_float4(sp[0], sp[1], sp[2], sp[3]);
-                        float* dst = obase + (long long)t * p.o[d].sT + c4;
-                        if (p.accum[d]) {
-                            const float4 old = *reinterpret_cast<const float4*>(dst);
-                            o4.x += old.x; o4.y += old.y; o4.z += old.z; o4.w += old.w;
-                        }
+                        if (p.accum[d]) { o4.x += oldv[pass].x; o4.y += oldv[pass].y; o4.z += oldv[pass].z; o4.w += oldv[pass].w; }
                         if (p.round_out[d]) { o4.x = tf32_rn(o4.x); o4.y = tf32_rn(o4.y); o4.z = tf32_rn(o4.z); o4.w = tf32_rn(o4.w); }
-                        *reinterpret_cast<float4*>(dst) = o4;
+                        *reinterpret_cast<float4*>(obase + (long long)t * p.o[d].sT + c4) = o4;
                     }
                 }
                 if (p.stats) {

