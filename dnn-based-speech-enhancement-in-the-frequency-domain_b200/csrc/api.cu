@@ -198,6 +198,7 @@ int sefd_cconvT2d_forward(const float* x0, const float* x1, const float* wr, con
     cudaMemsetAsync(c.dbias, 0, sizeof(float) * 1024, ST);
     SEFD_TRY(pack_op(wr, br, wi, bi, Cin, Cout, 1, c, ST, c.dbias));
     const int Ch = Cin / 2;
+    if (sefd_skinny_up_n2_eligible(Ch, Cout)) return sefd_skinny_up_n2(x0, x1, c.Wf, c.bias, y, B, F, T, ST);
     for (int ph = 0; ph < 2; ++ph) {
         TapGemmParams g;
         memset(&g, 0, sizeof(g));

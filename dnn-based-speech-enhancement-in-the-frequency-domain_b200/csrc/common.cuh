@@ -83,6 +83,9 @@ int sefd_get_engine_internal();
 // dedicated kernels for the 2-channel ends of the network (K = 2 or N = 2 per tap)
 bool sefd_skinny_conv_eligible(const TapGemmParams& p);
 int sefd_skinny_conv(const TapGemmParams& p, cudaStream_t st);
+bool sefd_skinny_up_n2_eligible(int Ch, int Cout);
+int sefd_skinny_up_n2(const float* x0, const float* x1, const float* W, const float* bias, float* y, int B, int F, int T,
+                      cudaStream_t st);
 bool sefd_skinny_wgrad_eligible(const WgradParams& p);
 int sefd_skinny_wgrad(const WgradParams& p, cudaStream_t st);
 int sefd_wgrad_simt(const WgradParams& p, cudaStream_t st);

@@ -32,7 +32,7 @@ struct ConvLayer {
     long long wr, br, wi, bi, gamma, beta, alpha;   // param offsets (gamma < 0: no BN/PReLU)
     long long rmean, rvar;                           // bn buffer offsets
     // workspace offsets (floats)
-    size_t y, z, Wf, Wt, bias, stats /*doubles*/, save, dz;
+    size_t y, z, Wf, Wt, bias, stats /*doubles*/, save, dz, dz2;
 };
 
 }  // namespace
@@ -204,7 +204,8 @@ sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode) {
         const size_t n = Bz * c.Fout * T * c.Cout;
         c.y = w.floats(n);
         c.z = w.floats(n);
-        c.dz = w.floats(n);
+        c.dz = w.floats(n);      // gradient through the skip connection (written by the decoder's data gradient)
+        c.dz2 = w.floats(n);     // gradient from the next encoder layer / the LSTM; BN backward sums the two
         c.Wf = w.floats(10ull * c.Cin * c.Cout);
         c.Wt = w.floats(10ull * c.Cin * c.Cout);
         c.bias = w.floats(c.Cout);
@@ -426,6 +427,10 @@ int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const 
         const int Ch = c.Cin / 2;
         const float* in0 = j == 0 ? ws + P->U : ws + P->dec[j - 1].z;
         const float* in1 = ws + P->enc[NL - 1 - j].z;
+        if (sefd_skinny_up_n2_eligible(Ch, c.Cout)) {       // decoder 5: both phases in one HBM-bound pass
+            SEFD_TRY(sefd_skinny_up_n2(in0, in1, ws + c.Wf, ws + c.bias, ws + c.y, B, c.Fin, T, st));
+            continue;
+        }
         for (int ph = 0; ph < 2; ++ph) {
             TapGemmParams g;
             memset(&g, 0, sizeof(g));
@@ -468,10 +473,11 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
     float* dY = ws + P->dY;
     float* dWs = ws + P->dWs;
 
-    auto bn_bwd = [&](const ConvLayer& c, int Ty, int tshift) -> int {
+    auto bn_bwd = [&](const ConvLayer& c, int Ty, int tshift, bool two) -> int {
         BnPreluBwdParams b;
         memset(&b, 0, sizeof(b));
         b.y = ws + c.y; b.dz = ws + c.dz; b.dy = dY;
+        b.dz2 = two ? ws + c.dz2 : nullptr;
         b.BF = B * c.Fout; b.Ty = Ty; b.T = T; b.tshift = tshift; b.C = c.Cout;
         b.n_stat = (double)B * c.Fout * Ty;
         b.gamma = prm + c.gamma; b.beta = prm + c.beta; b.alpha = prm + c.alpha; b.save = ws + c.save;
@@ -519,7 +525,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
         const float* in1 = ws + P->enc[NL - 1 - j].z;
         const float* dbias = nullptr;
         if (j != NL - 1) {
-            SEFD_TRY(bn_bwd(c, T + 1, 1));
+            SEFD_TRY(bn_bwd(c, T + 1, 1, false));
         } else {
             SEFD_TRY(sefd_colsum2(dY, 1, 0, (long long)B * c.Fout * (T + 1), c.Cout, c.Cout, wsd + P->red, ws + P->dbs, st));
             dbias = ws + P->dbs;
@@ -613,8 +619,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
                 g.W = ws + P->Wih1T; g.J = 1;
                 g.Wnk = ws + P->Wih1Q; g.nslabs = 1;
             } else {
-                g.o[0] = dst4(ws + P->enc[NL - 1].dz + q * 128, 4, T, 256, 128);
-                g.accum[0] = 1;                                   // the skip gradient from decoder 0 is already there
+                g.o[0] = dst4(ws + P->enc[NL - 1].dz2 + q * 128, 4, T, 256, 128);   // summed with the skip gradient by BN backward
                 g.W = ws + P->Wih0T; g.wJ = (long long)2 * G4 * 128; g.J = 4;
                 g.Wnk = ws + P->Wih0Q; g.nslabs = 4; g.wJ_slabs = 1;
             }
@@ -665,7 +670,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
     // ---- encoder backward ----
     for (int i = NL - 1; i >= 0; --i) {
         const ConvLayer& c = P->enc[i];
-        SEFD_TRY(bn_bwd(c, T, 0));
+        SEFD_TRY(bn_bwd(c, T, 0, true));
         WgradParams wg;
         memset(&wg, 0, sizeof(wg));
         if (i == 0) {
@@ -692,9 +697,8 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
                 memset(&g, 0, sizeof(g));
                 g.a[0] = src4(dY, c.Fout, T, c.Cout, c.Cout);
                 g.a[1] = no_src();
-                g.o[0] = dst4(ws + P->enc[i - 1].dz, c.Fin, T, c.Cin, c.Cin);
+                g.o[0] = dst4(ws + P->enc[i - 1].dz2, c.Fin, T, c.Cin, c.Cin);   // summed with the skip gradient by BN backward
                 g.o[1] = no_dst();
-                g.accum[0] = 1;                                   // skip gradient already stored by the decoder
                 g.W = ws + c.Wt; g.Wnk = ws + c.Wf; g.nslabs = 10;
                 g.B = B; g.J = c.Fout; g.Tout = T; g.Fin = c.Fout; g.Tin = T;
                 conv_taps_up(g, ph, 1);
@@ -758,6 +762,7 @@ int sefd_dccrn_tensor_info(const sefd_plan* P, const char* name, long long* off,
         if (f == "y") return set(c.y, B, c.Fout, dec ? T + 1 : T, c.Cout);
         if (f == "z" && !(dec && i == NL - 1)) return set(c.z, B, c.Fout, T, c.Cout);
         if (f == "dz" && !(dec && i == NL - 1)) return set(c.dz, B, c.Fout, T, c.Cout);
+        if (f == "dz2" && !dec) return set(c.dz2, B, c.Fout, T, c.Cout);
     }
     if (n.size() == 7 && n.compare(0, 4, "lstm") == 0 && n[5] == '.') {
         const int l = n[4] - '0';

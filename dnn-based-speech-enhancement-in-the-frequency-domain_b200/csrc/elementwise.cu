@@ -93,7 +93,11 @@ __global__ void __launch_bounds__(256) bn_prelu_bwd_reduce_kernel(const BnPreluB
             const int t = (int)(row % p.T);
             const long long bf = row / p.T;
             const float4 yv = __ldg(reinterpret_cast<const float4*>(p.y + ((bf * p.Ty + t + p.tshift) * C) + c));
-            const float4 dv = __ldg(reinterpret_cast<const float4*>(p.dz + row * C + c));
+            float4 dv = __ldg(reinterpret_cast<const float4*>(p.dz + row * C + c));
+            if (p.dz2) {
+                const float4 d2 = __ldg(reinterpret_cast<const float4*>(p.dz2 + row * C + c));
+                dv.x += d2.x; dv.y += d2.y; dv.z += d2.z; dv.w += d2.w;
+            }
             const float y4[4] = {yv.x, yv.y, yv.z, yv.w};
             const float d4[4] = {dv.x, dv.y, dv.z, dv.w};
 #pragma unroll
@@ -161,7 +165,13 @@ __global__ void __launch_bounds__(256) bn_prelu_bwd_apply_kernel(const BnPreluBw
         const int t = ty - p.tshift;
         const float4 yv = __ldg(reinterpret_cast<const float4*>(p.y + e * 4));
         float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t >= 0 && t < p.T) dv = __ldg(reinterpret_cast<const float4*>(p.dz + ((bf * p.T + t) * C) + c));
+        if (t >= 0 && t < p.T) {
+            dv = __ldg(reinterpret_cast<const float4*>(p.dz + ((bf * p.T + t) * C) + c));
+            if (p.dz2) {
+                const float4 d2 = __ldg(reinterpret_cast<const float4*>(p.dz2 + ((bf * p.T + t) * C) + c));
+                dv.x += d2.x; dv.y += d2.y; dv.z += d2.z; dv.w += d2.w;
+            }
+        }
         const float y4[4] = {yv.x, yv.y, yv.z, yv.w};
         const float d4[4] = {dv.x, dv.y, dv.z, dv.w};
         float o[4];
@@ -375,7 +385,7 @@ int sefd_bn_prelu_fwd(const BnPreluFwdParams& p, cudaStream_t st) {
 int sefd_bn_prelu_bwd(const BnPreluBwdParams& p, cudaStream_t st) {
     SEFD_REQUIRE(p.C % 4 == 0 && p.C <= MAXC && 256 % (p.C / 4) == 0, "bn_prelu_bwd: C=%d unsupported", p.C);
     sefd_prof_label("bn_prelu_bwd C%d rows%lld", p.C, (long long)p.BF * p.T);
-    SefdProfScope prof(SEFD_PROF_BN, 0, 4.0 * p.BF * p.C * (2.0 * p.T + 2.0 * p.T + p.Ty), st);
+    SefdProfScope prof(SEFD_PROF_BN, 0, 4.0 * p.BF * p.C * ((p.dz2 ? 6.0 : 4.0) * p.T + p.Ty), st);
     cudaMemsetAsync(p.red, 0, sizeof(double) * (2 * p.C + 1), st);
     const int lanes = 256 / (p.C / 4);
     long long g = ((long long)p.BF * p.T + lanes - 1) / lanes;

@@ -18,6 +18,7 @@ struct BnPreluFwdParams {
 struct BnPreluBwdParams {
     const float* y;        // [BF][Ty][C]
     const float* dz;       // [BF][T][C]
+    const float* dz2;      // optional second gradient source summed with dz (skip-connection gradient), or nullptr
     float* dy;             // [BF][Ty][C]
     int BF, Ty, T, tshift, C;
     double n_stat;

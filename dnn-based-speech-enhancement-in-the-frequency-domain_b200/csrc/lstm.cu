@@ -47,9 +47,9 @@ __global__ void __launch_bounds__(512, 1) lstm_fwd_kernel(const LstmFwdParams p)
     __syncthreads();
 
     for (int t = 0; t < p.T; ++t) {
-        float acc[R];
+        float acc[R], acc2[R];   // two independent FMA chains per row (the single chain was latency-bound at R = 1)
 #pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = pre[r];
+        for (int r = 0; r < R; ++r) { acc[r] = pre[r]; acc2[r] = 0.f; }
         if (t + 1 < p.T) {
 #pragma unroll
             for (int r = 0; r < R; ++r) pre[r] = valid[r] ? Gr[r][(size_t)(t + 1) * G4 + g] : 0.f;
@@ -60,9 +60,9 @@ __global__ void __launch_bounds__(512, 1) lstm_fwd_kernel(const LstmFwdParams p)
             for (int r = 0; r < R; ++r) {
                 const float4 h4 = *reinterpret_cast<const float4*>(&hs[r * H + 4 * k4]);
                 acc[r] = fmaf(wreg[4 * k4 + 0], h4.x, acc[r]);
-                acc[r] = fmaf(wreg[4 * k4 + 1], h4.y, acc[r]);
+                acc2[r] = fmaf(wreg[4 * k4 + 1], h4.y, acc2[r]);
                 acc[r] = fmaf(wreg[4 * k4 + 2], h4.z, acc[r]);
-                acc[r] = fmaf(wreg[4 * k4 + 3], h4.w, acc[r]);
+                acc2[r] = fmaf(wreg[4 * k4 + 3], h4.w, acc2[r]);
             }
         }
 #pragma unroll 4
@@ -73,14 +73,15 @@ __global__ void __launch_bounds__(512, 1) lstm_fwd_kernel(const LstmFwdParams p)
             for (int r = 0; r < R; ++r) {
                 const float4 h4 = *reinterpret_cast<const float4*>(&hs[r * H + KR + 4 * k4]);
                 acc[r] = fmaf(w0, h4.x, acc[r]);
-                acc[r] = fmaf(w1, h4.y, acc[r]);
+                acc2[r] = fmaf(w1, h4.y, acc2[r]);
                 acc[r] = fmaf(w2, h4.z, acc[r]);
-                acc[r] = fmaf(w3, h4.w, acc[r]);
+                acc2[r] = fmaf(w3, h4.w, acc2[r]);
             }
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const float a = gate == 2 ? tanhf(acc[r]) : sigmoidf_(acc[r]);
+            const float pa = acc[r] + acc2[r];
+            const float a = gate == 2 ? tanhf(pa) : sigmoidf_(pa);
             gs[r * G4 + g] = a;
             if (valid[r]) Gr[r][(size_t)t * G4 + g] = a;
         }
@@ -168,18 +169,18 @@ __global__ void __launch_bounds__(512, 1) lstm_bwd_kernel(const LstmBwdParams p)
             }
         }
         __syncthreads();
-        float acc[R];
+        float acc[R], acc2[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = 0.f;
+        for (int r = 0; r < R; ++r) acc[r] = acc2[r] = 0.f;
 #pragma unroll
         for (int g4 = 0; g4 < KR / 4; ++g4) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const float4 d4 = *reinterpret_cast<const float4*>(&dgs[r * G4 + q * H + 4 * g4]);
                 acc[r] = fmaf(wreg[4 * g4 + 0], d4.x, acc[r]);
-                acc[r] = fmaf(wreg[4 * g4 + 1], d4.y, acc[r]);
+                acc2[r] = fmaf(wreg[4 * g4 + 1], d4.y, acc2[r]);
                 acc[r] = fmaf(wreg[4 * g4 + 2], d4.z, acc[r]);
-                acc[r] = fmaf(wreg[4 * g4 + 3], d4.w, acc[r]);
+                acc2[r] = fmaf(wreg[4 * g4 + 3], d4.w, acc2[r]);
             }
         }
 #pragma unroll 4
@@ -190,13 +191,13 @@ __global__ void __launch_bounds__(512, 1) lstm_bwd_kernel(const LstmBwdParams p)
             for (int r = 0; r < R; ++r) {
                 const float4 d4 = *reinterpret_cast<const float4*>(&dgs[r * G4 + q * H + KR + 4 * g4]);
                 acc[r] = fmaf(w0, d4.x, acc[r]);
-                acc[r] = fmaf(w1, d4.y, acc[r]);
+                acc2[r] = fmaf(w1, d4.y, acc2[r]);
                 acc[r] = fmaf(w2, d4.z, acc[r]);
-                acc[r] = fmaf(w3, d4.w, acc[r]);
+                acc2[r] = fmaf(w3, d4.w, acc2[r]);
             }
         }
 #pragma unroll
-        for (int r = 0; r < R; ++r) part[(q * R + r) * H + k] = acc[r];
+        for (int r = 0; r < R; ++r) part[(q * R + r) * H + k] = acc[r] + acc2[r];
         __syncthreads();
         if (cr < R)
             dh_rec = part[(0 * R + cr) * H + cj] + part[(1 * R + cr) * H + cj] + part[(2 * R + cr) * H + cj] +

@@ -148,6 +148,95 @@ __global__ void __launch_bounds__(128) smalln_conv_kernel(const TapGemmParams p)
 //   wide_is_g = 0 (decoder 5): wide = A[b, j, u, k<64],  small = G[b, j*g_mul+g_off, u-dt, c<2]   -> dW[tap][k][c]
 // (for the second form the loop variable is the wide tensor's own time u = t + dt)
 // ---------------------------------------------------------------------------------------------------
+
+// ---------------------------------------------------------------------------------------------------
+// T4: decoder-5 forward = ConvTranspose (5,2)/(2,1) with N = 2 outputs from two 32-channel sources.
+// Scatter form: y[b, 2j+kf-2, t+kt, o] += sum_c x_s[b, j, t, c] * W[kf*2+kt][s*32+c][o].
+// One thread owns one (b, t) column of a strip of input rows and walks j; its 32 input channels sit in
+// registers, the 1280 weights are FFMA constant-bank operands (no shared-memory traffic at all), and the five
+// output rows an input row touches live in a sliding register window: after step j the rows 2j-2 and 2j-1
+// are complete and leave through one shuffle (the kt = 1 half belongs to the neighbouring frame).
+// Every input element is loaded exactly once (the gather form re-read it for each of its 10 taps).
+// ---------------------------------------------------------------------------------------------------
+__constant__ float c_upW[10 * 64 * 2];     // [slab = kf*2+kt][k = s*32+c][o]
+
+struct UpN2Params {
+    const float *x0, *x1;   // [B][F][T][32]
+    const float* bias;      // [2]
+    float* y;               // [B][2F][T+1][2]
+    int B, F, T, JC;
+};
+
+template <int S>
+__device__ __forceinline__ void up_n2_fma(const float4 (&x)[8], float (&acc)[5][2][2]) {
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+        const float xv[4] = {x[c4].x, x[c4].y, x[c4].z, x[c4].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int kf = 0; kf < 5; ++kf)
+#pragma unroll
+                for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+                    for (int o = 0; o < 2; ++o)
+                        acc[kf][kt][o] = fmaf(xv[i], c_upW[((kf * 2 + kt) * 64 + S * 32 + c4 * 4 + i) * 2 + o], acc[kf][kt][o]);
+    }
+}
+
+__global__ void __launch_bounds__(128) up_n2_kernel(const UpN2Params p) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int strip = blockIdx.x * 4 + warp;
+    const int t = strip * 31 - 1 + lane;           // input frame of this lane (lane 0 = halo of the strip)
+    const int b = blockIdx.z;
+    const int j0 = blockIdx.y * p.JC, j1 = min(p.F, j0 + p.JC);
+    if (strip * 31 > p.T) return;                  // whole warp beyond the T+1 output frames
+    const bool tin = t >= 0 && t < p.T;
+    const float b0 = p.bias ? __ldg(p.bias) : 0.f, b1 = p.bias ? __ldg(p.bias + 1) : 0.f;
+    float acc[5][2][2];
+#pragma unroll
+    for (int a = 0; a < 5; ++a) acc[a][0][0] = acc[a][0][1] = acc[a][1][0] = acc[a][1][1] = 0.f;
+
+    auto load = [&](const float* x, int j, float4 (&v)[8]) {
+        if (tin && j >= 0 && j < p.F) {
+            const float4* q = reinterpret_cast<const float4*>(x + (((long long)b * p.F + j) * p.T + t) * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __ldg(q + i);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    float4 xa[8], xb[8];
+    load(p.x0, j0 - 1, xa);
+    for (int j = j0 - 1; j <= j1; ++j) {
+        load(p.x1, j, xb);                         // in flight while source 0 is consumed
+        up_n2_fma<0>(xa, acc);
+        load(p.x0, j + 1, xa);                     // in flight while source 1 is consumed
+        up_n2_fma<1>(xb, acc);
+        // rows 2j-2 (window 0) and 2j-1 (window 1) are complete
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            const float n0 = __shfl_up_sync(0xffffffffu, acc[w][1][0], 1);
+            const float n1 = __shfl_up_sync(0xffffffffu, acc[w][1][1], 1);
+            const int row = 2 * j - 2 + w;
+            if (lane >= 1 && t <= p.T && row >= 2 * j0 && row < 2 * j1)
+                *reinterpret_cast<float2*>(p.y + (((long long)b * 2 * p.F + row) * (p.T + 1) + t) * 2) =
+                    make_float2(acc[w][0][0] + n0 + b0, acc[w][0][1] + n1 + b1);
+        }
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+                acc[0][kt][o] = acc[2][kt][o];
+                acc[1][kt][o] = acc[3][kt][o];
+                acc[2][kt][o] = acc[4][kt][o];
+                acc[3][kt][o] = 0.f;
+                acc[4][kt][o] = 0.f;
+            }
+    }
+}
+
 constexpr int SW_T = 512;      // max staged time extent (+2 halo)
 
 template <int WIDE>            // number of wide channels handled per lane: WIDE/32
@@ -187,30 +276,48 @@ __global__ void __launch_bounds__(256) smallside_wgrad_kernel(const WgradParams 
         __syncthreads();
         // wide tensor row(s): wide_is_g -> G at (b, j*g_mul+g_off[0]) ; else A sources at (b, j*a_mul + a_off[0])
         const int fw = wide_is_g ? j * p.g_mul + p.g_off[0] : j * p.a_mul + p.a_off[0];
-        for (int u = warp; u < Tw; u += 8) {
-            float wv[PER];
-            if (wide_is_g) {
+        // UN positions per warp iteration: all their (independent) global loads are issued before the FMAs, so a
+        // warp keeps UN x PER 128-byte requests in flight (one request per iteration left the kernel latency-bound
+        // at ~0.55 TB/s)
+        constexpr int UN = 8 / PER;
+        for (int u0 = warp; u0 < Tw; u0 += 8 * UN) {
+            float wv[UN][PER];
 #pragma unroll
-                for (int q = 0; q < PER; ++q)
-                    wv[q] = __ldg(p.g.p + b * p.g.sB + fw * p.g.sF + (long long)u * p.g.sT + lane + 32 * q);
-            } else {
+            for (int i = 0; i < UN; ++i) {
+                const int u = u0 + 8 * i;
 #pragma unroll
-                for (int q = 0; q < PER; ++q) {
-                    const int k = lane + 32 * q;
-                    wv[q] = k < p.a[0].C ? __ldg(p.a[0].p + b * p.a[0].sB + fw * p.a[0].sF + (long long)u * p.a[0].sT + k)
-                                         : __ldg(p.a[1].p + b * p.a[1].sB + fw * p.a[1].sF + (long long)u * p.a[1].sT + (k - p.a[0].C));
+                for (int q = 0; q < PER; ++q) wv[i][q] = 0.f;
+                if (u < Tw) {
+                    if (wide_is_g) {
+#pragma unroll
+                        for (int q = 0; q < PER; ++q)
+                            wv[i][q] = __ldg(p.g.p + b * p.g.sB + fw * p.g.sF + (long long)u * p.g.sT + lane + 32 * q);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < PER; ++q) {
+                            const int k = lane + 32 * q;
+                            wv[i][q] = k < p.a[0].C ? __ldg(p.a[0].p + b * p.a[0].sB + fw * p.a[0].sF + (long long)u * p.a[0].sT + k)
+                                                    : __ldg(p.a[1].p + b * p.a[1].sB + fw * p.a[1].sF + (long long)u * p.a[1].sT + (k - p.a[0].C));
+                        }
+                    }
                 }
             }
 #pragma unroll
-            for (int tap = 0; tap < SEFD_MAX_TAPS; ++tap) {
-                if (tap < p.ntaps) {
-                    // small-tensor time for this tap: A at t+dt when wide is G (t = u); G at u-dt when wide is A
-                    const int ts = wide_is_g ? u + p.dt[tap] : u - p.dt[tap];
-                    const float2 s = srow[tap][ts + 2];
+            for (int i = 0; i < UN; ++i) {
+                const int u = u0 + 8 * i;
+                if (u < Tw) {
 #pragma unroll
-                    for (int q = 0; q < PER; ++q) {
-                        acc[tap][0][q] = fmaf(s.x, wv[q], acc[tap][0][q]);
-                        acc[tap][1][q] = fmaf(s.y, wv[q], acc[tap][1][q]);
+                    for (int tap = 0; tap < SEFD_MAX_TAPS; ++tap) {
+                        if (tap < p.ntaps) {
+                            // small-tensor time for this tap: A at t+dt when wide is G (t = u); G at u-dt when wide is A
+                            const int ts = wide_is_g ? u + p.dt[tap] : u - p.dt[tap];
+                            const float2 s = srow[tap][ts + 2];
+#pragma unroll
+                            for (int q = 0; q < PER; ++q) {
+                                acc[tap][0][q] = fmaf(s.x, wv[i][q], acc[tap][0][q]);
+                                acc[tap][1][q] = fmaf(s.y, wv[i][q], acc[tap][1][q]);
+                            }
+                        }
                     }
                 }
             }
@@ -264,6 +371,28 @@ int sefd_skinny_conv(const TapGemmParams& p, cudaStream_t st) {
     return sefd_check_launch("skinny_conv");
 }
 
+
+// decoder-5 forward (both output-row phases in one launch).  W is the packed [10][64][2] operand (device memory);
+// it is copied into the constant bank in stream order.
+bool sefd_skinny_up_n2_eligible(int Ch, int Cout) { return Ch == 32 && Cout == 2; }
+
+int sefd_skinny_up_n2(const float* x0, const float* x1, const float* W, const float* bias, float* y, int B, int F, int T,
+                      cudaStream_t st) {
+    SEFD_REQUIRE((((uintptr_t)x0 | (uintptr_t)x1) & 15) == 0 && ((uintptr_t)y & 7) == 0, "skinny_up_n2: misaligned tensors");
+    sefd_prof_label("skinny_up_n2 K64 N2 taps10 J%d Tout%d", F, T + 1);
+    const double pos = (double)B * F * T;
+    SefdProfScope prof(SEFD_PROF_TAPGEMM, 2.0 * pos * 64 * 2 * 10, 4.0 * (pos * 64 + (double)B * 2 * F * (T + 1) * 2), st);
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_upW, W, sizeof(float) * 10 * 64 * 2, 0, cudaMemcpyDeviceToDevice, st);
+    SEFD_REQUIRE(e == cudaSuccess, "skinny_up_n2: constant upload failed: %s", cudaGetErrorString(e));
+    UpN2Params p;
+    p.x0 = x0; p.x1 = x1; p.bias = bias; p.y = y; p.B = B; p.F = F; p.T = T;
+    p.JC = F >= 64 ? 16 : (F >= 8 ? 8 : F);
+    const int strips = (T + 1 + 30) / 31;
+    dim3 grid((strips + 3) / 4, (F + p.JC - 1) / p.JC, B);
+    up_n2_kernel<<<grid, 128, 0, st>>>(p);
+    return sefd_check_launch("skinny_up_n2");
+}
+
 bool sefd_skinny_wgrad_eligible(const WgradParams& p) {
     const int K = p.a[0].C + p.a[1].C, N = p.g.C;
     if (p.Tg > SW_T || p.Ta > SW_T || p.ntaps > 10) return false;
@@ -284,7 +413,7 @@ int sefd_skinny_wgrad(const WgradParams& p, cudaStream_t st) {
     const int K = p.a[0].C + p.a[1].C, N = p.g.C;
     const int wide_is_g = K == 2;
     const int rows = p.B * p.J;
-    int ctas = 148 * 2;
+    int ctas = 148 * 4;
     if (ctas > rows) ctas = rows;
     const int rpc = (rows + ctas - 1) / ctas;
     ctas = (rows + rpc - 1) / rpc;

@@ -14,16 +14,25 @@ namespace {
 
 constexpr int WM = 128, PB = 32, CHB = PB * 32 * 4;   // 4 KB per [32 ch x 32 pos] box
 constexpr int STG_LD = 33, NTHREADS = 192;
-constexpr int MAX_OPS = 10, MAX_GROUPS = 5;
+constexpr int MAX_OPS = 10, MAX_TILES = 16, MAX_GROUPS = 5;
 constexpr int SMEM_BUDGET = 225 * 1024;
 
-// A tap group: per k-step the producer loads nA activation tiles and nG gradient tiles; op i multiplies
-// A slot op_a[i] with G slot op_g[i] into TMEM accumulator i (BN columns each) and ends up in slab op_slab[i].
+// A tap group: per k-step the producer loads nA activation tiles and nG gradient tiles into consecutive slots of the
+// stage (A slots a_sp chunks apart, then G slots BN/32 chunks apart).  MMA op i multiplies the A chunks starting at
+// chunk op_a[i] with the G chunks starting at chunk op_g[i] into the TMEM columns [op_col[i], op_col[i] + op_n[i]).
+// Taps are MERGED into one MMA where the operand layout allows it:
+//   * N-merge (narrow N): taps that share the A tile and whose G tiles sit in consecutive slots become one MMA with
+//     N = run x BN (the G tiles are successive 32-channel chunks of one MN-major operand);
+//   * M-merge (K < 128): taps that share the G tile and whose A tiles sit in consecutive slots fill the 128 rows of
+//     one MMA (row = tap_in_run * K + k) instead of leaving 128 - K rows of the tensor-core tile idle.
+// The accumulator is described to the epilogue as BN-wide tiles: tile tt holds tile_nsub[tt] row blocks of K
+// (or min(128, K - m0)) rows, block s belongs to weight slab tile_slab[tt][s].
 struct Group {
-    int nA, nG, nOps;
+    int nA, nG, nOps, nTiles;
     int a_roff[MAX_OPS], a_toff[MAX_OPS];    // A tile: row = j*a_mul + a_roff, time = t0 + a_toff
     int g_roff[MAX_OPS];                     // G tile: row = j*g_mul + g_roff, time = t0
-    int op_a[MAX_OPS], op_g[MAX_OPS], op_slab[MAX_OPS];
+    int op_a[MAX_OPS], op_g[MAX_OPS], op_n[MAX_OPS], op_col[MAX_OPS];
+    int tile_nsub[MAX_TILES], tile_slab[MAX_TILES][4];
 };
 
 struct WgParams {
@@ -136,9 +145,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            // D fp32, A/B tf32, both MN-major (bits 15, 16), N = BN, M = 128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(WM >> 4) << 24);
+            // D fp32, A/B tf32, both MN-major (bits 15, 16), M = 128; N is set per op (merged taps)
+            const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(WM >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0, aphase = 0;
             for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
@@ -154,14 +162,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                         const uint32_t sa = smem_u32(stages + stage * p.stage_bytes);
                         const uint32_t sg = sa + (uint32_t)(G.nA * p.a_sp * CHB);
                         for (int o = 0; o < G.nOps; ++o) {
-                            const uint32_t abase = sa + (uint32_t)(G.op_a[o] * p.a_sp * CHB);
-                            const uint32_t gbase = sg + (uint32_t)(G.op_g[o] * NG * CHB);
+                            const uint32_t abase = sa + (uint32_t)(G.op_a[o] * CHB);
+                            const uint32_t gbase = sg + (uint32_t)(G.op_g[o] * CHB);
+                            const uint32_t id = idesc0 | ((uint32_t)(G.op_n[o] >> 3) << 17);
 #pragma unroll
                             for (int k8 = 0; k8 < PB / 8; ++k8) {
                                 // MN-major tf32: SWIZZLE_128B_BASE32B (layout type 1), LBO = stride between 32-channel
                                 // chunks, SBO = one 4-position swizzle atom (probed on hardware: tools/umma_probe.cu)
-                                tc_mma_tf32(tmem_base + (uint32_t)(o * BN), make_desc_full(abase + k8 * 1024, CHB, 512, 1),
-                                            make_desc_full(gbase + k8 * 1024, CHB, 512, 1), idesc, acc | (uint32_t)(k8 > 0));
+                                tc_mma_tf32(tmem_base + (uint32_t)G.op_col[o], make_desc_full(abase + k8 * 1024, CHB, 512, 1),
+                                            make_desc_full(gbase + k8 * 1024, CHB, 512, 1), id, acc | (uint32_t)(k8 > 0));
                             }
                         }
                         acc = 1;
@@ -184,12 +193,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             const Group& G = p.grp[x.g];
             mbar_wait(smem_u32(tfull), aphase);
             tc_fence_after();
-            for (int o = 0; o < G.nOps; ++o) {
-                float* obase = p.out + x.split * p.split_stride + (long long)G.op_slab[o] * p.K * p.N + x.n0;
+            // rows of an M-merged tile: row r = sub * K + k; otherwise r = k - m0
+            const int rows_per_sub = p.K < WM ? p.K : WM;
+            for (int tt = 0; tt < G.nTiles; ++tt) {
+                float* tbase = p.out + x.split * p.split_stride + x.n0;
 #pragma unroll 1
                 for (int ch = 0; ch < NG; ++ch) {
                     float v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(o * BN + ch * 32), v);
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tt * BN + ch * 32), v);
                     asm volatile("bar.sync 1, 128;" ::: "memory");      // previous chunk's readers are done
                     float* srow = stg + row * STG_LD;
 #pragma unroll
@@ -199,10 +210,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                     for (int pass = 0; pass < 8; ++pass) {
                         const int idx = pass * 128 + et;
                         const int r = idx >> 3, c4 = (idx & 7) * 4;
-                        const int k = x.m0 + r;
-                        if (k < p.K) {
+                        const int sub = r / rows_per_sub;
+                        const int k = x.m0 + r - sub * rows_per_sub;
+                        if (sub < G.tile_nsub[tt] && k < p.K) {
                             const float* sp = stg + r * STG_LD + c4;
-                            *reinterpret_cast<float4*>(obase + (long long)k * p.N + ch * 32 + c4) =
+                            *reinterpret_cast<float4*>(tbase + ((long long)G.tile_slab[tt][sub] * p.K + k) * p.N + ch * 32 + c4) =
                                 make_float4(sp[0], sp[1], sp[2], sp[3]);
                         }
                     }
@@ -245,43 +257,138 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& g, c
     return sefd_check_launch("wgrad_tc");
 }
 
-// Partition the taps into groups that share operand tiles.  Taps with the same A tile (a_off, dt) share an A slot,
-// taps with the same G row share a G slot.  A group is grown tap-by-tap (in kf order) while its accumulators fit
-// TMEM (nOps * BN <= 512 columns) and its stage fits the shared-memory budget.
-int build_groups(const WgradParams& w, int BN, int nAc, WgParams& p) {
+// Partition the taps into MMA runs (see Group) and the runs into groups.  A group is grown run-by-run while its
+// accumulator tiles fit TMEM (nTiles * BN <= 512 columns) and its stage fits the shared-memory budget.
+struct Run {
+    int n;                 // taps in the run
+    int tap[8];
+    int mode;              // 0: single / N-merge (shared A), 1: M-merge (shared G)
+};
+
+int build_groups(const WgradParams& w, int BN, int K, int nAc, WgParams& p) {
     const int NG = BN / 32;
-    const int max_ops = 512 / BN < MAX_OPS ? 512 / BN : MAX_OPS;
     const int max_stage = 64 * 1024;
+    // ---- tap order: taps that share an A tile next to each other, ordered by G row (enables the N-merge) ----
+    int order[SEFD_MAX_TAPS], no = 0;
+    bool used[SEFD_MAX_TAPS] = {false};
+    for (int i = 0; i < w.ntaps; ++i) {
+        if (used[i]) continue;
+        int same[SEFD_MAX_TAPS], ns = 0;
+        for (int j2 = i; j2 < w.ntaps; ++j2)
+            if (!used[j2] && w.a_off[j2] == w.a_off[i] && w.dt[j2] == w.dt[i]) { same[ns++] = j2; used[j2] = true; }
+        for (int a = 0; a < ns; ++a)
+            for (int b2 = a + 1; b2 < ns; ++b2)
+                if (w.g_off[same[b2]] < w.g_off[same[a]]) { const int t = same[a]; same[a] = same[b2]; same[b2] = t; }
+        for (int a = 0; a < ns; ++a) order[no++] = same[a];
+    }
+    // ---- runs ----
+    const int m_merge = K < WM ? WM / K : 1;            // taps per MMA along M
+    const int n_merge = BN < 256 ? 256 / BN : 1;        // taps per MMA along N
+    Run runs[SEFD_MAX_TAPS];
+    int nr = 0;
+    for (int i = 0; i < no;) {
+        Run r;
+        memset(&r, 0, sizeof(r));
+        r.tap[0] = order[i];
+        r.n = 1;
+        const int t0 = order[i];
+        int j2 = i + 1;
+        // N-merge: same A tile, G rows ascending by one
+        while (j2 < no && r.n < n_merge && r.n < 8 && w.a_off[order[j2]] == w.a_off[t0] && w.dt[order[j2]] == w.dt[t0] &&
+               w.g_off[order[j2]] == w.g_off[order[j2 - 1]] + 1) {
+            r.tap[r.n++] = order[j2++];
+        }
+        if (r.n == 1 && m_merge > 1) {
+            // M-merge: same G row, distinct A tiles (they get consecutive slots below)
+            r.mode = 1;
+            while (j2 < no && r.n < m_merge && r.n < 4 && w.g_off[order[j2]] == w.g_off[t0] &&
+                   !(w.a_off[order[j2]] == w.a_off[order[j2 - 1]] && w.dt[order[j2]] == w.dt[order[j2 - 1]])) {
+                r.tap[r.n++] = order[j2++];
+            }
+        }
+        runs[nr++] = r;
+        i = j2;
+    }
+    // ---- groups ----
     p.ngroups = 0;
     Group cur;
     memset(&cur, 0, sizeof(cur));
-    auto flush = [&]() {
-        if (cur.nOps) p.grp[p.ngroups++] = cur;
-        memset(&cur, 0, sizeof(cur));
+    auto add_run = [&](Group g, const Run& r, bool* ok) -> Group {
+        *ok = true;
+        int a_slot[8], g_slot[8];
+        // G slots: an N-merged run needs r.n consecutive slots holding its rows in order - reuse such a window if the
+        // group already has one, else append fresh slots; single taps / M-merged runs share any matching slot
+        int q0 = -1;
+        for (int q = 0; q + r.n <= g.nG && q0 < 0; ++q) {
+            bool match = true;
+            for (int i = 0; i < (r.mode == 0 ? r.n : 1); ++i) match = match && g.g_roff[q + i] == w.g_off[r.tap[i]];
+            if (match) q0 = q;
+        }
+        if (r.mode == 1 && q0 < 0)
+            for (int q = 0; q < g.nG; ++q)
+                if (g.g_roff[q] == w.g_off[r.tap[0]]) q0 = q;
+        if (q0 < 0) {
+            const int need = r.mode == 0 ? r.n : 1;
+            if (g.nG + need > MAX_OPS) { *ok = false; return g; }
+            q0 = g.nG;
+            for (int i = 0; i < need; ++i) g.g_roff[g.nG++] = w.g_off[r.tap[i]];
+        }
+        for (int i = 0; i < r.n; ++i) g_slot[i] = r.mode == 0 ? q0 + i : q0;
+        for (int i = 0; i < r.n; ++i) {
+            const int t = r.tap[i];
+            int ia = -1;
+            // an M-merged run needs its A tiles in fresh consecutive slots; otherwise slots are shared
+            if (r.mode == 0)
+                for (int a = 0; a < g.nA; ++a)
+                    if (g.a_roff[a] == w.a_off[t] && g.a_toff[a] == w.dt[t]) ia = a;
+            if (ia < 0) {
+                if (g.nA >= MAX_OPS) { *ok = false; return g; }
+                ia = g.nA; g.a_roff[ia] = w.a_off[t]; g.a_toff[ia] = w.dt[t]; ++g.nA;
+            }
+            a_slot[i] = ia;
+        }
+        (void)g_slot;
+        if (g.nOps >= MAX_OPS) { *ok = false; return g; }
+        const int o = g.nOps++;
+        g.op_a[o] = a_slot[0] * nAc;
+        g.op_g[o] = g_slot[0] * NG;
+        g.op_col[o] = g.nTiles * BN;
+        if (r.mode == 1) {
+            if (g.nTiles + 1 > MAX_TILES) { *ok = false; return g; }
+            g.op_n[o] = BN;
+            g.tile_nsub[g.nTiles] = r.n;
+            for (int i = 0; i < r.n; ++i) g.tile_slab[g.nTiles][i] = w.wslab[r.tap[i]];
+            ++g.nTiles;
+        } else {
+            if (g.nTiles + r.n > MAX_TILES) { *ok = false; return g; }
+            g.op_n[o] = r.n * BN;
+            for (int i = 0; i < r.n; ++i) {
+                g.tile_nsub[g.nTiles] = 1;
+                g.tile_slab[g.nTiles][0] = w.wslab[r.tap[i]];
+                ++g.nTiles;
+            }
+        }
+        return g;
     };
-    for (int t = 0; t < w.ntaps; ++t) {
-        // find or add slots
-        Group trial = cur;
-        int ia = -1, ig = -1;
-        for (int a = 0; a < trial.nA; ++a)
-            if (trial.a_roff[a] == w.a_off[t] && trial.a_toff[a] == w.dt[t]) ia = a;
-        if (ia < 0) { ia = trial.nA; trial.a_roff[ia] = w.a_off[t]; trial.a_toff[ia] = w.dt[t]; ++trial.nA; }
-        for (int g = 0; g < trial.nG; ++g)
-            if (trial.g_roff[g] == w.g_off[t]) ig = g;
-        if (ig < 0) { ig = trial.nG; trial.g_roff[ig] = w.g_off[t]; ++trial.nG; }
-        trial.op_a[trial.nOps] = ia; trial.op_g[trial.nOps] = ig; trial.op_slab[trial.nOps] = w.wslab[t];
-        ++trial.nOps;
-        const int bytes = (trial.nA * nAc + trial.nG * NG) * CHB;   // A slots are spaced nAc chunks apart
-        if (cur.nOps && (trial.nOps > max_ops || bytes > max_stage)) {
-            flush();
-            --t;            // retry this tap in a fresh group
+    for (int i = 0; i < nr; ++i) {
+        bool ok;
+        Group trial = add_run(cur, runs[i], &ok);
+        const int bytes = (trial.nA * nAc + trial.nG * NG) * CHB;
+        if (!ok || trial.nTiles * BN > 512 || bytes > max_stage) {
+            if (!cur.nOps) return -1;                   // a single run does not fit
+            if (p.ngroups >= MAX_GROUPS) return -1;
+            p.grp[p.ngroups++] = cur;
+            memset(&cur, 0, sizeof(cur));
+            --i;                                        // retry this run in a fresh group
             continue;
         }
         cur = trial;
-        if (p.ngroups >= MAX_GROUPS) return -1;
     }
-    flush();
-    return p.ngroups <= MAX_GROUPS ? 0 : -1;
+    if (cur.nOps) {
+        if (p.ngroups >= MAX_GROUPS) return -1;
+        p.grp[p.ngroups++] = cur;
+    }
+    return 0;
 }
 
 }  // namespace
@@ -314,7 +421,7 @@ int sefd_wgrad_tc(const WgradParams& w, float* partial, long long cap_floats, in
     if (w.a[1].C) {
         while ((w.a[0].C / 32) % p.a_box || (w.a[1].C / 32) % p.a_box) p.a_box >>= 1;
     }
-    SEFD_REQUIRE(build_groups(w, BN, p.a_sp, p) == 0, "wgrad_tc: tap grouping failed");
+    SEFD_REQUIRE(build_groups(w, BN, K, p.a_sp, p) == 0, "wgrad_tc: tap grouping failed");
     int stage = 0;
     for (int g = 0; g < p.ngroups; ++g) {
         const int b = (p.grp[g].nA * p.a_sp + p.grp[g].nG * (BN / 32)) * CHB + 3 * CHB;   // + slack: the MMA always reads 4 chunks
@@ -333,7 +440,7 @@ int sefd_wgrad_tc(const WgradParams& w, float* partial, long long cap_floats, in
     long long splits = (2 * 148 + tiles - 1) / tiles;
     if (splits > rows) splits = rows;
     if (splits > cap_floats / one) splits = cap_floats / one;
-    if (splits > 64) splits = 64;
+    if (splits > 2 * 148) splits = 2 * 148;
     SEFD_REQUIRE(splits >= 1, "wgrad_tc: partial buffer too small");
     p.rows_per_split = (int)((rows + splits - 1) / splits);
     p.splits = (rows + p.rows_per_split - 1) / p.rows_per_split;
