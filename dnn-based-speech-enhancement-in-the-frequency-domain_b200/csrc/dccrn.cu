@@ -32,7 +32,7 @@ struct ConvLayer {
     long long wr, br, wi, bi, gamma, beta, alpha;   // param offsets (gamma < 0: no BN/PReLU)
     long long rmean, rvar;                           // bn buffer offsets
     // workspace offsets (floats)
-    size_t y, z, Wf, Wt, bias, stats /*doubles*/, save, dz, dz2;
+    size_t y, z, Wf, Wt, bias, stats /*doubles*/, save, dz, dz2, dy;
 };
 
 }  // namespace
@@ -206,6 +206,8 @@ sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode) {
         c.z = w.floats(n);
         c.dz = w.floats(n);      // gradient through the skip connection (written by the decoder's data gradient)
         c.dz2 = w.floats(n);     // gradient from the next encoder layer / the LSTM; BN backward sums the two
+        c.dy = w.floats(n);      // gradient w.r.t. the raw conv output (own buffer per layer: wgrad and dgrad of
+                                 // different layers never alias, so weight gradients may run on a side stream)
         c.Wf = w.floats(10ull * c.Cin * c.Cout);
         c.Wt = w.floats(10ull * c.Cin * c.Cout);
         c.bias = w.floats(c.Cout);
@@ -219,6 +221,7 @@ sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode) {
         ConvLayer& c = P->dec[j];
         const size_t ny = Bz * c.Fout * (T + 1) * c.Cout, nz = Bz * c.Fout * T * c.Cout;
         c.y = w.floats(ny);
+        c.dy = w.floats(ny);
         c.z = j != NL - 1 ? w.floats(nz) : 0;
         c.dz = j != NL - 1 ? w.floats(nz) : 0;
         c.Wf = w.floats(10ull * c.Cin * c.Cout);
@@ -254,7 +257,7 @@ sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode) {
     // backward scratch
     P->dU = w.floats(Bz * 4 * T * 256);
     P->dY_floats = max_y;
-    P->dY = w.floats(max_y);
+    P->dY = 0;
     if (max_w < 4ull * 128 * G4) max_w = 4ull * 128 * G4;
     P->dWs_floats = 16 * max_w;                   // room for the split partials of the tensor-core wgrad
     P->dWs = w.floats(16 * max_w);
@@ -470,13 +473,12 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
     float* ws = (float*)wsv;
     double* wsd = (double*)wsv;
     const int B = P->B, T = P->T, L = P->L;
-    float* dY = ws + P->dY;
     float* dWs = ws + P->dWs;
 
     auto bn_bwd = [&](const ConvLayer& c, int Ty, int tshift, bool two) -> int {
         BnPreluBwdParams b;
         memset(&b, 0, sizeof(b));
-        b.y = ws + c.y; b.dz = ws + c.dz; b.dy = dY;
+        b.y = ws + c.y; b.dz = ws + c.dz; b.dy = ws + c.dy;
         b.dz2 = two ? ws + c.dz2 : nullptr;
         b.BF = B * c.Fout; b.Ty = Ty; b.T = T; b.tshift = tshift; b.C = c.Cout;
         b.n_stat = (double)B * c.Fout * Ty;
@@ -511,7 +513,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
     {
         MaskIstftBwdParams m;
         memset(&m, 0, sizeof(m));
-        m.dwav = dwav; m.raw_wav = ws + P->raw_wav; m.spec = ws + P->spec; m.mask = ws + last.y; m.dmask = dY;
+        m.dwav = dwav; m.raw_wav = ws + P->raw_wav; m.spec = ws + P->spec; m.mask = ws + last.y; m.dmask = ws + last.dy;
         m.mT = 2; m.mF = (long long)(T + 1) * 2; m.mB = (long long)256 * (T + 1) * 2;
         m.m_tshift = 1; m.mode = P->mask_mode; m.B = B; m.L = L; m.T = T;
         SEFD_TRY(sefd_mask_istft_bwd_launch(m, st));
@@ -523,6 +525,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
         const int Ch = c.Cin / 2;
         const float* in0 = j == 0 ? ws + P->U : ws + P->dec[j - 1].z;
         const float* in1 = ws + P->enc[NL - 1 - j].z;
+        float* dY = ws + c.dy;
         const float* dbias = nullptr;
         if (j != NL - 1) {
             SEFD_TRY(bn_bwd(c, T + 1, 1, false));
@@ -670,6 +673,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
     // ---- encoder backward ----
     for (int i = NL - 1; i >= 0; --i) {
         const ConvLayer& c = P->enc[i];
+        float* dY = ws + c.dy;
         SEFD_TRY(bn_bwd(c, T, 0, true));
         WgradParams wg;
         memset(&wg, 0, sizeof(wg));
@@ -753,6 +757,8 @@ int sefd_dccrn_tensor_info(const sefd_plan* P, const char* name, long long* off,
     if (n == "dX") return set(P->dX, 2, B, T, RNN_H);
     if (n == "U") return set(P->U, B, 4, T, 256);
     if (n == "dU") return set(P->dU, B, 4, T, 256);
+    if (n == "dH") return set(P->dH, 2, 2 * B, T, RNN_H);
+    if (n == "dG") return set(P->dG, 2, 2 * B, T, G4);
     if (n.size() >= 6 && (n.compare(0, 3, "enc") == 0 || n.compare(0, 3, "dec") == 0)) {
         const bool dec = n[0] == 'd';
         const int i = n[3] - '0';
@@ -763,6 +769,7 @@ int sefd_dccrn_tensor_info(const sefd_plan* P, const char* name, long long* off,
         if (f == "z" && !(dec && i == NL - 1)) return set(c.z, B, c.Fout, T, c.Cout);
         if (f == "dz" && !(dec && i == NL - 1)) return set(c.dz, B, c.Fout, T, c.Cout);
         if (f == "dz2" && !dec) return set(c.dz2, B, c.Fout, T, c.Cout);
+        if (f == "dy") return set(c.dy, B, c.Fout, dec ? T + 1 : T, c.Cout);
     }
     if (n.size() == 7 && n.compare(0, 4, "lstm") == 0 && n[5] == '.') {
         const int l = n[4] - '0';

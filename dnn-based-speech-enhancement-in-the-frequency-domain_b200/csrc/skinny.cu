@@ -3,6 +3,8 @@
 // HBM-bound (intensity ~9 FLOP/B), so they are CUDA-core kernels organised around ONE pass
 // over the wide (32/64-channel) tensor with the 2-channel tensor read at the tap offsets.  Same TapGemmParams /
 // WgradParams contract as the generic engines.
+#include <string.h>
+
 #include "common.cuh"
 #include "prof.cuh"
 
@@ -16,7 +18,6 @@ template <int N>
 __global__ void __launch_bounds__(128) smallk_conv_kernel(const TapGemmParams p) {
     __shared__ __align__(16) float Ws[SEFD_MAX_TAPS * 2 * N];
     __shared__ float stg[128 * (N + 1)];
-    __shared__ float s_stat[2 * N];
     const int tid = threadIdx.x;
     const int ttiles = (p.Tout + 127) / 128;
     const int t0 = (blockIdx.x % ttiles) * 128;
@@ -72,7 +73,9 @@ __global__ void __launch_bounds__(128) smallk_conv_kernel(const TapGemmParams p)
         *reinterpret_cast<float4*>(dst) = v;
     }
     if (p.stats) {
-        // 128 threads: column c = tid % N, row part = tid / N
+        // 128 threads: column c = tid % N, row part = tid / N.  The partial sums are combined in a FIXED order
+        // (no floating-point atomics): the BatchNorm statistics - and with them every PReLU branch decision
+        // downstream - must not depend on the scheduling of this CTA's warps.
         constexpr int PARTS = 128 / N;
         const int c = tid % N, part = tid / N;
         float s1 = 0.f, s2 = 0.f;
@@ -83,14 +86,15 @@ __global__ void __launch_bounds__(128) smallk_conv_kernel(const TapGemmParams p)
                 s2 += x * x;
             }
         }
-        if (tid < 2 * N) s_stat[tid] = 0.f;
+        __syncthreads();                       // all reads of stg are done: reuse it for the partials
+        stg[part * 2 * N + c] = s1;
+        stg[part * 2 * N + N + c] = s2;
         __syncthreads();
-        atomicAdd(&s_stat[c], s1);
-        atomicAdd(&s_stat[N + c], s2);
-        __syncthreads();
-        if (tid < N) {
-            atomicAdd(p.stats + tid, (double)s_stat[tid]);
-            atomicAdd(p.stats + N + tid, (double)s_stat[N + tid]);
+        if (tid < 2 * N) {
+            float s = 0.f;
+#pragma unroll
+            for (int q = 0; q < PARTS; ++q) s += stg[q * 2 * N + tid];
+            atomicAdd(p.stats + tid, (double)s);
         }
     }
 }
@@ -237,17 +241,29 @@ __global__ void __launch_bounds__(128) up_n2_kernel(const UpN2Params p) {
     }
 }
 
-constexpr int SW_T = 512;      // max staged time extent (+2 halo)
+// distinct rows of the 2-channel operand touched by the taps (host-side dedupe of a_off / g_off)
+struct SkinnyAux {
+    int nslots;
+    int slot_off[SEFD_MAX_TAPS];     // row offset of slot s: row = j * mul + slot_off[s]
+    int tap_slot[SEFD_MAX_TAPS];
+    int tap_dt[SEFD_MAX_TAPS];       // time of the 2-channel operand relative to the wide operand's time
+};
 
-template <int WIDE>            // number of wide channels handled per lane: WIDE/32
-__global__ void __launch_bounds__(256) smallside_wgrad_kernel(const WgradParams p, int wide_is_g, int rows_per_cta) {
-    constexpr int PER = WIDE / 32;
-    __shared__ float2 srow[10][SW_T + 4];              // small tensor rows per tap (<= 10 taps), index = time + 2
+constexpr int SW_CH = 128;           // wide-operand positions per work item
+
+template <int PER, bool WIDE_IS_G>     // PER = wide channels per lane (WIDE / 32)
+__global__ void __launch_bounds__(256, 2) smallside_wgrad_kernel(const WgradParams p, const SkinnyAux aux, int chunks) {
+    constexpr int WIDE = 32 * PER;
+    constexpr int UN = 8 / PER;                          // positions whose wide loads are in flight together
+    constexpr int SLD = SW_CH + 4;                       // staged times [u_lo - 2, u_lo + SW_CH + 2)
+    constexpr int NPRE = (SEFD_MAX_TAPS * SLD + 255) / 256;
+    __shared__ float2 srow[SEFD_MAX_TAPS][SLD];
     __shared__ float sred[SEFD_MAX_TAPS * 2 * WIDE];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const TapSrc& small = wide_is_g ? p.a[0] : p.g;
-    const int Fs = wide_is_g ? p.Fa : p.Fg, Ts = wide_is_g ? p.Ta : p.Tg;
-    const int Tw = wide_is_g ? p.Tg : p.Ta;             // wide tensor time extent
+    const TapSrc& small = WIDE_IS_G ? p.a[0] : p.g;
+    const int Fs = WIDE_IS_G ? p.Fa : p.Fg, Ts = WIDE_IS_G ? p.Ta : p.Tg;
+    const int Tw = WIDE_IS_G ? p.Tg : p.Ta;              // wide tensor time extent
+    const int smul = WIDE_IS_G ? p.a_mul : p.g_mul;
     float acc[SEFD_MAX_TAPS][2][PER];
 #pragma unroll
     for (int a = 0; a < SEFD_MAX_TAPS; ++a)
@@ -256,67 +272,77 @@ __global__ void __launch_bounds__(256) smallside_wgrad_kernel(const WgradParams 
 #pragma unroll
             for (int q = 0; q < PER; ++q) acc[a][c][q] = 0.f;
 
-    const int rows = p.B * p.J;
-    const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
-    for (int r = r0; r < r1; ++r) {
+    // work item = (b, j) row x chunk of SW_CH positions.  The rows of the 2-channel operand the taps touch are
+    // staged in shared memory (prefetched into registers one item ahead), the wide operand is streamed once with
+    // UN x PER 128-byte requests in flight per warp.
+    const long long items = (long long)p.B * p.J * chunks;
+    const int nstage = aux.nslots * SLD;
+    float2 pre[NPRE];
+    auto fetch = [&](long long item) {
+        const int r = (int)(item / chunks), ch = (int)(item % chunks);
         const int b = r / p.J, j = r % p.J;
-        __syncthreads();
-        // stage the small tensor rows (zero outside the tensor)
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-            const int fs = wide_is_g ? j * p.a_mul + p.a_off[tap] : j * p.g_mul + p.g_off[tap];
-            const bool ok = fs >= 0 && fs < Fs;
-            const float* base = small.p + b * small.sB + (ok ? fs : 0) * small.sF;
-            for (int i = tid; i < Tw + 4; i += 256) {
-                const int ts = i - 2;
-                float2 v = make_float2(0.f, 0.f);
-                if (ok && ts >= 0 && ts < Ts) v = __ldg(reinterpret_cast<const float2*>(base + (long long)ts * small.sT));
-                srow[tap][i] = v;
+        const int u_lo = ch * SW_CH;
+#pragma unroll
+        for (int q = 0; q < NPRE; ++q) {
+            const int idx = tid + q * 256;
+            pre[q] = make_float2(0.f, 0.f);
+            if (idx < nstage) {
+                const int slot = idx / SLD, i = idx - slot * SLD;
+                const int fs = j * smul + aux.slot_off[slot], ts = u_lo - 2 + i;
+                if (fs >= 0 && fs < Fs && ts >= 0 && ts < Ts)
+                    pre[q] = __ldg(reinterpret_cast<const float2*>(small.p + b * small.sB + fs * small.sF + (long long)ts * small.sT));
             }
         }
+    };
+    long long item = blockIdx.x;
+    if (item < items) fetch(item);
+    for (; item < items; item += gridDim.x) {
+        __syncthreads();                                 // the previous item's readers are done
+#pragma unroll
+        for (int q = 0; q < NPRE; ++q) {
+            const int idx = tid + q * 256;
+            if (idx < nstage) (&srow[0][0])[idx] = pre[q];
+        }
         __syncthreads();
-        // wide tensor row(s): wide_is_g -> G at (b, j*g_mul+g_off[0]) ; else A sources at (b, j*a_mul + a_off[0])
-        const int fw = wide_is_g ? j * p.g_mul + p.g_off[0] : j * p.a_mul + p.a_off[0];
-        // UN positions per warp iteration: all their (independent) global loads are issued before the FMAs, so a
-        // warp keeps UN x PER 128-byte requests in flight (one request per iteration left the kernel latency-bound
-        // at ~0.55 TB/s)
-        constexpr int UN = 8 / PER;
-        for (int u0 = warp; u0 < Tw; u0 += 8 * UN) {
+        const int r = (int)(item / chunks), ch = (int)(item % chunks);
+        const int b = r / p.J, j = r % p.J;
+        const int u_lo = ch * SW_CH, u_hi = min(Tw, u_lo + SW_CH);
+        if (item + gridDim.x < items) fetch(item + gridDim.x);
+        const int fw = WIDE_IS_G ? j * p.g_mul + p.g_off[0] : j * p.a_mul + p.a_off[0];
+        const float* wbase[PER];
+        if (WIDE_IS_G) {
+#pragma unroll
+            for (int q = 0; q < PER; ++q) wbase[q] = p.g.p + b * p.g.sB + fw * p.g.sF + lane + 32 * q;
+        } else {
+#pragma unroll
+            for (int q = 0; q < PER; ++q) {
+                const int k = lane + 32 * q;
+                wbase[q] = k < p.a[0].C ? p.a[0].p + b * p.a[0].sB + fw * p.a[0].sF + k
+                                        : p.a[1].p + b * p.a[1].sB + fw * p.a[1].sF + (k - p.a[0].C);
+            }
+        }
+        const long long wsT = WIDE_IS_G ? p.g.sT : p.a[0].sT;    // both A sources share the time stride here
+        constexpr int PW = SW_CH / 8;                            // positions per warp
+        const int uw = u_lo + warp * PW;
+#pragma unroll 1
+        for (int h = 0; h < PW; h += UN) {
             float wv[UN][PER];
 #pragma unroll
+            for (int i = 0; i < UN; ++i)
+#pragma unroll
+                for (int q = 0; q < PER; ++q)
+                    wv[i][q] = uw + h + i < u_hi ? __ldg(wbase[q] + (long long)(uw + h + i) * wsT) : 0.f;
+#pragma unroll
             for (int i = 0; i < UN; ++i) {
-                const int u = u0 + 8 * i;
+                const int ul = warp * PW + h + i + 2;            // index into the staged rows (time u <-> u - u_lo + 2)
 #pragma unroll
-                for (int q = 0; q < PER; ++q) wv[i][q] = 0.f;
-                if (u < Tw) {
-                    if (wide_is_g) {
-#pragma unroll
-                        for (int q = 0; q < PER; ++q)
-                            wv[i][q] = __ldg(p.g.p + b * p.g.sB + fw * p.g.sF + (long long)u * p.g.sT + lane + 32 * q);
-                    } else {
+                for (int tap = 0; tap < SEFD_MAX_TAPS; ++tap) {
+                    if (tap < p.ntaps) {
+                        const float2 sv = srow[aux.tap_slot[tap]][ul + aux.tap_dt[tap]];
 #pragma unroll
                         for (int q = 0; q < PER; ++q) {
-                            const int k = lane + 32 * q;
-                            wv[i][q] = k < p.a[0].C ? __ldg(p.a[0].p + b * p.a[0].sB + fw * p.a[0].sF + (long long)u * p.a[0].sT + k)
-                                                    : __ldg(p.a[1].p + b * p.a[1].sB + fw * p.a[1].sF + (long long)u * p.a[1].sT + (k - p.a[0].C));
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < UN; ++i) {
-                const int u = u0 + 8 * i;
-                if (u < Tw) {
-#pragma unroll
-                    for (int tap = 0; tap < SEFD_MAX_TAPS; ++tap) {
-                        if (tap < p.ntaps) {
-                            // small-tensor time for this tap: A at t+dt when wide is G (t = u); G at u-dt when wide is A
-                            const int ts = wide_is_g ? u + p.dt[tap] : u - p.dt[tap];
-                            const float2 s = srow[tap][ts + 2];
-#pragma unroll
-                            for (int q = 0; q < PER; ++q) {
-                                acc[tap][0][q] = fmaf(s.x, wv[i][q], acc[tap][0][q]);
-                                acc[tap][1][q] = fmaf(s.y, wv[i][q], acc[tap][1][q]);
-                            }
+                            acc[tap][0][q] = fmaf(sv.x, wv[i][q], acc[tap][0][q]);
+                            acc[tap][1][q] = fmaf(sv.y, wv[i][q], acc[tap][1][q]);
                         }
                     }
                 }
@@ -324,6 +350,7 @@ __global__ void __launch_bounds__(256) smallside_wgrad_kernel(const WgradParams 
         }
     }
     // reduce the 8 warps through shared memory, then one atomic per output element and CTA
+    __syncthreads();
     for (int i = tid; i < p.ntaps * 2 * WIDE; i += 256) sred[i] = 0.f;
     __syncthreads();
 #pragma unroll
@@ -337,7 +364,7 @@ __global__ void __launch_bounds__(256) smallside_wgrad_kernel(const WgradParams 
     for (int i = tid; i < p.ntaps * 2 * WIDE; i += 256) {
         const int tap = i / (2 * WIDE), c = (i / WIDE) % 2, w = i % WIDE;
         // dW[slab][k][n]: encoder 0 -> k = c (2), n = w (WIDE) ; decoder 5 -> k = w (WIDE), n = c (2)
-        const long long off = wide_is_g ? ((long long)p.wslab[tap] * 2 + c) * WIDE + w
+        const long long off = WIDE_IS_G ? ((long long)p.wslab[tap] * 2 + c) * WIDE + w
                                         : ((long long)p.wslab[tap] * WIDE + w) * 2 + c;
         atomicAdd(p.dW + off, sred[i]);
     }
@@ -395,7 +422,7 @@ int sefd_skinny_up_n2(const float* x0, const float* x1, const float* W, const fl
 
 bool sefd_skinny_wgrad_eligible(const WgradParams& p) {
     const int K = p.a[0].C + p.a[1].C, N = p.g.C;
-    if (p.Tg > SW_T || p.Ta > SW_T || p.ntaps > 10) return false;
+    if (p.ntaps > SEFD_MAX_TAPS) return false;
     if (K == 2 && p.a[1].C == 0 && N == 32) {          // wide = G: all taps must share the G row and time
         for (int i = 0; i < p.ntaps; ++i)
             if (p.g_off[i] != p.g_off[0]) return false;
@@ -412,18 +439,31 @@ bool sefd_skinny_wgrad_eligible(const WgradParams& p) {
 int sefd_skinny_wgrad(const WgradParams& p, cudaStream_t st) {
     const int K = p.a[0].C + p.a[1].C, N = p.g.C;
     const int wide_is_g = K == 2;
-    const int rows = p.B * p.J;
-    int ctas = 148 * 4;
-    if (ctas > rows) ctas = rows;
-    const int rpc = (rows + ctas - 1) / ctas;
-    ctas = (rows + rpc - 1) / rpc;
+    const int Tw = wide_is_g ? p.Tg : p.Ta;
+    const int chunks = (Tw + SW_CH - 1) / SW_CH;
+    const long long items = (long long)p.B * p.J * chunks;
+    long long ctas = 148 * 2;
+    if (ctas > items) ctas = items;
+    SkinnyAux aux;
+    memset(&aux, 0, sizeof(aux));
+    for (int t = 0; t < p.ntaps; ++t) {
+        const int off = wide_is_g ? p.a_off[t] : p.g_off[t];
+        int s = -1;
+        for (int q = 0; q < aux.nslots; ++q)
+            if (aux.slot_off[q] == off) s = q;
+        if (s < 0) { s = aux.nslots++; aux.slot_off[s] = off; }
+        aux.tap_slot[t] = s;
+        // 2-channel operand time: A at t+dt when the wide operand is G (t = u); G at u-dt when the wide operand is A
+        aux.tap_dt[t] = wide_is_g ? p.dt[t] : -p.dt[t];
+        SEFD_REQUIRE(aux.tap_dt[t] >= -2 && aux.tap_dt[t] <= 2, "skinny_wgrad: time shift %d beyond the staged halo", aux.tap_dt[t]);
+    }
     const double pos = (double)p.B * p.J * p.Tg;
     sefd_prof_label("skinny_wgrad K%d N%d taps%d J%d", K, N, p.ntaps, p.J);
     SefdProfScope prof(SEFD_PROF_WGRAD, 2.0 * pos * K * N * p.ntaps,
                        4.0 * ((double)p.B * p.J * (p.a_mul > 1 ? p.a_mul : 1) * p.Ta * K +
                               (double)p.B * p.J * (p.g_mul > 1 ? p.g_mul : 1) * p.Tg * N), st);
-    if (wide_is_g) smallside_wgrad_kernel<32><<<ctas, 256, 0, st>>>(p, 1, rpc);
-    else if (K == 64) smallside_wgrad_kernel<64><<<ctas, 256, 0, st>>>(p, 0, rpc);
-    else smallside_wgrad_kernel<32><<<ctas, 256, 0, st>>>(p, 0, rpc);
+    if (wide_is_g) smallside_wgrad_kernel<1, true><<<(unsigned)ctas, 256, 0, st>>>(p, aux, chunks);
+    else if (K == 64) smallside_wgrad_kernel<2, false><<<(unsigned)ctas, 256, 0, st>>>(p, aux, chunks);
+    else smallside_wgrad_kernel<1, false><<<(unsigned)ctas, 256, 0, st>>>(p, aux, chunks);
     return sefd_check_launch("skinny_wgrad");
 }

@@ -58,7 +58,7 @@ struct Cfg {
     static constexpr int A_ROWS = PAIR ? 136 : TM;
     static constexpr int A_TILE = A_ROWS * KB * 4;
     static constexpr int B_BYTES = BN * KB * 4;
-    static constexpr int FIXED = TM * STG_LD * 4 + 2 * BN * 4 + (2 * MAX_STAGES + 4) * 8 + 64;
+    static constexpr int FIXED = TM * STG_LD * 4 + 8 * BN * 4 + (2 * MAX_STAGES + 4) * 8 + 64;
 };
 
 struct TileCoord {
@@ -84,7 +84,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     extern __shared__ __align__(1024) unsigned char smem[];
     float* stg = reinterpret_cast<float*>(smem + p.nstage * p.stage_bytes);
     float* s_stat = stg + TM * STG_LD;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + 2 * BN);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + 8 * BN);   // s_stat[part 0..3][sum | sum sq][BN]
     uint64_t* full = bars;
     uint64_t* empty = bars + MAX_STAGES;
     uint64_t* tfull = bars + 2 * MAX_STAGES;
@@ -107,7 +107,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < 2 * BN; i += NTHREADS) s_stat[i] = 0.f;
+    for (int i = threadIdx.x; i < 8 * BN; i += NTHREADS) s_stat[i] = 0.f;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512)
                      : "memory");
@@ -266,8 +266,9 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                             s2 += x * x;
                         }
                     }
-                    atomicAdd(&s_stat[ch * 32 + c], s1);
-                    atomicAdd(&s_stat[BN + ch * 32 + c], s2);
+                    // slot (part, column) is owned by this thread: plain adds, fixed order (deterministic statistics)
+                    s_stat[part * 2 * BN + ch * 32 + c] += s1;
+                    s_stat[part * 2 * BN + BN + ch * 32 + c] += s2;
                 }
             }
             if (++abuf == 2) { abuf = 0; aphase ^= 1; }
@@ -275,8 +276,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         if (p.stats) {
             asm volatile("bar.sync 1, 128;" ::: "memory");
             for (int i = et; i < BN; i += 128) {
-                atomicAdd(p.stats + i, (double)s_stat[i]);
-                atomicAdd(p.stats + p.N + i, (double)s_stat[BN + i]);
+                const float a = (s_stat[i] + s_stat[2 * BN + i]) + (s_stat[4 * BN + i] + s_stat[6 * BN + i]);
+                const float b = (s_stat[BN + i] + s_stat[3 * BN + i]) + (s_stat[5 * BN + i] + s_stat[7 * BN + i]);
+                atomicAdd(p.stats + i, (double)a);
+                atomicAdd(p.stats + p.N + i, (double)b);
             }
         }
     }

@@ -268,22 +268,27 @@ struct Run {
 int build_groups(const WgradParams& w, int BN, int K, int nAc, WgParams& p) {
     const int NG = BN / 32;
     const int max_stage = 64 * 1024;
-    // ---- tap order: taps that share an A tile next to each other, ordered by G row (enables the N-merge) ----
+    const int m_merge = K < WM ? WM / K : 1;            // taps per MMA along M
+    const int n_merge = BN <= 64 ? 256 / BN : 1;        // taps per MMA along N (wide tiles are efficient MMAs already)
+    // ---- tap order (narrow N only): taps that share an A tile next to each other, ordered by G row, so that they
+    // can be N-merged; otherwise the caller's order (kf-major: consecutive taps share the G tile) is kept ----
     int order[SEFD_MAX_TAPS], no = 0;
-    bool used[SEFD_MAX_TAPS] = {false};
-    for (int i = 0; i < w.ntaps; ++i) {
-        if (used[i]) continue;
-        int same[SEFD_MAX_TAPS], ns = 0;
-        for (int j2 = i; j2 < w.ntaps; ++j2)
-            if (!used[j2] && w.a_off[j2] == w.a_off[i] && w.dt[j2] == w.dt[i]) { same[ns++] = j2; used[j2] = true; }
-        for (int a = 0; a < ns; ++a)
-            for (int b2 = a + 1; b2 < ns; ++b2)
-                if (w.g_off[same[b2]] < w.g_off[same[a]]) { const int t = same[a]; same[a] = same[b2]; same[b2] = t; }
-        for (int a = 0; a < ns; ++a) order[no++] = same[a];
+    if (n_merge > 1) {
+        bool used[SEFD_MAX_TAPS] = {false};
+        for (int i = 0; i < w.ntaps; ++i) {
+            if (used[i]) continue;
+            int same[SEFD_MAX_TAPS], ns = 0;
+            for (int j2 = i; j2 < w.ntaps; ++j2)
+                if (!used[j2] && w.a_off[j2] == w.a_off[i] && w.dt[j2] == w.dt[i]) { same[ns++] = j2; used[j2] = true; }
+            for (int a = 0; a < ns; ++a)
+                for (int b2 = a + 1; b2 < ns; ++b2)
+                    if (w.g_off[same[b2]] < w.g_off[same[a]]) { const int t = same[a]; same[a] = same[b2]; same[b2] = t; }
+            for (int a = 0; a < ns; ++a) order[no++] = same[a];
+        }
+    } else {
+        for (int i = 0; i < w.ntaps; ++i) order[no++] = i;
     }
     // ---- runs ----
-    const int m_merge = K < WM ? WM / K : 1;            // taps per MMA along M
-    const int n_merge = BN < 256 ? 256 / BN : 1;        // taps per MMA along N
     Run runs[SEFD_MAX_TAPS];
     int nr = 0;
     for (int i = 0; i < no;) {
@@ -309,6 +314,12 @@ int build_groups(const WgradParams& w, int BN, int K, int nAc, WgParams& p) {
         runs[nr++] = r;
         i = j2;
     }
+    // runs that read the same G window next to each other (they then share the G slots of a group)
+    if (n_merge > 1)
+        for (int a = 1; a < nr; ++a)
+            for (int b2 = a; b2 > 0 && w.g_off[runs[b2].tap[0]] < w.g_off[runs[b2 - 1].tap[0]]; --b2) {
+                const Run t = runs[b2]; runs[b2] = runs[b2 - 1]; runs[b2 - 1] = t;
+            }
     // ---- groups ----
     p.ngroups = 0;
     Group cur;
@@ -421,7 +432,7 @@ int sefd_wgrad_tc(const WgradParams& w, float* partial, long long cap_floats, in
     if (w.a[1].C) {
         while ((w.a[0].C / 32) % p.a_box || (w.a[1].C / 32) % p.a_box) p.a_box >>= 1;
     }
-    SEFD_REQUIRE(build_groups(w, BN, K, p.a_sp, p) == 0, "wgrad_tc: tap grouping failed");
+    SEFD_REQUIRE(build_groups(w, BN, K, p.a_sp, p) == 0, "wgrad_tc: tap grouping failed (K %d N %d BN %d taps %d)", K, N, BN, w.ntaps);
     int stage = 0;
     for (int g = 0; g < p.ngroups; ++g) {
         const int b = (p.grp[g].nA * p.a_sp + p.grp[g].nG * (BN / 32)) * CHB + 3 * CHB;   // + slack: the MMA always reads 4 chunks

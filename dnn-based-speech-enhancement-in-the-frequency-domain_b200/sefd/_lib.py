@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsefd.so")
+LIB_PATH = os.environ.get("SEFD_LIB") or os.path.join(_HERE, "libsefd.so")   # SEFD_LIB: A/B-test another build
 
 _vp, _i, _f, _ll, _sz = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t
 
