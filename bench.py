@@ -30,7 +30,11 @@ import torch  # noqa: E402
 
 L = 48000
 METRIC = "utterances/sec DCCRN train step (3s@16kHz)"
-CATS = ["tapgemm (conv/convT/linear fwd+dgrad)", "wgrad", "bn_prelu", "lstm", "stft_istft_loss", "pack_reduce_adam"]
+# kernel categories of csrc/prof.cuh: (name, roofline that bounds it)
+CATS = [("tapgemm_tc (conv/convT/linear fwd+dgrad, tcgen05 tf32)", "tensor"), ("wgrad_tc (weight gradients, tcgen05 tf32)", "tensor"),
+        ("bn_prelu (fwd + 2-pass bwd)", "hbm"), ("lstm recurrence (latency-bound)", "hbm"), ("stft / mask+istft / loss", "hbm"),
+        ("pack / fold / reductions / adam", None), ("skinny 2-channel layers (CUDA cores)", "hbm")]
+NCU_TRAFFIC = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # per-kernel DRAM bytes per launch from the committed ncu capture
 
 
 def synthetic(B, seed, device=None, pin=False):
@@ -209,13 +213,6 @@ def main():
         lib.sefd_prof_enable(0)
         if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
             lib.sefd_prof_dump(os.path.join(ROOT, "gpurun_out", "launch_profile.csv").encode())
-        breakdown = {}
-        for c, name in enumerate(CATS):
-            t, n, f, b = C.c_double(), C.c_longlong(), C.c_double(), C.c_double()
-            lib.sefd_prof_get(c, C.byref(t), C.byref(n), C.byref(f), C.byref(b))
-            breakdown[name] = {"ms": round(t.value, 3), "launches": n.value, "gflop": round(f.value / 1e9, 1),
-                               "gbyte": round(b.value / 1e9, 3)}
-        lib.sefd_prof_reset()
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -223,21 +220,52 @@ def main():
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         bf16_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
-        src = "measured" if peaks else "fallback"
+        src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        tf32_peak = bf16_peak / 2.0                         # TF32 dense = 1/2 of the bf16 tensor rate
+        try:
+            traffic = json.load(open(NCU_TRAFFIC))
+        except OSError:
+            traffic = {}
+        breakdown = {}
+        for c, (name, bound) in enumerate(CATS):
+            t, n, f, b = C.c_double(), C.c_longlong(), C.c_double(), C.c_double()
+            lib.sefd_prof_get(c, C.byref(t), C.byref(n), C.byref(f), C.byref(b))
+            e = {"ms": round(t.value, 3), "launches": n.value, "gflop": round(f.value / 1e9, 1),
+                 "gbyte": round(b.value / 1e9, 3)}
+            if t.value > 0 and bound == "tensor":
+                e["tflops"] = round(f.value / 1e9 / t.value, 1)
+                e["frac_of_tf32_peak"] = round(e["tflops"] / tf32_peak, 3)
+            elif t.value > 0 and bound == "hbm":
+                e["gbs"] = round(b.value / 1e6 / t.value, 1)
+                e["frac_of_hbm_peak"] = round(e["gbs"] / hbm_peak, 3)
+            breakdown[name] = e
+        lib.sefd_prof_reset()
         top = max(breakdown, key=lambda k: breakdown[k]["ms"])
         bt = breakdown[top]
-        if bt["gflop"] > 0:
+        nl = max(bt["launches"], 1)
+        tkey = "tapgemm_tc_kernel" if top.startswith("tapgemm_tc") else ("wgrad_tc_kernel" if top.startswith("wgrad_tc") else None)
+        tr = None
+        if tkey:                      # launch-weighted mean over the template instances of the kernel
+            inst = [v for k, v in traffic.items() if k.startswith(tkey)]
+            if inst:
+                nn_ = sum(v["launches"] for v in inst)
+                tr = {"dram_bytes_per_launch": round(sum(v["dram_bytes_per_launch"] * v["launches"] for v in inst) / nn_),
+                      "source": f"profiles/ncu_traffic.json ({nn_} launches of one step; {inst[0]['source']})"}
+        if dict(CATS)[top] == "tensor":
             ach = bt["gflop"] / bt["ms"]                      # GFLOP / ms = TFLOP/s
-            peak = bf16_peak / 2.0                            # TF32 dense = 1/2 of the bf16 tensor rate
-            roofline = {"kernel": top, "bound": "tensor", "achieved": round(ach, 2), "peak": round(peak, 1),
-                        "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": None,
-                        "peak_source": f"{src} bf16 sustained / 2 (TF32 dense; operands fp32 today)",
-                        "avg_launch_ms": round(bt["ms"] / max(bt["launches"], 1), 4)}
+            roofline = {"kernel": top, "bound": "tensor", "achieved": round(ach, 2), "peak": round(tf32_peak, 1),
+                        "unit": "TFLOP/s", "frac": round(ach / tf32_peak, 4),
+                        "traffic": tr["dram_bytes_per_launch"] if tr else None,
+                        "algorithmic_bytes_per_launch": round(bt["gbyte"] * 1e9 / nl),
+                        "algorithmic_flops_per_launch": round(bt["gflop"] * 1e9 / nl),
+                        "peak_source": f"{src}: bf16 sustained / 2 (tcgen05 kind::tf32 dense rate)",
+                        "traffic_source": tr["source"] if tr else None,
+                        "avg_launch_ms": round(bt["ms"] / nl, 4), "launches": nl}
         else:
             ach = bt["gbyte"] / bt["ms"] * 1e3
             roofline = {"kernel": top, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",
                         "frac": round(ach / hbm_peak, 4), "traffic": None, "peak_source": src,
-                        "avg_launch_ms": round(bt["ms"] / max(bt["launches"], 1), 4)}
+                        "avg_launch_ms": round(bt["ms"] / nl, 4), "launches": nl}
 
     if world > 1:
         dist.barrier()

@@ -10,7 +10,8 @@ enum SefdProfCat {
     SEFD_PROF_LSTM = 3,      // recurrent kernels
     SEFD_PROF_STFT = 4,      // STFT, mask + ISTFT and its adjoint, loss passes
     SEFD_PROF_MISC = 5,      // weight packing / folding, small reductions, Adam
-    SEFD_PROF_NCAT = 6
+    SEFD_PROF_SKINNY = 6,    // CUDA-core kernels of the 2-channel ends (encoder 0, decoder 5): HBM-bound
+    SEFD_PROF_NCAT = 7
 };
 
 bool sefd_prof_on();

@@ -387,7 +387,7 @@ int sefd_skinny_conv(const TapGemmParams& p, cudaStream_t st) {
     const long long blocks = (long long)((p.Tout + 127) / 128) * p.B * p.J;
     const double pos = (double)p.B * p.J * p.Tout;
     sefd_prof_label("skinny_conv K%d N%d taps%d J%d Tout%d", K, N, p.ntaps, p.J, p.Tout);
-    SefdProfScope prof(SEFD_PROF_TAPGEMM, 2.0 * pos * N * K * p.ntaps,
+    SefdProfScope prof(SEFD_PROF_SKINNY, 2.0 * pos * N * K * p.ntaps,
                        4.0 * ((double)p.B * p.J * (p.fi_mul > 1 ? p.fi_mul : 1) * p.Tin * K + pos * N), st);
     if (K == 2) {
         if (N == 32) smallk_conv_kernel<32><<<(unsigned)blocks, 128, 0, st>>>(p);
@@ -408,7 +408,7 @@ int sefd_skinny_up_n2(const float* x0, const float* x1, const float* W, const fl
     SEFD_REQUIRE((((uintptr_t)x0 | (uintptr_t)x1) & 15) == 0 && ((uintptr_t)y & 7) == 0, "skinny_up_n2: misaligned tensors");
     sefd_prof_label("skinny_up_n2 K64 N2 taps10 J%d Tout%d", F, T + 1);
     const double pos = (double)B * F * T;
-    SefdProfScope prof(SEFD_PROF_TAPGEMM, 2.0 * pos * 64 * 2 * 10, 4.0 * (pos * 64 + (double)B * 2 * F * (T + 1) * 2), st);
+    SefdProfScope prof(SEFD_PROF_SKINNY, 2.0 * pos * 64 * 2 * 10, 4.0 * (pos * 64 + (double)B * 2 * F * (T + 1) * 2), st);
     cudaError_t e = cudaMemcpyToSymbolAsync(c_upW, W, sizeof(float) * 10 * 64 * 2, 0, cudaMemcpyDeviceToDevice, st);
     SEFD_REQUIRE(e == cudaSuccess, "skinny_up_n2: constant upload failed: %s", cudaGetErrorString(e));
     UpN2Params p;
@@ -459,7 +459,7 @@ int sefd_skinny_wgrad(const WgradParams& p, cudaStream_t st) {
     }
     const double pos = (double)p.B * p.J * p.Tg;
     sefd_prof_label("skinny_wgrad K%d N%d taps%d J%d", K, N, p.ntaps, p.J);
-    SefdProfScope prof(SEFD_PROF_WGRAD, 2.0 * pos * K * N * p.ntaps,
+    SefdProfScope prof(SEFD_PROF_SKINNY, 2.0 * pos * K * N * p.ntaps,
                        4.0 * ((double)p.B * p.J * (p.a_mul > 1 ? p.a_mul : 1) * p.Ta * K +
                               (double)p.B * p.J * (p.g_mul > 1 ? p.g_mul : 1) * p.Tg * N), st);
     if (wide_is_g) smallside_wgrad_kernel<1, true><<<(unsigned)ctas, 256, 0, st>>>(p, aux, chunks);

@@ -123,7 +123,8 @@ int sefd_dccrn_loss(const sefd_plan* plan, const float* out_wav, const float* ta
 
 /* ---- measurement support (bench.py): CUDA-event timing per kernel category on the launching stream.
  * categories: 0 tap-GEMM (conv/convT/linear fwd + dgrad), 1 weight gradients, 2 BN+PReLU passes,
- * 3 LSTM recurrence, 4 STFT/ISTFT/loss, 5 packing/reductions/Adam.  flops/bytes are the ALGORITHMIC figures
+ * 3 LSTM recurrence, 4 STFT/ISTFT/loss, 5 packing/reductions/Adam, 6 CUDA-core kernels of the 2-channel layers
+ * (encoder 0 / decoder 5 forward, data and weight gradients).  flops/bytes are the ALGORITHMIC figures
  * of the recorded launches (DESIGN.md states the formulas). */
 /* GEMM engine: 1 = tcgen05 TF32 tensor cores wherever a contraction is eligible (default), 0 = fp32 CUDA cores
  * everywhere (bit-for-bit the reference's fp32 arithmetic order aside; used by the parity tests as the exact engine). */
