@@ -132,7 +132,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     import models
     from sefd import _lib
@@ -204,13 +205,15 @@ def main():
 
     # ---------------- per-kernel-category CUDA-event timing (one extra profiled step) ----------------
     roofline, breakdown = None, None
+    # every rank runs the extra step (it contains the gradient all-reduce); only rank 0 records events
     if rank == 0:
-        import ctypes as C
         lib.sefd_prof_reset()
         lib.sefd_prof_enable(1)
-        ts.step(noisy, clean)
-        torch.cuda.synchronize()
-        lib.sefd_prof_enable(0)
+    ts.step(noisy, clean)
+    torch.cuda.synchronize()
+    lib.sefd_prof_enable(0)
+    if rank == 0:
+        import ctypes as C
         if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
             lib.sefd_prof_dump(os.path.join(ROOT, "gpurun_out", "launch_profile.csv").encode())
         peaks = {}

@@ -297,6 +297,7 @@ int sefd_bn_prelu_backward(const float* y, const float* dz, float* dy, long long
 
 int sefd_lstm_forward(const float* w_hh, float* gates, float* h, float* c, int rows, int T, void* stream) {
     LstmFwdParams p;
+    memset(&p, 0, sizeof(p));
     p.Whh = w_hh; p.G = gates; p.Hh = h; p.Cc = c; p.rows = rows; p.T = T;
     return sefd_lstm_fwd_launch(p, ST);
 }
@@ -304,6 +305,7 @@ int sefd_lstm_forward(const float* w_hh, float* gates, float* h, float* c, int r
 int sefd_lstm_backward(const float* w_hh, const float* gates, const float* c, const float* dh, float* dgates, int rows,
                        int T, void* stream) {
     LstmBwdParams p;
+    memset(&p, 0, sizeof(p));
     p.Whh = w_hh; p.G = gates; p.Cc = c; p.dH = dh; p.dG = dgates; p.rows = rows; p.T = T; p.round_tf32 = 0;
     return sefd_lstm_bwd_launch(p, ST);
 }
@@ -328,6 +330,21 @@ int sefd_dccrn_backward(const sefd_plan* plan, const float* params, const float*
                         size_t ws_bytes, void* stream) {
     SEFD_REQUIRE(plan && params && d_wav && grads && ws, "dccrn_backward: null argument");
     return sefd_backward_impl(plan, params, d_wav, grads, ws, ws_bytes, ST);
+}
+
+// ---- CRN (models.py:329-565) ----------------------------------------------------------------------
+sefd_plan* sefd_crn_plan_create(int B, int L) { return sefd_crn_plan_create_impl(B, L); }
+
+int sefd_crn_forward(const sefd_plan* plan, const float* params, float* bn_buffers, const float* noisy, const float* target,
+                     int train, float* est_mags, float* target_mags, float* out_wav, void* ws, size_t ws_bytes, void* stream) {
+    SEFD_REQUIRE(plan && params && noisy && out_wav && ws, "crn_forward: null argument");
+    return sefd_crn_forward_impl(plan, params, bn_buffers, noisy, target, train, est_mags, target_mags, out_wav, ws, ws_bytes, ST);
+}
+
+int sefd_crn_backward(const sefd_plan* plan, const float* params, const float* d_wav, float* grads, void* ws, size_t ws_bytes,
+                      void* stream) {
+    SEFD_REQUIRE(plan && params && d_wav && grads && ws, "crn_backward: null argument");
+    return sefd_crn_backward_impl(plan, params, d_wav, grads, ws, ws_bytes, ST);
 }
 
 }  // extern "C"

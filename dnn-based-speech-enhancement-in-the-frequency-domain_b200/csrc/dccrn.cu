@@ -2,107 +2,8 @@
 // sequencing of the kernels.  Mirrors DCCRN.forward (models.py:176-284) and the autograd graph the
 // reference gets from torch; see DESIGN.md for the dataflow and SURVEY.md appendix B for the
 // backward obligations.
-#include <string.h>
-
-#include <string>
-#include <vector>
-
-#include "dccrn.cuh"
+#include "plan.cuh"
 #include "taps.cuh"
-
-namespace {
-
-constexpr int NL = 6;            // encoder / decoder depth (config.py:50 dccrn_kernel_num)
-constexpr int NBIN = 257, HOP = 100;
-constexpr int RNN_H = 128, G4 = 512;
-constexpr float BN_EPS = 1e-5f, BN_MOM = 0.1f;
-
-inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-
-struct ParamInfo {
-    std::string name;
-    long long offset, numel;
-    int ndim;
-    long long shape[4];
-};
-
-struct ConvLayer {
-    int Cin, Cout;          // real channel counts (Cin includes the skip half for decoders)
-    int Fin, Fout;
-    long long wr, br, wi, bi, gamma, beta, alpha;   // param offsets (gamma < 0: no BN/PReLU)
-    long long rmean, rvar;                           // bn buffer offsets
-    // workspace offsets (floats)
-    size_t y, z, Wf, Wt, bias, stats /*doubles*/, save, dz, dz2, dy;
-};
-
-}  // namespace
-
-struct sefd_plan {
-    int B, L, T, mask_mode;
-    int ch[NL + 1], Fe[NL + 1];
-    ConvLayer enc[NL], dec[NL];
-    // LSTM parameter offsets [layer][lstm]
-    long long w_ih[2][2], w_hh[2][2], b_ih[2][2], b_hh[2][2], w_tr[2], b_tr[2];
-    std::vector<ParamInfo> params, buffers;
-    long long n_param_floats, n_buffer_floats;
-    // workspace (float offsets unless noted)
-    size_t ws_bytes;
-    size_t spec, raw_wav, dots /*double*/, stats_all /*double*/, stats_all_n;
-    size_t Gt[2], Hh[2], Cc[2], X1, X2, U;
-    size_t Wih0p, Wih0T, Wih0Q, Wih1p, Wih1T, Wih1Q, Whh[2], bsum[2], Wtrp, WtrT, btrp;
-    size_t dU, dY, dWs, dbs, red /*double*/, dX, dH, dG, dzd[NL];
-    size_t dY_floats, dWs_floats;
-};
-
-namespace {
-
-void add_param(sefd_plan* P, const std::string& name, long long& cursor, long long* off, std::initializer_list<long long> shape) {
-    ParamInfo pi;
-    pi.name = name;
-    pi.ndim = (int)shape.size();
-    pi.numel = 1;
-    int i = 0;
-    for (long long s : shape) {
-        pi.shape[i++] = s;
-        pi.numel *= s;
-    }
-    for (; i < 4; ++i) pi.shape[i] = 1;
-    pi.offset = cursor;
-    *off = cursor;
-    cursor += (pi.numel + 3) / 4 * 4;
-    P->params.push_back(pi);
-}
-
-void add_buffer(sefd_plan* P, const std::string& name, long long& cursor, long long* off, long long n) {
-    ParamInfo pi;
-    pi.name = name;
-    pi.ndim = 1;
-    pi.numel = n;
-    pi.shape[0] = n;
-    pi.shape[1] = pi.shape[2] = pi.shape[3] = 1;
-    pi.offset = cursor;
-    *off = cursor;
-    cursor += (n + 3) / 4 * 4;
-    P->buffers.push_back(pi);
-}
-
-struct Carver {
-    size_t cur = 0;   // bytes
-    size_t floats(size_t n) {
-        cur = align_up(cur, 256);
-        size_t o = cur / 4;
-        cur += n * 4;
-        return o;
-    }
-    size_t doubles(size_t n) {
-        cur = align_up(cur, 256);
-        size_t o = cur / 8;
-        cur += n * 8;
-        return o;
-    }
-};
-
-}  // namespace
 
 // ------------------------------------------------------------------------------------------------
 sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode) {
@@ -115,6 +16,7 @@ sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode) {
         return nullptr;
     }
     sefd_plan* P = new sefd_plan();
+    P->kind = 0;
     P->B = B;
     P->L = L;
     P->T = L / HOP + 3;
@@ -322,6 +224,7 @@ static int pack_weights(const sefd_plan* P, const float* prm, float* ws, cudaStr
 int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const float* noisy, const float* target,
                       int train, float* out_real, float* out_imag, float* out_wav, void* wsv, size_t ws_bytes,
                       cudaStream_t st) {
+    SEFD_REQUIRE(P->kind == 0, "dccrn_forward: not a DCCRN plan");
     SEFD_REQUIRE(ws_bytes >= P->ws_bytes, "forward: workspace too small (%zu < %zu)", ws_bytes, P->ws_bytes);
     SEFD_REQUIRE(((uintptr_t)wsv & 255) == 0 && ((uintptr_t)prm & 15) == 0, "forward: workspace/params misaligned");
     float* ws = (float*)wsv;
@@ -400,6 +303,7 @@ int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const 
                 SEFD_TRY(sefd_tapgemm(g, st));
             }
         LstmFwdParams lp;
+        memset(&lp, 0, sizeof(lp));
         lp.Whh = ws + P->Whh[l]; lp.G = ws + P->Gt[l]; lp.Hh = ws + P->Hh[l]; lp.Cc = ws + P->Cc[l];
         lp.rows = 2 * B; lp.T = T;
         SEFD_TRY(sefd_lstm_fwd_launch(lp, st));
@@ -604,6 +508,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
     for (int l = 1; l >= 0; --l) {
         SEFD_TRY(sefd_clstm_combine_bwd(ws + P->dX, ws + P->dH, nX, st));
         LstmBwdParams lb;
+        memset(&lb, 0, sizeof(lb));
         lb.Whh = ws + P->Whh[l]; lb.G = ws + P->Gt[l]; lb.Cc = ws + P->Cc[l]; lb.dH = ws + P->dH; lb.dG = ws + P->dG;
         lb.rows = 2 * B; lb.T = T; lb.round_tf32 = sefd_get_engine_internal() == 1;
         SEFD_TRY(sefd_lstm_bwd_launch(lb, st));
@@ -744,6 +649,7 @@ int sefd_dccrn_entry_info(const sefd_plan* plan, int kind, int idx, char* name, 
 
 int sefd_dccrn_tensor_info(const sefd_plan* P, const char* name, long long* off, int* ndim, long long shape[4]) {
     SEFD_REQUIRE(P != nullptr && name != nullptr, "tensor_info: null argument");
+    if (P->kind == 1) return sefd_crn_tensor_info(P, name, off, ndim, shape);
     const long long B = P->B, T = P->T;
     auto set = [&](size_t o, long long a, long long b, long long c, long long d) {
         *off = (long long)o; *ndim = 4; shape[0] = a; shape[1] = b; shape[2] = c; shape[3] = d;

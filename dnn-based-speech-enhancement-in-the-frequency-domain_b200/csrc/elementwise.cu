@@ -277,6 +277,40 @@ __global__ void fold_cconv_kernel(const CconvFoldParams p) {
     }
 }
 
+// real conv weights: slab = kf*2+kt is the innermost index of both torch layouts
+__global__ void pack_rconv_kernel(const RconvPackParams p) {
+    const int K = p.Ci, N = p.Co;
+    const long long total = 10ll * K * N;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(e % N);
+        const int k = (int)((e / N) % K);
+        const int slab = (int)(e / ((long long)N * K));
+        const long long widx = p.transposed ? ((long long)k * N + n) * 10 + slab : ((long long)n * K + k) * 10 + slab;
+        float v = p.w[widx];
+        if (p.round_tf32) v = tf32_rn(v);
+        p.Wf[e] = v;
+        p.Wt[((long long)slab * N + n) * K + k] = v;
+    }
+}
+
+__global__ void fold_rconv_kernel(const RconvFoldParams p) {
+    const int K = p.Ci, N = p.Co;
+    const long long total = 10ll * K * N;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int slab = (int)(e % 10);
+        int n, k;
+        if (p.transposed) { n = (int)((e / 10) % N); k = (int)(e / (10ll * N)); }
+        else { k = (int)((e / 10) % K); n = (int)(e / (10ll * K)); }
+        float a = 0.f;
+        for (int s = 0; s < p.nsplit; ++s) a += p.dWf[s * p.split_stride + ((long long)slab * K + k) * N + n];
+        p.dw[e] = a;
+    }
+    if (blockIdx.x == 0)
+        for (int n = threadIdx.x; n < N; n += blockDim.x) p.db[n] = p.dbias ? p.dbias[n] : 0.f;
+}
+
 // ------------------------------------------------------------------------------------
 // generic strided 2-term gather:  dst[i] = c0 * src0[map(i)] (+ c1 * src1[map(i)])
 // used for the LSTM / Linear weight (un)permutations, expressed as a 3-d index transpose:
@@ -406,6 +440,18 @@ int sefd_fold_cconv(const CconvFoldParams& p, cudaStream_t st) {
     SefdProfScope prof(SEFD_PROF_MISC, 0, 0, st);
     fold_cconv_kernel<<<grid_for(10ll * p.Ci2 * p.Co2), 256, 0, st>>>(p);
     return sefd_check_launch("fold_cconv");
+}
+
+int sefd_pack_rconv(const RconvPackParams& p, cudaStream_t st) {
+    SefdProfScope prof(SEFD_PROF_MISC, 0, 0, st);
+    pack_rconv_kernel<<<grid_for(10ll * p.Ci * p.Co), 256, 0, st>>>(p);
+    return sefd_check_launch("pack_rconv");
+}
+
+int sefd_fold_rconv(const RconvFoldParams& p, cudaStream_t st) {
+    SefdProfScope prof(SEFD_PROF_MISC, 0, 0, st);
+    fold_rconv_kernel<<<grid_for(10ll * p.Ci * p.Co), 256, 0, st>>>(p);
+    return sefd_check_launch("fold_rconv");
 }
 
 int sefd_permute3p(const Permute3Params& q, cudaStream_t st) {

@@ -48,6 +48,25 @@ struct CconvFoldParams {
     float *dwr, *dwi, *dbr, *dbi;
 };
 
+// real Conv2d / ConvTranspose2d weights (RealConv2d / RealConvTranspose2d, tools_for_model.py:341-425) <-> GEMM operands
+struct RconvPackParams {
+    const float* w;        // Conv2d [Co][Ci][5][2] or ConvTranspose2d [Ci][Co][5][2]
+    int Ci, Co, transposed;
+    float* Wf;             // [10][K = Ci][N = Co]
+    float* Wt;             // [10][N][K]
+    int round_tf32;
+};
+struct RconvFoldParams {
+    const float* dWf;      // nsplit x [10][K][N] partials
+    int nsplit;
+    long long split_stride;
+    const float* dbias;    // [Co] or nullptr (-> zeros: the bias sits in front of a BatchNorm)
+    int Ci, Co, transposed;
+    float *dw, *db;
+};
+int sefd_pack_rconv(const RconvPackParams& p, cudaStream_t st);
+int sefd_fold_rconv(const RconvFoldParams& p, cudaStream_t st);
+
 int sefd_bn_prelu_fwd(const BnPreluFwdParams& p, cudaStream_t st);
 int sefd_bn_prelu_bwd(const BnPreluBwdParams& p, cudaStream_t st);
 int sefd_pack_cconv(const CconvPackParams& p, cudaStream_t st);

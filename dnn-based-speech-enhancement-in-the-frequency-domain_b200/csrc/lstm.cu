@@ -214,7 +214,7 @@ int launch_fwd(const LstmFwdParams& p, cudaStream_t st) {
         cudaFuncSetAttribute(lstm_fwd_kernel<R, KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
     }
-    dim3 grid((p.rows + R - 1) / R, 2);
+    dim3 grid((p.rows + R - 1) / R, p.nl ? p.nl : 2);
     lstm_fwd_kernel<R, KR><<<grid, 512, smem, st>>>(p);
     return sefd_check_launch("lstm_fwd");
 }
@@ -226,11 +226,12 @@ int launch_bwd(const LstmBwdParams& p, cudaStream_t st) {
         cudaFuncSetAttribute(lstm_bwd_kernel<R, KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
     }
-    dim3 grid((p.rows + R - 1) / R, 2);
+    dim3 grid((p.rows + R - 1) / R, p.nl ? p.nl : 2);
     lstm_bwd_kernel<R, KR><<<grid, 512, smem, st>>>(p);
     return sefd_check_launch("lstm_bwd");
 }
-int pick_rows(int rows) {
+int pick_rows(int rows2) {
+    const int rows = (rows2 + 1) / 2;     // callers pass rows * nl; the table below is written for two LSTMs
     static int sms = 0;
     if (!sms) {
         int dev = 0;
@@ -245,7 +246,7 @@ int pick_rows(int rows) {
 }  // namespace
 
 int sefd_lstm_fwd_launch(const LstmFwdParams& p, cudaStream_t st) {
-    const int R = pick_rows(p.rows);
+    const int R = pick_rows(p.rows * (p.nl ? p.nl : 2));
     sefd_prof_label("lstm_fwd rows%d T%d R%d", p.rows, p.T, R);
     SefdProfScope prof(SEFD_PROF_LSTM, 4.0 * p.rows * p.T * 512.0 * 128.0, 4.0 * 2 * p.rows * p.T * (2 * 512.0 + 256.0), st);
     if (R == 1) return launch_fwd<1, 88>(p, st);
@@ -254,7 +255,7 @@ int sefd_lstm_fwd_launch(const LstmFwdParams& p, cudaStream_t st) {
 }
 
 int sefd_lstm_bwd_launch(const LstmBwdParams& p, cudaStream_t st) {
-    const int R = pick_rows(p.rows);
+    const int R = pick_rows(p.rows * (p.nl ? p.nl : 2));
     sefd_prof_label("lstm_bwd rows%d T%d R%d", p.rows, p.T, R);
     SefdProfScope prof(SEFD_PROF_LSTM, 4.0 * p.rows * p.T * 512.0 * 128.0, 4.0 * 2 * p.rows * p.T * (2 * 512.0 + 384.0), st);
     if (R == 1) return launch_bwd<1, 88>(p, st);

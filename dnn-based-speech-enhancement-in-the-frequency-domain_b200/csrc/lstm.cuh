@@ -9,6 +9,7 @@ struct LstmFwdParams {
     float* Hh;          // [2][rows][T][128]
     float* Cc;          // [2][rows][T][128]
     int rows, T;
+    int nl;             // LSTMs laid out back to back (0 = 2: the complex pair; 1: CRN's single nn.LSTM)
 };
 struct LstmBwdParams {
     const float* Whh;
@@ -18,6 +19,7 @@ struct LstmBwdParams {
     float* dG;          // [2][rows][T][512]  gradient w.r.t. the gate pre-activations
     int rows, T;
     int round_tf32;     // dG feeds tensor-core GEMMs
+    int nl;
 };
 int sefd_lstm_fwd_launch(const LstmFwdParams& p, cudaStream_t st);
 int sefd_lstm_bwd_launch(const LstmBwdParams& p, cudaStream_t st);

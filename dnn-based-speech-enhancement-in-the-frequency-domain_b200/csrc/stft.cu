@@ -147,7 +147,20 @@ __device__ __forceinline__ float2 apply_mask(int mode, float2 x, float2 m) {
         sincosf(ph, &sn, &cs);
         return make_float2(em * cs, em * sn);
     }
+    if (mode == SEFD_MASK_MAG) {          // m.x = real mask; m.y carries nothing
+        const float mag = sqrtf(x.x * x.x + x.y * x.y);
+        const float ph = atan2f(x.y, x.x);
+        const float em = tanhf(m.x) * mag;
+        float sn, cs;
+        sincosf(ph, &sn, &cs);
+        return make_float2(em * cs, em * sn);
+    }
     return x;   // SEFD_MASK_NONE: plain ISTFT of `spec`
+}
+__device__ __forceinline__ float2 load_mask(const MaskIstftParams& p, int b, int k, int t) {
+    const float* q = p.mask + b * p.mB + (long long)(k - 1) * p.mF + (long long)(t + p.m_tshift) * p.mT;
+    if (p.mode == SEFD_MASK_MAG) return make_float2(__ldg(q), 0.f);
+    return __ldg(reinterpret_cast<const float2*>(q));
 }
 
 __global__ void __launch_bounds__(256) mask_istft_fwd_kernel(const MaskIstftParams p) {
@@ -172,26 +185,30 @@ __global__ void __launch_bounds__(256) mask_istft_fwd_kernel(const MaskIstftPara
         const bool ob = vb && (la + 1 >= 3 ? la + 1 < 3 + IHB : c == 0);
         for (int k = tid64; k <= 256; k += 64) {
             float2 sa = make_float2(0.f, 0.f), sb = sa;
+            float ema = 0.f, emb = 0.f;
             if (va) {
                 const float2 x = __ldg(X + (long long)k * T + ta);
                 float2 m = make_float2(0.f, 0.f);
-                if (p.mode != SEFD_MASK_NONE && k >= 1)
-                    m = __ldg(reinterpret_cast<const float2*>(p.mask + b * p.mB + (long long)(k - 1) * p.mF +
-                                                              (long long)(ta + p.m_tshift) * p.mT));
+                if (p.mode != SEFD_MASK_NONE && k >= 1) m = load_mask(p, b, k, ta);
+                if (p.mode == SEFD_MASK_MAG) ema = tanhf(m.x) * sqrtf(x.x * x.x + x.y * x.y);
                 sa = (p.mode != SEFD_MASK_NONE && k == 0) ? make_float2(0.f, 0.f) : apply_mask(p.mode, x, m);
             }
             if (vb) {
                 const float2 x = __ldg(X + (long long)k * T + tb);
                 float2 m = make_float2(0.f, 0.f);
-                if (p.mode != SEFD_MASK_NONE && k >= 1)
-                    m = __ldg(reinterpret_cast<const float2*>(p.mask + b * p.mB + (long long)(k - 1) * p.mF +
-                                                              (long long)(tb + p.m_tshift) * p.mT));
+                if (p.mode != SEFD_MASK_NONE && k >= 1) m = load_mask(p, b, k, tb);
+                if (p.mode == SEFD_MASK_MAG) emb = tanhf(m.x) * sqrtf(x.x * x.x + x.y * x.y);
                 sb = (p.mode != SEFD_MASK_NONE && k == 0) ? make_float2(0.f, 0.f) : apply_mask(p.mode, x, m);
             }
             if (p.out_real) {
                 const long long o = ((long long)b * NBIN + k) * T;
-                if (oa) { p.out_real[o + ta] = sa.x; p.out_imag[o + ta] = sa.y; }
-                if (ob) { p.out_real[o + tb] = sb.x; p.out_imag[o + tb] = sb.y; }
+                if (p.mode == SEFD_MASK_MAG) {          // est_mags = tanh(mask) * |X| (models.py:521-522)
+                    if (oa) p.out_real[o + ta] = ema;
+                    if (ob) p.out_real[o + tb] = emb;
+                } else {
+                    if (oa) { p.out_real[o + ta] = sa.x; p.out_imag[o + ta] = sa.y; }
+                    if (ob) { p.out_real[o + tb] = sb.x; p.out_imag[o + tb] = sb.y; }
+                }
             }
             // Hermitian parts of the one-sided spectra, packed A + iB
             if (k == 0 || k == 256) {
@@ -300,6 +317,14 @@ __device__ __forceinline__ float2 mask_bwd(int mode, float2 x, float2 m, float2 
         if (mm > 0.f) { dmx += d_mm * m.x / mm; dmy += d_mm * m.y / mm; }
         return make_float2(dmx, dmy);
     }
+    if (mode == SEFD_MASK_MAG) {
+        const float mag = sqrtf(x.x * x.x + x.y * x.y);
+        const float ph = atan2f(x.y, x.x);
+        const float th = tanhf(m.x);
+        float sn, cs;
+        sincosf(ph, &sn, &cs);
+        return make_float2((1.f - th * th) * mag * (ds.x * cs + ds.y * sn), 0.f);
+    }
     return ds;   // NONE: gradient with respect to the spectrum itself
 }
 
@@ -367,20 +392,22 @@ __global__ void __launch_bounds__(256) mask_istft_bwd_kernel(const MaskIstftBwdP
         float2 x = make_float2(0.f, 0.f), m = x;
         if (p.mode != SEFD_MASK_NONE) {
             x = __ldg(X + (long long)k * T + t);
-            if (p.mode == SEFD_MASK_E)
-                m = __ldg(reinterpret_cast<const float2*>(p.mask + b * p.mB + (long long)(k - 1) * p.mF +
-                                                          (long long)(t + p.m_tshift) * p.mT));
+            const float* mq = p.mask + b * p.mB + (long long)(k - 1) * p.mF + (long long)(t + p.m_tshift) * p.mT;
+            if (p.mode == SEFD_MASK_E) m = __ldg(reinterpret_cast<const float2*>(mq));
+            if (p.mode == SEFD_MASK_MAG) m.x = __ldg(mq);
         }
         const float2 dm = mask_bwd(p.mode, x, m, ds);
-        *reinterpret_cast<float2*>(p.dmask + b * p.mB + (long long)(k - k_lo) * p.mF +
-                                   (long long)(t + p.m_tshift) * p.mT) = dm;
+        float* dq = p.dmask + b * p.mB + (long long)(k - k_lo) * p.mF + (long long)(t + p.m_tshift) * p.mT;
+        if (p.mode == SEFD_MASK_MAG) *dq = dm.x;
+        else *reinterpret_cast<float2*>(dq) = dm;
     }
     // frames in front of the shift (the decoder's dropped look-ahead frame) get zero gradient
     if (blockIdx.x == 0 && p.m_tshift > 0) {
         for (int e = tid; e < (NBIN - k_lo) * p.m_tshift; e += 256) {
             const int k = e / p.m_tshift, t = e % p.m_tshift;
-            *reinterpret_cast<float2*>(p.dmask + b * p.mB + (long long)k * p.mF + (long long)t * p.mT) =
-                make_float2(0.f, 0.f);
+            float* dq = p.dmask + b * p.mB + (long long)k * p.mF + (long long)t * p.mT;
+            if (p.mode == SEFD_MASK_MAG) *dq = 0.f;
+            else *reinterpret_cast<float2*>(dq) = make_float2(0.f, 0.f);
         }
     }
 }
@@ -507,7 +534,22 @@ __global__ void loss_bwd_kernel(const float* __restrict__ E, const float* __rest
     }
 }
 
+__global__ void spec_mag_kernel(const float2* __restrict__ spec, float* __restrict__ mag, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float2 x = __ldg(spec + i);
+        mag[i] = sqrtf(x.x * x.x + x.y * x.y);
+    }
+}
+
 }  // namespace
+
+int sefd_spec_mag_launch(const float* spec, float* mag, long long n, cudaStream_t st) {
+    long long g = (n + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    SefdProfScope prof(SEFD_PROF_STFT, 0, 12.0 * n, st);
+    spec_mag_kernel<<<(int)g, 256, 0, st>>>(reinterpret_cast<const float2*>(spec), mag, n);
+    return sefd_check_launch("spec_mag");
+}
 
 int sefd_stft_launch(const float* wav, float* spec, int B, int L, int T, cudaStream_t st) {
     SEFD_REQUIRE(L % HOP == 0 && T == L / HOP + 3, "stft: L=%d must be a multiple of %d and T=%d == L/hop+3", L, HOP, T);

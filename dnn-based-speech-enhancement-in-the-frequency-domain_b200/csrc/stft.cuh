@@ -1,7 +1,8 @@
 #pragma once
 #include "common.cuh"
 
-enum { SEFD_MASK_NONE = 0, SEFD_MASK_E = 1, SEFD_MASK_C = 2, SEFD_MASK_R = 3 };
+// SEFD_MASK_MAG: CRN's real T-F mask (models.py:518-524): one float per bin, est_mag = tanh(m) * |X|, noisy phase
+enum { SEFD_MASK_NONE = 0, SEFD_MASK_E = 1, SEFD_MASK_C = 2, SEFD_MASK_R = 3, SEFD_MASK_MAG = 4 };
 enum { SEFD_LOSS_MSE = 0, SEFD_LOSS_SDR = 1, SEFD_LOSS_SISNR = 2, SEFD_LOSS_SISDR = 3 };
 
 struct MaskIstftParams {
@@ -11,7 +12,7 @@ struct MaskIstftParams {
     int m_tshift;
     int mode;
     int B, L, T;
-    float *out_real, *out_imag;   // [B][257][T] or nullptr
+    float *out_real, *out_imag;   // [B][257][T] or nullptr (SEFD_MASK_MAG: out_real receives est_mags, out_imag is unused)
     float* out_wav;               // [B][L] clamped
     float* raw_wav;               // [B][L] before the clamp (kept for the backward) or nullptr
     const float* target;          // [B][L] or nullptr
@@ -31,6 +32,8 @@ struct MaskIstftBwdParams {
 };
 
 int sefd_stft_launch(const float* wav, float* spec, int B, int L, int T, cudaStream_t st);
+// ConvSTFT 'real' magnitudes (tools_for_model.py:63-66): spec [n][2] -> mag [n]
+int sefd_spec_mag_launch(const float* spec, float* mag, long long n, cudaStream_t st);
 int sefd_mask_istft_launch(const MaskIstftParams& p, cudaStream_t st);
 int sefd_mask_istft_bwd_launch(const MaskIstftBwdParams& p, cudaStream_t st);
 int sefd_loss_fwd_launch(const float* est, const float* tgt, int B, int L, int kind, double* dots, int dots_ready,

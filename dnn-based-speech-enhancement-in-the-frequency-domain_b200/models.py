@@ -116,5 +116,81 @@ def _not_built(name, row):
     return _Stub
 
 
-CRN = _not_built("CRN", "SURVEY.md §8 a13, BASELINE config 1")
+class CRN(nn.Module):
+    """Drop-in for models.py:329-565: real-valued conv recurrent network with a magnitude T-F mask.
+    forward(inputs, targets=0) -> (est_mags [B,257,T], target_mags [B,257,T], out_wav [B,L])."""
+
+    def __init__(self, rnn_layers=cfg.rnn_layers, rnn_input_size=getattr(cfg, "rnn_input_size", 512),
+                 rnn_units=cfg.rnn_units, win_len=cfg.win_len, win_inc=cfg.win_inc, fft_len=cfg.fft_len,
+                 win_type=cfg.window, masking_mode=cfg.masking_mode, kernel_size=5):
+        super().__init__()
+        kernel_num = list(cfg.dccrn_kernel_num)
+        unsupported = []
+        if (win_len, win_inc, fft_len) != (400, 100, 512):
+            unsupported.append(f"STFT geometry {(win_len, win_inc, fft_len)} (built: (400, 100, 512))")
+        if win_type not in ("hanning", "hann"):
+            unsupported.append(f"window {win_type!r} (built: periodic Hann)")
+        if kernel_num != _d.KERNEL_NUM or kernel_size != 5:
+            unsupported.append(f"kernel_num {kernel_num} / kernel_size {kernel_size}")
+        if rnn_units != 256 or rnn_input_size != 512:
+            unsupported.append(f"rnn_units={rnn_units}, rnn_input_size={rnn_input_size} (built: 256 / 512)")
+        if not cfg.skip_type:
+            unsupported.append("skip_type=False")
+        if masking_mode == "Direct(None make)":
+            unsupported.append("Direct spectral mapping (models.py:507-516)")
+        if unsupported:
+            raise NotImplementedError("sefd CRN: configuration outside the built path: " + "; ".join(unsupported))
+        self.win_len, self.win_inc, self.fft_len, self.win_type = win_len, win_inc, fft_len, win_type
+        self.rnn_input_size, self.rnn_units = rnn_input_size, rnn_units // 2
+        self.hidden_layers, self.kernel_size = rnn_layers, kernel_size      # rnn_layers is not passed to nn.LSTM (models.py:391-397)
+        self.kernel_num = [2] + kernel_num
+        self.masking_mode = masking_mode
+        self.stft = _d.STFTBuffers(win_len, fft_len, inverse=False)
+        self.istft = _d.STFTBuffers(win_len, fft_len, inverse=True)
+        self.encoder = nn.ModuleList()
+        self.decoder = nn.ModuleList()
+        kn = self.kernel_num
+        for i in range(len(kn) - 1):                                     # models.py:376-389
+            self.encoder.append(nn.Sequential(_d.RealConvParams(kn[i] // 2, kn[i + 1] // 2, transposed=False),
+                                              _d.BatchNormParams(kn[i + 1] // 2), _d.PReLUParams()))
+        self.enhance = _d.LSTMParams(self.rnn_input_size, self.rnn_units)   # models.py:391-397
+        self.tranform = _d.LinearParams(self.rnn_units, self.rnn_input_size)   # (sic) models.py:398
+        for idx in range(len(kn) - 1, 0, -1):                            # models.py:400-430
+            mods = [_d.RealConvParams(kn[idx], kn[idx - 1] // 2, transposed=True)]
+            if idx != 1:
+                mods += [_d.BatchNormParams(kn[idx - 1] // 2), _d.PReLUParams()]
+            self.decoder.append(nn.Sequential(*mods))
+
+    def _get_engine(self):
+        eng = self.__dict__.get("_engine")
+        if eng is None:
+            eng = _d.Engine(self, "E", family="crn")
+            self.__dict__["_engine"] = eng
+        return eng
+
+    def flatten_parameters(self):
+        self._get_engine().sync()
+
+    def forward(self, inputs, targets=0):
+        eng = self._get_engine()
+        tgt = targets if torch.is_tensor(targets) and targets.shape == inputs.shape else None
+        est_mags, target_mags, out_wav = eng.forward(inputs, tgt, self.training)
+        if self.training:
+            for m in self.modules():
+                if isinstance(m, _d.BatchNormParams):
+                    m.num_batches_tracked += 1
+        return est_mags, target_mags, out_wav
+
+    get_params = DCCRN.get_params
+
+    def loss(self, estimated, target, out_mags=0, target_mags=0, perceptual=False):
+        if perceptual:                                                   # models.py:553-557
+            if cfg.perceptual == "LMS":
+                return _tfl.get_array_lms_loss(target_mags, out_mags)
+            return _tfl.get_array_pmsqe_loss(target, estimated)
+        if cfg.loss not in _ops.LOSSES:
+            raise NotImplementedError(f"loss {cfg.loss!r}")
+        return _ops.loss(estimated, target, cfg.loss)
+
+
 FullSubNet = _not_built("FullSubNet", "SURVEY.md §8 a14, BASELINE config 3")

@@ -44,6 +44,9 @@ SIGNATURES = {
     "sefd_dccrn_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sefd_dccrn_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sefd_dccrn_loss": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "sefd_crn_plan_create": (_vp, [_i, _i]),
+    "sefd_crn_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "sefd_crn_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sefd_set_engine": (_i, [_i]),
     "sefd_get_engine": (_i, []),
     "sefd_launch_count": (_ll, []),

@@ -101,6 +101,18 @@ class ComplexLSTMParams(nn.Module):
             self.i_trans = LinearParams(hidden_size // 2, projection_dim // 2)
 
 
+class RealConvParams(nn.Module):
+    """RealConv2d / RealConvTranspose2d (tools_for_model.py:341-425): one nn.Conv2d / nn.ConvTranspose2d named `conv`,
+    default torch init drawn first, then N(0, 0.05) weights and zero bias (same RNG consumption as the reference)."""
+
+    def __init__(self, cin, cout, transposed):
+        super().__init__()
+        shape = (cin, cout, 5, 2) if transposed else (cout, cin, 5, 2)
+        self.conv = ConvParams(shape, cout)
+        nn.init.normal_(self.conv.weight.data, std=0.05)
+        nn.init.constant_(self.conv.bias, 0.0)
+
+
 class STFTBuffers(nn.Module):
     """Buffers the reference keeps in ConvSTFT / ConviSTFT (tools_for_model.py:16-33,46,81,88-89).  The CUDA
     kernels do not read them (they use the FFT closed form); they exist so checkpoints round-trip."""
@@ -124,9 +136,13 @@ class STFTBuffers(nn.Module):
 # plan + workspace cache
 # --------------------------------------------------------------------------------------------------
 class Plan:
-    def __init__(self, B, L, mode):
+    def __init__(self, B, L, mode, family="dccrn"):
         lib = _lib.load()
-        self.handle = lib.sefd_dccrn_plan_create(B, L, MODES[mode])
+        self.family = family
+        if family == "crn":
+            self.handle = lib.sefd_crn_plan_create(B, L)
+        else:
+            self.handle = lib.sefd_dccrn_plan_create(B, L, MODES[mode])
         if not self.handle:
             raise RuntimeError("sefd plan: " + lib.sefd_last_error().decode())
         self.B, self.L, self.T, self.mode = B, L, L // 100 + 3, mode
@@ -207,22 +223,58 @@ class _Forward(torch.autograd.Function):
         return (None, None, None, None) + grads
 
 
+class _ForwardCRN(torch.autograd.Function):
+    """Bridges torch autograd to sefd_crn_forward / sefd_crn_backward (CRN.forward, models.py:460-532)."""
+
+    @staticmethod
+    def forward(ctx, engine, noisy, target, train, *params):
+        plan = engine.plan(noisy.shape[0], noisy.shape[1])
+        dev = noisy.device
+        ws = plan.workspace(dev)
+        B, L, T = plan.B, plan.L, plan.T
+        est_mags = torch.empty(B, 257, T, device=dev)
+        target_mags = torch.empty(B, 257, T, device=dev) if target is not None else None
+        out_wav = torch.empty(B, L, device=dev)
+        plan.generation += 1
+        _lib.check(_lib.load().sefd_crn_forward(
+            plan.handle, ptr(engine.flat), ptr(engine.flat_buf), ptr(noisy), ptr(target), int(train),
+            ptr(est_mags), ptr(target_mags), ptr(out_wav), ptr(ws), plan.ws_bytes, stream()), "crn_forward")
+        ctx.engine, ctx.plan, ctx.generation = engine, plan, plan.generation
+        if target_mags is None:
+            target_mags = torch.zeros(0, device=dev)
+        ctx.mark_non_differentiable(est_mags, target_mags)
+        return est_mags, target_mags, out_wav
+
+    @staticmethod
+    def backward(ctx, _g_est, _g_tgt, g_wav):
+        engine, plan = ctx.engine, ctx.plan
+        if plan.generation != ctx.generation:
+            raise RuntimeError("sefd: the activation workspace of this forward was overwritten by a later forward "
+                               "of the same batch shape; call backward() before the next forward")
+        g_wav = g_wav.contiguous()
+        _lib.check(_lib.load().sefd_crn_backward(plan.handle, ptr(engine.flat), ptr(g_wav), ptr(engine.flat_grad),
+                                                 ptr(plan.ws), plan.ws_bytes, stream()), "crn_backward")
+        grads = tuple(engine.flat_grad[o: o + n].view(shape) for (_, o, n, shape) in plan.params)
+        return (None, None, None, None) + grads
+
+
 class Engine:
-    """Owns the flat parameter / gradient / BN-statistics buffers of one DCCRN module and keeps the module's
+    """Owns the flat parameter / gradient / BN-statistics buffers of one DCCRN / CRN module and keeps the module's
     nn.Parameters aliased onto them."""
 
-    def __init__(self, module, mode):
+    def __init__(self, module, mode, family="dccrn"):
         self.module = module
         self.mode = mode
+        self.family = family
         self.plans = {}
         self.flat = self.flat_grad = self.flat_buf = None
-        self._layout = Plan(1, 100, mode)          # layout is independent of (B, L)
+        self._layout = Plan(1, 100, mode, family)  # layout is independent of (B, L)
         self.param_list = None
 
     def plan(self, B, L):
         key = (B, L)
         if key not in self.plans:
-            self.plans[key] = Plan(B, L, self.mode)
+            self.plans[key] = Plan(B, L, self.mode, self.family)
         return self.plans[key]
 
     def _named(self):
@@ -279,4 +331,5 @@ class Engine:
         if target is not None:
             target = target.contiguous().float()
         params = [p for p, _, _, _ in self.param_list]
-        return _Forward.apply(self, noisy, target, train, *params)
+        fn = _ForwardCRN if self.family == "crn" else _Forward
+        return fn.apply(self, noisy, target, train, *params)

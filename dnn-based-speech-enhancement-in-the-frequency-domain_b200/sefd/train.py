@@ -47,14 +47,16 @@ class TrainStep:
         s = self._scratch(B, L, noisy.device)
         st = stream()
         plan.generation += 1
-        _lib.check(lib.sefd_dccrn_forward(plan.handle, ptr(eng.flat), ptr(eng.flat_buf), ptr(noisy), ptr(clean), 1,
-                                          None, None, ptr(s["wav"]), ptr(ws), plan.ws_bytes, st), "dccrn_forward")
+        fwd, bwd = (lib.sefd_crn_forward, lib.sefd_crn_backward) if eng.family == "crn" else \
+                   (lib.sefd_dccrn_forward, lib.sefd_dccrn_backward)
+        _lib.check(fwd(plan.handle, ptr(eng.flat), ptr(eng.flat_buf), ptr(noisy), ptr(clean), 1,
+                       None, None, ptr(s["wav"]), ptr(ws), plan.ws_bytes, st), eng.family + "_forward")
         _lib.check(lib.sefd_dccrn_loss(plan.handle, ptr(s["wav"]), ptr(clean), self.kind, 1, ptr(s["loss"]),
                                        ptr(s["coef"]), ptr(ws), st), "dccrn_loss")
         _lib.check(lib.sefd_loss_backward(ptr(s["wav"]), ptr(clean), ptr(s["coef"]), None, ptr(s["dwav"]), B, L, st),
                    "loss_backward")
-        _lib.check(lib.sefd_dccrn_backward(plan.handle, ptr(eng.flat), ptr(s["dwav"]), ptr(eng.flat_grad), ptr(ws),
-                                           plan.ws_bytes, st), "dccrn_backward")
+        _lib.check(bwd(plan.handle, ptr(eng.flat), ptr(s["dwav"]), ptr(eng.flat_grad), ptr(ws),
+                       plan.ws_bytes, st), eng.family + "_backward")
         return s["loss"]
 
     def step(self, noisy, clean):

@@ -121,6 +121,19 @@ int sefd_dccrn_backward(const sefd_plan* plan, const float* params, const float*
 int sefd_dccrn_loss(const sefd_plan* plan, const float* out_wav, const float* target, int kind, int reuse_dots,
                     float* loss, float* coef, void* ws, void* stream);
 
+/* ---- model level: CRN.forward / autograd backward (models.py:329-565; RealConv2d / RealConvTranspose2d,
+ * tools_for_model.py:341-425).  The plan is the same opaque type: every sefd_dccrn_* accessor above
+ * (workspace_bytes, param_floats, buffer_floats, num_params, num_buffers, entry_info, tensor_info, plan_destroy,
+ * loss) also serves a CRN plan; state_dict keys are the reference's (encoder.i.0.conv.weight, enhance.weight_ih_l0,
+ * tranform.weight, ...).  Mask: est_mags = tanh(out) * |X| with the noisy phase (models.py:518-524).
+ * est_mags / target_mags [B][257][T] may be NULL (target_mags also needs `target`). */
+sefd_plan* sefd_crn_plan_create(int B, int L);
+int sefd_crn_forward(const sefd_plan* plan, const float* params, float* bn_buffers, const float* noisy,
+                     const float* target, int train, float* est_mags, float* target_mags, float* out_wav, void* ws,
+                     size_t ws_bytes, void* stream);
+int sefd_crn_backward(const sefd_plan* plan, const float* params, const float* d_wav, float* grads, void* ws,
+                      size_t ws_bytes, void* stream);
+
 /* ---- measurement support (bench.py): CUDA-event timing per kernel category on the launching stream.
  * categories: 0 tap-GEMM (conv/convT/linear fwd + dgrad), 1 weight gradients, 2 BN+PReLU passes,
  * 3 LSTM recurrence, 4 STFT/ISTFT/loss, 5 packing/reductions/Adam, 6 CUDA-core kernels of the 2-channel layers

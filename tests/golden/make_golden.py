@@ -180,5 +180,86 @@ def main():
           f"n_params={out['n_params']}")
 
 
+def main_crn():
+    """BASELINE.json configs[0]: CRN, magnitude T-F mask, MSE loss, batch 2, on the reference's own CPU path."""
+    cfg, models, tfl = import_reference()
+    torch.set_num_threads(8)
+    out = {}
+    cfg.loss = "MSE"
+    torch.manual_seed(0)
+    m = models.CRN(masking_mode="E")
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    keys = list(sd0.keys())
+    out["init_keys"] = np.array(keys)
+    out["init_sum"] = np.array([float(sd0[k].double().sum()) for k in keys])
+    out["init_abs"] = np.array([float(sd0[k].double().abs().sum()) for k in keys])
+    out["n_params"] = np.array(sum(p.numel() for p in m.parameters()))
+    out["param_names"] = np.array([n for n, _ in m.named_parameters()])
+    B, L = 2, 4000
+    for inputs_name, (noisy, clean) in {"rand": batch(B, L), "speech": speechlike(B, L)}.items():
+        for loss_name in ["MSE", "SI-SNR"]:
+            cfg.loss = loss_name
+            m.load_state_dict(sd0)
+            m.train()
+            m.zero_grad()
+            est, tgt, wav = m(noisy, clean)
+            loss = m.loss(wav, clean)
+            loss.backward()
+            tag = f"small_{inputs_name}_{loss_name}"
+            out[tag + "_loss"] = np.array(loss.item())
+            out[tag + "_gnorm"] = np.array([float(p.grad.double().norm()) for _, p in m.named_parameters()])
+            if loss_name == "MSE":
+                out[tag + "_wav"] = wav.detach().numpy()
+                out[tag + "_est_mags"] = est.detach().numpy()
+                out[tag + "_target_mags"] = tgt.detach().numpy()
+                for n, p in m.named_parameters():
+                    g = p.grad.detach().reshape(-1)
+                    out[tag + "_grad::" + n] = (g if g.numel() <= 4096 else g[:: g.numel() // 2048][:2048]).numpy()
+    cfg.loss = "MSE"
+    noisy, clean = speechlike(B, L)
+    m.load_state_dict(sd0)
+    m.train()
+    m(noisy, clean)
+    for k, v in m.state_dict().items():
+        if "running" in k:
+            out["small_speech_bn::" + k] = v.numpy().copy()   # copy: the buffers are updated in place below
+    m.eval()
+    with torch.no_grad():
+        _, _, wav = m(noisy, clean)
+    out["small_speech_eval_wav"] = wav.numpy()
+    # three Adam steps
+    m.load_state_dict(sd0)
+    m.train()
+    opt = torch.optim.Adam(m.parameters(), lr=cfg.learning_rate)
+    losses = []
+    for _ in range(3):
+        _, _, wav = m(noisy, clean)
+        loss = m.loss(wav, clean)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    out["adam3_losses"] = np.array(losses)
+    out["adam3_param_sum"] = np.array([float(p.double().sum()) for p in m.parameters()])
+    # full-length config-1 case: batch 2, 3 s @ 16 kHz
+    m.load_state_dict(sd0)
+    m.train()
+    m.zero_grad()
+    noisy, clean = batch(2, 48000)
+    _, _, wav = m(noisy, clean)
+    loss = m.loss(wav, clean)
+    loss.backward()
+    out["full_loss"] = np.array(loss.item())
+    out["full_wav_head"] = wav.detach()[:, :2048].numpy()
+    out["full_wav_rms"] = np.array(float(wav.double().pow(2).mean().sqrt()))
+    out["full_gnorm"] = np.array([float(p.grad.double().norm()) for p in m.parameters()])
+    np.savez_compressed(os.path.join(HERE, "crn_golden.npz"), **out)
+    sz = os.path.getsize(os.path.join(HERE, "crn_golden.npz"))
+    print(f"wrote crn_golden.npz ({sz/1e3:.1f} kB), {len(out)} arrays; full_loss={out['full_loss']}, n_params={out['n_params']}")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "crn":
+        main_crn()
+    else:
+        main()
