@@ -64,10 +64,31 @@ def test_dropin_refuses_cpu_and_unbuilt_configs():
         m(torch.zeros(1, 4000))
     with pytest.raises(NotImplementedError):
         models.DCCRN(masking_mode="Direct(None make)")
+    crn = models.CRN()                         # built; like DCCRN it has no CPU path
+    with pytest.raises(RuntimeError, match="CUDA"):
+        crn(torch.zeros(1, 4000))
     with pytest.raises(NotImplementedError):
-        models.CRN()
+        models.CRN(masking_mode="Direct(None make)")
     with pytest.raises(NotImplementedError):
         models.FullSubNet()
+
+
+def test_crn_dropin_layout_and_init_match_reference():
+    import numpy as np
+    import models
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "crn_golden.npz"))
+    torch.manual_seed(0)
+    m = models.CRN()
+    sd = m.state_dict()
+    keys = [str(k) for k in g["init_keys"]]
+    assert list(sd.keys()) == keys
+    for k, s_, a in zip(keys, g["init_sum"], g["init_abs"]):
+        v = sd[k].double()
+        assert abs(float(v.sum()) - s_) <= 1e-6 * max(1.0, abs(a)), k
+        assert abs(float(v.abs().sum()) - a) <= 1e-6 * max(1.0, abs(a)), k
+    plan = D.Plan(2, 4000, "E", family="crn")
+    assert [n for n, _, _, _ in plan.params] == [str(n) for n in g["param_names"]]
+    assert sum(n for _, _, n, _ in plan.params) == int(g["n_params"]) == 1703436
 
 
 def test_fft_index_algebra_on_host(tmp_path):
