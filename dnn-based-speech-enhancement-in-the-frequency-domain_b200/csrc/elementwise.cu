@@ -245,17 +245,13 @@ __global__ void pack_cconv_kernel(const CconvPackParams p) {
 __global__ void fold_cconv_kernel(const CconvFoldParams p) {
     const int K = 2 * p.Ci2, N = 2 * p.Co2;
     const long long total = 10ll * p.Ci2 * p.Co2;
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
-         e += (long long)gridDim.x * blockDim.x) {
-        const int slab = (int)(e % 10);
-        int ni, ki;
-        if (p.transposed) {
-            ni = (int)((e / 10) % p.Co2);
-            ki = (int)(e / (10ll * p.Co2));
-        } else {
-            ki = (int)((e / 10) % p.Ci2);
-            ni = (int)(e / (10ll * p.Ci2));
-        }
+    // thread order (slab, ki, ni) with ni fastest: the nsplit x 4 partial-gradient reads are coalesced; only the single
+    // write per element is strided (parameter layout [..][..][5][2] has the tap index innermost)
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int ni = (int)(t % p.Co2);
+        const int ki = (int)((t / p.Co2) % p.Ci2);
+        const int slab = (int)(t / ((long long)p.Co2 * p.Ci2));
         const int kr = kinv(0, ki, p.Ci2, p.two_src), kim = kinv(1, ki, p.Ci2, p.two_src);
         float rr = 0.f, ii = 0.f, ri = 0.f, ir = 0.f;
         for (int s = 0; s < p.nsplit; ++s) {
@@ -265,6 +261,7 @@ __global__ void fold_cconv_kernel(const CconvFoldParams p) {
             ri += d[(long long)kr * N + p.Co2 + ni];
             ir += d[(long long)kim * N + ni];
         }
+        const long long e = p.transposed ? ((long long)ki * p.Co2 + ni) * 10 + slab : ((long long)ni * p.Ci2 + ki) * 10 + slab;
         p.dwr[e] = rr + ii;
         p.dwi[e] = ri - ir;
     }
@@ -297,14 +294,14 @@ __global__ void pack_rconv_kernel(const RconvPackParams p) {
 __global__ void fold_rconv_kernel(const RconvFoldParams p) {
     const int K = p.Ci, N = p.Co;
     const long long total = 10ll * K * N;
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
-         e += (long long)gridDim.x * blockDim.x) {
-        const int slab = (int)(e % 10);
-        int n, k;
-        if (p.transposed) { n = (int)((e / 10) % N); k = (int)(e / (10ll * N)); }
-        else { k = (int)((e / 10) % K); n = (int)(e / (10ll * K)); }
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {          // (slab, k, n) order: coalesced partial reads
+        const int n = (int)(t % N);
+        const int k = (int)((t / N) % K);
+        const int slab = (int)(t / ((long long)N * K));
         float a = 0.f;
-        for (int s = 0; s < p.nsplit; ++s) a += p.dWf[s * p.split_stride + ((long long)slab * K + k) * N + n];
+        for (int s = 0; s < p.nsplit; ++s) a += p.dWf[s * p.split_stride + t];
+        const long long e = p.transposed ? ((long long)k * N + n) * 10 + slab : ((long long)n * K + k) * 10 + slab;
         p.dw[e] = a;
     }
     if (blockIdx.x == 0)

@@ -11,10 +11,11 @@
 //                 MMA descriptor starts 128 B = one row further).
 //   warp 1      : MMA issuer    - 4 x tcgen05.mma (K = 8) per (tap, k-block) into a 128 x BN fp32 accumulator in
 //                 TMEM; tcgen05.commit releases the stage (empty[]) and publishes the accumulator (tfull[])
-//   warps 2..5  : epilogue      - tcgen05.ld 32 columns at a time, + bias, stage through padded shared memory,
-//                 coalesced 128-byte row stores (optionally += / tf32-rounded) and per-channel sum / sum-of-squares
-//                 for the following BatchNorm; two accumulators (TMEM double buffer) let the epilogue of tile i
-//                 overlap the main loop of tile i+1.
+//   warps 2..5  : epilogue      - tcgen05.ld 32 columns at a time (thread = row: 128 contiguous output bytes), + bias,
+//                 optional += / tf32 rounding, four 256-bit stores per thread straight from registers (no smem
+//                 staging, no barriers); per-channel sum / sum-of-squares for the following BatchNorm through a
+//                 31-shuffle transposing butterfly; two accumulators (TMEM double buffer) let the epilogue of
+//                 tile i overlap the main loop of tile i+1.
 // (ncu, round 1: with one TMA instruction per 16-24 KB the single producer thread was ~64 % busy issuing and the
 //  small-tile layers sat at a 0.3 ms floor; hence the multi-block boxes.)
 #include <cuda.h>
@@ -50,6 +51,7 @@ struct TcParams {
     int t_tiles, n_tiles;
     long long total_tiles;
     int kbs, nstage, stage_bytes, a_bytes;               // k-blocks per stage, pipeline depth, bytes
+    int vec8;                                            // destinations are 32-byte aligned: 256-bit stores
 };
 
 template <int BN>
@@ -58,7 +60,7 @@ struct Cfg {
     static constexpr int A_ROWS = PAIR ? 136 : TM;
     static constexpr int A_TILE = A_ROWS * KB * 4;
     static constexpr int B_BYTES = BN * KB * 4;
-    static constexpr int FIXED = TM * STG_LD * 4 + 8 * BN * 4 + (2 * MAX_STAGES + 4) * 8 + 64;
+    static constexpr int FIXED = 8 * BN * 4 + (2 * MAX_STAGES + 4) * 8 + 64;
 };
 
 struct TileCoord {
@@ -82,8 +84,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     using C = Cfg<BN>;
     // declared alignment keeps every derived pointer in the shared address space (LDS/STS/ATOMS, not generic)
     extern __shared__ __align__(1024) unsigned char smem[];
-    float* stg = reinterpret_cast<float*>(smem + p.nstage * p.stage_bytes);
-    float* s_stat = stg + TM * STG_LD;
+    float* s_stat = reinterpret_cast<float*>(smem + p.nstage * p.stage_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + 8 * BN);   // s_stat[part 0..3][sum | sum sq][BN]
     uint64_t* full = bars;
     uint64_t* empty = bars + MAX_STAGES;
@@ -189,6 +190,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
     } else {
         // ================= epilogue (128 threads; thread = accumulator row) =================
+        // Straight from registers: tcgen05.ld hands every thread 32 consecutive channels of its own row (128 B), which
+        // leave as four 256-bit stores (full 32-byte sectors) - no shared-memory staging, no barriers.  The BatchNorm
+        // statistics are reduced with a 31-shuffle transposing butterfly (lane c ends up with column c's sum over the
+        // warp's 32 rows) into per-warp slots of s_stat (fixed order: deterministic).
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;
         const int et = threadIdx.x - 64;        // 0..127
@@ -205,6 +210,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             mbar_wait(smem_u32(&tfull[abuf]), aphase);
             tc_fence_after();
             const int fo = tc.j * p.fo_mul + p.fo_off;
+            const int t = tc.t0 + row;
+            const bool rv = t < p.Tout;
 #pragma unroll 1
             for (int ch = 0; ch < BN / 32; ++ch) {
                 float v[32];
@@ -215,60 +222,67 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                     if (lane == 0) mbar_arrive(smem_u32(&tempty[abuf]));
                 }
                 const int n = tc.n0 + ch * 32;
-                float bv = 0.f;                 // lane i holds bias[n + i]; broadcast below
-                if (p.bias) bv = __ldg(p.bias + p.bJ * tc.j + n + lane);
-                asm volatile("bar.sync 1, 128;" ::: "memory");          // readers of the previous chunk are done
-                float* srow = stg + row * STG_LD;
+                if (!nk) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float x = (nk ? v[i] : 0.f) + __shfl_sync(0xffffffffu, bv, i);
-                    srow[i] = x;
+                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const int d = n < N0 ? 0 : 1;
-                const int nn = d ? n - N0 : n;
-                float* obase = p.o[d].p + tc.b * p.o[d].sB + fo * p.o[d].sF + nn;
-                // gradient accumulation: issue all eight loads of the old values first (independent, one DRAM
-                // latency) instead of a load -> add -> store chain per pass
-                float4 oldv[8];
-                if (p.accum[d]) {
+                if (p.bias) {                   // same 128 bytes for every lane: L1 broadcast
+                    const float4* bp = reinterpret_cast<const float4*>(p.bias + p.bJ * tc.j + n);
 #pragma unroll
-                    for (int pass = 0; pass < 8; ++pass) {
-                        const int idx = pass * 128 + et;
-                        const int r = idx >> 3, c4 = (idx & 7) * 4;
-                        const int t = tc.t0 + r;
-                        oldv[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (t < p.Tout) oldv[pass] = __ldcg(reinterpret_cast<const float4*>(obase + (long long)t * p.o[d].sT + c4));
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 b4 = __ldg(bp + i);
+                        v[4 * i + 0] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
                     }
                 }
+                const int d = n < N0 ? 0 : 1;
+                const int nn = d ? n - N0 : n;
+                if (rv) {
+                    float* dst = p.o[d].p + tc.b * p.o[d].sB + fo * p.o[d].sF + (long long)t * p.o[d].sT + nn;
+                    if (p.accum[d]) {
 #pragma unroll
-                for (int pass = 0; pass < 8; ++pass) {
-                    const int idx = pass * 128 + et;
-                    const int r = idx >> 3, c4 = (idx & 7) * 4;
-                    const int t = tc.t0 + r;
-                    if (t < p.Tout) {
-                        const float* sp = stg + r * STG_LD + c4;
-                        float4 o4 = make_float4(sp[0], sp[1], sp[2], sp[3]);
-                        if (p.accum[d]) { o4.x += oldv[pass].x; o4.y += oldv[pass].y; o4.z += oldv[pass].z; o4.w += oldv[pass].w; }
-                        if (p.round_out[d]) { o4.x = tf32_rn(o4.x); o4.y = tf32_rn(o4.y); o4.z = tf32_rn(o4.z); o4.w = tf32_rn(o4.w); }
-                        *reinterpret_cast<float4*>(obase + (long long)t * p.o[d].sT + c4) = o4;
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 o4 = __ldcg(reinterpret_cast<const float4*>(dst) + i);
+                            v[4 * i + 0] += o4.x; v[4 * i + 1] += o4.y; v[4 * i + 2] += o4.z; v[4 * i + 3] += o4.w;
+                        }
+                    }
+                    if (p.round_out[d]) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = tf32_rn(v[i]);
+                    }
+                    if (p.vec8) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8 * i),
+                                         "f"(v[8 * i]), "f"(v[8 * i + 1]), "f"(v[8 * i + 2]), "f"(v[8 * i + 3]), "f"(v[8 * i + 4]),
+                                         "f"(v[8 * i + 5]), "f"(v[8 * i + 6]), "f"(v[8 * i + 7])
+                                         : "memory");
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                     }
                 }
                 if (p.stats) {
-                    const int c = et & 31, part = et >> 5;
-                    float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
+                    float w[32];
+#pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        const int r = part * 32 + i;
-                        if (tc.t0 + r < p.Tout) {
-                            const float x = stg[r * STG_LD + c];
-                            s1 += x;
-                            s2 += x * x;
+                        v[i] = rv ? v[i] : 0.f;
+                        w[i] = v[i] * v[i];
+                    }
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < off; ++i) {
+                            const float sv = up ? v[i] : v[i + off], kv = up ? v[i + off] : v[i];
+                            const float sw = up ? w[i] : w[i + off], kw = up ? w[i + off] : w[i];
+                            v[i] = kv + __shfl_xor_sync(0xffffffffu, sv, off);
+                            w[i] = kw + __shfl_xor_sync(0xffffffffu, sw, off);
                         }
                     }
-                    // slot (part, column) is owned by this thread: plain adds, fixed order (deterministic statistics)
-                    s_stat[part * 2 * BN + ch * 32 + c] += s1;
-                    s_stat[part * 2 * BN + BN + ch * 32 + c] += s2;
+                    // slot (warp quarter, column) is owned by this lane: plain adds, fixed order
+                    s_stat[q * 2 * BN + ch * 32 + lane] += v[0];
+                    s_stat[q * 2 * BN + BN + ch * 32 + lane] += w[0];
                 }
             }
             if (++abuf == 2) { abuf = 0; aphase ^= 1; }
@@ -371,6 +385,7 @@ bool sefd_tapgemm_tc_eligible(const TapGemmParams& p) {
         if (((uintptr_t)p.o[d].p & 15) || p.o[d].sT % 4 || p.o[d].sF % 4 || p.o[d].sB % 4) return false;
     }
     if ((uintptr_t)p.Wnk & 15) return false;
+    if (p.bias && (((uintptr_t)p.bias & 15) || p.bJ % 4)) return false;
     return true;
 }
 
@@ -413,6 +428,9 @@ int sefd_tapgemm_tc(const TapGemmParams& g, cudaStream_t st) {
             }
         }
     }
+    p.vec8 = 1;
+    for (int d = 0; d < 2; ++d)
+        if (g.o[d].N && (((uintptr_t)g.o[d].p & 31) || g.o[d].sT % 8 || g.o[d].sF % 8 || g.o[d].sB % 8)) p.vec8 = 0;
     p.C0 = g.a[0].C; p.C1 = g.a[1].C; p.N = N; p.wJ_slabs = g.wJ_slabs;
     p.t_tiles = (g.Tout + TM - 1) / TM;
     p.n_tiles = N / BN;

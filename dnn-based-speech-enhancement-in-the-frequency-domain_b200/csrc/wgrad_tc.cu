@@ -435,7 +435,8 @@ int sefd_wgrad_tc(const WgradParams& w, float* partial, long long cap_floats, in
     SEFD_REQUIRE(build_groups(w, BN, K, p.a_sp, p) == 0, "wgrad_tc: tap grouping failed (K %d N %d BN %d taps %d)", K, N, BN, w.ntaps);
     int stage = 0;
     for (int g = 0; g < p.ngroups; ++g) {
-        const int b = (p.grp[g].nA * p.a_sp + p.grp[g].nG * (BN / 32)) * CHB + 3 * CHB;   // + slack: the MMA always reads 4 chunks
+        const int b = (p.grp[g].nA * p.a_sp + p.grp[g].nG * (BN / 32)) * CHB +
+                      (K < WM ? 3 * CHB : 0);   // slack only when an A slot is narrower than the 4 chunks an MMA reads
         if (b > stage) stage = b;
     }
     p.stage_bytes = stage;
