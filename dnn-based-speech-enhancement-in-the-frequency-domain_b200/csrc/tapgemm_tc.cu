@@ -29,7 +29,6 @@ namespace {
 
 constexpr int TM = 128;                 // tile rows = consecutive time positions of one (b, f) row
 constexpr int KB = 32;                  // fp32 channels per k-block = 128 B = swizzle span
-constexpr int STG_LD = 33;
 constexpr int NTHREADS = 192;
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_BUDGET = 225 * 1024;
@@ -92,7 +91,9 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // canonical warp index: the shuffle makes it warp-uniform FOR THE COMPILER, so the role branches below are uniform
+    // branches and the MMA / TMA warps keep their descriptors in uniform registers (no R2UR per instruction)
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const int kgroups = (p.C0 + p.C1) / KB / p.kbs;
     const int kg0 = p.C0 / KB / p.kbs;          // k-groups that come from source 0
 
@@ -121,8 +122,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const uint32_t smem_base = smem_u32(smem);
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
+        // ================= TMA producer (warp-uniform loops, elected lane issues) =================
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -138,19 +139,22 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                         mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
                         const uint32_t fb = smem_u32(&full[stage]);
                         const uint32_t sa = smem_base + (uint32_t)(stage * p.stage_bytes);
-                        mbar_expect_tx(fb, bytes);
-                        if (kg < kg0) tma_load_5d(&tmA0, fb, sa, 0, tin, kg * p.kbs, fi, tc.b);
-                        else tma_load_5d(&tmA1, fb, sa, 0, tin, (kg - kg0) * p.kbs, fi, tc.b);
-                        if (n == 2) tma_load_4d(&tmW2, fb, sa + p.a_bytes, 0, tc.n0, kg * p.kbs, slab);
-                        else tma_load_4d(&tmW1, fb, sa + p.a_bytes, 0, tc.n0, kg * p.kbs, slab);
+                        if (elect_one_sync()) {
+                            mbar_expect_tx(fb, bytes);
+                            if (kg < kg0) tma_load_5d(&tmA0, fb, sa, 0, tin, kg * p.kbs, fi, tc.b);
+                            else tma_load_5d(&tmA1, fb, sa, 0, tin, (kg - kg0) * p.kbs, fi, tc.b);
+                            if (n == 2) tma_load_4d(&tmW2, fb, sa + p.a_bytes, 0, tc.n0, kg * p.kbs, slab);
+                            else tma_load_4d(&tmW1, fb, sa + p.a_bytes, 0, tc.n0, kg * p.kbs, slab);
+                        }
+                        __syncwarp();
                         if (++stage == p.nstage) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer (warp-uniform loops, elected lane issues) =================
+        {
             // instruction descriptor: D fp32, A/B tf32, both K-major, N = BN, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             int stage = 0, abuf = 0;
@@ -175,16 +179,18 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                                 const uint64_t bd = make_desc(sa + (uint32_t)(p.a_bytes + (p.it_wt[it][w] * p.kbs + kb) * C::B_BYTES));
 #pragma unroll
                                 for (int k8 = 0; k8 < KB / 8; ++k8) {
-                                    tc_mma_tf32(d_tmem, ad + 2 * k8, bd + 2 * k8, idesc, acc);   // +32 B per K=8 step
+                                    if (elect_one_sync()) tc_mma_tf32(d_tmem, ad + 2 * k8, bd + 2 * k8, idesc, acc);   // +32 B per K=8 step
                                     acc = 1;
                                 }
                             }
                         }
-                        tc_commit(smem_u32(&empty[stage]));
+                        if (elect_one_sync()) tc_commit(smem_u32(&empty[stage]));
+                        __syncwarp();
                         if (++stage == p.nstage) { stage = 0; phase ^= 1; }
                     }
                 }
-                tc_commit(smem_u32(&tfull[abuf]));
+                if (elect_one_sync()) tc_commit(smem_u32(&tfull[abuf]));
+                __syncwarp();
                 if (++abuf == 2) { abuf = 0; aphase ^= 1; }
             }
         }

@@ -51,6 +51,20 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// One elected lane of a converged warp.  The tensor-core / TMA warps run their loops WARP-UNIFORMLY (all 32 lanes compute
+// addresses, descriptors and phases) and only the instruction itself is predicated on the elected lane: inside an
+// `if (lane == 0)` region the compiler cannot prove uniformity and wraps every UTCMMA / UTMALDG in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop (~18 instructions, measured: the issue rate of small-N MMAs was
+// the limiter of the 32/64-channel layers).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {

@@ -81,7 +81,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     uint64_t* tfull = bars + 16;
     uint64_t* tempty = bars + 17;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // canonical (compiler-visible warp-uniform) warp index, see tapgemm_tc.cu
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();
@@ -143,8 +144,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer (warp-uniform loops, elected lane issues) =================
+        {
             // D fp32, A/B tf32, both MN-major (bits 15, 16), M = 128; N is set per op (merged taps)
             const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(WM >> 4) << 24);
             int stage = 0;
@@ -169,16 +170,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                             for (int k8 = 0; k8 < PB / 8; ++k8) {
                                 // MN-major tf32: SWIZZLE_128B_BASE32B (layout type 1), LBO = stride between 32-channel
                                 // chunks, SBO = one 4-position swizzle atom (probed on hardware: tools/umma_probe.cu)
-                                tc_mma_tf32(tmem_base + (uint32_t)G.op_col[o], make_desc_full(abase + k8 * 1024, CHB, 512, 1),
-                                            make_desc_full(gbase + k8 * 1024, CHB, 512, 1), id, acc | (uint32_t)(k8 > 0));
+                                if (elect_one_sync())
+                                    tc_mma_tf32(tmem_base + (uint32_t)G.op_col[o], make_desc_full(abase + k8 * 1024, CHB, 512, 1),
+                                                make_desc_full(gbase + k8 * 1024, CHB, 512, 1), id, acc | (uint32_t)(k8 > 0));
                             }
                         }
                         acc = 1;
-                        tc_commit(smem_u32(&empty[stage]));
+                        if (elect_one_sync()) tc_commit(smem_u32(&empty[stage]));
+                        __syncwarp();
                         if (++stage == p.nstage) { stage = 0; phase ^= 1; }
                     }
                 }
-                tc_commit(smem_u32(tfull));
+                if (elect_one_sync()) tc_commit(smem_u32(tfull));
+                __syncwarp();
                 aphase ^= 1;
             }
         }
