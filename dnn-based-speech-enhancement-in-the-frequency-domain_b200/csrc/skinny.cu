@@ -14,42 +14,36 @@ namespace {
 // T1: K = 2 per tap -> N in {32, 64}   (encoder-0 forward, decoder-5 data gradient)
 // one thread = one output position; the <= 20 input scalars come straight from global (coalesced float2).
 // ---------------------------------------------------------------------------------------------------
+__constant__ float c_smallkW[10 * 2 * 64];     // [tap][k][n] of the current launch (stream-ordered upload)
+
 template <int N>
 __global__ void __launch_bounds__(128) smallk_conv_kernel(const TapGemmParams p) {
-    __shared__ __align__(16) float Ws[SEFD_MAX_TAPS * 2 * N];
     __shared__ float stg[128 * (N + 1)];
     const int tid = threadIdx.x;
     const int ttiles = (p.Tout + 127) / 128;
     const int t0 = (blockIdx.x % ttiles) * 128;
     const int row = blockIdx.x / ttiles;
     const int b = row / p.J, j = row % p.J;
-    for (int i = tid; i < p.ntaps * 2 * N; i += 128) {
-        const int tap = i / (2 * N), r = i % (2 * N);
-        Ws[i] = p.W[(long long)p.wslab[tap] * 2 * N + r];
-    }
-    __syncthreads();
     float acc[N];
 #pragma unroll
     for (int n = 0; n < N; ++n) acc[n] = p.bias ? __ldg(p.bias + n) : 0.f;
     const int t = t0 + tid;
-    for (int tap = 0; tap < p.ntaps; ++tap) {
-        const int fi = j * p.fi_mul + p.df[tap];
-        if (fi < 0 || fi >= p.Fin) continue;
-        const int tin = t + p.dt[tap];
-        float2 x = make_float2(0.f, 0.f);
-        if (tin >= 0 && tin < p.Tin)
-            x = __ldg(reinterpret_cast<const float2*>(p.a[0].p + b * p.a[0].sB + fi * p.a[0].sF + (long long)tin * p.a[0].sT));
-        const float4* w0 = reinterpret_cast<const float4*>(Ws + tap * 2 * N);
-        const float4* w1 = reinterpret_cast<const float4*>(Ws + tap * 2 * N + N);
+    // the 10 taps are unrolled: the weights are constant-bank FFMA operands (no shared-memory traffic); the <= 20
+    // input scalars come straight from global (coalesced float2)
+    float2 x[10];
 #pragma unroll
-        for (int n4 = 0; n4 < N / 4; ++n4) {
-            const float4 a = w0[n4], c = w1[n4];
-            acc[4 * n4 + 0] = fmaf(x.x, a.x, fmaf(x.y, c.x, acc[4 * n4 + 0]));
-            acc[4 * n4 + 1] = fmaf(x.x, a.y, fmaf(x.y, c.y, acc[4 * n4 + 1]));
-            acc[4 * n4 + 2] = fmaf(x.x, a.z, fmaf(x.y, c.z, acc[4 * n4 + 2]));
-            acc[4 * n4 + 3] = fmaf(x.x, a.w, fmaf(x.y, c.w, acc[4 * n4 + 3]));
-        }
+    for (int tap = 0; tap < 10; ++tap) {
+        const int fi = j * p.fi_mul + p.df[tap];
+        const int tin = t + p.dt[tap];
+        x[tap] = make_float2(0.f, 0.f);
+        if (fi >= 0 && fi < p.Fin && tin >= 0 && tin < p.Tin)
+            x[tap] = __ldg(reinterpret_cast<const float2*>(p.a[0].p + b * p.a[0].sB + fi * p.a[0].sF + (long long)tin * p.a[0].sT));
     }
+#pragma unroll
+    for (int tap = 0; tap < 10; ++tap)
+#pragma unroll
+        for (int n = 0; n < N; ++n)
+            acc[n] = fmaf(x[tap].x, c_smallkW[(tap * 2 + 0) * N + n], fmaf(x[tap].y, c_smallkW[(tap * 2 + 1) * N + n], acc[n]));
 #pragma unroll
     for (int n = 0; n < N; ++n) stg[tid * (N + 1) + n] = acc[n];
     __syncthreads();
@@ -251,10 +245,9 @@ struct SkinnyAux {
 
 constexpr int SW_CH = 128;           // wide-operand positions per work item
 
-template <int PER, bool WIDE_IS_G>     // PER = wide channels per lane (WIDE / 32)
+template <int PER, bool WIDE_IS_G, int NT>     // PER = wide channels per lane (WIDE / 32); NT = taps (compile time: no guards)
 __global__ void __launch_bounds__(256, 2) smallside_wgrad_kernel(const WgradParams p, const SkinnyAux aux, int chunks) {
     constexpr int WIDE = 32 * PER;
-    constexpr int UN = 8 / PER;                          // positions whose wide loads are in flight together
     constexpr int SLD = SW_CH + 4;                       // staged times [u_lo - 2, u_lo + SW_CH + 2)
     constexpr int NPRE = (SEFD_MAX_TAPS * SLD + 255) / 256;
     __shared__ float2 srow[SEFD_MAX_TAPS][SLD];
@@ -264,9 +257,9 @@ __global__ void __launch_bounds__(256, 2) smallside_wgrad_kernel(const WgradPara
     const int Fs = WIDE_IS_G ? p.Fa : p.Fg, Ts = WIDE_IS_G ? p.Ta : p.Tg;
     const int Tw = WIDE_IS_G ? p.Tg : p.Ta;              // wide tensor time extent
     const int smul = WIDE_IS_G ? p.a_mul : p.g_mul;
-    float acc[SEFD_MAX_TAPS][2][PER];
+    float acc[NT][2][PER];
 #pragma unroll
-    for (int a = 0; a < SEFD_MAX_TAPS; ++a)
+    for (int a = 0; a < NT; ++a)
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -294,20 +287,18 @@ __global__ void __launch_bounds__(256, 2) smallside_wgrad_kernel(const WgradPara
             }
         }
     };
+    constexpr int PW = SW_CH / 8;                            // positions per warp and item
+    // staged-row element of tap `tap` for this warp's position i: sbase[soff[tap] + i]  (time u <-> index u - u_lo + 2)
+    const float2* sbase = &srow[0][0];
+    int soff[NT];
+#pragma unroll
+    for (int tap = 0; tap < NT; ++tap) soff[tap] = aux.tap_slot[tap] * SLD + warp * PW + 2 + aux.tap_dt[tap];
     long long item = blockIdx.x;
     if (item < items) fetch(item);
     for (; item < items; item += gridDim.x) {
-        __syncthreads();                                 // the previous item's readers are done
-#pragma unroll
-        for (int q = 0; q < NPRE; ++q) {
-            const int idx = tid + q * 256;
-            if (idx < nstage) (&srow[0][0])[idx] = pre[q];
-        }
-        __syncthreads();
         const int r = (int)(item / chunks), ch = (int)(item % chunks);
         const int b = r / p.J, j = r % p.J;
         const int u_lo = ch * SW_CH, u_hi = min(Tw, u_lo + SW_CH);
-        if (item + gridDim.x < items) fetch(item + gridDim.x);
         const int fw = WIDE_IS_G ? j * p.g_mul + p.g_off[0] : j * p.a_mul + p.a_off[0];
         const float* wbase[PER];
         if (WIDE_IS_G) {
@@ -322,31 +313,35 @@ __global__ void __launch_bounds__(256, 2) smallside_wgrad_kernel(const WgradPara
             }
         }
         const long long wsT = WIDE_IS_G ? p.g.sT : p.a[0].sT;    // both A sources share the time stride here
-        constexpr int PW = SW_CH / 8;                            // positions per warp
         const int uw = u_lo + warp * PW;
-#pragma unroll 1
-        for (int h = 0; h < PW; h += UN) {
-            float wv[UN][PER];
+        // all of this warp's wide-operand loads for the item are issued BEFORE the staging barriers: PW x PER
+        // 128-byte requests per warp are in flight while the 2-channel rows are written to shared memory
+        float wv[PW][PER];
 #pragma unroll
-            for (int i = 0; i < UN; ++i)
+        for (int i = 0; i < PW; ++i)
 #pragma unroll
-                for (int q = 0; q < PER; ++q)
-                    wv[i][q] = uw + h + i < u_hi ? __ldg(wbase[q] + (long long)(uw + h + i) * wsT) : 0.f;
+            for (int q = 0; q < PER; ++q)
+                wv[i][q] = uw + i < u_hi ? __ldg(wbase[q] + (long long)(uw + i) * wsT) : 0.f;
+        __syncthreads();                                 // the previous item's readers are done
 #pragma unroll
-            for (int i = 0; i < UN; ++i) {
-                const int ul = warp * PW + h + i + 2;            // index into the staged rows (time u <-> u - u_lo + 2)
+        for (int q = 0; q < NPRE; ++q) {
+            const int idx = tid + q * 256;
+            if (idx < nstage) (&srow[0][0])[idx] = pre[q];
+        }
+        __syncthreads();
+        if (item + gridDim.x < items) fetch(item + gridDim.x);
 #pragma unroll
-                for (int tap = 0; tap < SEFD_MAX_TAPS; ++tap) {
-                    if (tap < p.ntaps) {
-                        const float2 sv = srow[aux.tap_slot[tap]][ul + aux.tap_dt[tap]];
+        for (int i = 0; i < PW; ++i) {
+            float2 sv[NT];
 #pragma unroll
-                        for (int q = 0; q < PER; ++q) {
-                            acc[tap][0][q] = fmaf(sv.x, wv[i][q], acc[tap][0][q]);
-                            acc[tap][1][q] = fmaf(sv.y, wv[i][q], acc[tap][1][q]);
-                        }
-                    }
+            for (int tap = 0; tap < NT; ++tap) sv[tap] = sbase[soff[tap] + i];     // LDS.64 [reg + immediate], all independent
+#pragma unroll
+            for (int tap = 0; tap < NT; ++tap)
+#pragma unroll
+                for (int q = 0; q < PER; ++q) {
+                    acc[tap][0][q] = fmaf(sv[tap].x, wv[i][q], acc[tap][0][q]);
+                    acc[tap][1][q] = fmaf(sv[tap].y, wv[i][q], acc[tap][1][q]);
                 }
-            }
         }
     }
     // reduce the 8 warps through shared memory, then one atomic per output element and CTA
@@ -354,12 +349,11 @@ __global__ void __launch_bounds__(256, 2) smallside_wgrad_kernel(const WgradPara
     for (int i = tid; i < p.ntaps * 2 * WIDE; i += 256) sred[i] = 0.f;
     __syncthreads();
 #pragma unroll
-    for (int tap = 0; tap < SEFD_MAX_TAPS; ++tap)
-        if (tap < p.ntaps)
+    for (int tap = 0; tap < NT; ++tap)
 #pragma unroll
-            for (int c = 0; c < 2; ++c)
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
-                for (int q = 0; q < PER; ++q) atomicAdd(&sred[(tap * 2 + c) * WIDE + lane + 32 * q], acc[tap][c][q]);
+            for (int q = 0; q < PER; ++q) atomicAdd(&sred[(tap * 2 + c) * WIDE + lane + 32 * q], acc[tap][c][q]);
     __syncthreads();
     for (int i = tid; i < p.ntaps * 2 * WIDE; i += 256) {
         const int tap = i / (2 * WIDE), c = (i / WIDE) % 2, w = i % WIDE;
@@ -376,8 +370,11 @@ bool sefd_skinny_conv_eligible(const TapGemmParams& p) {
     const int N = p.o[0].N + p.o[1].N, K = p.a[0].C + p.a[1].C;
     if (p.wJ != 0 || p.bJ != 0) return false;
     if (K == 2 && p.a[1].C == 0 && (N == 32 || N == 64) && p.o[0].N % 4 == 0 && p.a[0].sT % 2 == 0 && p.a[0].sF % 2 == 0 &&
-        p.a[0].sB % 2 == 0)
+        p.a[0].sB % 2 == 0 && p.ntaps == 10) {
+        for (int i = 0; i < 10; ++i)
+            if (p.wslab[i] != i) return false;           // the constant-bank kernel takes the 10 slabs in order
         return true;
+    }
     if (N == 2 && p.o[1].N == 0 && !p.stats && p.a[0].C % 4 == 0 && p.a[1].C % 4 == 0 && K <= 128) return true;
     return false;
 }
@@ -390,6 +387,8 @@ int sefd_skinny_conv(const TapGemmParams& p, cudaStream_t st) {
     SefdProfScope prof(SEFD_PROF_SKINNY, 2.0 * pos * N * K * p.ntaps,
                        4.0 * ((double)p.B * p.J * (p.fi_mul > 1 ? p.fi_mul : 1) * p.Tin * K + pos * N), st);
     if (K == 2) {
+        cudaError_t e = cudaMemcpyToSymbolAsync(c_smallkW, p.W, sizeof(float) * 10 * 2 * N, 0, cudaMemcpyDeviceToDevice, st);
+        SEFD_REQUIRE(e == cudaSuccess, "skinny_conv: constant upload failed: %s", cudaGetErrorString(e));
         if (N == 32) smallk_conv_kernel<32><<<(unsigned)blocks, 128, 0, st>>>(p);
         else smallk_conv_kernel<64><<<(unsigned)blocks, 128, 0, st>>>(p);
     } else {
@@ -422,7 +421,7 @@ int sefd_skinny_up_n2(const float* x0, const float* x1, const float* W, const fl
 
 bool sefd_skinny_wgrad_eligible(const WgradParams& p) {
     const int K = p.a[0].C + p.a[1].C, N = p.g.C;
-    if (p.ntaps > SEFD_MAX_TAPS) return false;
+    if (p.ntaps != 10) return false;              // the kernel is instantiated for the 10-tap (5,2) conv
     if (K == 2 && p.a[1].C == 0 && N == 32) {          // wide = G: all taps must share the G row and time
         for (int i = 0; i < p.ntaps; ++i)
             if (p.g_off[i] != p.g_off[0]) return false;
@@ -462,8 +461,8 @@ int sefd_skinny_wgrad(const WgradParams& p, cudaStream_t st) {
     SefdProfScope prof(SEFD_PROF_SKINNY, 2.0 * pos * K * N * p.ntaps,
                        4.0 * ((double)p.B * p.J * (p.a_mul > 1 ? p.a_mul : 1) * p.Ta * K +
                               (double)p.B * p.J * (p.g_mul > 1 ? p.g_mul : 1) * p.Tg * N), st);
-    if (wide_is_g) smallside_wgrad_kernel<1, true><<<(unsigned)ctas, 256, 0, st>>>(p, aux, chunks);
-    else if (K == 64) smallside_wgrad_kernel<2, false><<<(unsigned)ctas, 256, 0, st>>>(p, aux, chunks);
-    else smallside_wgrad_kernel<1, false><<<(unsigned)ctas, 256, 0, st>>>(p, aux, chunks);
+    if (wide_is_g) smallside_wgrad_kernel<1, true, 10><<<(unsigned)ctas, 256, 0, st>>>(p, aux, chunks);
+    else if (K == 64) smallside_wgrad_kernel<2, false, 10><<<(unsigned)ctas, 256, 0, st>>>(p, aux, chunks);
+    else smallside_wgrad_kernel<1, false, 10><<<(unsigned)ctas, 256, 0, st>>>(p, aux, chunks);
     return sefd_check_launch("skinny_wgrad");
 }
