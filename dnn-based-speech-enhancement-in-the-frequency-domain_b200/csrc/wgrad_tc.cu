@@ -453,7 +453,10 @@ int sefd_wgrad_tc(const WgradParams& w, float* partial, long long cap_floats, in
     const int rows = w.B * w.J;
     const long long tiles = (long long)p.ngroups * p.m_tiles * p.n_tiles;
     const long long one = (long long)nslabs * K * N;
-    long long splits = (2 * 148 + tiles - 1) / tiles;
+    // units = tiles x splits are dealt round-robin to the 148 persistent CTAs: aim for just UNDER two full rounds
+    // (300 units made three rounds, the third 3 % full: 2.03 rounds of work in the time of 3)
+    long long splits = (2 * 148) / tiles;
+    if (splits < 1) splits = 1;
     if (splits > rows) splits = rows;
     if (splits > cap_floats / one) splits = cap_floats / one;
     if (splits > 2 * 148) splits = 2 * 148;
