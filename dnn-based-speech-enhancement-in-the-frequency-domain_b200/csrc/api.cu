@@ -177,15 +177,14 @@ int sefd_cconv2d_backward(const float* x, const float* wr, const float* wi, cons
     f.dwr = dwr; f.dwi = dwi; f.dbr = dbr; f.dbi = dbi;
     SEFD_TRY(sefd_fold_cconv(f, ST));
     if (dx) {
-        for (int ph = 0; ph < 2; ++ph) {
+        {
             TapGemmParams g;
             memset(&g, 0, sizeof(g));
             g.a[0] = src4(dy, F / 2, T, Cout, Cout);
             g.o[0] = dst4(dx, F, T, Cin, Cin);
             g.W = c.Wt; g.Wnk = c.Wf; g.nslabs = 10;
             g.B = B; g.J = F / 2; g.Tout = T; g.Fin = F / 2; g.Tin = T;
-            conv_taps_up(g, ph, 1);
-            SEFD_TRY(sefd_tapgemm(g, ST));
+            SEFD_TRY(sefd_tapgemm_up(g, 1, ST));   // both output-row phases (one fused launch on tcgen05)
         }
     }
     return 0;
@@ -199,7 +198,7 @@ int sefd_cconvT2d_forward(const float* x0, const float* x1, const float* wr, con
     SEFD_TRY(pack_op(wr, br, wi, bi, Cin, Cout, 1, c, ST, c.dbias));
     const int Ch = Cin / 2;
     if (sefd_skinny_up_n2_eligible(Ch, Cout)) return sefd_skinny_up_n2(x0, x1, c.Wf, c.bias, y, B, F, T, ST);
-    for (int ph = 0; ph < 2; ++ph) {
+    {
         TapGemmParams g;
         memset(&g, 0, sizeof(g));
         g.a[0] = src4(x0, F, T, Ch, Ch);
@@ -207,8 +206,7 @@ int sefd_cconvT2d_forward(const float* x0, const float* x1, const float* wr, con
         g.o[0] = dst4(y, 2 * F, T + 1, Cout, Cout);
         g.W = c.Wf; g.Wnk = c.Wt; g.nslabs = 10; g.bias = c.bias;
         g.B = B; g.J = F; g.Tout = T + 1; g.Fin = F; g.Tin = T;
-        conv_taps_up(g, ph, 0);
-        SEFD_TRY(sefd_tapgemm(g, ST));
+        SEFD_TRY(sefd_tapgemm_up(g, 0, ST));   // both output-row phases (one fused launch on tcgen05)
     }
     return 0;
 }

@@ -59,6 +59,10 @@ struct TapGemmParams {
     int df[SEFD_MAX_TAPS], dt[SEFD_MAX_TAPS], wslab[SEFD_MAX_TAPS];
     int accum[2];
     int round_out[2];    // round the stored values to tf32 (the destination feeds a tensor-core GEMM)
+    // tensor-core engine only: nacc = 2 computes TWO output rows per tile (row j*fo_mul + fo_off + tap_acc[tap]) from
+    // one set of activation tiles - the two output-row phases of a stride-2 "up" conv share their input rows
+    int nacc;            // 0 / 1: one output row per tile
+    int tap_acc[SEFD_MAX_TAPS];
 };
 
 // dW[wslab[tap]][k][n] += sum_{b,j,t} A[b, j*a_mul+a_off[tap], t+dt[tap], k] * G[b, j*g_mul+g_off[tap], t, n]
@@ -79,6 +83,10 @@ bool sefd_tapgemm_tc_eligible(const TapGemmParams& p);
 int sefd_tapgemm_tc(const TapGemmParams& p, cudaStream_t st);
 // dispatch: tensor-core engine when selected (default) and the problem is eligible, else the fp32 engine
 int sefd_tapgemm(const TapGemmParams& p, cudaStream_t st);
+// stride-2 "up" conv (convT forward: mode 0, conv data gradient: mode 1): both output-row phases.  `g` carries the
+// sources / destinations / weights / B, J, Tout, Fin, Tin; taps and row mapping are filled in here.  One fused launch
+// on the tensor-core engine when eligible (N <= 128), else one launch per phase.
+int sefd_tapgemm_up(const TapGemmParams& g, int mode, cudaStream_t st);
 int sefd_get_engine_internal();
 // dedicated kernels for the 2-channel ends of the network (K = 2 or N = 2 per tap)
 bool sefd_skinny_conv_eligible(const TapGemmParams& p);

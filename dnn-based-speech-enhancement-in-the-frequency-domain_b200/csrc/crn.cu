@@ -283,7 +283,7 @@ int sefd_crn_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, co
         const int Ch = c.Cin / 2;
         const float* in0 = j == 0 ? ws + P->U : ws + P->dec[j - 1].z;
         const float* in1 = ws + P->enc[NL - 1 - j].z;
-        for (int ph = 0; ph < 2; ++ph) {
+        {
             TapGemmParams g;
             memset(&g, 0, sizeof(g));
             g.a[0] = src4(in0, c.Fin, T, Ch, Ch);
@@ -293,8 +293,7 @@ int sefd_crn_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, co
             g.W = ws + c.Wf; g.Wnk = ws + c.Wt; g.nslabs = 10; g.bias = prm + c.br;
             g.stats = (train && j != NL - 1) ? wsd + c.stats : nullptr;
             g.B = B; g.J = c.Fin; g.Tout = T + 1; g.Fin = c.Fin; g.Tin = T;
-            conv_taps_up(g, ph, 0);
-            SEFD_TRY(sefd_tapgemm(g, st));
+            SEFD_TRY(sefd_tapgemm_up(g, 0, st));   // both output-row phases (one fused launch on tcgen05)
         }
         if (j != NL - 1) SEFD_TRY(bn(c, T + 1, 1));
     }
@@ -511,7 +510,7 @@ int sefd_crn_backward_impl(const sefd_plan* P, const float* prm, const float* dw
         SEFD_TRY(sefd_wgrad(wg, dWs, (long long)P->dWs_floats, 10, &nsplit, &sstride, st));
         SEFD_TRY(fold(c, false, nullptr));
         if (i > 0) {
-            for (int ph = 0; ph < 2; ++ph) {
+            {
                 TapGemmParams g;
                 memset(&g, 0, sizeof(g));
                 g.a[0] = src4(dY, c.Fout, T, c.Cout, c.Cout);
@@ -520,8 +519,7 @@ int sefd_crn_backward_impl(const sefd_plan* P, const float* prm, const float* dw
                 g.o[1] = no_dst();
                 g.W = ws + c.Wt; g.Wnk = ws + c.Wf; g.nslabs = 10;
                 g.B = B; g.J = c.Fout; g.Tout = T; g.Fin = c.Fout; g.Tin = T;
-                conv_taps_up(g, ph, 1);
-                SEFD_TRY(sefd_tapgemm(g, st));
+                SEFD_TRY(sefd_tapgemm_up(g, 1, st));   // both output-row phases (one fused launch on tcgen05)
             }
         }
     }

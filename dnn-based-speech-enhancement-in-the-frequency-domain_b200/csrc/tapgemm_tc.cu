@@ -32,6 +32,9 @@ constexpr int KB = 32;                  // fp32 channels per k-block = 128 B = s
 constexpr int NTHREADS = 192;
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_BUDGET = 225 * 1024;
+#ifndef SEFD_FUSE_UP_MAX_N
+#define SEFD_FUSE_UP_MAX_N 128      // widest N for which the two output-row phases of an up-conv share one launch
+#endif
 
 struct TcParams {
     TapDst o[2];
@@ -42,10 +45,11 @@ struct TcParams {
     int B, J, Tout, Fin;
     int fi_mul, fo_mul, fo_off;
     // work items: one activation tile per item, shared by up to two taps whose time shifts differ by one frame
-    int nitems;
+    int nitems, nacc;                                    // nacc: output rows (accumulators) per tile, 1 or 2
     int it_df[SEFD_MAX_TAPS], it_dt0[SEFD_MAX_TAPS], it_n[SEFD_MAX_TAPS];
-    int it_slab_lo[SEFD_MAX_TAPS];                       // first weight slab of the item's box
-    int it_wt[SEFD_MAX_TAPS][2], it_roff[SEFD_MAX_TAPS][2];   // per tap: weight sub-tile (0/1) and activation row offset
+    int it_slab_lo[SEFD_MAX_TAPS], it_wbox[SEFD_MAX_TAPS];   // first weight slab / slabs (1, 2 or 4) of the item's box
+    // per tap of an item: weight sub-tile inside the box, activation row offset (0/1), accumulator (output-row phase)
+    int it_wt[SEFD_MAX_TAPS][4], it_roff[SEFD_MAX_TAPS][4], it_acc[SEFD_MAX_TAPS][4];
     int C0, C1, N, wJ_slabs;
     int t_tiles, n_tiles;
     long long total_tiles;
@@ -79,7 +83,8 @@ __device__ __forceinline__ TileCoord decode(const TcParams& p, long long tile, i
 template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const TcParams p) {
+                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                  const __grid_constant__ CUtensorMap tmW4, const TcParams p) {
     using C = Cfg<BN>;
     // declared alignment keeps every derived pointer in the shared address space (LDS/STS/ATOMS, not generic)
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -131,10 +136,10 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                 for (int it = 0; it < p.nitems; ++it) {
                     const int fi = tc.j * p.fi_mul + p.it_df[it];
                     if (fi < 0 || fi >= p.Fin) continue;
-                    const int n = p.it_n[it];
+                    const int wbox = p.it_wbox[it];
                     const int tin = tc.t0 + p.it_dt0[it];
                     const int slab = tc.j * p.wJ_slabs + p.it_slab_lo[it];
-                    const uint32_t bytes = (uint32_t)(p.a_bytes + n * p.kbs * C::B_BYTES);
+                    const uint32_t bytes = (uint32_t)(p.a_bytes + wbox * p.kbs * C::B_BYTES);
                     for (int kg = 0; kg < kgroups; ++kg) {
                         mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
                         const uint32_t fb = smem_u32(&full[stage]);
@@ -143,7 +148,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                             mbar_expect_tx(fb, bytes);
                             if (kg < kg0) tma_load_5d(&tmA0, fb, sa, 0, tin, kg * p.kbs, fi, tc.b);
                             else tma_load_5d(&tmA1, fb, sa, 0, tin, (kg - kg0) * p.kbs, fi, tc.b);
-                            if (n == 2) tma_load_4d(&tmW2, fb, sa + p.a_bytes, 0, tc.n0, kg * p.kbs, slab);
+                            if (wbox == 4) tma_load_4d(&tmW4, fb, sa + p.a_bytes, 0, tc.n0, kg * p.kbs, slab);
+                            else if (wbox == 2) tma_load_4d(&tmW2, fb, sa + p.a_bytes, 0, tc.n0, kg * p.kbs, slab);
                             else tma_load_4d(&tmW1, fb, sa + p.a_bytes, 0, tc.n0, kg * p.kbs, slab);
                         }
                         __syncwarp();
@@ -164,7 +170,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                 mbar_wait(smem_u32(&tempty[abuf]), aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(abuf * 256);
-                uint32_t acc = 0;
+                uint32_t acc0 = 0, acc1 = 0;            // per accumulator: 0 until its first MMA of this tile
                 for (int it = 0; it < p.nitems; ++it) {
                     const int fi = tc.j * p.fi_mul + p.it_df[it];
                     if (fi < 0 || fi >= p.Fin) continue;
@@ -174,13 +180,16 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                         tc_fence_after();
                         const uint32_t sa = smem_base + (uint32_t)(stage * p.stage_bytes);
                         for (int w = 0; w < n; ++w) {
+                            const int a = p.it_acc[it][w];
+                            const uint32_t dt = d_tmem + (uint32_t)(a * BN);
                             for (int kb = 0; kb < p.kbs; ++kb) {
                                 const uint64_t ad = make_desc(sa + (uint32_t)(kb * C::A_TILE + p.it_roff[it][w] * 128));
                                 const uint64_t bd = make_desc(sa + (uint32_t)(p.a_bytes + (p.it_wt[it][w] * p.kbs + kb) * C::B_BYTES));
 #pragma unroll
                                 for (int k8 = 0; k8 < KB / 8; ++k8) {
-                                    if (elect_one_sync()) tc_mma_tf32(d_tmem, ad + 2 * k8, bd + 2 * k8, idesc, acc);   // +32 B per K=8 step
-                                    acc = 1;
+                                    const uint32_t accf = a ? acc1 : acc0;
+                                    if (elect_one_sync()) tc_mma_tf32(dt, ad + 2 * k8, bd + 2 * k8, idesc, accf);   // +32 B per K=8 step
+                                    if (a) acc1 = 1; else acc0 = 1;
                                 }
                             }
                         }
@@ -208,21 +217,27 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const int N0 = p.o[0].N;
         for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const TileCoord tc = decode(p, tile, BN);
-            int nk = 0;
+            int nk0 = 0, nk1 = 0;                // taps that contributed to each accumulator (0: the row is bias only)
             for (int it = 0; it < p.nitems; ++it) {
                 const int fi = tc.j * p.fi_mul + p.it_df[it];
-                nk += (fi >= 0 && fi < p.Fin);
+                if (fi >= 0 && fi < p.Fin)
+                    for (int w = 0; w < p.it_n[it]; ++w) {
+                        if (p.it_acc[it][w]) ++nk1; else ++nk0;
+                    }
             }
             mbar_wait(smem_u32(&tfull[abuf]), aphase);
             tc_fence_after();
-            const int fo = tc.j * p.fo_mul + p.fo_off;
             const int t = tc.t0 + row;
             const bool rv = t < p.Tout;
+            const int nchunks = p.nacc * (BN / 32);
 #pragma unroll 1
-            for (int ch = 0; ch < BN / 32; ++ch) {
+            for (int cc = 0; cc < nchunks; ++cc) {
+                const int a = cc / (BN / 32), ch = cc - a * (BN / 32);
+                const int nk = a ? nk1 : nk0;
+                const int fo = tc.j * p.fo_mul + p.fo_off + a;
                 float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * 256 + ch * 32), v);
-                if (ch == BN / 32 - 1) {        // accumulator fully read: hand the TMEM buffer back to the MMA warp
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * 256 + a * BN + ch * 32), v);
+                if (cc == nchunks - 1) {        // accumulators fully read: hand the TMEM buffer back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&tempty[abuf]));
@@ -313,8 +328,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 }
 
 template <int BN>
-int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w1, const CUtensorMap& w2, const TcParams& p,
-           int smem, cudaStream_t st) {
+int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w1, const CUtensorMap& w2, const CUtensorMap& w4,
+           const TcParams& p, int smem, cudaStream_t st) {
     static int cur = 0;
     if (smem > cur) {
         cudaFuncSetAttribute(tapgemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -327,7 +342,7 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w1, 
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const int grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
-    tapgemm_tc_kernel<BN><<<grid, NTHREADS, smem, st>>>(a0, a1, w1, w2, p);
+    tapgemm_tc_kernel<BN><<<grid, NTHREADS, smem, st>>>(a0, a1, w1, w2, w4, p);
     return sefd_check_launch("tapgemm_tc");
 }
 
@@ -345,33 +360,38 @@ int run(const TapGemmParams& g, TcParams& p, cudaStream_t st) {
     using C = Cfg<BN>;
     const int N = p.N, K = p.C0 + p.C1;
     // k-blocks per stage: as many as keep >= 3 stages in flight
+    int wmax = 1;                                  // widest weight box of any item (1, 2 or 4 taps)
+    for (int it = 0; it < p.nitems; ++it)
+        if (p.it_wbox[it] > wmax) wmax = p.it_wbox[it];
     int kbs = 4;
     for (;; kbs >>= 1) {
         const bool div = (p.C0 / KB) % kbs == 0 && (p.C1 == 0 || (p.C1 / KB) % kbs == 0);
-        const int stage = kbs * (C::A_TILE + (C::PAIR ? 2 : 1) * C::B_BYTES);
+        const int stage = kbs * (C::A_TILE + wmax * C::B_BYTES);
         if (kbs == 1 || (div && (SMEM_BUDGET - C::FIXED) / stage >= 3)) break;
     }
     p.kbs = kbs;
     p.a_bytes = kbs * C::A_TILE;
-    p.stage_bytes = kbs * (C::A_TILE + (C::PAIR ? 2 : 1) * C::B_BYTES);
+    p.stage_bytes = kbs * (C::A_TILE + wmax * C::B_BYTES);
     p.nstage = (SMEM_BUDGET - C::FIXED) / p.stage_bytes;
     if (p.nstage > MAX_STAGES) p.nstage = MAX_STAGES;
     SEFD_REQUIRE(p.nstage >= 2, "tapgemm_tc: no room for a pipeline (stage %d bytes)", p.stage_bytes);
     const int smem = p.nstage * p.stage_bytes + C::FIXED;
 
-    CUtensorMap a0, a1, w1, w2;
+    CUtensorMap a0, a1, w1, w2, w4;
     SEFD_TRY(make_act_map5(&a0, g.a[0], g.Fin, g.Tin, g.B, C::A_ROWS, kbs));
     if (g.a[1].C) SEFD_TRY(make_act_map5(&a1, g.a[1], g.Fin, g.Tin, g.B, C::A_ROWS, kbs));
     else a1 = a0;
     SEFD_TRY(make_w_map(&w1, g, K, N, BN, kbs, 1));
-    if (C::PAIR) SEFD_TRY(make_w_map(&w2, g, K, N, BN, kbs, 2));
+    if (wmax >= 2) SEFD_TRY(make_w_map(&w2, g, K, N, BN, kbs, 2));
     else w2 = w1;
+    if (wmax >= 4) SEFD_TRY(make_w_map(&w4, g, K, N, BN, kbs, 4));
+    else w4 = w1;
     const double pos = (double)g.B * g.J * g.Tout;
-    sefd_prof_label("tapgemm_tc BN%d K%d N%d taps%d items%d kbs%d x%d J%d Tout%d tiles%lld", BN, K, N, g.ntaps, p.nitems, kbs,
-                    p.nstage, g.J, g.Tout, p.total_tiles);
+    sefd_prof_label("tapgemm_tc BN%d K%d N%d taps%d items%d acc%d kbs%d x%d J%d Tout%d tiles%lld", BN, K, N, g.ntaps, p.nitems,
+                    p.nacc, kbs, p.nstage, g.J, g.Tout, p.total_tiles);
     SefdProfScope prof(SEFD_PROF_TAPGEMM, 2.0 * pos * N * K * g.ntaps,
-                       4.0 * ((double)g.B * g.J * (g.fi_mul > 1 ? g.fi_mul : 1) * g.Tin * K + pos * N), st);
-    return launch<BN>(a0, a1, w1, w2, p, smem, st);
+                       4.0 * ((double)g.B * g.J * (g.fi_mul > 1 ? g.fi_mul : 1) * g.Tin * K + pos * N * p.nacc), st);
+    return launch<BN>(a0, a1, w1, w2, w4, p, smem, st);
 }
 
 }  // namespace
@@ -406,32 +426,46 @@ int sefd_tapgemm_tc(const TapGemmParams& g, cudaStream_t st) {
     p.bias = g.bias; p.bJ = g.bJ; p.stats = g.stats;
     p.B = g.B; p.J = g.J; p.Tout = g.Tout; p.Fin = g.Fin;
     p.fi_mul = g.fi_mul; p.fo_mul = g.fo_mul; p.fo_off = g.fo_off;
-    // pair up taps on the same source row whose time shifts differ by one frame and whose weight slabs are
-    // adjacent (BN <= 128 only: there the activation traffic dominates)
+    // Work items: taps that read the same source row in a one-frame window share ONE activation tile (136 rows; the
+    // later tap's MMA descriptor starts one row further) when their weight slabs fit one box of 1, 2 or 4 consecutive
+    // slabs (BN <= 128 only: there the activation traffic dominates).  With nacc = 2 the taps of both output-row
+    // phases land in the same item and feed different accumulators.
+    p.nacc = g.nacc == 2 ? 2 : 1;
+    SEFD_REQUIRE(p.nacc == 1 || BN <= 128, "tapgemm_tc: two output rows per tile need N <= 128");
     const bool pair = BN <= 128;
     bool used[SEFD_MAX_TAPS] = {false};
     p.nitems = 0;
     for (int i = 0; i < g.ntaps; ++i) {
         if (used[i]) continue;
         const int it = p.nitems++;
-        p.it_df[it] = g.df[i]; p.it_dt0[it] = g.dt[i]; p.it_n[it] = 1;
-        p.it_slab_lo[it] = g.wslab[i]; p.it_wt[it][0] = 0; p.it_roff[it][0] = 0;
+        int mem[4], nm = 0;
+        mem[nm++] = i;
         used[i] = true;
-        if (!pair) continue;
-        for (int j2 = i + 1; j2 < g.ntaps; ++j2) {
-            if (used[j2] || g.df[j2] != g.df[i]) continue;
-            const int d = g.dt[j2] - g.dt[i], ds = g.wslab[j2] - g.wslab[i];
-            if ((d == 1 || d == -1) && (ds == 1 || ds == -1)) {
+        int dt_lo = g.dt[i], dt_hi = g.dt[i], s_lo = g.wslab[i], s_hi = g.wslab[i];
+        if (pair) {
+            for (int j2 = i + 1; j2 < g.ntaps && nm < 4; ++j2) {
+                if (used[j2] || g.df[j2] != g.df[i]) continue;
+                const int nlo = g.dt[j2] < dt_lo ? g.dt[j2] : dt_lo, nhi = g.dt[j2] > dt_hi ? g.dt[j2] : dt_hi;
+                const int slo = g.wslab[j2] < s_lo ? g.wslab[j2] : s_lo, shi = g.wslab[j2] > s_hi ? g.wslab[j2] : s_hi;
+                int span = shi - slo + 1;
+                span = span <= 1 ? 1 : (span <= 2 ? 2 : 4);
+                if (nhi - nlo > 1 || shi - slo >= 4 || slo + span > g.nslabs) continue;
+                mem[nm++] = j2;
                 used[j2] = true;
-                p.it_n[it] = 2;
-                p.it_dt0[it] = d == 1 ? g.dt[i] : g.dt[j2];
-                p.it_slab_lo[it] = ds == 1 ? g.wslab[i] : g.wslab[j2];
-                p.it_roff[it][0] = d == 1 ? 0 : 1;          // tap i
-                p.it_roff[it][1] = d == 1 ? 1 : 0;          // tap j2
-                p.it_wt[it][0] = ds == 1 ? 0 : 1;
-                p.it_wt[it][1] = ds == 1 ? 1 : 0;
-                break;
+                dt_lo = nlo; dt_hi = nhi; s_lo = slo; s_hi = shi;
             }
+        }
+        const int span = s_hi - s_lo + 1;
+        p.it_df[it] = g.df[i];
+        p.it_dt0[it] = dt_lo;
+        p.it_n[it] = nm;
+        p.it_slab_lo[it] = s_lo;
+        p.it_wbox[it] = span <= 1 ? 1 : (span <= 2 ? 2 : 4);
+        for (int w = 0; w < nm; ++w) {
+            const int tp = mem[w];
+            p.it_roff[it][w] = g.dt[tp] - dt_lo;
+            p.it_wt[it][w] = g.wslab[tp] - s_lo;
+            p.it_acc[it][w] = p.nacc == 2 ? g.tap_acc[tp] : 0;
         }
     }
     p.vec8 = 1;
@@ -452,9 +486,44 @@ int sefd_tapgemm_tc(const TapGemmParams& g, cudaStream_t st) {
 static int g_engine = 1;   // 0: fp32 CUDA-core engine everywhere (exact; tests), 1: tcgen05 TF32 where eligible
 
 int sefd_tapgemm(const TapGemmParams& p, cudaStream_t st) {
+    SEFD_REQUIRE(p.nacc != 2, "tapgemm: two output rows per tile are a tensor-core-engine feature (use sefd_tapgemm_up)");
     if (sefd_skinny_conv_eligible(p)) return sefd_skinny_conv(p, st);
     if (g_engine == 1 && sefd_tapgemm_tc_eligible(p)) return sefd_tapgemm_tc(p, st);
     return sefd_tapgemm_simt(p, st);
+}
+
+int sefd_tapgemm_up(const TapGemmParams& g0, int mode, cudaStream_t st) {
+    const int N = g0.o[0].N + g0.o[1].N;
+    TapGemmParams f = g0;
+    // fused: all 10 taps, tap_acc = output-row phase (kf & 1)
+    f.ntaps = 0;
+    for (int kf = 0; kf < 5; ++kf)
+        for (int kt = 0; kt < 2; ++kt) {
+            const int i = f.ntaps++;
+            const int ph = kf & 1;
+            f.df[i] = (2 + ph - kf) / 2;         // even: kf 0,2,4 -> +1,0,-1 ; odd: kf 1,3 -> +1,0
+            f.dt[i] = mode == 0 ? -kt : 1 - kt;
+            f.wslab[i] = kf * 2 + kt;
+            f.tap_acc[i] = ph;
+        }
+    f.fi_mul = 1; f.fo_mul = 2; f.fo_off = 0; f.nacc = 2;
+    if (g_engine == 1 && N % 32 == 0 && N <= SEFD_FUSE_UP_MAX_N && !sefd_skinny_conv_eligible(f) && sefd_tapgemm_tc_eligible(f))
+        return sefd_tapgemm_tc(f, st);
+    for (int ph = 0; ph < 2; ++ph) {
+        TapGemmParams g = g0;
+        g.nacc = 0;
+        g.ntaps = 0;
+        for (int kf = ph; kf < 5; kf += 2)
+            for (int kt = 0; kt < 2; ++kt) {
+                const int i = g.ntaps++;
+                g.df[i] = (2 + ph - kf) / 2;
+                g.dt[i] = mode == 0 ? -kt : 1 - kt;
+                g.wslab[i] = kf * 2 + kt;
+            }
+        g.fi_mul = 1; g.fo_mul = 2; g.fo_off = ph;
+        SEFD_TRY(sefd_tapgemm(g, st));
+    }
+    return 0;
 }
 
 extern "C" int sefd_set_engine(int engine) {
