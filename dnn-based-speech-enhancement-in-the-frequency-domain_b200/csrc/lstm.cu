@@ -40,19 +40,27 @@ __global__ void __launch_bounds__(512, 1) lstm_fwd_kernel(const LstmFwdParams p)
     const bool cvalid = cr < R && row0 + cr < p.rows;
     const size_t hbase = ((size_t)lstm * p.rows + (cvalid ? row0 + cr : 0)) * p.T * H + cj;
     float c = 0.f;
-    float pre[R];
+    // the input projections of the next PF steps are prefetched
+    constexpr int PF = 1;      // deeper prefetch costs registers (spills at R = 1) and did not pay: the step is shared-memory bound
+    float pre[PF][R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) pre[r] = valid[r] ? Gr[r][g] : 0.f;
+    for (int d = 0; d < PF; ++d)
+#pragma unroll
+        for (int r = 0; r < R; ++r) pre[d][r] = (valid[r] && d < p.T) ? Gr[r][(size_t)d * G4 + g] : 0.f;
     const int gate = g >> 7;
     __syncthreads();
 
-    for (int t = 0; t < p.T; ++t) {
-        float acc[R], acc2[R];   // two independent FMA chains per row (the single chain was latency-bound at R = 1)
+    for (int t0 = 0; t0 < p.T; t0 += PF) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) { acc[r] = pre[r]; acc2[r] = 0.f; }
-        if (t + 1 < p.T) {
+      for (int d = 0; d < PF; ++d) {
+        const int t = t0 + d;
+        if (t >= p.T) break;
+        float acc[R], acc2[R];   // two independent FMA chains per row
 #pragma unroll
-            for (int r = 0; r < R; ++r) pre[r] = valid[r] ? Gr[r][(size_t)(t + 1) * G4 + g] : 0.f;
+        for (int r = 0; r < R; ++r) { acc[r] = pre[d][r]; acc2[r] = 0.f; }
+        if (t + PF < p.T) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) pre[d][r] = valid[r] ? Gr[r][(size_t)(t + PF) * G4 + g] : 0.f;
         }
 #pragma unroll
         for (int k4 = 0; k4 < KR / 4; ++k4) {
@@ -98,8 +106,10 @@ __global__ void __launch_bounds__(512, 1) lstm_fwd_kernel(const LstmFwdParams p)
             }
         }
         __syncthreads();
+      }
     }
 }
+
 
 template <int R, int KR>
 __global__ void __launch_bounds__(512, 1) lstm_bwd_kernel(const LstmBwdParams p) {
@@ -124,27 +134,39 @@ __global__ void __launch_bounds__(512, 1) lstm_bwd_kernel(const LstmBwdParams p)
     float* dGp = p.dG + row * p.T * G4 + cj;
 
     float dc_next = 0.f, dh_rec = 0.f;
-    // software prefetch of the next step's operands
-    float n_i = 0.f, n_f = 0.f, n_g = 0.f, n_o = 0.f, n_cprev = 0.f, n_dh = 0.f, c_t = 0.f;
-    if (cvalid) {
-        const int t = p.T - 1;
-        n_i = Gp[(size_t)t * G4]; n_f = Gp[(size_t)t * G4 + H]; n_g = Gp[(size_t)t * G4 + 2 * H]; n_o = Gp[(size_t)t * G4 + 3 * H];
-        c_t = Cp[(size_t)t * H];
-        n_cprev = t > 0 ? Cp[(size_t)(t - 1) * H] : 0.f;
-        n_dh = dHp[(size_t)t * H];
+    // software prefetch, PF steps deep (a step is shorter than a DRAM round trip): slot d holds the operands of the
+    // step that runs (d) iterations from now; c_t chains through n_cprev
+    constexpr int PF = 3;
+    float n_i[PF], n_f[PF], n_g[PF], n_o[PF], n_c[PF], n_cprev[PF], n_dh[PF];
+#pragma unroll
+    for (int d = 0; d < PF; ++d) {
+        n_i[d] = n_f[d] = n_g[d] = n_o[d] = n_c[d] = n_cprev[d] = n_dh[d] = 0.f;
+        const int t = p.T - 1 - d;
+        if (cvalid && t >= 0) {
+            n_i[d] = Gp[(size_t)t * G4]; n_f[d] = Gp[(size_t)t * G4 + H]; n_g[d] = Gp[(size_t)t * G4 + 2 * H]; n_o[d] = Gp[(size_t)t * G4 + 3 * H];
+            n_c[d] = Cp[(size_t)t * H];
+            n_cprev[d] = t > 0 ? Cp[(size_t)(t - 1) * H] : 0.f;
+            n_dh[d] = dHp[(size_t)t * H];
+        }
     }
     __syncthreads();
 
-    for (int t = p.T - 1; t >= 0; --t) {
+    for (int t0 = p.T - 1; t0 >= 0; t0 -= PF) {
+#pragma unroll
+      for (int d = 0; d < PF; ++d) {
+        const int t = t0 - d;
+        if (t < 0) break;
         if (cr < R) {
-            const float ig = n_i, fg = n_f, gg = n_g, og = n_o, cprev = n_cprev, dho = n_dh;
-            const float ct = c_t;
-            c_t = cprev;
-            if (cvalid && t > 0) {
-                const int u = t - 1;
-                n_i = Gp[(size_t)u * G4]; n_f = Gp[(size_t)u * G4 + H]; n_g = Gp[(size_t)u * G4 + 2 * H]; n_o = Gp[(size_t)u * G4 + 3 * H];
-                n_cprev = u > 0 ? Cp[(size_t)(u - 1) * H] : 0.f;
-                n_dh = dHp[(size_t)u * H];
+            const float ig = n_i[d], fg = n_f[d], gg = n_g[d], og = n_o[d], cprev = n_cprev[d], dho = n_dh[d];
+            const float ct = n_c[d];
+            {
+                const int u = t - PF;
+                if (cvalid && u >= 0) {
+                    n_i[d] = Gp[(size_t)u * G4]; n_f[d] = Gp[(size_t)u * G4 + H]; n_g[d] = Gp[(size_t)u * G4 + 2 * H]; n_o[d] = Gp[(size_t)u * G4 + 3 * H];
+                    n_c[d] = Cp[(size_t)u * H];
+                    n_cprev[d] = u > 0 ? Cp[(size_t)(u - 1) * H] : 0.f;
+                    n_dh[d] = dHp[(size_t)u * H];
+                }
             }
             const float dh = dho + dh_rec;
             const float tc = tanhf(ct);
@@ -202,6 +224,7 @@ __global__ void __launch_bounds__(512, 1) lstm_bwd_kernel(const LstmBwdParams p)
         if (cr < R)
             dh_rec = part[(0 * R + cr) * H + cj] + part[(1 * R + cr) * H + cj] + part[(2 * R + cr) * H + cj] +
                      part[(3 * R + cr) * H + cj];
+      }
     }
 }
 
@@ -258,7 +281,7 @@ int sefd_lstm_bwd_launch(const LstmBwdParams& p, cudaStream_t st) {
     const int R = pick_rows(p.rows * (p.nl ? p.nl : 2));
     sefd_prof_label("lstm_bwd rows%d T%d R%d", p.rows, p.T, R);
     SefdProfScope prof(SEFD_PROF_LSTM, 4.0 * p.rows * p.T * 512.0 * 128.0, 4.0 * 2 * p.rows * p.T * (2 * 512.0 + 384.0), st);
-    if (R == 1) return launch_bwd<1, 88>(p, st);
+    if (R == 1) return launch_bwd<1, 76>(p, st);
     if (R == 2) return launch_bwd<2, 80>(p, st);
     return launch_bwd<4, 64>(p, st);
 }
