@@ -327,7 +327,15 @@ int sefd_dccrn_forward(const sefd_plan* plan, const float* params, float* bn_buf
 int sefd_dccrn_backward(const sefd_plan* plan, const float* params, const float* d_wav, float* grads, void* ws,
                         size_t ws_bytes, void* stream) {
     SEFD_REQUIRE(plan && params && d_wav && grads && ws, "dccrn_backward: null argument");
-    return sefd_backward_impl(plan, params, d_wav, grads, ws, ws_bytes, ST);
+    return sefd_backward_impl(plan, params, d_wav, nullptr, nullptr, grads, ws, ws_bytes, ST);
+}
+
+int sefd_dccrn_backward_spec(const sefd_plan* plan, const float* params, const float* d_wav, const float* d_out_real,
+                             const float* d_out_imag, float* grads, void* ws, size_t ws_bytes, void* stream) {
+    SEFD_REQUIRE(plan && params && grads && ws, "dccrn_backward_spec: null argument");
+    SEFD_REQUIRE(d_wav || d_out_real, "dccrn_backward_spec: no gradient given");
+    SEFD_REQUIRE((d_out_real == nullptr) == (d_out_imag == nullptr), "dccrn_backward_spec: d_out_real and d_out_imag go together");
+    return sefd_backward_impl(plan, params, d_wav, d_out_real, d_out_imag, grads, ws, ws_bytes, ST);
 }
 
 // ---- CRN (models.py:329-565) ----------------------------------------------------------------------

@@ -370,8 +370,8 @@ int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const 
 }
 
 // ------------------------------------------------------------------------------------------------
-int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, float* grads, void* wsv,
-                       size_t ws_bytes, cudaStream_t st) {
+int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, const float* dreal, const float* dimag,
+                       float* grads, void* wsv, size_t ws_bytes, cudaStream_t st) {
     SEFD_REQUIRE(ws_bytes >= P->ws_bytes, "backward: workspace too small");
     float* ws = (float*)wsv;
     double* wsd = (double*)wsv;
@@ -417,6 +417,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
         MaskIstftBwdParams m;
         memset(&m, 0, sizeof(m));
         m.dwav = dwav; m.raw_wav = ws + P->raw_wav; m.spec = ws + P->spec; m.mask = ws + last.y; m.dmask = ws + last.dy;
+        m.dreal = dreal; m.dimag = dimag;
         m.mT = 2; m.mF = (long long)(T + 1) * 2; m.mB = (long long)256 * (T + 1) * 2;
         m.m_tshift = 1; m.mode = P->mask_mode; m.B = B; m.L = L; m.T = T;
         SEFD_TRY(sefd_mask_istft_bwd_launch(m, st));

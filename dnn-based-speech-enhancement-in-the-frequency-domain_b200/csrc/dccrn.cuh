@@ -9,8 +9,8 @@ sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode);
 int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const float* noisy, const float* target,
                       int train, float* out_real, float* out_imag, float* out_wav, void* ws, size_t ws_bytes,
                       cudaStream_t st);
-int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, float* grads, void* ws,
-                       size_t ws_bytes, cudaStream_t st);
+int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, const float* dreal, const float* dimag,
+                       float* grads, void* ws, size_t ws_bytes, cudaStream_t st);
 
 // CRN (crn.cu): same plan type (kind = 1), own forward / backward
 sefd_plan* sefd_crn_plan_create_impl(int B, int L);

@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(256) mask_istft_bwd_kernel(const MaskIstftBwdP
         float v = 0.f;
         if (n >= 0 && n < L) {
             const long long o = (long long)b * L + n;
-            v = __ldg(p.dwav + o);
+            v = p.dwav ? __ldg(p.dwav + o) : 0.f;
             if (p.raw_wav) {
                 const float raw = __ldg(p.raw_wav + o);
                 if (!(raw >= -1.f && raw <= 1.f)) v = 0.f;
@@ -388,7 +388,12 @@ __global__ void __launch_bounds__(256) mask_istft_bwd_kernel(const MaskIstftBwdP
     for (int e = tid; e < NBIN * SF; e += 256) {
         const int k = e / SF, f = e % SF, t = t0 + f;
         if (t >= T || k < k_lo) continue;
-        const float2 ds = S.out[k][f];
+        float2 ds = S.out[k][f];
+        if (p.dreal) {
+            const long long o = ((long long)b * NBIN + k) * T + t;
+            ds.x += __ldg(p.dreal + o);
+            ds.y += __ldg(p.dimag + o);
+        }
         float2 x = make_float2(0.f, 0.f), m = x;
         if (p.mode != SEFD_MASK_NONE) {
             x = __ldg(X + (long long)k * T + t);

@@ -20,7 +20,9 @@ struct MaskIstftParams {
 };
 
 struct MaskIstftBwdParams {
-    const float* dwav;       // [B][L]
+    const float *dreal, *dimag;   // optional [B][257][T]: gradient arriving directly at the masked spectrum (perceptual
+                                  // losses on out_real / out_imag, models.py:305-312); added to the ISTFT adjoint
+    const float* dwav;       // [B][L] (may be nullptr: no gradient through the waveform)
     const float* raw_wav;    // [B][L] or nullptr (no clamp gating)
     const float* spec;       // [B][257][T][2]
     const float* mask;       // as above (only read for mode E)

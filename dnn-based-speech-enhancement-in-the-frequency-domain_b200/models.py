@@ -99,7 +99,9 @@ class DCCRN(nn.Module):
     def loss(self, estimated, target, real_spec=0, img_spec=0, perceptual=False):
         if perceptual:                                                   # models.py:304-314
             if cfg.perceptual == "LMS":
-                return _tfl.get_array_lms_loss(target, estimated)
+                # clean_mags = sqrt(|STFT(target)|^2 + 1e-7), est_mags = sqrt(real_spec^2 + img_spec^2 + 1e-7) and the
+                # log-mel distance are one fused kernel; gradients reach the mask through real_spec / img_spec
+                return _ops.lms_loss_spec(real_spec, img_spec, target)
             return _tfl.get_array_pmsqe_loss(target, estimated)
         if cfg.loss not in _ops.LOSSES:
             raise NotImplementedError(f"loss {cfg.loss!r}")

@@ -43,7 +43,10 @@ SIGNATURES = {
     "sefd_dccrn_tensor_info": (_i, [_vp, C.c_char_p, C.POINTER(_ll), C.POINTER(_i), C.POINTER(_ll)]),
     "sefd_dccrn_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sefd_dccrn_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "sefd_dccrn_backward_spec": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sefd_dccrn_loss": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "sefd_lms_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "sefd_lms_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "sefd_crn_plan_create": (_vp, [_i, _i]),
     "sefd_crn_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sefd_crn_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -207,18 +207,30 @@ class _Forward(torch.autograd.Function):
             plan.handle, ptr(engine.flat), ptr(engine.flat_buf), ptr(noisy), ptr(target), int(train),
             ptr(out_real), ptr(out_imag), ptr(out_wav), ptr(ws), plan.ws_bytes, stream()), "dccrn_forward")
         ctx.engine, ctx.plan, ctx.generation = engine, plan, plan.generation
-        ctx.mark_non_differentiable(out_real, out_imag)
+        ctx.set_materialize_grads(False)       # unused outputs arrive as None, not as zero tensors
         return out_real, out_imag, out_wav
 
     @staticmethod
-    def backward(ctx, _g_real, _g_imag, g_wav):
+    def backward(ctx, g_real, g_imag, g_wav):
         engine, plan = ctx.engine, ctx.plan
         if plan.generation != ctx.generation:
             raise RuntimeError("sefd: the activation workspace of this forward was overwritten by a later forward "
                                "of the same batch shape; call backward() before the next forward")
-        g_wav = g_wav.contiguous()
-        _lib.check(_lib.load().sefd_dccrn_backward(plan.handle, ptr(engine.flat), ptr(g_wav), ptr(engine.flat_grad),
-                                                   ptr(plan.ws), plan.ws_bytes, stream()), "dccrn_backward")
+        lib = _lib.load()
+        g_wav = None if g_wav is None else g_wav.contiguous().float()
+        if g_real is None and g_imag is None:
+            if g_wav is None:
+                raise RuntimeError("sefd: backward() reached the DCCRN forward without any gradient")
+            _lib.check(lib.sefd_dccrn_backward(plan.handle, ptr(engine.flat), ptr(g_wav), ptr(engine.flat_grad),
+                                               ptr(plan.ws), plan.ws_bytes, stream()), "dccrn_backward")
+        else:
+            # a loss on the masked spectrum (perceptual LMS branch, models.py:305-312) sends gradients to out_real / out_imag
+            ref = g_real if g_real is not None else g_imag
+            g_real = (torch.zeros_like(ref) if g_real is None else g_real).contiguous().float()
+            g_imag = (torch.zeros_like(ref) if g_imag is None else g_imag).contiguous().float()
+            _lib.check(lib.sefd_dccrn_backward_spec(plan.handle, ptr(engine.flat), ptr(g_wav), ptr(g_real), ptr(g_imag),
+                                                    ptr(engine.flat_grad), ptr(plan.ws), plan.ws_bytes, stream()),
+                       "dccrn_backward_spec")
         grads = tuple(engine.flat_grad[o: o + n].view(shape) for (_, o, n, shape) in plan.params)
         return (None, None, None, None) + grads
 

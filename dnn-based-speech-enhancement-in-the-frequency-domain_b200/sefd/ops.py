@@ -236,3 +236,81 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-3, betas=(0.9, 0.9
     _req(params, grads, exp_avg, exp_avg_sq)
     _lib.check(_lib.load().sefd_adam_step(ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq), params.numel(), lr,
                                           betas[0], betas[1], eps, step, gscale, stream()), "adam_step")
+
+
+# ---- LMS perceptual loss (tools_for_loss.py:111-249) -------------------------------------------------
+_MEL = {}
+
+
+def mel_filterbank(num_coeffs, fft_size=512, fs=16000):
+    """melFilterBank(numCoeffs, fftSize) of the reference (tools_for_loss.py:144-188), restated with the same numpy
+    operations so that the float32 rounding of the band edges follows the installed numpy exactly as the reference's
+    would: [num_coeffs, fft_size // 2 + 1] triangular filters."""
+    import math
+    import numpy as np
+    max_hz, bins = fs / 2, fft_size // 2 + 1
+    f2m = lambda f: 1127.01048 * math.log(1 + f / 700.0)
+    m2f = lambda m: 700 * (math.exp(m / 1127.01048) - 1)
+    max_mel, min_mel = f2m(max_hz), f2m(0)
+    centres = np.array(range(num_coeffs + 2)).astype(np.float32)
+    centres = centres * (max_mel - min_mel) / (num_coeffs + 1) + min_mel
+    for i in range(num_coeffs + 2):
+        centres[i] = m2f(centres[i])
+        centres[i] = math.floor(bins * centres[i] / max_hz)
+    mat = np.zeros((num_coeffs, bins))
+    for i in range(1, num_coeffs + 1):
+        lo, mid, hi = int(centres[i - 1]), int(centres[i]), int(centres[i + 1])
+        for j in range(lo, mid):
+            mat[i - 1, j] = (float(j) - lo) / (mid - lo)
+        for j in range(mid, hi):
+            mat[i - 1, j] = 1 - ((float(j) - mid) / (hi - mid))
+    return mat
+
+
+def _mel_matrices(device):
+    key = str(device)
+    if key not in _MEL:
+        import numpy as np
+        f = np.concatenate([mel_filterbank(m) for m in (16, 32, 64)], 0).astype(np.float32)     # [112, 257]
+        ft = torch.from_numpy(f).contiguous().to(device)
+        _MEL[key] = (ft.t().contiguous(), ft)                                                     # F [257,112], Ft [112,257]
+    return _MEL[key]
+
+
+class _Lms(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, clean, mags):
+        _req(a, b, clean)
+        B, _, T = a.shape
+        F, Ft = _mel_matrices(a.device)
+        scratch = torch.empty(1, device=a.device, dtype=torch.float64)
+        loss = torch.empty(1, device=a.device)
+        _lib.check(_lib.load().sefd_lms_forward(ptr(a), ptr(b), ptr(clean), ptr(F), B, T, int(mags), ptr(scratch), ptr(loss),
+                                                stream()), "lms_forward")
+        ctx.save_for_backward(a, b if b is not None else a, clean)
+        ctx.mags = mags
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        a, b, clean = ctx.saved_tensors
+        B, _, T = a.shape
+        F, Ft = _mel_matrices(a.device)
+        gout = gout.contiguous().float()
+        da = torch.empty_like(a)
+        db = None if ctx.mags else torch.empty_like(a)
+        _lib.check(_lib.load().sefd_lms_backward(ptr(a), None if ctx.mags else ptr(b), ptr(clean), ptr(F), ptr(Ft), ptr(gout),
+                                                 B, T, int(ctx.mags), ptr(da), ptr(db), stream()), "lms_backward")
+        return da, db, None, None
+
+
+def lms_loss_spec(est_real, est_imag, target_wav):
+    """DCCRN.loss(..., perceptual=True) with cfg.perceptual == 'LMS' (models.py:305-312): est_real / est_imag [B,257,T]
+    masked spectrum, target_wav [B,L].  Gradients flow to est_real and est_imag."""
+    clean = stft(target_wav)                                                       # [B,257,T,2]
+    return _Lms.apply(est_real.contiguous(), est_imag.contiguous(), clean, False)
+
+
+def lms_loss_mags(clean_mags, est_mags):
+    """get_array_lms_loss(clean_array, est_array) (tools_for_loss.py:241-249) on magnitude arrays [B,257,T]."""
+    return _Lms.apply(est_mags.contiguous(), None, clean_mags.contiguous(), True)

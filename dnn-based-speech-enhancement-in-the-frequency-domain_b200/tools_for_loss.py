@@ -25,7 +25,9 @@ def si_sdr(reference, estimation, eps=1e-8):
 
 
 def get_array_lms_loss(clean_array, est_array):
-    raise NotImplementedError("sefd: LMS perceptual loss is not built yet (SURVEY.md §8(f) rank 3)")
+    """tools_for_loss.py:241-249: mean over the batch of the multi-scale log-mel distance (scales 16/32/64) between two
+    magnitude arrays [B,257,T]; differentiable with respect to est_array."""
+    return _ops.lms_loss_mags(clean_array, est_array)
 
 
 def get_array_pmsqe_loss(clean_array, est_array):

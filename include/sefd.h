@@ -54,6 +54,19 @@ int sefd_loss_forward(const float* est, const float* target, int B, int L, int k
 int sefd_loss_backward(const float* est, const float* target, const float* coef, const float* gout, float* d_est,
                        int B, int L, void* stream);
 
+/* LMS perceptual loss (get_array_lms_loss, tools_for_loss.py:111-249; called from DCCRN.loss models.py:305-312):
+ * log-mel-spectrum RMSE at mel scales 16/32/64 between sqrt(|STFT(target)|^2 + 1e-7) and
+ * sqrt(out_real^2 + out_imag^2 + 1e-7), rows formed by the reference's x.view(-1, 257) reshape.
+ * est_real / est_imag [B][257][T]; clean_spec [B][257][T][2] (sefd_stft_forward of the target);
+ * F [257][112] = the three melFilterBank(M, 512)^T side by side (M = 16, 32, 64), Ft [112][257] its transpose (built
+ * by the host exactly like the reference builds them); scratch: 1 double; loss: 1 float.
+ * inputs_are_mags = 1: est_real and clean_spec already hold magnitudes [B][257][T] (the generic
+ * get_array_lms_loss(clean_mags, est_mags) signature); est_imag / d_imag are then unused. */
+int sefd_lms_forward(const float* est_real, const float* est_imag, const float* clean_spec, const float* F, int B, int T,
+                     int inputs_are_mags, double* scratch, float* loss, void* stream);
+int sefd_lms_backward(const float* est_real, const float* est_imag, const float* clean_spec, const float* F, const float* Ft,
+                      const float* gout, int B, int T, int inputs_are_mags, float* d_real, float* d_imag, void* stream);
+
 /* ComplexConv2d (tools_for_model.py:199-269: kernel (5,2), stride (2,1), pad (2,0), causal pad 1) and
  * ComplexConvTranspose2d (tools_for_model.py:272-338: + output_padding (1,0)); channels-last tensors.
  *   conv : x [B][F][T][Cin]          -> y [B][F/2][T][Cout]
@@ -117,6 +130,10 @@ int sefd_dccrn_forward(const sefd_plan* plan, const float* params, float* bn_buf
 /* d_wav [B][L] -> grads (flat, same layout as params; every entry is overwritten) */
 int sefd_dccrn_backward(const sefd_plan* plan, const float* params, const float* d_wav, float* grads, void* ws,
                         size_t ws_bytes, void* stream);
+/* same, with an additional gradient arriving at the masked spectrum out_real / out_imag [B][257][T] (perceptual losses,
+ * models.py:305-312); d_wav or the pair (d_out_real, d_out_imag) may be NULL */
+int sefd_dccrn_backward_spec(const sefd_plan* plan, const float* params, const float* d_wav, const float* d_out_real,
+                             const float* d_out_imag, float* grads, void* ws, size_t ws_bytes, void* stream);
 /* loss on the plan's own outputs, reusing dot products gathered by the forward epilogue when `target` was given */
 int sefd_dccrn_loss(const sefd_plan* plan, const float* out_wav, const float* target, int kind, int reuse_dots,
                     float* loss, float* coef, void* ws, void* stream);

@@ -393,6 +393,51 @@ def dccrn_loss(estimated, target, loss: str = "SI-SNR"):
 
 
 # --------------------------------------------------------------------------------------
+# LMS perceptual loss (tools_for_loss.py:111-249)
+# --------------------------------------------------------------------------------------
+def mel_filterbank(num_coeffs: int, fft_size: int = FFT_LEN, fs: int = 16000) -> np.ndarray:
+    """melFilterBank (tools_for_loss.py:144-188): [num_coeffs, fft_size/2+1] triangular filters whose edges are
+    floor(bins * f / (fs/2)) of mel-spaced centre frequencies held in a float32 array."""
+    max_hz, bins = fs / 2, fft_size // 2 + 1
+    to_mel = lambda f: 1127.01048 * math.log(1 + f / 700.0)
+    to_hz = lambda m: 700 * (math.exp(m / 1127.01048) - 1)
+    c = np.arange(num_coeffs + 2).astype(np.float32) * (to_mel(max_hz) - to_mel(0)) / (num_coeffs + 1) + to_mel(0)
+    for i in range(num_coeffs + 2):
+        c[i] = to_hz(c[i])
+        c[i] = math.floor(bins * c[i] / max_hz)
+    mat = np.zeros((num_coeffs, bins))
+    for i in range(1, num_coeffs + 1):
+        lo, mid, hi = int(c[i - 1]), int(c[i]), int(c[i + 1])
+        mat[i - 1, lo:mid] = (np.arange(lo, mid, dtype=np.float64) - lo) / max(mid - lo, 1)
+        mat[i - 1, mid:hi] = 1 - (np.arange(mid, hi, dtype=np.float64) - mid) / max(hi - mid, 1)
+    return mat
+
+
+def lms_loss(clean_mags: torch.Tensor, est_mags: torch.Tensor, scales=(16, 32, 64)) -> torch.Tensor:
+    """get_array_lms_loss(clean_array, est_array) (tools_for_loss.py:241-249) with perceptual_distance (:219-237),
+    perceptual_transform (:195-216; note x.view(-1, 257) on a [257, T] array) and rmse (:123-131)."""
+    banks = [torch.from_numpy(mel_filterbank(m).T.astype(np.float32)) for m in scales]
+    total = 0
+    for i in range(clean_mags.shape[0]):
+        dists = []
+        for fb in banks:
+            lt = torch.log(torch.mm(clean_mags[i].reshape(-1, FFT_LEN // 2 + 1) / FFT_LEN, fb) + 1e-7)
+            lp = torch.log(torch.mm(est_mags[i].reshape(-1, FFT_LEN // 2 + 1) / FFT_LEN, fb) + 1e-7)
+            dists.append(torch.sqrt(torch.mean((lp - lt) ** 2, dim=-1) + 1e-7).mean())
+        total = total + torch.stack(dists).mean()
+    return total / clean_mags.shape[0]
+
+
+def dccrn_lms_loss(sd, out_real, out_imag, target):
+    """DCCRN.loss(..., perceptual=True), cfg.perceptual == 'LMS' (models.py:305-312)."""
+    spec = conv_stft(target, sd["stft.weight"][:, 0, :].to(target.dtype))
+    f = FFT_LEN // 2 + 1
+    clean_mags = torch.sqrt(spec[:, :f] ** 2 + spec[:, f:] ** 2 + 1e-7)
+    est_mags = torch.sqrt(out_real ** 2 + out_imag ** 2 + 1e-7)
+    return lms_loss(clean_mags, est_mags)
+
+
+# --------------------------------------------------------------------------------------
 # train step (trainer.py:27-37 + train_interface.py:59)
 # --------------------------------------------------------------------------------------
 class OracleTrainer:

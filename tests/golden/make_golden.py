@@ -20,7 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("SEFD_REFERENCE", "/root/reference")
 
 
-def import_reference():
+def import_reference(perceptual=False):
     sys.path.insert(0, REF)
     for n in ["matplotlib", "matplotlib.pylab", "asteroid", "asteroid.losses", "asteroid_filterbanks"]:
         sys.modules[n] = types.ModuleType(n)
@@ -40,7 +40,7 @@ def import_reference():
     with contextlib.redirect_stdout(io.StringIO()):
         import config as cfg
     cfg.DEVICE, cfg.window = "cpu", "hann"
-    cfg.loss, cfg.lstm, cfg.skip_type, cfg.perceptual = "SI-SNR", "complex", True, False
+    cfg.loss, cfg.lstm, cfg.skip_type, cfg.perceptual = "SI-SNR", "complex", True, perceptual
     import models
     import tools_for_loss
     return cfg, models, tools_for_loss
@@ -258,8 +258,44 @@ def main_crn():
     print(f"wrote crn_golden.npz ({sz/1e3:.1f} kB), {len(out)} arrays; full_loss={out['full_loss']}, n_params={out['n_params']}")
 
 
+def main_lms():
+    """LMS perceptual loss (tools_for_loss.py:111-249) and the DCCRN perceptual train step of
+    trainer.model_perceptual_train (trainer.py:44-70): loss = (main + perceptual) / 2."""
+    cfg, models, tfl = import_reference(perceptual="LMS")     # MEL_SCALES is fixed at import (tools_for_loss.py:117-120)
+    torch.set_num_threads(8)
+    out = {}
+    # op level: two magnitude arrays, gradient with respect to the estimate
+    g = torch.Generator().manual_seed(11)
+    clean = torch.rand(2, 257, 43, generator=g) * 3 + 0.01
+    est = (clean * (0.5 + torch.rand(2, 257, 43, generator=g))).requires_grad_(True)
+    loss = tfl.get_array_lms_loss(clean, est)
+    loss.backward()
+    out["op_clean"], out["op_est"] = clean.numpy(), est.detach().numpy()
+    out["op_loss"] = np.array(loss.item())
+    out["op_grad"] = est.grad.numpy().copy()
+    # model level
+    torch.manual_seed(0)
+    m = models.DCCRN(masking_mode="C").train()
+    noisy, clean_w = speechlike(2, 4000)
+    real, imag, wav = m(noisy, clean_w)
+    main = m.loss(wav, clean_w)
+    perc = m.loss(wav, clean_w, real, imag, perceptual=True)
+    total = (main + perc) / 2
+    total.backward()
+    out["model_main"], out["model_perc"], out["model_total"] = np.array(main.item()), np.array(perc.item()), np.array(total.item())
+    out["param_names"] = np.array([n for n, _ in m.named_parameters()])
+    out["model_gnorm"] = np.array([float(p.grad.double().norm()) for _, p in m.named_parameters()])
+    for n, p in m.named_parameters():
+        gr = p.grad.detach().reshape(-1)
+        out["model_grad::" + n] = (gr if gr.numel() <= 4096 else gr[:: gr.numel() // 2048][:2048]).numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "lms_golden.npz"), **out)
+    print(f"wrote lms_golden.npz, op_loss={out['op_loss']}, model main/perc/total = {out['model_main']}, {out['model_perc']}, {out['model_total']}")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "crn":
+    if len(sys.argv) > 1 and sys.argv[1] == "lms":
+        main_lms()
+    elif len(sys.argv) > 1 and sys.argv[1] == "crn":
         main_crn()
     else:
         main()
