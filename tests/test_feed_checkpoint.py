@@ -1,0 +1,108 @@
+"""Data feed sharding (vs torch's DistributedSampler) and checkpoint conversion (vs torch.optim.Adam) - SURVEY.md §8(f)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from sefd import checkpoint as ck
+from sefd import feed
+
+
+@pytest.mark.parametrize("n,world", [(10, 1), (10, 3), (7, 2), (64, 8)])
+@pytest.mark.parametrize("shuffle", [True, False])
+def test_shard_indices_match_distributed_sampler(n, world, shuffle):
+    from torch.utils.data import DistributedSampler
+    ds = list(range(n))
+    for epoch in (0, 3):
+        seen = []
+        for rank in range(world):
+            s = DistributedSampler(ds, num_replicas=world, rank=rank, shuffle=shuffle, seed=5)
+            s.set_epoch(epoch)
+            ours = feed.shard_indices(n, epoch, 5, shuffle, rank, world)
+            assert ours == list(iter(s))
+            seen += ours
+        assert set(seen) == set(range(n))
+
+
+def _layout(shapes):
+    out, off = [], 0
+    for i, sh in enumerate(shapes):
+        n = int(np.prod(sh))
+        out.append((f"p{i}", off, n, tuple(sh)))
+        off += (n + 3) // 4 * 4
+    return out, off
+
+
+def test_adam_state_round_trip_against_torch_adam():
+    torch.manual_seed(0)
+    shapes = [(4, 3, 5, 2), (4,), (1,), (16, 8)]
+    params = [torch.nn.Parameter(torch.randn(*s)) for s in shapes]
+    opt = torch.optim.Adam(params, lr=1e-3)
+    for _ in range(3):
+        for p in params:
+            p.grad = torch.randn_like(p)
+        opt.step()
+    layout, n_flat = _layout(shapes)
+    sd = opt.state_dict()
+    m, v, step = ck.adam_state_to_flat(sd, layout, n_flat)
+    assert step == 3
+    for (name, off, n, shape), p in zip(layout, params):
+        assert torch.equal(m[off:off + n].view(shape), opt.state[p]["exp_avg"])
+        assert torch.equal(v[off:off + n].view(shape), opt.state[p]["exp_avg_sq"])
+    back = ck.flat_to_adam_state(m, v, step, layout)
+    opt2 = torch.optim.Adam([torch.nn.Parameter(p.detach().clone()) for p in params], lr=1e-3)
+    opt2.load_state_dict(back)                        # the format torch.optim.Adam accepts
+    for p, p2 in zip(params, opt2.param_groups[0]["params"]):
+        g = torch.randn_like(p)
+        p.grad, p2.grad = g, g.clone()
+    opt.step(); opt2.step()
+    for p, p2 in zip(params, opt2.param_groups[0]["params"]):
+        assert torch.allclose(p, p2, atol=0, rtol=0)
+
+
+@pytest.mark.gpu
+def test_feeder_yields_the_sharded_batches():
+    rng = np.random.default_rng(0)
+    data = rng.standard_normal((37, 2, 800)).astype(np.float32)
+    for rank in range(2):
+        f = feed.WaveFeeder(data, batch=4, shuffle=True, seed=3, rank=rank, world=2)
+        f.set_epoch(1)
+        idx = feed.shard_indices(37, 1, 3, True, rank, 2)
+        # the yielded tensors are views of the double buffer: valid until the iteration after next, so consume in the loop
+        got = [(x.clone(), y.clone()) for x, y in f]
+        assert len(got) == len(f) == len(idx) // 4
+        for i, (x, y) in enumerate(got):
+            ids = idx[4 * i:4 * i + 4]
+            assert x.is_cuda and x.shape == (4, 800)
+            np.testing.assert_array_equal(x.cpu().numpy(), data[ids, 0])
+            np.testing.assert_array_equal(y.cpu().numpy(), data[ids, 1])
+
+
+@pytest.mark.gpu
+def test_checkpoint_round_trip_with_flat_adam(tmp_path):
+    import models
+    from oracle import dccrn_oracle as O
+    from sefd.train import TrainStep
+    models.cfg.loss = "SI-SNR"
+    sd0 = O.init_state(0)
+    noisy, clean = O.synthetic_batch(2, 4000)
+    m = models.DCCRN(masking_mode="C"); m.load_state_dict(sd0); m = m.cuda().train()
+    ts = TrainStep(m, lr=1e-3, loss="SI-SNR")
+    for _ in range(2):
+        ts.step(noisy.cuda(), clean.cuda())
+    path = os.path.join(tmp_path, "chkpt_2.pt")
+    ck.save_checkpoint(path, m, ts, epoch=2)
+    # the file has the reference's layout and loads into plain torch objects
+    blob = torch.load(path, map_location="cpu")
+    assert set(blob) == {"model", "optimizer", "epoch"} and set(blob["model"].keys()) == set(sd0.keys())
+    torch.optim.Adam([torch.nn.Parameter(torch.zeros_like(p)) for p in m.parameters()], lr=1e-3).load_state_dict(blob["optimizer"])
+    # resume in a fresh model + optimizer and take the same third step
+    m2 = models.DCCRN(masking_mode="C").cuda().train()
+    ts2 = TrainStep(m2, lr=1e-3, loss="SI-SNR")
+    assert ck.load_checkpoint(path, m2, ts2) == 3
+    l1 = float(ts.step(noisy.cuda(), clean.cuda()))
+    l2 = float(ts2.step(noisy.cuda(), clean.cuda()))
+    assert l1 == pytest.approx(l2, rel=1e-6)
+    for (n1, p1), (n2, p2) in zip(m.named_parameters(), m2.named_parameters()):
+        assert torch.allclose(p1, p2, rtol=1e-5, atol=1e-7), n1
