@@ -73,7 +73,7 @@ int sefd_istft_backward(const float* dwav, float* dspec, int B, int L, void* str
 int sefd_mask_istft_forward(const float* spec, const float* mask, int mode, int B, int L, float* out_real,
                             float* out_imag, float* out_wav, float* raw_wav, void* stream) {
     CHECK_L(L);
-    SEFD_REQUIRE(mode >= SEFD_MASK_E && mode <= SEFD_MASK_R, "mask mode %d unsupported", mode);
+    SEFD_REQUIRE((mode >= SEFD_MASK_E && mode <= SEFD_MASK_R) || mode == SEFD_MASK_DIRECT, "mask mode %d unsupported", mode);
     const int T = L / 100 + 3;
     MaskIstftParams m;
     memset(&m, 0, sizeof(m));
@@ -86,7 +86,7 @@ int sefd_mask_istft_forward(const float* spec, const float* mask, int mode, int 
 int sefd_mask_istft_backward(const float* dwav, const float* raw_wav, const float* spec, const float* mask, int mode,
                              int B, int L, float* dmask, void* stream) {
     CHECK_L(L);
-    SEFD_REQUIRE(mode >= SEFD_MASK_E && mode <= SEFD_MASK_R, "mask mode %d unsupported", mode);
+    SEFD_REQUIRE((mode >= SEFD_MASK_E && mode <= SEFD_MASK_R) || mode == SEFD_MASK_DIRECT, "mask mode %d unsupported", mode);
     const int T = L / 100 + 3;
     MaskIstftBwdParams m;
     memset(&m, 0, sizeof(m));

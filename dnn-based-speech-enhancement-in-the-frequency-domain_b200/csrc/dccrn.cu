@@ -11,8 +11,8 @@ sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode) {
         sefd_set_error("plan: need B > 0 and L a positive multiple of %d (got B=%d L=%d)", HOP, B, L);
         return nullptr;
     }
-    if (mask_mode < SEFD_MASK_E || mask_mode > SEFD_MASK_R) {
-        sefd_set_error("plan: masking mode %d unsupported (E=1, C=2, R=3)", mask_mode);
+    if (!((mask_mode >= SEFD_MASK_E && mask_mode <= SEFD_MASK_R) || mask_mode == SEFD_MASK_DIRECT)) {
+        sefd_set_error("plan: masking mode %d unsupported (E=1, C=2, R=3, Direct=5)", mask_mode);
         return nullptr;
     }
     sefd_plan* P = new sefd_plan();

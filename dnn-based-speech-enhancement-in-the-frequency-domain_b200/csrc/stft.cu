@@ -147,6 +147,7 @@ __device__ __forceinline__ float2 apply_mask(int mode, float2 x, float2 m) {
         sincosf(ph, &sn, &cs);
         return make_float2(em * cs, em * sn);
     }
+    if (mode == SEFD_MASK_DIRECT) return m;
     if (mode == SEFD_MASK_MAG) {          // m.x = real mask; m.y carries nothing
         const float mag = sqrtf(x.x * x.x + x.y * x.y);
         const float ph = atan2f(x.y, x.x);
@@ -317,6 +318,7 @@ __device__ __forceinline__ float2 mask_bwd(int mode, float2 x, float2 m, float2 
         if (mm > 0.f) { dmx += d_mm * m.x / mm; dmy += d_mm * m.y / mm; }
         return make_float2(dmx, dmy);
     }
+    if (mode == SEFD_MASK_DIRECT) return ds;
     if (mode == SEFD_MASK_MAG) {
         const float mag = sqrtf(x.x * x.x + x.y * x.y);
         const float ph = atan2f(x.y, x.x);

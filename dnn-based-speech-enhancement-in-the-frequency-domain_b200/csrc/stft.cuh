@@ -2,7 +2,9 @@
 #include "common.cuh"
 
 // SEFD_MASK_MAG: CRN's real T-F mask (models.py:518-524): one float per bin, est_mag = tanh(m) * |X|, noisy phase
-enum { SEFD_MASK_NONE = 0, SEFD_MASK_E = 1, SEFD_MASK_C = 2, SEFD_MASK_R = 3, SEFD_MASK_MAG = 4 };
+// SEFD_MASK_DIRECT: spectral mapping, masking_mode 'Direct(None make)' (models.py:232-250): the decoder output IS the
+// enhanced spectrum (bins 1..256; DC zero-padded)
+enum { SEFD_MASK_NONE = 0, SEFD_MASK_E = 1, SEFD_MASK_C = 2, SEFD_MASK_R = 3, SEFD_MASK_MAG = 4, SEFD_MASK_DIRECT = 5 };
 enum { SEFD_LOSS_MSE = 0, SEFD_LOSS_SDR = 1, SEFD_LOSS_SISNR = 2, SEFD_LOSS_SISDR = 3 };
 
 struct MaskIstftParams {

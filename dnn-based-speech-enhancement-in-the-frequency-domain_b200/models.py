@@ -36,7 +36,7 @@ class DCCRN(nn.Module):
         if not cfg.skip_type or use_cbn:
             unsupported.append("skip_type=False / use_cbn=True")
         if masking_mode not in _ops.MODES:
-            unsupported.append(f"masking_mode {masking_mode!r} (built: E, C, R)")
+            unsupported.append(f"masking_mode {masking_mode!r} (built: E, C, R, Direct(None make))")
         if unsupported:
             raise NotImplementedError("sefd DCCRN: configuration outside the built hot path: " + "; ".join(unsupported))
 
@@ -88,6 +88,11 @@ class DCCRN(nn.Module):
                 if isinstance(m, _d.BatchNormParams):
                     m.num_batches_tracked += 1
         self.__dict__["_last"] = (out_wav, tgt)
+        if self.masking_mode == "Direct(None make)":                     # spectral mapping, models.py:232-250
+            if tgt is None:
+                raise ValueError("Direct(None make) needs the target waveforms (models.py:234)")
+            tspec = _ops.stft(tgt)                                       # [B,257,T,2]
+            return out_real, tspec[..., 0], out_imag, tspec[..., 1], out_wav
         return out_real, out_imag, out_wav
 
     def get_params(self, weight_decay=0.0):

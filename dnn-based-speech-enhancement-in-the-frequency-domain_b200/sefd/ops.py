@@ -7,7 +7,7 @@ import torch
 
 from . import _lib
 
-MODES = {"E": 1, "C": 2, "R": 3}
+MODES = {"E": 1, "C": 2, "R": 3, "Direct(None make)": 5}
 LOSSES = {"MSE": 0, "SDR": 1, "SI-SNR": 2, "SI-SDR": 3}
 
 
@@ -94,7 +94,10 @@ def mask_istft_backward(dwav, raw, spec, mask, mode):
 class _Loss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, est, tgt, kind):
-        est, tgt = est.contiguous(), tgt.contiguous()
+        # rows = everything but the last axis (tools_for_loss.py:17-44 reduce over the last axis with keepdim and then
+        # average over the rest; for [B, L] waveforms rows = B, for the [B, 257, T] spectra of the Direct mode rows = B*257)
+        ctx.shape = est.shape
+        est, tgt = est.contiguous().reshape(-1, est.shape[-1]), tgt.contiguous().reshape(-1, tgt.shape[-1])
         _req(est, tgt)
         B, L = est.shape
         scratch = torch.empty(8 * B, device=est.device, dtype=torch.float64)
@@ -113,7 +116,7 @@ class _Loss(torch.autograd.Function):
         d = torch.empty_like(est)
         _lib.check(_lib.load().sefd_loss_backward(ptr(est), ptr(tgt), ptr(coef), ptr(gout), ptr(d), B, L, stream()),
                    "loss_backward")
-        return d, None, None
+        return d.reshape(ctx.shape), None, None
 
 
 def loss(est, tgt, name):

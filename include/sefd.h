@@ -22,7 +22,7 @@ extern "C" {
 typedef struct sefd_plan sefd_plan;
 
 /* masking modes (config.py:27, models.py:258-276) and losses (config.py:23, models.py:315-323) */
-enum { SEFD_MODE_E = 1, SEFD_MODE_C = 2, SEFD_MODE_R = 3 };
+enum { SEFD_MODE_E = 1, SEFD_MODE_C = 2, SEFD_MODE_R = 3, SEFD_MODE_DIRECT = 5 /* 'Direct(None make)', models.py:232-250 */ };
 enum { SEFD_MSE = 0, SEFD_SDR = 1, SEFD_SI_SNR = 2, SEFD_SI_SDR = 3 };
 
 int sefd_abi_version(void);

@@ -339,6 +339,8 @@ def dccrn_forward(sd: Dict[str, torch.Tensor], wav: torch.Tensor, masking_mode: 
         out_imag = real * mask_imag + imag * mask_real
     elif masking_mode == "R":                                          # models.py:275-276
         out_real, out_imag = real * mask_real, imag * mask_imag
+    elif masking_mode == "Direct(None make)":                          # models.py:238-243: spectral mapping
+        out_real, out_imag = mask_real, mask_imag
     else:
         raise ValueError(masking_mode)
 

@@ -292,8 +292,34 @@ def main_lms():
     print(f"wrote lms_golden.npz, op_loss={out['op_loss']}, model main/perc/total = {out['model_main']}, {out['model_perc']}, {out['model_total']}")
 
 
+def main_direct():
+    """masking_mode 'Direct(None make)' (models.py:232-250) with the loop of trainer.dccrn_direct_train (trainer.py:122-150):
+    loss = (loss(out_real, target_real) + loss(out_imag, target_imag)) / 2."""
+    cfg, models, tfl = import_reference()
+    torch.set_num_threads(8)
+    out = {}
+    noisy, clean = speechlike(2, 4000)
+    for loss_name in ["MSE", "SI-SNR"]:
+        cfg.loss = loss_name
+        torch.manual_seed(0)
+        m = models.DCCRN(masking_mode="Direct(None make)").train()
+        o_r, t_r, o_i, t_i, wav = m(noisy, clean)
+        loss = (m.loss(o_r, t_r) + m.loss(o_i, t_i)) / 2
+        loss.backward()
+        out[loss_name + "_loss"] = np.array(loss.item())
+        out[loss_name + "_gnorm"] = np.array([float(p.grad.double().norm()) for _, p in m.named_parameters()])
+        if loss_name == "MSE":
+            out["wav"], out["out_real"], out["target_real"] = wav.detach().numpy(), o_r.detach().numpy(), t_r.detach().numpy()
+            out["param_names"] = np.array([n for n, _ in m.named_parameters()])
+    cfg.loss = "SI-SNR"
+    np.savez_compressed(os.path.join(HERE, "direct_golden.npz"), **out)
+    print("wrote direct_golden.npz", out["MSE_loss"], out["SI-SNR_loss"])
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "lms":
+    if len(sys.argv) > 1 and sys.argv[1] == "direct":
+        main_direct()
+    elif len(sys.argv) > 1 and sys.argv[1] == "lms":
         main_lms()
     elif len(sys.argv) > 1 and sys.argv[1] == "crn":
         main_crn()

@@ -62,8 +62,11 @@ def test_dropin_refuses_cpu_and_unbuilt_configs():
     m = models.DCCRN(masking_mode="C")
     with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.zeros(1, 4000))
+    models.DCCRN(masking_mode="Direct(None make)")          # spectral mapping is built
     with pytest.raises(NotImplementedError):
-        models.DCCRN(masking_mode="Direct(None make)")
+        models.DCCRN(masking_mode="X")
+    with pytest.raises(NotImplementedError):
+        models.DCCRN(use_cbn=True)
     crn = models.CRN()                         # built; like DCCRN it has no CPU path
     with pytest.raises(RuntimeError, match="CUDA"):
         crn(torch.zeros(1, 4000))
