@@ -152,12 +152,17 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput ----------------
-    for _ in range(args.warmup):
-        ts.step(noisy, clean)
-    barrier()
+    # the clock sampler (nvidia-smi -lms 100) needs a few hundred ms to come up: it starts before the warm-up (the same
+    # step, so the same load) and runs until the end of the timed region
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        ts.step(noisy, clean)
+    barrier()
+    for _ in range(25):                 # ~0.5 s of extra untimed steps on EVERY rank (same count: each holds an all-reduce)
+        ts.step(noisy, clean)
+    barrier()
     n0 = lib.sefd_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
