@@ -350,7 +350,13 @@ int sefd_crn_forward(const sefd_plan* plan, const float* params, float* bn_buffe
 int sefd_crn_backward(const sefd_plan* plan, const float* params, const float* d_wav, float* grads, void* ws, size_t ws_bytes,
                       void* stream) {
     SEFD_REQUIRE(plan && params && d_wav && grads && ws, "crn_backward: null argument");
-    return sefd_crn_backward_impl(plan, params, d_wav, grads, ws, ws_bytes, ST);
+    return sefd_crn_backward_impl(plan, params, d_wav, nullptr, grads, ws, ws_bytes, ST);
+}
+
+int sefd_crn_backward_spec(const sefd_plan* plan, const float* params, const float* d_wav, const float* d_est_mags, float* grads,
+                           void* ws, size_t ws_bytes, void* stream) {
+    SEFD_REQUIRE(plan && params && grads && ws && (d_wav || d_est_mags), "crn_backward_spec: null argument");
+    return sefd_crn_backward_impl(plan, params, d_wav, d_est_mags, grads, ws, ws_bytes, ST);
 }
 
 }  // extern "C"

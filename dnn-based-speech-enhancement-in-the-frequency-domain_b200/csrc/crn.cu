@@ -315,7 +315,7 @@ int sefd_crn_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, co
 }
 
 // ------------------------------------------------------------------------------------------------
-int sefd_crn_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, float* grads, void* wsv,
+int sefd_crn_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, const float* dmags, float* grads, void* wsv,
                            size_t ws_bytes, cudaStream_t st) {
     SEFD_REQUIRE(P->kind == 1, "crn_backward: not a CRN plan");
     SEFD_REQUIRE(ws_bytes >= P->ws_bytes, "crn_backward: workspace too small");
@@ -360,6 +360,7 @@ int sefd_crn_backward_impl(const sefd_plan* P, const float* prm, const float* dw
         MaskIstftBwdParams m;
         memset(&m, 0, sizeof(m));
         m.dwav = dwav; m.raw_wav = ws + P->raw_wav; m.spec = ws + P->spec; m.mask = ws + last.y; m.dmask = ws + last.dy;
+        m.dreal = dmags;                 // gradient at est_mags (perceptual LMS branch of CRN.loss, models.py:553-555)
         m.mT = 1; m.mF = (long long)(T + 1); m.mB = (long long)256 * (T + 1);
         m.m_tshift = 1; m.mode = SEFD_MASK_MAG; m.B = B; m.L = L; m.T = T;
         SEFD_TRY(sefd_mask_istft_bwd_launch(m, st));

@@ -17,6 +17,6 @@ sefd_plan* sefd_crn_plan_create_impl(int B, int L);
 int sefd_crn_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const float* noisy, const float* target,
                           int train, float* est_mags, float* target_mags, float* out_wav, void* ws, size_t ws_bytes,
                           cudaStream_t st);
-int sefd_crn_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, float* grads, void* ws,
+int sefd_crn_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, const float* dmags, float* grads, void* ws,
                            size_t ws_bytes, cudaStream_t st);
 int sefd_crn_tensor_info(const sefd_plan* P, const char* name, long long* off, int* ndim, long long shape[4]);

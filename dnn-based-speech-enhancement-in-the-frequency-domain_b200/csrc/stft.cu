@@ -391,10 +391,15 @@ __global__ void __launch_bounds__(256) mask_istft_bwd_kernel(const MaskIstftBwdP
         const int k = e / SF, f = e % SF, t = t0 + f;
         if (t >= T || k < k_lo) continue;
         float2 ds = S.out[k][f];
+        float dmag = 0.f;                 // SEFD_MASK_MAG: gradient arriving at est_mags = tanh(mask) |X|
         if (p.dreal) {
             const long long o = ((long long)b * NBIN + k) * T + t;
-            ds.x += __ldg(p.dreal + o);
-            ds.y += __ldg(p.dimag + o);
+            if (p.mode == SEFD_MASK_MAG) {
+                dmag = __ldg(p.dreal + o);
+            } else {
+                ds.x += __ldg(p.dreal + o);
+                ds.y += __ldg(p.dimag + o);
+            }
         }
         float2 x = make_float2(0.f, 0.f), m = x;
         if (p.mode != SEFD_MASK_NONE) {
@@ -403,7 +408,11 @@ __global__ void __launch_bounds__(256) mask_istft_bwd_kernel(const MaskIstftBwdP
             if (p.mode == SEFD_MASK_E) m = __ldg(reinterpret_cast<const float2*>(mq));
             if (p.mode == SEFD_MASK_MAG) m.x = __ldg(mq);
         }
-        const float2 dm = mask_bwd(p.mode, x, m, ds);
+        float2 dm = mask_bwd(p.mode, x, m, ds);
+        if (p.mode == SEFD_MASK_MAG && p.dreal) {
+            const float th = tanhf(m.x);
+            dm.x += dmag * (1.f - th * th) * sqrtf(x.x * x.x + x.y * x.y);
+        }
         float* dq = p.dmask + b * p.mB + (long long)(k - k_lo) * p.mF + (long long)(t + p.m_tshift) * p.mT;
         if (p.mode == SEFD_MASK_MAG) *dq = dm.x;
         else *reinterpret_cast<float2*>(dq) = dm;

@@ -23,6 +23,7 @@ struct MaskIstftParams {
 
 struct MaskIstftBwdParams {
     const float *dreal, *dimag;   // optional [B][257][T]: gradient arriving directly at the masked spectrum (perceptual
+                                  // (SEFD_MASK_MAG: dreal = gradient at est_mags, dimag unused)
                                   // losses on out_real / out_imag, models.py:305-312); added to the ISTFT adjoint
     const float* dwav;       // [B][L] (may be nullptr: no gradient through the waveform)
     const float* raw_wav;    // [B][L] or nullptr (no clamp gating)

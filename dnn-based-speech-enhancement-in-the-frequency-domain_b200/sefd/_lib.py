@@ -50,6 +50,7 @@ SIGNATURES = {
     "sefd_crn_plan_create": (_vp, [_i, _i]),
     "sefd_crn_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sefd_crn_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "sefd_crn_backward_spec": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sefd_set_engine": (_i, [_i]),
     "sefd_get_engine": (_i, []),
     "sefd_launch_count": (_ll, []),

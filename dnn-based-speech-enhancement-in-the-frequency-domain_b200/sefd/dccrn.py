@@ -254,18 +254,23 @@ class _ForwardCRN(torch.autograd.Function):
         ctx.engine, ctx.plan, ctx.generation = engine, plan, plan.generation
         if target_mags is None:
             target_mags = torch.zeros(0, device=dev)
-        ctx.mark_non_differentiable(est_mags, target_mags)
+        ctx.mark_non_differentiable(target_mags)
+        ctx.set_materialize_grads(False)
         return est_mags, target_mags, out_wav
 
     @staticmethod
-    def backward(ctx, _g_est, _g_tgt, g_wav):
+    def backward(ctx, g_est, _g_tgt, g_wav):
         engine, plan = ctx.engine, ctx.plan
         if plan.generation != ctx.generation:
             raise RuntimeError("sefd: the activation workspace of this forward was overwritten by a later forward "
                                "of the same batch shape; call backward() before the next forward")
-        g_wav = g_wav.contiguous()
-        _lib.check(_lib.load().sefd_crn_backward(plan.handle, ptr(engine.flat), ptr(g_wav), ptr(engine.flat_grad),
-                                                 ptr(plan.ws), plan.ws_bytes, stream()), "crn_backward")
+        if g_est is None and g_wav is None:
+            raise RuntimeError("sefd: backward() reached the CRN forward without any gradient")
+        g_wav = None if g_wav is None else g_wav.contiguous().float()
+        g_est = None if g_est is None else g_est.contiguous().float()
+        _lib.check(_lib.load().sefd_crn_backward_spec(plan.handle, ptr(engine.flat), ptr(g_wav), ptr(g_est),
+                                                      ptr(engine.flat_grad), ptr(plan.ws), plan.ws_bytes, stream()),
+                   "crn_backward_spec")
         grads = tuple(engine.flat_grad[o: o + n].view(shape) for (_, o, n, shape) in plan.params)
         return (None, None, None, None) + grads
 

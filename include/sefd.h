@@ -150,6 +150,10 @@ int sefd_crn_forward(const sefd_plan* plan, const float* params, float* bn_buffe
                      size_t ws_bytes, void* stream);
 int sefd_crn_backward(const sefd_plan* plan, const float* params, const float* d_wav, float* grads, void* ws,
                       size_t ws_bytes, void* stream);
+/* same, with an additional gradient arriving at est_mags [B][257][T] (CRN.loss perceptual branch, models.py:553-555);
+ * d_wav or d_est_mags may be NULL */
+int sefd_crn_backward_spec(const sefd_plan* plan, const float* params, const float* d_wav, const float* d_est_mags,
+                           float* grads, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- measurement support (bench.py): CUDA-event timing per kernel category on the launching stream.
  * categories: 0 tap-GEMM (conv/convT/linear fwd + dgrad), 1 weight gradients, 2 BN+PReLU passes,

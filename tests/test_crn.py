@@ -234,3 +234,41 @@ def test_crn_gpu_eval_adam_and_full_length(crn_golden, sd0, engine):
         if n.endswith("conv.bias") and not n.startswith("decoder.5."):
             continue
         assert abs(gn[i] - ref[i]) <= (5e-2 if tf else 5e-3) * ref[i] + 1e-3 * ref.max(), (n, gn[i], ref[i])
+
+
+@pytest.mark.gpu
+def test_crn_gpu_gradient_through_est_mags(sd0):
+    """A loss on the magnitude output (trainer.crn_direct_train: model.loss(output_mag, target_mag), trainer.py:168-169;
+    CRN.loss perceptual branch models.py:553-555) sends a gradient to est_mags; checked against the oracle's autograd.
+    (LMS itself is not used here: tanh(out) * |X| can be negative, so log-mel of est_mags is NaN in the reference too.)
+    fp32 engine; (waveform MSE + magnitude MSE) / 2."""
+    import models
+    from sefd import _lib
+    lib = _lib.load()
+    lib.sefd_set_engine(0)
+    models.cfg.loss = "MSE"
+    try:
+        noisy, clean = _inputs("speech")
+        tr = O.OracleTrainer(sd0, loss="MSE")
+        for k in tr.keys:
+            tr.sd[k].grad = None
+        est_r, tgt_r, wav_r = O.crn_forward(tr.sd, noisy, clean, train=True, taps={})
+        ref_total = (O.crn_loss(wav_r, clean, "MSE") + O.crn_loss(est_r, tgt_r, "MSE")) / 2
+        ref_total.backward()
+        m = _build(sd0)
+        est, tgt, wav = m(noisy.to(DEV), clean.to(DEV))
+        total = (m.loss(wav, clean.to(DEV)) + m.loss(est, tgt)) / 2
+        total.backward()
+        assert float(total) == pytest.approx(float(ref_total), rel=2e-4)
+        grads = tr.grads()
+        gmax = max(float(g.abs().max()) for g in grads.values())
+        for name, p in m.named_parameters():
+            if name.endswith("conv.bias") and not name.startswith("decoder.5."):
+                continue
+            g64, r64 = p.grad.detach().double().cpu(), grads[name].detach().double()
+            e, s = float((g64 - r64).abs().max()), float(r64.abs().max())
+            cosv = float((g64.reshape(-1) * r64.reshape(-1)).sum() / (g64.norm() * r64.norm() + 1e-30))
+            assert e <= 5e-3 * s + 1e-6 * gmax or cosv > 0.9995, (name, e, s, cosv)
+    finally:
+        models.cfg.loss = "SI-SNR"
+        lib.sefd_set_engine(1)
