@@ -2,7 +2,10 @@
 // sequencing of the kernels.  Mirrors DCCRN.forward (models.py:176-284) and the autograd graph the
 // reference gets from torch; see DESIGN.md for the dataflow and SURVEY.md appendix B for the
 // backward obligations.
+#include <stdlib.h>
+
 #include "plan.cuh"
+#include "prof.cuh"
 #include "taps.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -165,6 +168,7 @@ sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode) {
     P->dWs = w.floats(16 * max_w);
     P->dbs = w.floats(1024);
     P->red = w.doubles(2 * 512 + 8);
+    P->red2 = w.doubles(2 * 512 + 8);
     P->dX = w.floats(2 * Bz * T * RNN_H);
     P->dH = w.floats(2 * 2 * Bz * T * RNN_H);
     P->dG = w.floats(2 * 2 * Bz * T * G4);
@@ -393,12 +397,37 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
     };
     int nsplit = 1;
     long long sstride = 0;
+    // ---- side stream: everything that only post-processes a finished weight gradient (fold / un-permute of the split
+    // partials, bias column sums) is off the critical chain bn_bwd -> dgrad -> bn_bwd ...; these kernels are tiny
+    // (no shared memory, few CTAs) and co-reside with the persistent GEMM CTAs.  Hazards: the partial buffer dWs and the
+    // LSTM gate-gradient buffer dG are overwritten by later main-stream kernels -> join before those.
+    static const bool use_side = getenv("SEFD_SIDE_STREAM") == nullptr || atoi(getenv("SEFD_SIDE_STREAM")) != 0;
+    cudaStream_t sx = st;
+    bool pending = false;
+    if (use_side && !sefd_prof_on()) {
+        if (!P->side) {
+            SEFD_REQUIRE(cudaStreamCreateWithFlags(&P->side, cudaStreamNonBlocking) == cudaSuccess, "backward: side stream");
+            cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&P->ev_join, cudaEventDisableTiming);
+        }
+        sx = P->side;
+    }
+    auto fork = [&]() {           // the side stream sees everything enqueued on the main stream so far
+        if (sx != st) { cudaEventRecord(P->ev_fork, st); cudaStreamWaitEvent(sx, P->ev_fork, 0); }
+    };
+    auto side_done = [&]() {
+        if (sx != st) { cudaEventRecord(P->ev_join, sx); pending = true; }
+    };
+    auto join = [&]() {           // the main stream waits for the side work issued so far
+        if (pending) { cudaStreamWaitEvent(st, P->ev_join, 0); pending = false; }
+    };
+    double* red_side = wsd + (sx != st ? P->red2 : P->red);
     auto fold = [&](const ConvLayer& c, bool dec, const float* dbias) -> int {
         CconvFoldParams f;
         f.dWf = dWs; f.dbias = dbias; f.nsplit = nsplit; f.split_stride = sstride;
         f.Ci2 = c.Cin / 2; f.Co2 = c.Cout / 2; f.transposed = dec; f.two_src = dec;
         f.dwr = grads + c.wr; f.dwi = grads + c.wi; f.dbr = grads + c.br; f.dbi = grads + c.bi;
-        return sefd_fold_cconv(f, st);
+        return sefd_fold_cconv(f, sx);
     };
 
     // sum the wgrad split partials while un-permuting into the reference's parameter layout
@@ -408,7 +437,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
         q.src = src; q.dst = dst; q.na = na; q.nb = nb; q.nc = nc; q.sa = sa; q.sb = sb; q.sc = sc;
         q.da = (long long)nb * nc; q.db = nc; q.dc = 1;
         q.accumulate = accumulate; q.nsplit = nsplit; q.split_stride = sstride; q.round_tf32 = 0;
-        return sefd_permute3p(q, st);
+        return sefd_permute3p(q, sx);
     };
 
     // ---- ISTFT^T and mask Jacobian -> d(mask) laid out like dec[5].y ----
@@ -431,12 +460,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
         const float* in1 = ws + P->enc[NL - 1 - j].z;
         float* dY = ws + c.dy;
         const float* dbias = nullptr;
-        if (j != NL - 1) {
-            SEFD_TRY(bn_bwd(c, T + 1, 1, false));
-        } else {
-            SEFD_TRY(sefd_colsum2(dY, 1, 0, (long long)B * c.Fout * (T + 1), c.Cout, c.Cout, wsd + P->red, ws + P->dbs, st));
-            dbias = ws + P->dbs;
-        }
+        if (j != NL - 1) SEFD_TRY(bn_bwd(c, T + 1, 1, false));
         // weight gradient
         WgradParams wg;
         memset(&wg, 0, sizeof(wg));
@@ -451,8 +475,15 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
                 const int i = kf * 2 + kt;
                 wg.a_off[i] = 0; wg.g_off[i] = kf - 2; wg.dt[i] = -kt; wg.wslab[i] = i;
             }
+        join();
         SEFD_TRY(sefd_wgrad(wg, dWs, (long long)P->dWs_floats, 10, &nsplit, &sstride, st));
+        fork();
+        if (j == NL - 1) {        // decoder 5 has no BatchNorm behind it: its bias gradient is the column sum of dY
+            SEFD_TRY(sefd_colsum2(dY, 1, 0, (long long)B * c.Fout * (T + 1), c.Cout, c.Cout, red_side, ws + P->dbs, sx));
+            dbias = ws + P->dbs;
+        }
         SEFD_TRY(fold(c, true, dbias));
+        side_done();
         // data gradient: d(in0) and d(skip)
         TapGemmParams g;
         memset(&g, 0, sizeof(g));
@@ -493,19 +524,25 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
         wg.B = B; wg.J = 1; wg.Tg = T; wg.Fa = 1; wg.Ta = T; wg.Fg = 4;
         wg.a_mul = 0; wg.g_mul = 0; wg.ntaps = 4;
         for (int d = 0; d < 4; ++d) { wg.a_off[d] = 0; wg.g_off[d] = d; wg.dt[d] = 0; wg.wslab[d] = d; }
+        join();
         SEFD_TRY(sefd_wgrad(wg, dWs, (long long)P->dWs_floats, 4, &nsplit, &sstride, st));
         // dWs[d][k][c] -> grads[c][d][k]
+        fork();
         SEFD_TRY(unperm(dWs, grads + P->w_tr[q], 128, 4, 128, 1, 128 * 128, 128, 0));
+        side_done();
     }
+    fork();
     // db_tr[q][c*4+d] = sum_{b,t} dU[b][d][t][q*128+c]
     for (int d = 0; d < 4; ++d)
         SEFD_TRY(sefd_colsum2(ws + P->dU + (size_t)d * T * 256, B, (long long)4 * T * 256, T, 256, 256,
-                              wsd + P->red, ws + P->dbs + d * 256, st));
+                              red_side, ws + P->dbs + d * 256, sx));
     for (int q = 0; q < 2; ++q)   // dbs[d][q*128+c] -> grads[c*4+d]
-        SEFD_TRY(sefd_permute3(ws + P->dbs + q * 128, grads + P->b_tr[q], 1, 128, 4, 0, 1, 256, 0, st));
+        SEFD_TRY(sefd_permute3(ws + P->dbs + q * 128, grads + P->b_tr[q], 1, 128, 4, 0, 1, 256, 0, sx));
+    side_done();
 
     // ---- LSTM backward (layer 1 then layer 0) ----
     for (int l = 1; l >= 0; --l) {
+        join();                                            // side kernels of the previous layer still read dG
         SEFD_TRY(sefd_clstm_combine_bwd(ws + P->dX, ws + P->dH, nX, st));
         LstmBwdParams lb;
         memset(&lb, 0, sizeof(lb));
@@ -545,14 +582,20 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
             wg.dW = dWs;
             wg.B = 2 * B; wg.J = 1; wg.Tg = T; wg.Fa = 1; wg.Ta = T; wg.Fg = 1;
             wg.ntaps = 1; wg.dt[0] = -1;
+            join();
             SEFD_TRY(sefd_wgrad(wg, dWs, (long long)P->dWs_floats, 1, &nsplit, &sstride, st));
+            fork();
             SEFD_TRY(unperm(dWs, grads + P->w_hh[l][p], G4, 1, 128, 1, 0, G4, 0));   // [k][n] -> [n][k]
+            side_done();
             // W_ih
             if (l == 1) {
                 wg.a[0] = src4(ws + P->X1, 1, T, RNN_H, RNN_H);      // [q][B] rows are contiguous = 2B rows
                 wg.dt[0] = 0;
+                join();
                 SEFD_TRY(sefd_wgrad(wg, dWs, (long long)P->dWs_floats, 1, &nsplit, &sstride, st));
+                fork();
                 SEFD_TRY(unperm(dWs, grads + P->w_ih[1][p], G4, 1, 128, 1, 0, G4, 0));
+                side_done();
             } else {
                 for (int q = 0; q < 2; ++q) {
                     WgradParams w0;
@@ -564,14 +607,19 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
                     w0.B = B; w0.J = 1; w0.Tg = T; w0.Fa = 4; w0.Ta = T; w0.Fg = 1;
                     w0.a_mul = 0; w0.g_mul = 0; w0.ntaps = 4;
                     for (int d = 0; d < 4; ++d) { w0.a_off[d] = d; w0.g_off[d] = 0; w0.dt[d] = 0; w0.wslab[d] = d; }
+                    join();
                     SEFD_TRY(sefd_wgrad(w0, dWs, (long long)P->dWs_floats, 4, &nsplit, &sstride, st));
                     // dWs[d][c][n] -> grads[n][c][d]   (the second part accumulates onto the first)
+                    fork();
                     SEFD_TRY(unperm(dWs, grads + P->w_ih[0][p], G4, 128, 4, 1, G4, (long long)128 * G4, q));
+                    side_done();
                 }
             }
             // biases: both get sum over rows and time of dG
-            SEFD_TRY(sefd_colsum2(dGp, 1, 0, (long long)2 * B * T, G4, G4, wsd + P->red, grads + P->b_ih[l][p], st));
-            SEFD_TRY(sefd_permute3(grads + P->b_ih[l][p], grads + P->b_hh[l][p], 1, 1, G4, 0, 0, 1, 0, st));
+            fork();
+            SEFD_TRY(sefd_colsum2(dGp, 1, 0, (long long)2 * B * T, G4, G4, red_side, grads + P->b_ih[l][p], sx));
+            SEFD_TRY(sefd_permute3(grads + P->b_ih[l][p], grads + P->b_hh[l][p], 1, 1, G4, 0, 0, 1, 0, sx));
+            side_done();
         }
     }
 
@@ -598,8 +646,11 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
                 const int k = kf * 2 + kt;
                 wg.a_off[k] = kf - 2; wg.g_off[k] = 0; wg.dt[k] = kt - 1; wg.wslab[k] = k;
             }
+        join();
         SEFD_TRY(sefd_wgrad(wg, dWs, (long long)P->dWs_floats, 10, &nsplit, &sstride, st));
+        fork();
         SEFD_TRY(fold(c, false, nullptr));
+        side_done();
         if (i > 0) {
             {
                 TapGemmParams g;
@@ -614,6 +665,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
             }
         }
     }
+    join();                                                // the caller's stream sees every gradient
     return 0;
 }
 
@@ -624,7 +676,15 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
 
 extern "C" {
 
-void sefd_dccrn_plan_destroy(sefd_plan* plan) { delete plan; }
+void sefd_dccrn_plan_destroy(sefd_plan* plan) {
+    if (plan && plan->side) {
+        cudaStreamSynchronize(plan->side);
+        cudaStreamDestroy(plan->side);
+        cudaEventDestroy(plan->ev_fork);
+        cudaEventDestroy(plan->ev_join);
+    }
+    delete plan;
+}
 size_t sefd_dccrn_workspace_bytes(const sefd_plan* plan) { return plan ? plan->ws_bytes : 0; }
 long long sefd_dccrn_param_floats(const sefd_plan* plan) { return plan ? plan->n_param_floats : 0; }
 long long sefd_dccrn_buffer_floats(const sefd_plan* plan) { return plan ? plan->n_buffer_floats : 0; }

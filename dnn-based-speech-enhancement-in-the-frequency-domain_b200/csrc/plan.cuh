@@ -52,6 +52,10 @@ struct sefd_plan {
     size_t Wih0p, Wih0T, Wih0Q, Wih1p, Wih1T, Wih1Q, Whh[2], bsum[2], Wtrp, WtrT, btrp;
     size_t dU, dY, dWs, dbs, red /*double*/, dX, dH, dG, dzd[NL];
     size_t dY_floats, dWs_floats;
+    // side stream of the backward: gradient folds / un-permutes / bias column sums run beside the GEMM chain
+    mutable cudaStream_t side = nullptr;
+    mutable cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    size_t red2 = 0;          /*double*/
     // CRN only (crn.cu)
     long long c_wih, c_whh, c_bih, c_bhh, c_wtr, c_btr;       // parameter offsets of enhance / tranform
     size_t mag, tmag, tspec, WihP, WihT;                      // workspace offsets (floats)
