@@ -315,7 +315,14 @@ int sefd_adam_step(float* params, const float* grads, float* exp_avg, float* exp
 }
 
 // ---- model level ------------------------------------------------------------------------------
-sefd_plan* sefd_dccrn_plan_create(int B, int L, int masking_mode) { return sefd_plan_create_impl(B, L, masking_mode); }
+sefd_plan* sefd_dccrn_plan_create(int B, int L, int masking_mode) { return sefd_plan_create_impl(B, L, masking_mode, 0); }
+sefd_plan* sefd_dccrn_plan_create_ex(int B, int L, int masking_mode, int flags) {
+    if (flags & ~SEFD_PLAN_NO_SKIP) {
+        sefd_set_error("plan: unknown flag bits 0x%x", flags & ~SEFD_PLAN_NO_SKIP);
+        return nullptr;
+    }
+    return sefd_plan_create_impl(B, L, masking_mode, flags);
+}
 
 int sefd_dccrn_forward(const sefd_plan* plan, const float* params, float* bn_buffers, const float* noisy,
                        const float* target, int train, float* out_real, float* out_imag, float* out_wav, void* ws,

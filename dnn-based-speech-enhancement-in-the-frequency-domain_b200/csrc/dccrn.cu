@@ -9,7 +9,7 @@
 #include "taps.cuh"
 
 // ------------------------------------------------------------------------------------------------
-sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode) {
+sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode, int flags) {
     if (B <= 0 || L <= 0 || L % HOP != 0) {
         sefd_set_error("plan: need B > 0 and L a positive multiple of %d (got B=%d L=%d)", HOP, B, L);
         return nullptr;
@@ -24,6 +24,7 @@ sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode) {
     P->L = L;
     P->T = L / HOP + 3;
     P->mask_mode = mask_mode;
+    P->skip = (flags & SEFD_PLAN_NO_SKIP) ? 0 : 1;
     const int kn[NL + 1] = {2, 32, 64, 128, 256, 256, 256};
     for (int i = 0; i <= NL; ++i) {
         P->ch[i] = kn[i];
@@ -50,7 +51,7 @@ sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode) {
     for (int j = 0; j < NL; ++j) {
         ConvLayer& c = P->dec[j];
         const int idx = NL - j;
-        c.Cin = 2 * kn[idx];
+        c.Cin = (P->skip ? 2 : 1) * kn[idx];
         c.Cout = kn[idx - 1];
         c.Fin = P->Fe[idx];
         c.Fout = 2 * c.Fin;
@@ -185,7 +186,7 @@ static int pack_weights(const sefd_plan* P, const float* prm, float* ws, cudaStr
         CconvPackParams pp;
         pp.wr = prm + c.wr; pp.wi = prm + c.wi; pp.br = prm + c.br; pp.bi = prm + c.bi;
         pp.Ci2 = c.Cin / 2; pp.Co2 = c.Cout / 2;
-        pp.transposed = e >= NL; pp.two_src = e >= NL;
+        pp.transposed = e >= NL; pp.two_src = e >= NL && P->skip;
         pp.Wf = ws + c.Wf; pp.Wt = ws + c.Wt; pp.bias = ws + c.bias;
         pp.round_tf32 = sefd_get_engine_internal() == 1 && c.Cin % 32 == 0 && (c.Cout % 32 == 0);
         SEFD_TRY(sefd_pack_cconv(pp, st));
@@ -335,10 +336,10 @@ int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const 
     // ---- decoder (models.py:222-226): convT on complex_cat(out, skip), BN over T+1 frames, drop frame 0 ----
     for (int j = 0; j < NL; ++j) {
         const ConvLayer& c = P->dec[j];
-        const int Ch = c.Cin / 2;
+        const int Ch = P->skip ? c.Cin / 2 : c.Cin;       // channels per source
         const float* in0 = j == 0 ? ws + P->U : ws + P->dec[j - 1].z;
         const float* in1 = ws + P->enc[NL - 1 - j].z;
-        if (sefd_skinny_up_n2_eligible(Ch, c.Cout)) {       // decoder 5: both phases in one HBM-bound pass
+        if (P->skip && sefd_skinny_up_n2_eligible(Ch, c.Cout)) {       // decoder 5: both phases in one HBM-bound pass
             SEFD_TRY(sefd_skinny_up_n2(in0, in1, ws + c.Wf, ws + c.bias, ws + c.y, B, c.Fin, T, st));
             continue;
         }
@@ -346,7 +347,7 @@ int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const 
             TapGemmParams g;
             memset(&g, 0, sizeof(g));
             g.a[0] = src4(in0, c.Fin, T, Ch, Ch);
-            g.a[1] = src4(in1, c.Fin, T, Ch, Ch);
+            g.a[1] = P->skip ? src4(in1, c.Fin, T, Ch, Ch) : no_src();
             g.o[0] = dst4(ws + c.y, c.Fout, T + 1, c.Cout, c.Cout);
             g.o[1] = no_dst();
             g.W = ws + c.Wf; g.Wnk = ws + c.Wt; g.nslabs = 10; g.bias = ws + c.bias;
@@ -425,7 +426,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
     auto fold = [&](const ConvLayer& c, bool dec, const float* dbias) -> int {
         CconvFoldParams f;
         f.dWf = dWs; f.dbias = dbias; f.nsplit = nsplit; f.split_stride = sstride;
-        f.Ci2 = c.Cin / 2; f.Co2 = c.Cout / 2; f.transposed = dec; f.two_src = dec;
+        f.Ci2 = c.Cin / 2; f.Co2 = c.Cout / 2; f.transposed = dec; f.two_src = dec && P->skip;
         f.dwr = grads + c.wr; f.dwi = grads + c.wi; f.dbr = grads + c.br; f.dbi = grads + c.bi;
         return sefd_fold_cconv(f, sx);
     };
@@ -455,7 +456,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
     // ---- decoder backward ----
     for (int j = NL - 1; j >= 0; --j) {
         const ConvLayer& c = P->dec[j];
-        const int Ch = c.Cin / 2;
+        const int Ch = P->skip ? c.Cin / 2 : c.Cin;
         const float* in0 = j == 0 ? ws + P->U : ws + P->dec[j - 1].z;
         const float* in1 = ws + P->enc[NL - 1 - j].z;
         float* dY = ws + c.dy;
@@ -465,7 +466,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
         WgradParams wg;
         memset(&wg, 0, sizeof(wg));
         wg.a[0] = src4(in0, c.Fin, T, Ch, Ch);
-        wg.a[1] = src4(in1, c.Fin, T, Ch, Ch);
+        wg.a[1] = P->skip ? src4(in1, c.Fin, T, Ch, Ch) : no_src();
         wg.g = src4(dY, c.Fout, T + 1, c.Cout, c.Cout);
         wg.dW = dWs;
         wg.B = B; wg.J = c.Fin; wg.Tg = T + 1; wg.Fa = c.Fin; wg.Ta = T; wg.Fg = c.Fout;
@@ -490,7 +491,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
         g.a[0] = src4(dY, c.Fout, T + 1, c.Cout, c.Cout);
         g.a[1] = no_src();
         g.o[0] = dst4(j == 0 ? ws + P->dU : ws + P->dec[j - 1].dz, c.Fin, T, Ch, Ch);
-        g.o[1] = dst4(ws + P->enc[NL - 1 - j].dz, c.Fin, T, Ch, Ch);
+        g.o[1] = P->skip ? dst4(ws + P->enc[NL - 1 - j].dz, c.Fin, T, Ch, Ch) : no_dst();
         g.W = ws + c.Wt; g.Wnk = ws + c.Wf; g.nslabs = 10;
         g.round_out[0] = (j == 0) && sefd_get_engine_internal() == 1;      // dU feeds the projection GEMMs
         g.B = B; g.J = c.Fin; g.Tout = T; g.Fin = c.Fout; g.Tin = T + 1;
@@ -564,7 +565,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
                 g.W = ws + P->Wih1T; g.J = 1;
                 g.Wnk = ws + P->Wih1Q; g.nslabs = 1;
             } else {
-                g.o[0] = dst4(ws + P->enc[NL - 1].dz2 + q * 128, 4, T, 256, 128);   // summed with the skip gradient by BN backward
+                g.o[0] = dst4(ws + (P->skip ? P->enc[NL - 1].dz2 : P->enc[NL - 1].dz) + q * 128, 4, T, 256, 128);   // summed with the skip gradient by BN backward
                 g.W = ws + P->Wih0T; g.wJ = (long long)2 * G4 * 128; g.J = 4;
                 g.Wnk = ws + P->Wih0Q; g.nslabs = 4; g.wJ_slabs = 1;
             }
@@ -627,7 +628,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
     for (int i = NL - 1; i >= 0; --i) {
         const ConvLayer& c = P->enc[i];
         float* dY = ws + c.dy;
-        SEFD_TRY(bn_bwd(c, T, 0, true));
+        SEFD_TRY(bn_bwd(c, T, 0, P->skip != 0));     // without skip connections the only gradient is in dz
         WgradParams wg;
         memset(&wg, 0, sizeof(wg));
         if (i == 0) {
@@ -657,7 +658,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
                 memset(&g, 0, sizeof(g));
                 g.a[0] = src4(dY, c.Fout, T, c.Cout, c.Cout);
                 g.a[1] = no_src();
-                g.o[0] = dst4(ws + P->enc[i - 1].dz2, c.Fin, T, c.Cin, c.Cin);   // summed with the skip gradient by BN backward
+                g.o[0] = dst4(ws + (P->skip ? P->enc[i - 1].dz2 : P->enc[i - 1].dz), c.Fin, T, c.Cin, c.Cin);   // summed with the skip gradient by BN backward
                 g.o[1] = no_dst();
                 g.W = ws + c.Wt; g.Wnk = ws + c.Wf; g.nslabs = 10;
                 g.B = B; g.J = c.Fout; g.Tout = T; g.Fin = c.Fout; g.Tin = T;

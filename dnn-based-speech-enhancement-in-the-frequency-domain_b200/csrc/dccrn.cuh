@@ -5,7 +5,7 @@
 #include "stft.cuh"
 
 struct sefd_plan;
-sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode);
+sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode, int flags);
 int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const float* noisy, const float* target,
                       int train, float* out_real, float* out_imag, float* out_wav, void* ws, size_t ws_bytes,
                       cudaStream_t st);

@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 
+#include "../../include/sefd.h"
 #include "dccrn.cuh"
 
 namespace {
@@ -39,6 +40,7 @@ struct ConvLayer {
 struct sefd_plan {
     int kind;                 // 0: DCCRN (complex), 1: CRN (real)
     int B, L, T, mask_mode;
+    int skip = 1;             // 1: decoder convs read complex_cat(out, encoder skip) (cfg.skip_type, models.py:107-169)
     int ch[NL + 1], Fe[NL + 1];
     ConvLayer enc[NL], dec[NL];
     // LSTM parameter offsets [layer][lstm]

@@ -33,8 +33,8 @@ class DCCRN(nn.Module):
             unsupported.append(f"kernel_num {kernel_num} / kernel_size {kernel_size}")
         if rnn_layers != 2 or rnn_units != 256 or cfg.lstm != "complex":
             unsupported.append(f"rnn_layers={rnn_layers}, rnn_units={rnn_units}, lstm={cfg.lstm!r} (built: 2 x complex LSTM 256)")
-        if not cfg.skip_type or use_cbn:
-            unsupported.append("skip_type=False / use_cbn=True")
+        if use_cbn:
+            unsupported.append("use_cbn=True (ComplexBatchNorm, tools_for_model.py:430-603)")
         if masking_mode not in _ops.MODES:
             unsupported.append(f"masking_mode {masking_mode!r} (built: E, C, R, Direct(None make))")
         if unsupported:
@@ -44,6 +44,7 @@ class DCCRN(nn.Module):
         self.rnn_units, self.hidden_layers, self.kernel_size = rnn_units, rnn_layers, kernel_size
         self.kernel_num = [2] + kernel_num
         self.masking_mode = masking_mode
+        self.skip_type = bool(cfg.skip_type)
 
         self.stft = _d.STFTBuffers(win_len, fft_len, inverse=False)
         self.istft = _d.STFTBuffers(win_len, fft_len, inverse=True)
@@ -61,7 +62,7 @@ class DCCRN(nn.Module):
                 projection_dim=hidden_dim * kn[-1] if i == rnn_layers - 1 else None))
         self.enhance = nn.Sequential(*rnns)
         for idx in range(len(kn) - 1, 0, -1):                            # models.py:107-137
-            mods = [_d.ComplexConvParams(kn[idx] * 2, kn[idx - 1], transposed=True)]
+            mods = [_d.ComplexConvParams(kn[idx] * (2 if self.skip_type else 1), kn[idx - 1], transposed=True)]   # :138-169 without skip
             if idx != 1:
                 mods += [_d.BatchNormParams(kn[idx - 1]), _d.PReLUParams()]
             self.decoder.append(nn.Sequential(*mods))
@@ -72,7 +73,7 @@ class DCCRN(nn.Module):
     def _get_engine(self):
         eng = self.__dict__.get("_engine")
         if eng is None:
-            eng = _d.Engine(self, self.masking_mode)
+            eng = _d.Engine(self, self.masking_mode, skip=self.skip_type)
             self.__dict__["_engine"] = eng
         return eng
 

@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .ops import LOSSES, MODES, ptr, stream
+from .ops import LOSSES, MODES, PLAN_NO_SKIP, ptr, stream
 
 KERNEL_NUM = [32, 64, 128, 256, 256, 256]
 
@@ -136,13 +136,14 @@ class STFTBuffers(nn.Module):
 # plan + workspace cache
 # --------------------------------------------------------------------------------------------------
 class Plan:
-    def __init__(self, B, L, mode, family="dccrn"):
+    def __init__(self, B, L, mode, family="dccrn", skip=True):
         lib = _lib.load()
         self.family = family
+        self.skip = skip
         if family == "crn":
             self.handle = lib.sefd_crn_plan_create(B, L)
         else:
-            self.handle = lib.sefd_dccrn_plan_create(B, L, MODES[mode])
+            self.handle = lib.sefd_dccrn_plan_create_ex(B, L, MODES[mode], 0 if skip else PLAN_NO_SKIP)
         if not self.handle:
             raise RuntimeError("sefd plan: " + lib.sefd_last_error().decode())
         self.B, self.L, self.T, self.mode = B, L, L // 100 + 3, mode
@@ -279,19 +280,20 @@ class Engine:
     """Owns the flat parameter / gradient / BN-statistics buffers of one DCCRN / CRN module and keeps the module's
     nn.Parameters aliased onto them."""
 
-    def __init__(self, module, mode, family="dccrn"):
+    def __init__(self, module, mode, family="dccrn", skip=True):
         self.module = module
         self.mode = mode
         self.family = family
+        self.skip = skip
         self.plans = {}
         self.flat = self.flat_grad = self.flat_buf = None
-        self._layout = Plan(1, 100, mode, family)  # layout is independent of (B, L)
+        self._layout = Plan(1, 100, mode, family, skip)  # layout is independent of (B, L)
         self.param_list = None
 
     def plan(self, B, L):
         key = (B, L)
         if key not in self.plans:
-            self.plans[key] = Plan(B, L, self.mode, self.family)
+            self.plans[key] = Plan(B, L, self.mode, self.family, self.skip)
         return self.plans[key]
 
     def _named(self):

@@ -8,6 +8,7 @@ import torch
 from . import _lib
 
 MODES = {"E": 1, "C": 2, "R": 3, "Direct(None make)": 5}
+PLAN_NO_SKIP = 1          # include/sefd.h: SEFD_PLAN_NO_SKIP
 LOSSES = {"MSE": 0, "SDR": 1, "SI-SNR": 2, "SI-SDR": 3}
 
 

@@ -108,6 +108,10 @@ int sefd_adam_step(float* params, const float* grads, float* exp_avg, float* exp
 
 /* ---- model level: DCCRN.forward / autograd backward (models.py:176-284) ---------------------- */
 sefd_plan* sefd_dccrn_plan_create(int B, int L, int masking_mode);
+/* flags: SEFD_PLAN_NO_SKIP builds the decoder of cfg.skip_type = False (models.py:138-169, 227-230): the transposed
+ * convolutions read the previous output only (Cin = kernel_num[idx], no complex_cat with the encoder output) */
+#define SEFD_PLAN_NO_SKIP 1
+sefd_plan* sefd_dccrn_plan_create_ex(int B, int L, int masking_mode, int flags);
 void sefd_dccrn_plan_destroy(sefd_plan* plan);
 size_t sefd_dccrn_workspace_bytes(const sefd_plan* plan);
 long long sefd_dccrn_param_floats(const sefd_plan* plan);    /* size of the flat parameter / gradient buffer */

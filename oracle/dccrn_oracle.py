@@ -75,7 +75,7 @@ def conv_istft(spec: torch.Tensor, k_s: torch.Tensor, window: torch.Tensor,
 # --------------------------------------------------------------------------------------
 # parameter construction in the reference's RNG order (models.py:17-170)
 # --------------------------------------------------------------------------------------
-def init_state(seed: int = 0, kernel_num: Optional[List[int]] = None) -> Dict[str, torch.Tensor]:
+def init_state(seed: int = 0, kernel_num: Optional[List[int]] = None, skip_type: bool = True) -> Dict[str, torch.Tensor]:
     """State dict with the reference's keys/shapes and, for a given torch seed, its values.
 
     Built by instantiating torch.nn modules in the same order as DCCRN.__init__
@@ -124,7 +124,7 @@ def init_state(seed: int = 0, kernel_num: Optional[List[int]] = None) -> Dict[st
 
     j = 0
     for idx in range(len(kn) - 1, 0, -1):
-        cplx(f"decoder.{j}.0.", nn.ConvTranspose2d, kn[idx] * 2, kn[idx - 1],
+        cplx(f"decoder.{j}.0.", nn.ConvTranspose2d, kn[idx] * (2 if skip_type else 1), kn[idx - 1],   # models.py:107-169
              padding=(2, 0), output_padding=(1, 0))
         if idx != 1:
             bn_prelu(f"decoder.{j}.1.", f"decoder.{j}.2.", kn[idx - 1])
@@ -304,7 +304,8 @@ def dccrn_forward(sd: Dict[str, torch.Tensor], wav: torch.Tensor, masking_mode: 
 
     for j in range(n_layers):                                          # models.py:222-226
         p = f"decoder.{j}.0."
-        out = complex_cat(out, enc_out[-1 - j])
+        if sd[p + "real_conv.weight"].shape[0] == out.shape[1]:      # cfg.skip_type (models.py:222-230): the
+            out = complex_cat(out, enc_out[-1 - j])                     # weights carry 2x the input channels
         out = complex_conv_transpose2d(out, sd[p + "real_conv.weight"], sd[p + "real_conv.bias"],
                                        sd[p + "imag_conv.weight"], sd[p + "imag_conv.bias"])
         if taps is not None:

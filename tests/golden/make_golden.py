@@ -316,8 +316,42 @@ def main_direct():
     print("wrote direct_golden.npz", out["MSE_loss"], out["SI-SNR_loss"])
 
 
+def main_noskip():
+    """cfg.skip_type = False: decoder without skip connections (models.py:138-169, 227-230).  cfg.skip_type is read when the
+    model is constructed and again in forward, so it is set before either."""
+    cfg, models, tfl = import_reference()
+    cfg.skip_type = False
+    torch.set_num_threads(8)
+    out = {}
+    noisy, clean = speechlike(2, 4000)
+    torch.manual_seed(0)
+    m = models.DCCRN(masking_mode="C").train()
+    sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    o_r, o_i, wav = m(noisy, clean)
+    loss = m.loss(wav, clean)
+    loss.backward()
+    out["loss"] = np.array(loss.item())
+    out["wav"], out["out_real"] = wav.detach().numpy(), o_r.detach().numpy()
+    names = [n for n, _ in m.named_parameters()]
+    out["param_names"] = np.array(names)
+    out["param_shapes"] = np.array([str(tuple(p.shape)) for _, p in m.named_parameters()])
+    out["gnorm"] = np.array([float(p.grad.double().norm()) for _, p in m.named_parameters()])
+    for n, p in m.named_parameters():                      # small tensors whole, large ones as a strided sample (stride 97)
+        gflat = p.grad.reshape(-1)
+        out["grad:" + n] = (gflat if gflat.numel() <= 4096 else gflat[::97]).numpy().copy()
+    for k in ("decoder.0.0.real_conv.weight", "decoder.5.0.imag_conv.weight", "encoder.0.0.real_conv.weight"):
+        out["init:" + k] = sd0[k].reshape(-1)[::97].numpy().copy()           # pins the RNG stream of the construction order
+    m.eval()
+    with torch.no_grad():
+        out["eval_wav"] = m(noisy)[2].numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "noskip_golden.npz"), **out)
+    print("wrote noskip_golden.npz", out["loss"], len(names))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "direct":
+    if len(sys.argv) > 1 and sys.argv[1] == "noskip":
+        main_noskip()
+    elif len(sys.argv) > 1 and sys.argv[1] == "direct":
         main_direct()
     elif len(sys.argv) > 1 and sys.argv[1] == "lms":
         main_lms()
