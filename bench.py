@@ -120,6 +120,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="utterances per GPU (BASELINE configs[1]: 32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--perceptual", default=None, choices=["PMSQE"],
+                    help="time the perceptual train step (SI-SNR + PMSQE) / 2 of BASELINE configs[3] (per-GPU slice of 32) instead")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -144,7 +146,9 @@ def main():
     model = models.DCCRN(masking_mode="C").to(dev).train()
     B = args.batch
     noisy, clean = synthetic(B, 1234 + rank, dev)
-    ts = TrainStep(model, lr=1e-3, loss="SI-SNR")
+    ts = TrainStep(model, lr=1e-3, loss="SI-SNR", perceptual=args.perceptual)
+    if args.perceptual:
+        models.cfg.perceptual = args.perceptual
 
     def barrier():
         if world > 1:
@@ -187,8 +191,10 @@ def main():
     def e2e_step():
         inputs = h_noisy.to(dev, non_blocking=True)
         targets = h_clean.to(dev, non_blocking=True)
-        _, _, outputs = model(inputs, targets)
+        real_spec, img_spec, outputs = model(inputs, targets)
         lo = model.loss(outputs, targets)
+        if args.perceptual:                    # trainer.model_perceptual_train, trainer.py:59-67 (r1 = r2 = 1)
+            lo = (lo + model.loss(outputs, targets, real_spec, img_spec, perceptual=True)) / 2
         opt.zero_grad()
         lo.backward()
         opt.step()
@@ -282,7 +288,7 @@ def main():
         return
 
     cpu = None
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and not args.perceptual:
         rate, dt, cores = cpu_step_rate(4, 2, 1)
         cpu = {"value": round(rate, 3), "unit": "utterances/s", "cores": cores, "kind": "port",
                "sample": "2 train steps of 4 utterances (3 s each) after 1 warm-up, oracle/dccrn_oracle.py"}
@@ -291,7 +297,9 @@ def main():
         "metric": METRIC, "value": round(value, 2), "unit": "utterances/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "DCCRN mask C, SI-SNR loss, Adam, 3s@16kHz, batch 32 per GPU (BASELINE configs[1])",
+        "config": {"workload": ("DCCRN mask C, (SI-SNR + PMSQE) / 2 perceptual step, Adam, 3s@16kHz, batch 32 per GPU (BASELINE "
+                                "configs[3] slice; PMSQE parity unpinned)") if args.perceptual else
+                               "DCCRN mask C, SI-SNR loss, Adam, 3s@16kHz, batch 32 per GPU (BASELINE configs[1])",
                    "batch_per_gpu": B, "global_batch": B * world, "samples": L, "parallelism": f"dp{world}",
                    "l2": "per-step working set (~6 GB of activations) >> 126 MB L2, no flush needed",
                    "final_loss": round(final_loss, 4)},

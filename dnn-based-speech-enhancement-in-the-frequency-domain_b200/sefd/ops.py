@@ -318,3 +318,85 @@ def lms_loss_spec(est_real, est_imag, target_wav):
 def lms_loss_mags(clean_mags, est_mags):
     """get_array_lms_loss(clean_array, est_array) (tools_for_loss.py:241-249) on magnitude arrays [B,257,T]."""
     return _Lms.apply(est_mags.contiguous(), None, clean_mags.contiguous(), True)
+
+
+# ---- PMSQE perceptual loss (tools_for_loss.py:255-269; arithmetic of asteroid's SingleSrcPMSQE: parity unpinned) -------
+_PMSQE = {}
+
+
+def pmsqe_tables(bark_matrix=None, abs_thresh_power=None, modified_zwicker_power=None, width_of_band_bark=None,
+                 mask_sll=None):
+    """Packed float32 table vector of sefd_pmsqe_*: [bark 257x49 | thresholds 49 | Zwicker powers 49 | widths 49 | SLL mask
+    257].  Defaults are SingleSrcPMSQE's 16 kHz constants rebuilt from the ITU-T P.862 tables (sefd/p862_16k.py): Bark
+    matrix = band membership of the 256 bins x pow_dens_correction_factor, modified Zwicker power
+    0.23 * clip(6 / (centre + 2), 1, 2) ** 0.15, SLL mask over bins 11..104 times the sqrt-hann power correction
+    2 * (512 + 2) / 512**2.  Any argument may be replaced by asteroid's own buffer of the same name."""
+    import numpy as np
+    from . import p862_16k as p
+    if bark_matrix is None:
+        bark_matrix = np.zeros((257, 49))
+        f = 0
+        for k, n in enumerate(p.NR_OF_HZ_BANDS_PER_BARK_BAND):
+            bark_matrix[f:f + n, k] = p.POW_DENS_CORRECTION_FACTOR[k]
+            f += n
+    if abs_thresh_power is None:
+        abs_thresh_power = p.ABS_THRESH_POWER
+    if modified_zwicker_power is None:
+        modified_zwicker_power = 0.23 * np.clip(6.0 / (np.asarray(p.CENTRE_OF_BAND_BARK) + 2.0), 1.0, 2.0) ** 0.15
+    if width_of_band_bark is None:
+        width_of_band_bark = p.WIDTH_OF_BAND_BARK
+    if mask_sll is None:
+        mask_sll = np.zeros(257)
+        mask_sll[11], mask_sll[12:104], mask_sll[104] = 0.5 * 25.0 / 31.25, 1.0, 0.5
+        mask_sll = mask_sll * 2.0 * (512 + 2.0) / 512 ** 2
+    parts = [np.asarray(bark_matrix, dtype=np.float64).reshape(257 * 49), np.asarray(abs_thresh_power, dtype=np.float64),
+             np.asarray(modified_zwicker_power, dtype=np.float64), np.asarray(width_of_band_bark, dtype=np.float64),
+             np.asarray(mask_sll, dtype=np.float64)]
+    assert [a.size for a in parts] == [257 * 49, 49, 49, 49, 257]
+    return torch.from_numpy(np.concatenate(parts).astype(np.float32))
+
+
+def _pmsqe_tables(device):
+    key = str(device)
+    if key not in _PMSQE:
+        t = pmsqe_tables()
+        assert t.numel() == _lib.load().sefd_pmsqe_table_floats()
+        _PMSQE[key] = t.to(device)
+    return _PMSQE[key]
+
+
+class _Pmsqe(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, est, clean, tables):
+        _req(est, clean, tables)
+        N, L = est.shape
+        lib = _lib.load()
+        nbytes = lib.sefd_pmsqe_workspace_bytes(N, L)
+        if nbytes == 0:
+            raise ValueError(f"PMSQE: waveforms must be 1..4 whole seconds at 16 kHz (tools_for_loss.py:264), got {L} samples")
+        ws = torch.empty(nbytes, device=est.device, dtype=torch.uint8)
+        loss = torch.empty(1, device=est.device)
+        _lib.check(lib.sefd_pmsqe_forward(ptr(est), ptr(clean), N, L, ptr(tables), ptr(ws), nbytes, ptr(loss), stream()),
+                   "pmsqe_forward")
+        ctx.save_for_backward(ws, tables)
+        ctx.shape = (N, L)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        ws, tables = ctx.saved_tensors
+        N, L = ctx.shape
+        gout = gout.contiguous().float()
+        d = torch.empty(N, L, device=ws.device)
+        _lib.check(_lib.load().sefd_pmsqe_backward(ptr(gout), N, L, ptr(tables), ptr(ws), ws.numel(), ptr(d), stream()),
+                   "pmsqe_backward")
+        return d, None, None
+
+
+def pmsqe_loss(clean_wav, est_wav, tables=None):
+    """get_array_pmsqe_loss(clean_array, est_array) (tools_for_loss.py:259-269): [N, L] waveforms (or [N, 1, L]), L a whole
+    number of seconds; differentiable with respect to est_wav."""
+    if clean_wav.dim() == 3:
+        clean_wav, est_wav = clean_wav.reshape(clean_wav.shape[0], -1), est_wav.reshape(est_wav.shape[0], -1)
+    tables = _pmsqe_tables(est_wav.device) if tables is None else tables.to(est_wav.device).float().contiguous()
+    return _Pmsqe.apply(est_wav.contiguous().float(), clean_wav.contiguous().float(), tables)

@@ -9,11 +9,18 @@ import torch
 
 from . import _lib
 from . import dist as _dist
+from . import ops as _ops
 from .ops import LOSSES, ptr, stream
 
 
 class TrainStep:
-    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, loss="SI-SNR", process_group=None):
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, loss="SI-SNR", process_group=None, perceptual=False):
+        """perceptual = 'PMSQE': the step of trainer.model_perceptual_train (trainer.py:44-70) with r1 = r2 = 1,
+        loss = (main + PMSQE(out_wav, clean)) / 2 (BASELINE configs[3])."""
+        if perceptual not in (False, None, "PMSQE"):
+            raise NotImplementedError(f"TrainStep: perceptual={perceptual!r} (built here: 'PMSQE'; LMS runs through the "
+                                      "autograd drop-in, models.DCCRN.loss(..., perceptual=True))")
+        self.perceptual = perceptual or False
         self.model = model
         self.engine = model._get_engine()
         self.engine.sync()
@@ -53,8 +60,26 @@ class TrainStep:
                        None, None, ptr(s["wav"]), ptr(ws), plan.ws_bytes, st), eng.family + "_forward")
         _lib.check(lib.sefd_dccrn_loss(plan.handle, ptr(s["wav"]), ptr(clean), self.kind, 1, ptr(s["loss"]),
                                        ptr(s["coef"]), ptr(ws), st), "dccrn_loss")
-        _lib.check(lib.sefd_loss_backward(ptr(s["wav"]), ptr(clean), ptr(s["coef"]), None, ptr(s["dwav"]), B, L, st),
-                   "loss_backward")
+        if self.perceptual == "PMSQE":
+            if "pws" not in s:
+                nbytes = lib.sefd_pmsqe_workspace_bytes(B, L)
+                if nbytes == 0:
+                    raise ValueError(f"PMSQE: waveforms must be 1..4 whole seconds at 16 kHz, got {L} samples")
+                s.update(pws=torch.empty(nbytes, device=noisy.device, dtype=torch.uint8), ploss=torch.empty(1, device=noisy.device),
+                         dpw=torch.empty(B, L, device=noisy.device), half=torch.full((1,), 0.5, device=noisy.device),
+                         tables=_ops._pmsqe_tables(noisy.device))
+            nb = s["pws"].numel()
+            _lib.check(lib.sefd_pmsqe_forward(ptr(s["wav"]), ptr(clean), B, L, ptr(s["tables"]), ptr(s["pws"]), nb,
+                                              ptr(s["ploss"]), st), "pmsqe_forward")
+            _lib.check(lib.sefd_loss_backward(ptr(s["wav"]), ptr(clean), ptr(s["coef"]), ptr(s["half"]), ptr(s["dwav"]), B, L,
+                                              st), "loss_backward")
+            _lib.check(lib.sefd_pmsqe_backward(ptr(s["half"]), B, L, ptr(s["tables"]), ptr(s["pws"]), nb, ptr(s["dpw"]), st),
+                       "pmsqe_backward")
+            s["dwav"].add_(s["dpw"])
+            s["loss"].add_(s["ploss"]).mul_(0.5)
+        else:
+            _lib.check(lib.sefd_loss_backward(ptr(s["wav"]), ptr(clean), ptr(s["coef"]), None, ptr(s["dwav"]), B, L, st),
+                       "loss_backward")
         _lib.check(bwd(plan.handle, ptr(eng.flat), ptr(s["dwav"]), ptr(eng.flat_grad), ptr(ws),
                        plan.ws_bytes, st), eng.family + "_backward")
         return s["loss"]

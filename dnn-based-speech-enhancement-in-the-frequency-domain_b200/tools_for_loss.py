@@ -31,5 +31,8 @@ def get_array_lms_loss(clean_array, est_array):
 
 
 def get_array_pmsqe_loss(clean_array, est_array):
-    raise NotImplementedError("sefd: PMSQE perceptual loss is not built yet (SURVEY.md §8 a12; its arithmetic lives "
-                              "in the un-vendored asteroid package: parity unpinned)")
+    """tools_for_loss.py:259-269: PIT-wrapped PMSQE between the 1-second chunks of the two waveform batches [N, L].
+    PARITY UNPINNED: the reference delegates the arithmetic to asteroid (SingleSrcPMSQE / PITLossWrapper / STFTFB), which is
+    not part of the reference tree; csrc/pmsqe.cu restates the published algorithm with every perceptual table as an input
+    (sefd.ops.pmsqe_tables accepts asteroid's own buffers)."""
+    return _ops.pmsqe_loss(clean_array, est_array)

@@ -67,6 +67,21 @@ int sefd_lms_forward(const float* est_real, const float* est_imag, const float* 
 int sefd_lms_backward(const float* est_real, const float* est_imag, const float* clean_spec, const float* F, const float* Ft,
                       const float* gout, int B, int T, int inputs_are_mags, float* d_real, float* d_imag, void* stream);
 
+/* PMSQE perceptual loss: get_array_pmsqe_loss(clean_array, est_array), tools_for_loss.py:255-269 =
+ * PITLossWrapper(SingleSrcPMSQE(), 'pw_pt') on mag(Encoder(STFTFB(512, 512, stride 256))) of the waveforms cut into
+ * 1-second chunks.  PARITY UNPINNED (the arithmetic is asteroid's, absent from the reference tree): see csrc/pmsqe.cu and
+ * oracle/pmsqe_oracle.py.  est_wav / clean_wav [N][L], L = S * 16000 with S <= 4.
+ * tables: sefd_pmsqe_table_floats() floats = [bark_matrix 257 x 49 | abs_thresh_power 49 | modified_zwicker_power 49 |
+ * width_of_band_bark 49 | mask_sll 257] (SingleSrcPMSQE's buffers; the host builds them from the ITU-T P.862 tables or
+ * passes asteroid's own).  ws: sefd_pmsqe_workspace_bytes(N, L) bytes, filled by forward and read by backward.
+ * backward: d_est [N][L] = gout[0] * d loss / d est_wav (gout may be NULL = 1). */
+int sefd_pmsqe_table_floats(void);
+size_t sefd_pmsqe_workspace_bytes(int N, int L);
+int sefd_pmsqe_forward(const float* est_wav, const float* clean_wav, int N, int L, const float* tables, void* ws,
+                       size_t ws_bytes, float* loss, void* stream);
+int sefd_pmsqe_backward(const float* gout, int N, int L, const float* tables, void* ws, size_t ws_bytes, float* d_est,
+                        void* stream);
+
 /* ComplexConv2d (tools_for_model.py:199-269: kernel (5,2), stride (2,1), pad (2,0), causal pad 1) and
  * ComplexConvTranspose2d (tools_for_model.py:272-338: + output_padding (1,0)); channels-last tensors.
  *   conv : x [B][F][T][Cin]          -> y [B][F/2][T][Cout]
