@@ -180,8 +180,9 @@ sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode, int flags) {
 // ------------------------------------------------------------------------------------------------
 // weight packing (once per forward; the packed operands are reused by the backward)
 // ------------------------------------------------------------------------------------------------
-static int pack_weights(const sefd_plan* P, const float* prm, float* ws, cudaStream_t st) {
-    for (int e = 0; e < 2 * NL; ++e) {
+// part 0: encoder convs (needed first); part 1: decoder convs, LSTM and projection operands (needed after the encoder)
+static int pack_weights(const sefd_plan* P, const float* prm, float* ws, int part, cudaStream_t st) {
+    for (int e = part ? NL : 0; e < (part ? 2 * NL : NL); ++e) {
         const ConvLayer& c = e < NL ? P->enc[e] : P->dec[e - NL];
         CconvPackParams pp;
         pp.wr = prm + c.wr; pp.wi = prm + c.wi; pp.br = prm + c.br; pp.bi = prm + c.bi;
@@ -191,6 +192,7 @@ static int pack_weights(const sefd_plan* P, const float* prm, float* ws, cudaStr
         pp.round_tf32 = sefd_get_engine_internal() == 1 && c.Cin % 32 == 0 && (c.Cout % 32 == 0);
         SEFD_TRY(sefd_pack_cconv(pp, st));
     }
+    if (!part) return 0;
     const int tf = sefd_get_engine_internal() == 1;
     auto perm = [&](const float* src, float* dst, int na, int nb, int nc, long long sa, long long sb, long long sc,
                     long long da, long long db, long long dc) -> int {
@@ -236,7 +238,24 @@ int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const 
     double* wsd = (double*)wsv;
     const int B = P->B, T = P->T, L = P->L;
     cudaMemsetAsync(wsd + P->stats_all, 0, sizeof(double) * P->stats_all_n, st);
-    SEFD_TRY(pack_weights(P, prm, ws, st));
+    // the ~30 small pack / permute launches for the decoder, LSTM and projection operands run on the plan's side stream
+    // beside the STFT and the encoder (their consumers start after the encoder); the fork event orders them after every
+    // earlier reader of the packed buffers (the previous step's backward)
+    static const bool use_side = getenv("SEFD_SIDE_STREAM") == nullptr || atoi(getenv("SEFD_SIDE_STREAM")) != 0;
+    cudaStream_t sx = st;
+    if (use_side && !sefd_prof_on()) {
+        if (!P->side) {
+            SEFD_REQUIRE(cudaStreamCreateWithFlags(&P->side, cudaStreamNonBlocking) == cudaSuccess, "forward: side stream");
+            cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&P->ev_join, cudaEventDisableTiming);
+        }
+        sx = P->side;
+        cudaEventRecord(P->ev_fork, st);
+        cudaStreamWaitEvent(sx, P->ev_fork, 0);
+    }
+    SEFD_TRY(pack_weights(P, prm, ws, 1, sx));
+    if (sx != st) cudaEventRecord(P->ev_join, sx);
+    SEFD_TRY(pack_weights(P, prm, ws, 0, st));
     SEFD_TRY(sefd_stft_launch(noisy, ws + P->spec, B, L, T, st));
 
     auto bn = [&](const ConvLayer& c, int Ty, int tshift) -> int {
@@ -278,6 +297,7 @@ int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const 
         SEFD_TRY(bn(c, T, 0));
     }
 
+    if (sx != st) cudaStreamWaitEvent(st, P->ev_join, 0);      // packed LSTM / projection / decoder operands are ready
     // ---- complex LSTM x2 (tools_for_model.py:162-177) ----
     const size_t rowsz = (size_t)T * G4;
     for (int l = 0; l < 2; ++l) {
