@@ -348,8 +348,49 @@ def main_noskip():
     print("wrote noskip_golden.npz", out["loss"], len(names))
 
 
+def main_fullsubnet():
+    """BASELINE.json configs[2] at a small size: FullSubNet, loop body of trainer.fullsubnet_train (trainer.py:97-107), MSE
+    between cIRM and cRM.  The model is put in eval() so that the inter-layer LSTM dropout (0.8) is inactive (SURVEY.md 8(d)
+    config 3: eval-mode dropout for parity); autograd still runs."""
+    cfg, models, tfl = import_reference()
+    import tools_for_model as tools
+    torch.set_num_threads(8)
+    cfg.loss = "MSE"
+    out = {}
+    torch.manual_seed(0)
+    m = models.FullSubNet()
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    keys = list(sd0.keys())
+    out["init_keys"] = np.array(keys)
+    out["init_shapes"] = np.array([str(tuple(sd0[k].shape)) for k in keys])
+    out["init_sum"] = np.array([float(sd0[k].double().sum()) for k in keys])
+    out["init_abs"] = np.array([float(sd0[k].double().abs().sum()) for k in keys])
+    out["n_params"] = np.array(sum(p.numel() for p in m.parameters()))
+    m.eval()
+    noisy, clean = speechlike(2, 4000)
+    nc, cc = tools.stft(noisy), tools.stft(clean)
+    noisy_mag, _ = tools.mag_phase(nc)
+    cirm = tools.build_complex_ideal_ratio_mask(nc, cc)
+    crm = m(noisy_mag)
+    loss = m.loss(cirm, crm)
+    loss.backward()
+    out["noisy_mag"], out["cIRM"], out["cRM"] = noisy_mag.numpy(), cirm.numpy(), crm.detach().numpy()
+    out["loss"] = np.array(loss.item())
+    out["param_names"] = np.array([n for n, _ in m.named_parameters()])
+    out["gnorm"] = np.array([float(p.grad.double().norm()) for _, p in m.named_parameters()])
+    for n, p in m.named_parameters():
+        g = p.grad.detach().reshape(-1)
+        out["grad::" + n] = (g if g.numel() <= 4096 else g[::997]).numpy().copy()
+    out["decompressed"] = tools.decompress_cIRM(crm.detach()).numpy()          # trainer.py:341: the validation path's inverse
+    np.savez_compressed(os.path.join(HERE, "fullsubnet_golden.npz"), **out)
+    sz = os.path.getsize(os.path.join(HERE, "fullsubnet_golden.npz"))
+    print(f"wrote fullsubnet_golden.npz ({sz/1e3:.1f} kB); loss={out['loss']}, n_params={out['n_params']}, T={crm.shape[2]}")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "noskip":
+    if len(sys.argv) > 1 and sys.argv[1] == "fullsubnet":
+        main_fullsubnet()
+    elif len(sys.argv) > 1 and sys.argv[1] == "noskip":
         main_noskip()
     elif len(sys.argv) > 1 and sys.argv[1] == "direct":
         main_direct()

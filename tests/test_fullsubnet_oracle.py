@@ -1,0 +1,76 @@
+"""FullSubNet: the oracle restatement against fixtures of the unmodified reference
+(tests/golden/make_golden.py fullsubnet).  The CUDA path of this row is not built yet; the drop-in raises."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import fullsubnet_oracle as FS
+
+
+@pytest.fixture(scope="module")
+def fs_golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "fullsubnet_golden.npz"), allow_pickle=False)
+
+
+def _speech(B=2, L=4000):
+    g = torch.Generator().manual_seed(7)
+    t = torch.arange(L, dtype=torch.float32) / 16000.0
+    clean = torch.stack([0.2 * torch.sin(2 * np.pi * (200.0 + 150.0 * b + 300.0 * t) * t) *
+                         (0.5 + 0.5 * torch.sin(2 * np.pi * 3.0 * t + b)) for b in range(B)])
+    return clean + 0.05 * torch.randn(B, L, generator=g), clean
+
+
+def test_init_matches_reference_rng_stream(fs_golden):
+    sd = FS.init_state(0)
+    keys = [str(k) for k in fs_golden["init_keys"]]
+    assert list(sd.keys()) == keys
+    assert [str(tuple(sd[k].shape)) for k in keys] == [str(s) for s in fs_golden["init_shapes"]]
+    np.testing.assert_allclose([float(sd[k].double().sum()) for k in keys], fs_golden["init_sum"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose([float(sd[k].double().abs().sum()) for k in keys], fs_golden["init_abs"], rtol=1e-9)
+    assert sum(v.numel() for v in sd.values()) == int(fs_golden["n_params"]) == 5637635
+
+
+def test_features_and_masks(fs_golden):
+    noisy, clean = _speech()
+    nc, cc = FS.stft(noisy), FS.stft(clean)
+    ref = torch.stft(noisy, 512, 300, 400, window=torch.hann_window(400), return_complex=True)
+    assert float((nc - ref).abs().max()) < 2e-5                                 # explicit framing + rFFT == torch.stft
+    mag, _ = FS.mag_phase(nc)
+    np.testing.assert_allclose(mag.numpy(), fs_golden["noisy_mag"], atol=2e-5)
+    cirm = FS.build_complex_ideal_ratio_mask(nc, cc)
+    np.testing.assert_allclose(cirm.numpy(), fs_golden["cIRM"], atol=2e-3, rtol=1e-3)   # 1 / (|noisy|^2 + eps) amplifies
+    x = torch.randn(2, 1, 9, 5, generator=torch.Generator().manual_seed(1))
+    u = FS.unfold(x, 2)
+    assert u.shape == (2, 9, 1, 5, 5)
+    xp = torch.nn.functional.pad(x.reshape(2, 1, 9, 5), [0, 0, 2, 2], mode="reflect")
+    assert torch.equal(u[:, 4, 0], xp[:, 0, 4:9])
+    assert torch.equal(u[:, 0, 0, 0], x[:, 0, 2])                               # reflect: row -2 is row 2
+    m = torch.from_numpy(fs_golden["cRM"])
+    np.testing.assert_allclose(FS.decompress_cirm(m).numpy(), fs_golden["decompressed"], rtol=1e-5, atol=1e-6)
+
+
+def test_forward_loss_and_gradients(fs_golden):
+    sd = {k: v.clone().requires_grad_(True) for k, v in FS.init_state(0).items()}
+    noisy, clean = _speech()
+    taps = {}
+    loss = FS.train_step_loss(sd, noisy, clean, taps)
+    loss.backward()
+    np.testing.assert_allclose(taps["cRM"].numpy(), fs_golden["cRM"], atol=2e-5)
+    assert float(loss.detach()) == pytest.approx(float(fs_golden["loss"]), rel=2e-4)
+    names = [str(n) for n in fs_golden["param_names"]]
+    gn = np.array([float(sd[k].grad.double().norm()) for k in names])
+    np.testing.assert_allclose(gn, fs_golden["gnorm"], rtol=2e-3, atol=1e-7)
+    for k in names:
+        g = sd[k].grad.reshape(-1)
+        g = g if g.numel() <= 4096 else g[::997]
+        r = fs_golden["grad::" + k]
+        np.testing.assert_allclose(g.numpy(), r, atol=2e-3 * max(float(np.abs(r).max()), 1e-8), err_msg=k)
+
+
+def test_dropin_still_raises_for_fullsubnet():
+    import models
+    with pytest.raises(NotImplementedError):
+        models.FullSubNet()
