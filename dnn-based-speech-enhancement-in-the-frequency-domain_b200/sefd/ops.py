@@ -400,3 +400,49 @@ def pmsqe_loss(clean_wav, est_wav, tables=None):
         clean_wav, est_wav = clean_wav.reshape(clean_wav.shape[0], -1), est_wav.reshape(est_wav.shape[0], -1)
     tables = _pmsqe_tables(est_wav.device) if tables is None else tables.to(est_wav.device).float().contiguous()
     return _Pmsqe.apply(est_wav.contiguous().float(), clean_wav.contiguous().float(), tables)
+
+
+# ---- FullSubNet feature / target side (trainer.fullsubnet_train, trainer.py:97-104) ---------------------------------------
+def fsn_stft(y):
+    """tools.stft (tools_for_model.py:628-648): [B, L] -> complex64 [B, 257, L // 300 + 1]."""
+    _req(y)
+    B, L = y.shape
+    T = _lib.load().sefd_fsn_frames(L)
+    out = torch.empty(B, 257, T, 2, device=y.device)
+    _lib.check(_lib.load().sefd_fsn_stft(ptr(y), B, L, ptr(out), stream()), "fsn_stft")
+    return torch.view_as_complex(out)
+
+
+def fsn_features(noisy, clean):
+    """The feature / target computation of the fullsubnet_train loop in one kernel: (noisy_mag [B,257,T], cIRM [B,257,T,2])."""
+    _req(noisy, clean)
+    B, L = noisy.shape
+    T = _lib.load().sefd_fsn_frames(L)
+    mag = torch.empty(B, 257, T, device=noisy.device)
+    cirm = torch.empty(B, 257, T, 2, device=noisy.device)
+    _lib.check(_lib.load().sefd_fsn_features(ptr(noisy), ptr(clean), B, L, ptr(mag), ptr(cirm), stream()), "fsn_features")
+    return mag, cirm
+
+
+def fsn_mag_phase(c):
+    r = torch.view_as_real(c).contiguous()
+    _req(r)
+    mag, phase = torch.empty(c.shape, device=c.device), torch.empty(c.shape, device=c.device)
+    _lib.check(_lib.load().sefd_fsn_mag_phase(ptr(r), c.numel(), ptr(mag), ptr(phase), stream()), "fsn_mag_phase")
+    return mag, phase
+
+
+def fsn_cirm(noisy, clean):
+    a, b = torch.view_as_real(noisy).contiguous(), torch.view_as_real(clean).contiguous()
+    _req(a, b)
+    out = torch.empty_like(a)
+    _lib.check(_lib.load().sefd_fsn_cirm(ptr(a), ptr(b), noisy.numel(), ptr(out), stream()), "fsn_cirm")
+    return out
+
+
+def fsn_decompress_cirm(mask):
+    m = mask.contiguous().float()
+    _req(m)
+    out = torch.empty_like(m)
+    _lib.check(_lib.load().sefd_fsn_decompress_cirm(ptr(m), m.numel(), ptr(out), stream()), "fsn_decompress_cirm")
+    return out

@@ -205,8 +205,34 @@ def _fullsubnet_only(name):
     return f
 
 
-stft = _fullsubnet_only("stft")
+def stft(y, n_fft=512, hop_length=300, win_length=400):
+    """tools_for_model.py:628-648 (torch.stft, centred, reflect padding, periodic Hann): [B, L] -> complex [B, 257, T]."""
+    if (n_fft, hop_length, win_length) != (512, 300, 400):
+        raise NotImplementedError("sefd: tools.stft is built for the reference geometry n_fft 512 / hop 300 / win 400")
+    return _ops.fsn_stft(y.float().contiguous())
+
+
+def mag_phase(complex_tensor):
+    """tools_for_model.py:682-683."""
+    return _ops.fsn_mag_phase(complex_tensor)
+
+
+def build_complex_ideal_ratio_mask(noisy, clean):
+    """tools_for_model.py:686-705 (+ compress_cIRM :708-717): complex [B, F, T] x2 -> [B, F, T, 2]."""
+    return _ops.fsn_cirm(noisy, clean)
+
+
+def decompress_cIRM(mask, K=10, limit=9.9):
+    """tools_for_model.py:720-723."""
+    if (K, limit) != (10, 9.9):
+        raise NotImplementedError("sefd: decompress_cIRM is built for K = 10, limit = 9.9")
+    return _ops.fsn_decompress_cirm(mask)
+
+
+def fullsubnet_features(noisy_wav, clean_wav):
+    """The four feature / target calls of trainer.fullsubnet_train (trainer.py:97-104) fused into one kernel:
+    returns (noisy_mag [B, 257, T], cIRM [B, 257, T, 2])."""
+    return _ops.fsn_features(noisy_wav.float().contiguous(), clean_wav.float().contiguous())
+
+
 istft = _fullsubnet_only("istft")
-mag_phase = _fullsubnet_only("mag_phase")
-build_complex_ideal_ratio_mask = _fullsubnet_only("build_complex_ideal_ratio_mask")
-decompress_cIRM = _fullsubnet_only("decompress_cIRM")

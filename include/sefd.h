@@ -82,6 +82,18 @@ int sefd_pmsqe_forward(const float* est_wav, const float* clean_wav, int N, int 
 int sefd_pmsqe_backward(const float* gout, int N, int L, const float* tables, void* ws, size_t ws_bytes, float* d_est,
                         void* stream);
 
+/* FullSubNet feature / target side of trainer.fullsubnet_train (trainer.py:97-104): torch.stft geometry n_fft 512, hop 300,
+ * win 400 (centred, reflect padding); T = sefd_fsn_frames(L) = L / 300 + 1.
+ *   sefd_fsn_features: tools.stft x2 + tools.mag_phase + tools.build_complex_ideal_ratio_mask fused (tools_for_model.py:
+ *                      628-717): noisy, clean [B][L] -> noisy_mag [B][257][T], cirm [B][257][T][2]
+ *   sefd_fsn_stft / _mag_phase / _cirm / _decompress_cirm: the same functions one by one (spec = complex viewed as [..][2]) */
+int sefd_fsn_frames(int L);
+int sefd_fsn_features(const float* noisy, const float* clean, int B, int L, float* noisy_mag, float* cirm, void* stream);
+int sefd_fsn_stft(const float* wav, int B, int L, float* spec, void* stream);
+int sefd_fsn_mag_phase(const float* spec, long long n, float* mag, float* phase, void* stream);
+int sefd_fsn_cirm(const float* noisy_spec, const float* clean_spec, long long n, float* cirm, void* stream);
+int sefd_fsn_decompress_cirm(const float* mask, long long n, float* out, void* stream);
+
 /* ComplexConv2d (tools_for_model.py:199-269: kernel (5,2), stride (2,1), pad (2,0), causal pad 1) and
  * ComplexConvTranspose2d (tools_for_model.py:272-338: + output_padding (1,0)); channels-last tensors.
  *   conv : x [B][F][T][Cin]          -> y [B][F/2][T][Cout]

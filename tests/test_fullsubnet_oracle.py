@@ -74,3 +74,44 @@ def test_dropin_still_raises_for_fullsubnet():
     import models
     with pytest.raises(NotImplementedError):
         models.FullSubNet()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,L", [(2, 4000), (3, 48000), (1, 4801)])
+def test_feature_kernels_gpu(fs_golden, B, L):
+    """tools.stft / mag_phase / build_complex_ideal_ratio_mask / decompress_cIRM and the fused feature kernel (the feature /
+    target side of trainer.fullsubnet_train) against the oracle and, at the fixture size, the reference's own values."""
+    import tools_for_model as tools
+    if (B, L) == (2, 4000):
+        noisy, clean = _speech(B, L)
+    else:
+        g = torch.Generator().manual_seed(L)
+        clean = 0.1 * torch.randn(B, L, generator=g)
+        noisy = clean + 0.05 * torch.randn(B, L, generator=g)
+    nc_ref, cc_ref = FS.stft(noisy), FS.stft(clean)
+    nd, cd = noisy.cuda(), clean.cuda()
+    nc, cc = tools.stft(nd), tools.stft(cd)
+    assert nc.shape == nc_ref.shape and nc.dtype == torch.complex64
+    scale = float(nc_ref.abs().max())
+    assert float((nc.cpu() - nc_ref).abs().max()) < 2e-6 * scale + 1e-6
+    mag, phase = tools.mag_phase(nc)
+    mref, pref = FS.mag_phase(nc_ref)
+    assert float((mag.cpu() - mref).abs().max()) < 2e-6 * scale + 1e-6
+    big = mref > 1e-3 * scale                                   # the angle of a near-zero bin is ill-conditioned
+    dphi = torch.remainder(phase.cpu() - pref + np.pi, 2 * np.pi) - np.pi
+    assert float(dphi[big].abs().max()) < 1e-3
+    # the mask divides by |noisy|^2: compare where the division is well conditioned, and bound everything by K = 10
+    cirm = tools.build_complex_ideal_ratio_mask(nc, cc)
+    cref = FS.build_complex_ideal_ratio_mask(nc_ref, cc_ref)
+    assert cirm.shape == cref.shape and float(cirm.abs().max()) <= 10.0
+    ok = big[..., None].expand_as(cref)
+    assert float((cirm.cpu() - cref)[ok].abs().max()) < 5e-3
+    fmag, fcirm = tools.fullsubnet_features(nd, cd)
+    assert float((fmag - mag).abs().max()) < 2e-6 * scale + 1e-6
+    assert float((fcirm.cpu() - cref)[ok].abs().max()) < 5e-3
+    dec = tools.decompress_cIRM(cirm)
+    np.testing.assert_allclose(dec.cpu().numpy(), FS.decompress_cirm(cirm.cpu()).numpy(), rtol=2e-4, atol=2e-4)
+    if (B, L) == (2, 4000):
+        np.testing.assert_allclose(fmag.cpu().numpy(), fs_golden["noisy_mag"], atol=2e-5)
+        gref = torch.from_numpy(fs_golden["cIRM"])
+        assert float((fcirm.cpu() - gref)[ok].abs().max()) < 5e-3
