@@ -156,9 +156,21 @@ __global__ void __launch_bounds__(256) bn_prelu_bwd_apply_kernel(const BnPreluBw
     __syncthreads();
     const float alpha = p.alpha[0];
     const long long total = (long long)p.BF * p.Ty * C4;
+    // the grid stride (gridDim * 256) is a multiple of C4 (C4 divides 256), so a thread keeps its channel quad for the whole
+    // loop: the per-channel constants live in registers instead of being re-read for every element
+    const int c = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) % C4) * 4;
+    float k_istd[4], k_mean[4], k_gam[4], k_bet[4], k_mg[4], k_mgx[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        k_istd[i] = p.save[C + c + i];
+        k_mean[i] = p.save[c + i];
+        k_gam[i] = p.gamma[c + i];
+        k_bet[i] = p.beta[c + i];
+        k_mg[i] = s_mg[c + i];
+        k_mgx[i] = s_mgx[c + i];
+    }
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(e % C4) * 4;
         const long long row = e / C4;
         const int ty = (int)(row % p.Ty);
         const long long bf = row / p.Ty;
@@ -177,12 +189,12 @@ __global__ void __launch_bounds__(256) bn_prelu_bwd_apply_kernel(const BnPreluBw
         float o[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const float istd = p.save[C + c + i];
-            const float xh = (y4[i] - p.save[c + i]) * istd;
-            const float gam = p.gamma[c + i];
-            const float u = fmaf(gam, xh, p.beta[c + i]);
+            const float istd = k_istd[i];
+            const float xh = (y4[i] - k_mean[i]) * istd;
+            const float gam = k_gam[i];
+            const float u = fmaf(gam, xh, k_bet[i]);
             const float g = u > 0.f ? d4[i] : alpha * d4[i];
-            o[i] = gam * istd * (g - s_mg[c + i] - xh * s_mgx[c + i]);
+            o[i] = gam * istd * (g - k_mg[i] - xh * k_mgx[i]);
             if (p.round_tf32) o[i] = tf32_rn(o[i]);
         }
         *reinterpret_cast<float4*>(p.dy + e * 4) = make_float4(o[0], o[1], o[2], o[3]);
