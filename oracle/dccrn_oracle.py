@@ -75,7 +75,8 @@ def conv_istft(spec: torch.Tensor, k_s: torch.Tensor, window: torch.Tensor,
 # --------------------------------------------------------------------------------------
 # parameter construction in the reference's RNG order (models.py:17-170)
 # --------------------------------------------------------------------------------------
-def init_state(seed: int = 0, kernel_num: Optional[List[int]] = None, skip_type: bool = True) -> Dict[str, torch.Tensor]:
+def init_state(seed: int = 0, kernel_num: Optional[List[int]] = None, skip_type: bool = True,
+               lstm: str = "complex") -> Dict[str, torch.Tensor]:
     """State dict with the reference's keys/shapes and, for a given torch seed, its values.
 
     Built by instantiating torch.nn modules in the same order as DCCRN.__init__
@@ -110,7 +111,14 @@ def init_state(seed: int = 0, kernel_num: Optional[List[int]] = None, skip_type:
         bn_prelu(f"encoder.{i}.1.", f"encoder.{i}.2.", kn[i + 1])
 
     hidden_dim = FFT_LEN // (2 ** len(kn))
-    for l in range(RNN_LAYERS):
+    if lstm == "real":                                   # cfg.lstm == 'real' (models.py:96-105): one 2-layer nn.LSTM + Linear
+        m = nn.LSTM(input_size=hidden_dim * kn[-1], hidden_size=RNN_UNITS, num_layers=2, dropout=0.0)
+        for name, p in m.named_parameters():
+            sd[f"enhance.{name}"] = p.data.clone()
+        m = nn.Linear(RNN_UNITS, hidden_dim * kn[-1])
+        sd["tranform.weight"] = m.weight.data.clone()
+        sd["tranform.bias"] = m.bias.data.clone()
+    for l in range(RNN_LAYERS if lstm != "real" else 0):
         in_sz = (hidden_dim * kn[-1] if l == 0 else RNN_UNITS) // 2
         for part in ("real", "imag"):
             m = nn.LSTM(in_sz, RNN_UNITS // 2, num_layers=1)
@@ -290,17 +298,28 @@ def dccrn_forward(sd: Dict[str, torch.Tensor], wav: torch.Tensor, masking_mode: 
 
     B, C, D, T = out.shape                                             # models.py:200-220
     o = out.permute(3, 0, 1, 2)
-    r = o[:, :, :C // 2].reshape(T, B, C // 2 * D)
-    i_ = o[:, :, C // 2:].reshape(T, B, C // 2 * D)
-    if taps is not None:
-        taps["lstm_in_r"], taps["lstm_in_i"] = r, i_
-    for l in range(RNN_LAYERS):
-        r, i_ = complex_lstm(r, i_, sd, f"enhance.{l}.", project=(l == RNN_LAYERS - 1))
+    if "enhance.weight_ih_l0" in sd:                                   # cfg.lstm == 'real' (models.py:213-218)
+        x = o.reshape(T, B, C * D)
+        lstm = lstm_fused if USE_FUSED_LSTM else lstm_seq
+        for l in range(2):
+            x = lstm(x, sd[f"enhance.weight_ih_l{l}"], sd[f"enhance.weight_hh_l{l}"], sd[f"enhance.bias_ih_l{l}"],
+                     sd[f"enhance.bias_hh_l{l}"])
         if taps is not None:
-            taps[f"lstm{l}_r"], taps[f"lstm{l}_i"] = r, i_
-    r = r.reshape(T, B, C // 2, D)
-    i_ = i_.reshape(T, B, C // 2, D)
-    out = torch.cat([r, i_], 2).permute(1, 2, 3, 0)
+            taps["lstm_real"] = x
+        x = F.linear(x, sd["tranform.weight"], sd["tranform.bias"])
+        out = x.reshape(T, B, C, D).permute(1, 2, 3, 0)
+    else:                                                              # cfg.lstm == 'complex' (models.py:201-212)
+        r = o[:, :, :C // 2].reshape(T, B, C // 2 * D)
+        i_ = o[:, :, C // 2:].reshape(T, B, C // 2 * D)
+        if taps is not None:
+            taps["lstm_in_r"], taps["lstm_in_i"] = r, i_
+        for l in range(RNN_LAYERS):
+            r, i_ = complex_lstm(r, i_, sd, f"enhance.{l}.", project=(l == RNN_LAYERS - 1))
+            if taps is not None:
+                taps[f"lstm{l}_r"], taps[f"lstm{l}_i"] = r, i_
+        r = r.reshape(T, B, C // 2, D)
+        i_ = i_.reshape(T, B, C // 2, D)
+        out = torch.cat([r, i_], 2).permute(1, 2, 3, 0)
 
     for j in range(n_layers):                                          # models.py:222-226
         p = f"decoder.{j}.0."

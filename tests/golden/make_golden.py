@@ -387,8 +387,38 @@ def main_fullsubnet():
     print(f"wrote fullsubnet_golden.npz ({sz/1e3:.1f} kB); loss={out['loss']}, n_params={out['n_params']}, T={crm.shape[2]}")
 
 
+def main_reallstm():
+    """cfg.lstm = 'real' (models.py:96-105, 213-218): one 2-layer nn.LSTM(1024 -> 256) + Linear(256 -> 1024) instead of
+    the complex LSTM pair.  Oracle fixture only: the CUDA path of this variant is not built yet."""
+    cfg, models, tfl = import_reference()
+    cfg.lstm = "real"
+    torch.set_num_threads(8)
+    out = {}
+    noisy, clean = speechlike(2, 4000)
+    torch.manual_seed(0)
+    m = models.DCCRN(masking_mode="C").train()
+    sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    o_r, o_i, wav = m(noisy, clean)
+    loss = m.loss(wav, clean)
+    loss.backward()
+    out["loss"] = np.array(loss.item())
+    out["wav"], out["out_real"] = wav.detach().numpy(), o_r.detach().numpy()
+    out["param_names"] = np.array([n for n, _ in m.named_parameters()])
+    out["param_shapes"] = np.array([str(tuple(p.shape)) for _, p in m.named_parameters()])
+    out["gnorm"] = np.array([float(p.grad.double().norm()) for _, p in m.named_parameters()])
+    for n, p in m.named_parameters():
+        gflat = p.grad.reshape(-1)
+        out["grad:" + n] = (gflat if gflat.numel() <= 4096 else gflat[::997]).numpy().copy()
+    for k in ("enhance.weight_hh_l1", "tranform.weight", "decoder.0.0.real_conv.weight"):
+        out["init:" + k] = sd0[k].reshape(-1)[::97].numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "reallstm_golden.npz"), **out)
+    print("wrote reallstm_golden.npz", out["loss"], len(out["param_names"]))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "fullsubnet":
+    if len(sys.argv) > 1 and sys.argv[1] == "reallstm":
+        main_reallstm()
+    elif len(sys.argv) > 1 and sys.argv[1] == "fullsubnet":
         main_fullsubnet()
     elif len(sys.argv) > 1 and sys.argv[1] == "noskip":
         main_noskip()
