@@ -128,6 +128,80 @@ __global__ void fsn_decompress_kernel(const float* __restrict__ m, long long n, 
     }
 }
 
+// tools.istft (tools_for_model.py:651-679) = torch.istft(features, 512, 300, 400, hann_window(400), length): per frame
+// irfft_512 (1/512, imaginary parts of DC / Nyquist ignored), times the centred window, overlap-add at hop 300, divided by the
+// overlap-added squared window, trimmed by n_fft / 2 at the front.  Output-centric: one CTA owns IH hops of output samples
+// and transforms the IH + 2 frames that touch them (two frames per complex inverse FFT, Hermitian packing), so the
+// overlap-add needs no atomics and is deterministic.  MAGPH: the input is (mag, phase) instead of a complex spectrum.
+constexpr int IH = 8;
+struct IfsnSmem {
+    float2 fft[4][NF];
+    float2 tw[NF];
+    float win[NF];
+    float fr[IH + 4][NF];
+};
+
+template <bool MAGPH>
+__global__ void __launch_bounds__(256) fsn_istft_kernel(const float* __restrict__ in0, const float* __restrict__ in1, int T,
+                                                        int len, float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    IfsnSmem& sm = *reinterpret_cast<IfsnSmem*>(raw);
+    const int bi = blockIdx.y, h0 = blockIdx.x * IH;          // hops h0 .. h0 + IH - 1 of the padded signal
+    const int tid = threadIdx.x, g = tid >> 6, t64 = tid & 63;
+    fsn_tables(sm.tw, sm.win);
+    __syncthreads();
+    const int fbase = h0 - 1;                                  // frames fbase .. fbase + IH + 2 (IH + 3 would be unused)
+    for (int r = 0; r < (IH + 4) / 8 + ((IH + 4) % 8 ? 1 : 0); ++r) {
+        const int j0 = (4 * r + g) * 2;                        // local frame pair (j0, j0 + 1)
+        const int fa = fbase + j0, fb = fa + 1;
+        const bool va = j0 < IH + 4 && fa >= 0 && fa < T, vb = j0 + 1 < IH + 4 && fb >= 0 && fb < T;
+        float2* s = sm.fft[g];
+        for (int k = t64; k <= 256; k += 64) {
+            float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+            const size_t base = ((size_t)bi * NB + k) * T;
+            if (MAGPH) {
+                if (va) { float sn, cs; sincosf(in1[base + fa], &sn, &cs); const float m = in0[base + fa]; a = make_float2(m * cs, m * sn); }
+                if (vb) { float sn, cs; sincosf(in1[base + fb], &sn, &cs); const float m = in0[base + fb]; b = make_float2(m * cs, m * sn); }
+            } else {
+                const float2* sp = reinterpret_cast<const float2*>(in0);
+                if (va) a = sp[base + fa];
+                if (vb) b = sp[base + fb];
+            }
+            if (k == 0 || k == 256) {
+                s[k] = make_float2(a.x, b.x);
+            } else {
+                s[k] = make_float2(a.x - b.y, a.y + b.x);
+                s[NF - k] = make_float2(a.x + b.y, -a.y + b.x);
+            }
+        }
+        __syncthreads();
+        fft512_cta<true>(s, sm.tw, t64);
+        if (j0 < IH + 4) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int n = t64 + 64 * i;
+                const float w = sm.win[n] * (1.f / NF);
+                sm.fr[j0][n] = va ? w * s[n].x : 0.f;
+                if (j0 + 1 < IH + 4) sm.fr[j0 + 1][n] = vb ? w * s[n].y : 0.f;
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < IH * FHOP; i += 256) {
+        const int p = h0 * FHOP + i;                           // padded coordinate
+        const int o = p - NF / 2;
+        if (o < 0 || o >= len) continue;
+        const int f1 = p / FHOP, f2 = f1 - 1;                  // the (at most) two frames covering p
+        float v = 0.f, env = 0.f;
+        if (f1 < T) { const int n = p - f1 * FHOP; v += sm.fr[f1 - fbase][n]; env += sm.win[n] * sm.win[n]; }
+        if (f2 >= 0 && f2 < T) {
+            const int n = p - f2 * FHOP;
+            if (n < NF) { v += sm.fr[f2 - fbase][n]; env += sm.win[n] * sm.win[n]; }
+        }
+        out[(size_t)bi * len + o] = env > 1e-11f ? v / env : 0.f;
+    }
+}
+
 template <int MODE>
 int launch_stft(const float* a, const float* b, int B, int L, float* mag, float* out2, cudaStream_t st) {
     const int T = L / FHOP + 1;
@@ -173,6 +247,24 @@ int sefd_fsn_cirm(const float* noisy_spec, const float* clean_spec, long long n,
                                                                     reinterpret_cast<const float2*>(clean_spec), n,
                                                                     reinterpret_cast<float2*>(cirm));
     return sefd_check_launch("fsn_cirm");
+}
+/* spec [B][257][T][2] (or mag, phase [B][257][T] when phase != NULL) -> wav [B][len] */
+int sefd_fsn_istft(const float* spec_or_mag, const float* phase, int B, int T, int len, float* wav, void* stream) {
+    SEFD_REQUIRE(spec_or_mag && wav && B > 0 && T > 0 && len > 0, "fsn_istft: bad argument");
+    // samples no frame covers (len beyond 300 (T - 1) + 256) come out as zeros, like torch.istft's right padding
+    cudaStream_t st = (cudaStream_t)stream;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(fsn_istft_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IfsnSmem));
+        cudaFuncSetAttribute(fsn_istft_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IfsnSmem));
+        attr = true;
+    }
+    const int hops = (NF / 2 + len + FHOP - 1) / FHOP;
+    dim3 grid((hops + IH - 1) / IH, B);
+    SefdProfScope prof(SEFD_PROF_STFT, 0, 4.0 * B * (2.0 * NB * T + len), st);
+    if (phase) fsn_istft_kernel<true><<<grid, 256, sizeof(IfsnSmem), st>>>(spec_or_mag, phase, T, len, wav);
+    else fsn_istft_kernel<false><<<grid, 256, sizeof(IfsnSmem), st>>>(spec_or_mag, nullptr, T, len, wav);
+    return sefd_check_launch("fsn_istft");
 }
 int sefd_fsn_decompress_cirm(const float* mask, long long n, float* out, void* stream) {
     SEFD_REQUIRE(mask && out && n > 0, "fsn_decompress_cirm: bad argument");

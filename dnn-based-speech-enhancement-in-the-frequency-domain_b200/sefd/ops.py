@@ -446,3 +446,22 @@ def fsn_decompress_cirm(mask):
     out = torch.empty_like(m)
     _lib.check(_lib.load().sefd_fsn_decompress_cirm(ptr(m), m.numel(), ptr(out), stream()), "fsn_decompress_cirm")
     return out
+
+
+def fsn_istft(features, length=None, use_mag_phase=False):
+    """tools.istft (tools_for_model.py:651-679): complex [B, 257, T] (or its real view [B, 257, T, 2], or (mag, phase) with
+    use_mag_phase) -> [B, length]; length defaults to 300 (T - 1) like torch.istft."""
+    if use_mag_phase:
+        mag, phase = features
+        a, b = mag.contiguous().float(), phase.contiguous().float()
+        _req(a, b)
+        B, _, T = a.shape
+    else:
+        a = (torch.view_as_real(features) if torch.is_complex(features) else features).contiguous().float()
+        b = None
+        _req(a)
+        B, _, T, _ = a.shape
+    n = 300 * (T - 1) if length is None else int(length)
+    out = torch.empty(B, n, device=a.device)
+    _lib.check(_lib.load().sefd_fsn_istft(ptr(a), ptr(b), B, T, n, ptr(out), stream()), "fsn_istft")
+    return out

@@ -235,4 +235,9 @@ def fullsubnet_features(noisy_wav, clean_wav):
     return _ops.fsn_features(noisy_wav.float().contiguous(), clean_wav.float().contiguous())
 
 
-istft = _fullsubnet_only("istft")
+def istft(features, n_fft=512, hop_length=300, win_length=400, length=None, use_mag_phase=False):
+    """tools_for_model.py:651-679 (torch.istft, centred, periodic Hann): [B, 257, T] complex (or [B, 257, T, 2], or
+    (mag, phase) with use_mag_phase) -> [B, length]."""
+    if (n_fft, hop_length, win_length) != (512, 300, 400):
+        raise NotImplementedError("sefd: tools.istft is built for the reference geometry n_fft 512 / hop 300 / win 400")
+    return _ops.fsn_istft(features, length=length, use_mag_phase=use_mag_phase)

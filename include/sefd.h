@@ -93,6 +93,9 @@ int sefd_fsn_stft(const float* wav, int B, int L, float* spec, void* stream);
 int sefd_fsn_mag_phase(const float* spec, long long n, float* mag, float* phase, void* stream);
 int sefd_fsn_cirm(const float* noisy_spec, const float* clean_spec, long long n, float* cirm, void* stream);
 int sefd_fsn_decompress_cirm(const float* mask, long long n, float* out, void* stream);
+/* tools.istft (tools_for_model.py:651-679, torch.istft 512 / 300 / 400, centred, Hann): spec [B][257][T][2], or magnitude and
+ * phase [B][257][T] when phase != NULL (use_mag_phase=True), -> wav [B][len] */
+int sefd_fsn_istft(const float* spec_or_mag, const float* phase, int B, int T, int len, float* wav, void* stream);
 
 /* ComplexConv2d (tools_for_model.py:199-269: kernel (5,2), stride (2,1), pad (2,0), causal pad 1) and
  * ComplexConvTranspose2d (tools_for_model.py:272-338: + output_padding (1,0)); channels-last tensors.

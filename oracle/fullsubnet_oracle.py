@@ -62,6 +62,27 @@ def stft(y: torch.Tensor) -> torch.Tensor:
     return torch.fft.rfft(frames * w, dim=-1).transpose(1, 2)                  # [B, 257, T]
 
 
+def istft(spec: torch.Tensor, length: Optional[int] = None) -> torch.Tensor:
+    """tools.istft (tools_for_model.py:651-679) = torch.istft(spec, 512, 300, 400, hann_window(400), length=length), restated:
+    irfft per frame, centred window, overlap-add at hop 300, division by the overlap-added squared window, n_fft / 2 trimmed
+    at the front: complex [B, 257, T] -> [B, length or 300 (T - 1)]."""
+    B, _, T = spec.shape
+    w = torch.hann_window(WIN, dtype=torch.float32)
+    lpad = (N_FFT - WIN) // 2
+    w = F.pad(w, [lpad, N_FFT - WIN - lpad])
+    frames = torch.fft.irfft(spec.transpose(1, 2), n=N_FFT, dim=-1) * w               # [B, T, 512]
+    full = N_FFT + HOP * (T - 1)
+    y = frames.new_zeros(B, full)
+    env = frames.new_zeros(full)
+    for t in range(T):
+        y[:, t * HOP:t * HOP + N_FFT] += frames[:, t]
+        env[t * HOP:t * HOP + N_FFT] += w * w
+    n = HOP * (T - 1) if length is None else length
+    y, env = y[:, N_FFT // 2:N_FFT // 2 + n], env[N_FFT // 2:N_FFT // 2 + n]
+    out = torch.where(env > 1e-11, y / env.clamp_min(1e-11), torch.zeros_like(y))
+    return F.pad(out, [0, n - out.shape[1]]) if out.shape[1] < n else out
+
+
 def mag_phase(c: torch.Tensor):
     return torch.abs(c), torch.angle(c)                                        # tools_for_model.py:682-683
 

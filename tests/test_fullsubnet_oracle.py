@@ -115,3 +115,36 @@ def test_feature_kernels_gpu(fs_golden, B, L):
         np.testing.assert_allclose(fmag.cpu().numpy(), fs_golden["noisy_mag"], atol=2e-5)
         gref = torch.from_numpy(fs_golden["cIRM"])
         assert float((fcirm.cpu() - gref)[ok].abs().max()) < 5e-3
+
+
+def test_istft_oracle_matches_torch():
+    noisy, _ = _speech(2, 4000)
+    spec = FS.stft(noisy)
+    for length in (None, 4000, 3900):
+        ref = torch.istft(spec, 512, 300, 400, window=torch.hann_window(400), length=length)
+        got = FS.istft(spec, length)
+        assert got.shape == ref.shape
+        assert float((got - ref).abs().max()) < 2e-6
+    assert float((FS.istft(spec, 4000) - noisy).abs().max()) < 1e-5          # analysis-synthesis round trip
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,L", [(2, 4000), (3, 48000), (1, 4801)])
+def test_istft_gpu(B, L):
+    import tools_for_model as tools
+    g = torch.Generator().manual_seed(L + 1)
+    x = 0.1 * torch.randn(B, L, generator=g)
+    spec = FS.stft(x)
+    # an arbitrary (not STFT-consistent) spectrum exercises the overlap-add, not just the round trip
+    spec2 = spec * torch.exp(1j * 0.3 * torch.randn(spec.shape, generator=g)) * (1 + 0.2 * torch.randn(spec.shape, generator=g))
+    for s, n in ((spec, L), (spec2, L), (spec2, None), (spec2, L - 77)):
+        ref = FS.istft(s, n)
+        got = tools.istft(s.cuda(), length=n)
+        assert got.shape == ref.shape
+        assert float((got.cpu() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
+    got = tools.istft(torch.view_as_real(spec2).cuda(), length=L)                 # the reference passes the real view
+    assert float((got.cpu() - FS.istft(spec2, L)).abs().max()) < 2e-5
+    mag, phase = spec2.abs(), torch.angle(spec2)
+    got = tools.istft((mag.cuda(), phase.cuda()), length=L, use_mag_phase=True)
+    assert float((got.cpu() - FS.istft(spec2, L)).abs().max()) < 5e-5
+    assert float((tools.istft(tools.stft(x.cuda()), length=L).cpu() - x).abs().max()) < 1e-5     # round trip on the device
