@@ -100,3 +100,35 @@ def test_fft_index_algebra_on_host(tmp_path):
     subprocess.check_call(["g++", "-O2", "-o", exe, src])
     out = subprocess.check_output([exe]).decode()
     assert "max abs err" in out
+
+
+def test_host_side_guards_of_the_later_additions():
+    """Argument handling that needs no GPU: table packing overrides, unbuilt variants fail loudly, CPU tensors are refused."""
+    import numpy as np
+    import tools_for_model as tools
+    import tools_for_loss as tfl
+    from sefd import ops
+    from sefd.train import TrainStep
+    t0 = ops.pmsqe_tables()
+    t1 = ops.pmsqe_tables(bark_matrix=np.ones((257, 49)), mask_sll=np.zeros(257))
+    assert t0.shape == t1.shape == (257 * 49 + 3 * 49 + 257,)
+    assert float(t1[: 257 * 49].sum()) == 257 * 49 and float(t1[-257:].abs().sum()) == 0.0
+    assert torch.equal(t0[257 * 49: 257 * 49 + 147], t1[257 * 49: 257 * 49 + 147])       # untouched tables keep their defaults
+    with pytest.raises((AssertionError, ValueError)):
+        ops.pmsqe_tables(bark_matrix=np.ones((10, 49)))
+    x = torch.zeros(2, 4000)
+    for call in (lambda: tools.stft(x), lambda: tools.fullsubnet_features(x, x), lambda: tfl.get_array_pmsqe_loss(x, x),
+                 lambda: tools.istft(torch.zeros(2, 257, 14, 2))):
+        with pytest.raises(RuntimeError, match="CUDA"):
+            call()
+    with pytest.raises(NotImplementedError):
+        tools.stft(x, n_fft=1024)
+    with pytest.raises(NotImplementedError):
+        tools.istft(torch.zeros(2, 257, 14, 2), hop_length=128)
+    with pytest.raises(NotImplementedError):
+        tools.decompress_cIRM(torch.zeros(4), K=5)
+
+    class _M:                                      # TrainStep validates `perceptual` before it touches the model
+        pass
+    with pytest.raises(NotImplementedError):
+        TrainStep(_M(), perceptual="LMS")
