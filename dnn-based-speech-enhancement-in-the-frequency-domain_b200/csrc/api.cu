@@ -7,6 +7,8 @@
 
 #include "../../include/sefd.h"
 #include "dccrn.cuh"
+#include "fsnet.cuh"
+#include "lstm_seq.cuh"
 #include "taps.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -364,6 +366,28 @@ int sefd_crn_backward_spec(const sefd_plan* plan, const float* params, const flo
                            void* ws, size_t ws_bytes, void* stream) {
     SEFD_REQUIRE(plan && params && grads && ws && (d_wav || d_est_mags), "crn_backward_spec: null argument");
     return sefd_crn_backward_impl(plan, params, d_wav, d_est_mags, grads, ws, ws_bytes, ST);
+}
+
+// ---- FullSubNet (models.py:568-682) ------------------------------------------------------------------
+sefd_plan* sefd_fsn_plan_create(int B, int frames) { return sefd_fsn_plan_create_impl(B, frames); }
+
+int sefd_fsn_forward(const sefd_plan* plan, const float* params, const float* noisy_mag, int train, float dropout_p,
+                     const float* mask_fb, const float* mask_sb, unsigned long long seed, float* crm, void* ws, size_t ws_bytes,
+                     void* stream) {
+    SEFD_REQUIRE(plan && params && noisy_mag && crm && ws, "fsn_forward: null argument");
+    return sefd_fsn_forward_impl(plan, params, noisy_mag, train, dropout_p, mask_fb, mask_sb, seed, crm, ws, ws_bytes, ST);
+}
+
+int sefd_dropout_forward(const float* x, float* y, long long n, float p, const float* mask, unsigned long long seed,
+                         unsigned int stream_id, void* stream) {
+    SEFD_REQUIRE(x && y && n > 0, "dropout_forward: bad argument");
+    return sefd_dropout_apply(x, y, n, p, mask, seed, stream_id, 0, ST);
+}
+
+int sefd_fsn_backward(const sefd_plan* plan, const float* params, const float* d_crm, float* grads, void* ws, size_t ws_bytes,
+                      void* stream) {
+    SEFD_REQUIRE(plan && params && d_crm && grads && ws, "fsn_backward: null argument");
+    return sefd_fsn_backward_impl(plan, params, d_crm, grads, ws, ws_bytes, ST);
 }
 
 }  // extern "C"

@@ -4,6 +4,7 @@
 // backward obligations.
 #include <stdlib.h>
 
+#include "fsnet.cuh"
 #include "plan.cuh"
 #include "prof.cuh"
 #include "taps.cuh"
@@ -704,6 +705,7 @@ void sefd_dccrn_plan_destroy(sefd_plan* plan) {
         cudaEventDestroy(plan->ev_fork);
         cudaEventDestroy(plan->ev_join);
     }
+    if (plan && plan->fsn) sefd_fsn_plan_free_ext(plan);
     delete plan;
 }
 size_t sefd_dccrn_workspace_bytes(const sefd_plan* plan) { return plan ? plan->ws_bytes : 0; }
@@ -730,6 +732,7 @@ int sefd_dccrn_entry_info(const sefd_plan* plan, int kind, int idx, char* name, 
 int sefd_dccrn_tensor_info(const sefd_plan* P, const char* name, long long* off, int* ndim, long long shape[4]) {
     SEFD_REQUIRE(P != nullptr && name != nullptr, "tensor_info: null argument");
     if (P->kind == 1) return sefd_crn_tensor_info(P, name, off, ndim, shape);
+    if (P->kind == 2) return sefd_fsn_tensor_info(P, name, off, ndim, shape);
     const long long B = P->B, T = P->T;
     auto set = [&](size_t o, long long a, long long b, long long c, long long d) {
         *off = (long long)o; *ndim = 4; shape[0] = a; shape[1] = b; shape[2] = c; shape[3] = d;

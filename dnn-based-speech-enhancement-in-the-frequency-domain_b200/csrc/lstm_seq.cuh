@@ -1,0 +1,67 @@
+// Time-major nn.LSTM layer engine for FullSubNet's SequenceModel (tools_for_model.py:726-795) and cfg.lstm = 'real'
+// (models.py:96-105): any hidden size that is a multiple of 64, any number of independent sequences ("rows").
+//
+// Layout: every per-step tensor is [T][rows][C] (time-major), so that step t of ALL sequences is one dense
+// [rows x C] matrix: the recurrence h_{t-1} W_hh^T is a plain GEMM per step and the tile of a GEMM CTA is 128
+// consecutive sequences.  The 4H gate columns are stored INTERLEAVED in chunks of 64 hidden units,
+//     n' = (u / 64) * 256 + gate * 64 + (u % 64)        (reference order n = gate * H + u, gates i, f, g, o)
+// so that one 256-column accumulator tile of the recurrent GEMM holds i, f, g, o of the same 64 units and the LSTM
+// cell can run in the GEMM epilogue (lstm_step_tc.cu); packed weights / bias use the same column order.
+#pragma once
+#include "common.cuh"
+
+struct SeqLstmWeights {
+    const float* Wih_nk;   // [4H'][I]   (n' rows, k contiguous)  forward operand of the tensor-core engine / dgrad "W"
+    const float* Wih_kn;   // [I][4H']                            forward operand of the fp32 engine / dgrad "Wnk"
+    const float* Whh_nk;   // [4H'][H]
+    const float* Whh_kn;   // [H][4H']
+    const float* bias;     // [4H'] = b_ih + b_hh
+    int I, H;              // I = input width as stored (padded to a multiple of 32)
+};
+
+struct SeqLstmPackParams {
+    const float *w_ih, *w_hh, *b_ih, *b_hh;   // reference layouts: [4H][I_real], [4H][H], [4H], [4H]
+    int I_real, I, H;
+    float *Wih_nk, *Wih_kn, *Whh_nk, *Whh_kn, *bias;
+    int round_tf32;
+};
+int sefd_seqlstm_pack(const SeqLstmPackParams& p, cudaStream_t st);
+
+// dW[n][k] (reference layout [4H][K_real]) = sum_s part[s][k][n'(n)]   (partials [nsplit][K][4H'] of sefd_wgrad)
+int sefd_seqlstm_fold_wgrad(const float* part, int nsplit, long long split_stride, int K, int K_real, int H, float* dW,
+                            cudaStream_t st);
+// db_ih[n] = db_hh[n] = sum_blk part[blk][n'(n)]
+int sefd_seqlstm_fold_bias(const float* part, int nblk, int H, float* db_ih, float* db_hh, cudaStream_t st);
+
+struct SeqLstmFwdParams {
+    const float* x;        // [T][rows][I] layer input (tf32-rounded when the tensor-core engine is on)
+    SeqLstmWeights w;
+    float* gates;          // [T][rows][4H'] out: activated gates (kept for the backward)
+    float* h;              // [T][rows][H]
+    float* c;              // [T][rows][H]
+    int rows, T;
+    int round_h;           // h feeds tensor-core GEMMs: round to tf32 while writing
+};
+int sefd_seqlstm_forward(const SeqLstmFwdParams& p, cudaStream_t st);
+
+struct SeqLstmBwdParams {
+    SeqLstmWeights w;
+    float* gates;          // in: activated gates; out: gradient w.r.t. the gate pre-activations (in place)
+    const float* c;        // [T][rows][H]
+    const float* dh_out;   // [T][rows][H] gradient arriving at every h_t from above
+    float* dh_rec;         // [rows][H] scratch: recurrent gradient
+    float* dc;             // [rows][H] scratch: cell-state gradient carried backwards
+    float* bias_part;      // [sefd_seqlstm_bias_blocks(rows)][4H'] per-block column sums of dG over all steps
+    int rows, T;
+    int round_tf32;        // dG feeds tensor-core GEMMs
+};
+int sefd_seqlstm_bias_blocks(int rows);
+int sefd_seqlstm_backward(const SeqLstmBwdParams& p, cudaStream_t st);
+
+// nn.LSTM(dropout = p) between stacked layers (tools_for_model.py:746): dst = src * m, m = 0 or 1 / (1 - p).
+// mask != null: injected multiplier tensor (tests); else Philox4x32-10 keyed by (seed, stream) and the element index.
+int sefd_dropout_apply(const float* src, float* dst, long long n, float p, const float* mask, unsigned long long seed,
+                       unsigned int stream_id, int round_tf32, cudaStream_t st);
+
+// 1: fused tcgen05 step kernels (GEMM + LSTM cell in the epilogue), 0: generic tap-GEMM per step + cell kernels
+int sefd_seqlstm_fused_enabled();

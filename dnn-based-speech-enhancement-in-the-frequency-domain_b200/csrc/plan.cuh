@@ -37,8 +37,12 @@ struct ConvLayer {
 
 }  // namespace
 
+struct FsnExt;               // fsnet.cu
+
 struct sefd_plan {
-    int kind;                 // 0: DCCRN (complex), 1: CRN (real)
+    int kind;                 // 0: DCCRN (complex), 1: CRN (real), 2: FullSubNet (fsnet.cu; everything below except the
+                              // parameter list / workspace size lives in `fsn`)
+    FsnExt* fsn = nullptr;
     int B, L, T, mask_mode;
     int skip = 1;             // 1: decoder convs read complex_cat(out, encoder skip) (cfg.skip_type, models.py:107-169)
     int ch[NL + 1], Fe[NL + 1];

@@ -114,16 +114,6 @@ class DCCRN(nn.Module):
         return _ops.loss(estimated, target, cfg.loss)
 
 
-def _not_built(name, row):
-    class _Stub(nn.Module):
-        def __init__(self, *a, **k):
-            super().__init__()
-            raise NotImplementedError(f"sefd: {name} is not built yet ({row}); only the DCCRN hot path is. "
-                                      "There is deliberately no PyTorch fallback.")
-    _Stub.__name__ = name
-    return _Stub
-
-
 class CRN(nn.Module):
     """Drop-in for models.py:329-565: real-valued conv recurrent network with a magnitude T-F mask.
     forward(inputs, targets=0) -> (est_mags [B,257,T], target_mags [B,257,T], out_wav [B,L])."""
@@ -201,4 +191,76 @@ class CRN(nn.Module):
         return _ops.loss(estimated, target, cfg.loss)
 
 
-FullSubNet = _not_built("FullSubNet", "SURVEY.md §8 a14, BASELINE config 3")
+class FullSubNet(nn.Module):
+    """Drop-in for models.py:568-682: forward(noisy_mag [B, 257, T] or [B, 1, 257, T]) -> cRM [B, 257, T, 2];
+    loss(estimated, target) with cfg.loss = 'MSE' (trainer.fullsubnet_train, trainer.py:97-107).
+
+    The reference's nn.LSTM(dropout=0.8) between the stacked layers (tools_for_model.py:746) is active in train() mode:
+    the masks come from a Philox stream seeded from torch's generator (one draw per forward), or from `dropout_masks`
+    = (mask_fb [T+2, B, 512], mask_sb [T+2, B*257, 384]) multipliers when a caller injects them (parity tests)."""
+
+    def __init__(self, sb_num_neighbors=getattr(cfg, "sb_num_neighbors", 15), fb_num_neighbors=getattr(cfg, "fb_num_neighbors", 0),
+                 num_freqs=getattr(cfg, "num_freqs", 257), look_ahead=getattr(cfg, "look_ahead", 2),
+                 sequence_model=getattr(cfg, "sequence_model", "LSTM"),
+                 fb_output_activate_function=getattr(cfg, "fb_output_activate_function", "ReLU"),
+                 sb_output_activate_function=getattr(cfg, "sb_output_activate_function", None),
+                 fb_model_hidden_size=getattr(cfg, "fb_model_hidden_size", 512),
+                 sb_model_hidden_size=getattr(cfg, "sb_model_hidden_size", 384),
+                 weight_init=getattr(cfg, "weight_init", False), norm_type=getattr(cfg, "norm_type", "offline_laplace_norm")):
+        super().__init__()
+        got = (sb_num_neighbors, fb_num_neighbors, num_freqs, look_ahead, sequence_model, fb_output_activate_function,
+               sb_output_activate_function, fb_model_hidden_size, sb_model_hidden_size, bool(weight_init), norm_type)
+        built = (15, 0, 257, 2, "LSTM", "ReLU", None, 512, 384, False, "offline_laplace_norm")
+        if got != built:
+            raise NotImplementedError(f"sefd FullSubNet: configuration {got} outside the built path {built} (config.py:71-80)")
+        from sefd import fullsubnet as _f
+        self.fb_model = _f.SequenceModelParams(num_freqs, num_freqs, fb_model_hidden_size)                   # models.py:600-608
+        self.sb_model = _f.SequenceModelParams((sb_num_neighbors * 2 + 1) + (fb_num_neighbors * 2 + 1), 2,  # models.py:610-618
+                                               sb_model_hidden_size)
+        self.sb_num_neighbors, self.fb_num_neighbors, self.look_ahead = sb_num_neighbors, fb_num_neighbors, look_ahead
+        self.dropout = 0.8                                                                                # tools_for_model.py:746
+        self.dropout_masks = None
+
+    def _get_engine(self):
+        eng = self.__dict__.get("_engine")
+        if eng is None:
+            eng = _d.Engine(self, None, family="fsn")
+            self.__dict__["_engine"] = eng
+        return eng
+
+    def flatten_parameters(self):
+        self._get_engine().sync()
+
+    def forward(self, noisy_mag):
+        from sefd import fullsubnet as _f
+        if noisy_mag.dim() == 4:
+            if noisy_mag.shape[1] != 1:
+                raise ValueError("FullSubNet takes the mag feature as inputs (one channel, models.py:642)")
+            noisy_mag = noisy_mag[:, 0]
+        noisy_mag = noisy_mag.contiguous().float()
+        _ops._req(noisy_mag)
+        if noisy_mag.shape[1] != 257:
+            raise ValueError(f"FullSubNet: expected 257 frequency bins, got {noisy_mag.shape[1]}")
+        eng = self._get_engine()
+        eng.sync()
+        mask_fb = mask_sb = None
+        seed = 0
+        p = self.dropout if self.training else 0.0
+        if self.training and p > 0:
+            if self.dropout_masks is not None:
+                mask_fb, mask_sb = (m.contiguous().float() for m in self.dropout_masks)
+                T, B = noisy_mag.shape[2] + self.look_ahead, noisy_mag.shape[0]
+                if tuple(mask_fb.shape) != (T, B, 512) or tuple(mask_sb.shape) != (T, B * 257, 384):
+                    raise ValueError("FullSubNet.dropout_masks: expected [T+2, B, 512] and [T+2, B*257, 384]")
+                _ops._req(mask_fb, mask_sb)
+            else:
+                seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+        params = [q for q, _, _, _ in eng.param_list]
+        return _f._ForwardFSN.apply(eng, noisy_mag, self.training, p, mask_fb, mask_sb, seed, *params)
+
+    def loss(self, estimated, target):
+        # called as model.loss(cIRM, cRM) (trainer.py:107): the second argument carries the gradient.  MSE is symmetric.
+        if cfg.loss != "MSE":
+            raise NotImplementedError(f"sefd FullSubNet: loss {cfg.loss!r} (built: 'MSE', models.py:675-676)")
+        a, b = (target, estimated) if target.requires_grad or not estimated.requires_grad else (estimated, target)
+        return _ops.loss(a.reshape(a.shape[0], -1), b.detach().reshape(b.shape[0], -1), "MSE")

@@ -63,6 +63,10 @@ SIGNATURES = {
     "sefd_crn_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sefd_crn_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sefd_crn_backward_spec": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "sefd_fsn_plan_create": (_vp, [_i, _i]),
+    "sefd_fsn_forward": (_i, [_vp, _vp, _vp, _i, _f, _vp, _vp, C.c_ulonglong, _vp, _vp, _sz, _vp]),
+    "sefd_fsn_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "sefd_dropout_forward": (_i, [_vp, _vp, _ll, _f, _vp, C.c_ulonglong, C.c_uint, _vp]),
     "sefd_set_engine": (_i, [_i]),
     "sefd_get_engine": (_i, []),
     "sefd_launch_count": (_ll, []),

@@ -142,11 +142,13 @@ class Plan:
         self.skip = skip
         if family == "crn":
             self.handle = lib.sefd_crn_plan_create(B, L)
+        elif family == "fsn":                      # L = number of STFT frames of noisy_mag
+            self.handle = lib.sefd_fsn_plan_create(B, L)
         else:
             self.handle = lib.sefd_dccrn_plan_create_ex(B, L, MODES[mode], 0 if skip else PLAN_NO_SKIP)
         if not self.handle:
             raise RuntimeError("sefd plan: " + lib.sefd_last_error().decode())
-        self.B, self.L, self.T, self.mode = B, L, L // 100 + 3, mode
+        self.B, self.L, self.T, self.mode = B, L, (L + 2 if family == "fsn" else L // 100 + 3), mode
         self.ws_bytes = lib.sefd_dccrn_workspace_bytes(self.handle)
         self.n_param = lib.sefd_dccrn_param_floats(self.handle)
         self.n_buf = lib.sefd_dccrn_buffer_floats(self.handle)
@@ -232,7 +234,9 @@ class _Forward(torch.autograd.Function):
             _lib.check(lib.sefd_dccrn_backward_spec(plan.handle, ptr(engine.flat), ptr(g_wav), ptr(g_real), ptr(g_imag),
                                                     ptr(engine.flat_grad), ptr(plan.ws), plan.ws_bytes, stream()),
                        "dccrn_backward_spec")
-        grads = tuple(engine.flat_grad[o: o + n].view(shape) for (_, o, n, shape) in plan.params)
+        engine.backwards_since_step += 1
+        flat = engine.flat_grad.clone()     # p.grad must never alias the buffer the next backward overwrites (AccumulateGrad
+        grads = tuple(flat[o: o + n].view(shape) for (_, o, n, shape) in plan.params)   # may keep the tensor it is handed)
         return (None, None, None, None) + grads
 
 
@@ -272,7 +276,9 @@ class _ForwardCRN(torch.autograd.Function):
         _lib.check(_lib.load().sefd_crn_backward_spec(plan.handle, ptr(engine.flat), ptr(g_wav), ptr(g_est),
                                                       ptr(engine.flat_grad), ptr(plan.ws), plan.ws_bytes, stream()),
                    "crn_backward_spec")
-        grads = tuple(engine.flat_grad[o: o + n].view(shape) for (_, o, n, shape) in plan.params)
+        engine.backwards_since_step += 1
+        flat = engine.flat_grad.clone()     # p.grad must never alias the buffer the next backward overwrites (AccumulateGrad
+        grads = tuple(flat[o: o + n].view(shape) for (_, o, n, shape) in plan.params)   # may keep the tensor it is handed)
         return (None, None, None, None) + grads
 
 
@@ -287,8 +293,9 @@ class Engine:
         self.skip = skip
         self.plans = {}
         self.flat = self.flat_grad = self.flat_buf = None
-        self._layout = Plan(1, 100, mode, family, skip)  # layout is independent of (B, L)
+        self._layout = Plan(1, 1 if family == "fsn" else 100, mode, family, skip)  # layout is independent of (B, L)
         self.param_list = None
+        self.backwards_since_step = 0       # autograd backwards that wrote flat_grad since the last FlatAdam.step()
 
     def plan(self, B, L):
         key = (B, L)

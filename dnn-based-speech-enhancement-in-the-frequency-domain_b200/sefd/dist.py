@@ -28,3 +28,14 @@ def allreduce_sum_(flat, group=None):
     if w > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     return 1.0 / w
+
+
+def broadcast_from_rank0_(engine, group=None):
+    """DDP's constructor-time broadcast: every rank takes rank 0's parameters and BatchNorm buffers (the reference never
+    seeds the RNG, so without this each replica would start from its own random init and never agree)."""
+    if world_size(group) <= 1:
+        return
+    engine.sync()
+    dist.broadcast(engine.flat, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    if engine.flat_buf is not None and engine.flat_buf.numel():
+        dist.broadcast(engine.flat_buf, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)

@@ -5,8 +5,10 @@ DataLoader(batch_size, shuffle=True, drop_last=True, pin_memory=True)) with a fe
 flight: indices -> pinned staging buffer -> asynchronous H2D copy on a side stream, double-buffered, so the copy of
 batch i+1 overlaps the train step of batch i.  Utterances are sharded over ranks exactly like
 torch.utils.data.DistributedSampler (same permutation for a given seed / epoch, wrap-around padding, rank-strided).
-Yields (inputs [B, L], targets [B, L]) float32 CUDA tensors, like the reference loop expects after `.to(DEVICE)`;
-they are views of a double buffer, valid until the iteration after the next one starts (consume them in the loop).
+Yields (inputs [B, L], targets [B, L]) CONTIGUOUS float32 CUDA tensors (separate device buffers: the kernels index rows
+with stride L), like the reference loop expects after `.to(DEVICE)`; they are views of a ring of three slots, valid until
+the iteration after the next one starts (consume them in the loop).  Three slots, so that the host gather of batch i+1
+never has to wait for the consumer of the slot it overwrites (batch i-2) while step i is still to be enqueued.
 """
 import math
 
@@ -30,6 +32,8 @@ def shard_indices(n, epoch=0, seed=0, shuffle=True, rank=0, world=1):
 
 
 class WaveFeeder:
+    SLOTS = 3
+
     def __init__(self, data, batch, device="cuda", shuffle=True, drop_last=True, seed=0, rank=None, world=None):
         if isinstance(data, str):
             data = np.load(data)                                    # dataloader.py:42
@@ -45,11 +49,12 @@ class WaveFeeder:
         if self.device.type != "cuda":
             raise RuntimeError("WaveFeeder stages batches for a CUDA device (no CPU path)")
         L = data.shape[2]
-        self._pinned = [torch.empty(self.batch, 2, L, dtype=torch.float32).pin_memory() for _ in range(2)]
-        self._dev = [torch.empty(self.batch, 2, L, dtype=torch.float32, device=self.device) for _ in range(2)]
+        self._pinned = [torch.empty(self.batch, 2, L, dtype=torch.float32).pin_memory() for _ in range(self.SLOTS)]
+        self._dev = [(torch.empty(self.batch, L, dtype=torch.float32, device=self.device),
+                      torch.empty(self.batch, L, dtype=torch.float32, device=self.device)) for _ in range(self.SLOTS)]
         self._stream = torch.cuda.Stream(device=self.device)
-        self._ready = [torch.cuda.Event() for _ in range(2)]      # copy into slot finished
-        self._free = [torch.cuda.Event() for _ in range(2)]       # consumer finished with slot
+        self._ready = [torch.cuda.Event() for _ in range(self.SLOTS)]      # copy into slot finished
+        self._free = [torch.cuda.Event() for _ in range(self.SLOTS)]       # consumer finished with slot
 
     def set_epoch(self, epoch):
         self.epoch = int(epoch)
@@ -68,7 +73,8 @@ class WaveFeeder:
         buf = self._pinned[slot]
         np.take(self.data, ids, axis=0, out=buf.numpy()[:n])       # gather straight into pinned memory
         with torch.cuda.stream(self._stream):
-            self._dev[slot][:n].copy_(buf[:n], non_blocking=True)
+            self._dev[slot][0][:n].copy_(buf[:n, 0], non_blocking=True)
+            self._dev[slot][1][:n].copy_(buf[:n, 1], non_blocking=True)
             self._ready[slot].record(self._stream)
         return n
 
@@ -81,10 +87,10 @@ class WaveFeeder:
             e.record(cur)
         n_next = self._stage(0, batches[0])
         for i in range(len(batches)):
-            slot, n = i & 1, n_next
+            slot, n = i % self.SLOTS, n_next
             if i + 1 < len(batches):
-                n_next = self._stage(slot ^ 1, batches[i + 1])     # in flight while batch i is consumed
+                n_next = self._stage((i + 1) % self.SLOTS, batches[i + 1])     # in flight while batch i is consumed
             cur.wait_event(self._ready[slot])
-            d = self._dev[slot]
-            yield d[:n, 0], d[:n, 1]
+            noisy, clean = self._dev[slot]
+            yield noisy[:n], clean[:n]
             self._free[slot].record(cur)

@@ -18,8 +18,8 @@ def _req(*ts):
             continue
         if not t.is_cuda:
             raise RuntimeError("sefd: tensors must live on a CUDA device (no CPU fallback on this path)")
-        if t.dtype != torch.float32 and t.dtype != torch.float64:
-            raise RuntimeError(f"sefd: expected float32 tensor, got {t.dtype}")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"sefd: expected float32 tensor, got {t.dtype} (the kernels read float*; cast with .float())")
         if not t.is_contiguous():
             raise RuntimeError("sefd: tensors must be contiguous")
 
@@ -28,8 +28,9 @@ def ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
-def stream():
-    return torch.cuda.current_stream().cuda_stream
+def stream(t=None):
+    """Current stream of the tensor's device (of the current device when no tensor is given)."""
+    return torch.cuda.current_stream(t.device if t is not None else None).cuda_stream
 
 
 def frames(L):

@@ -34,6 +34,7 @@ class TrainStep:
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
         self._bufs = {}
+        _dist.broadcast_from_rank0_(self.engine, self.pg)                 # every replica starts from rank 0's weights
 
     def _scratch(self, B, L, dev):
         key = (B, L)
@@ -48,7 +49,10 @@ class TrainStep:
         lib = _lib.load()
         eng = self.engine
         eng.sync()
-        B, L = noisy.shape
+        if noisy.dim() != 2 or noisy.shape != clean.shape:
+            raise ValueError(f"TrainStep: expected noisy, clean of one shape [B, L], got {tuple(noisy.shape)} / {tuple(clean.shape)}")
+        _ops._req(noisy, clean)       # CUDA, float32, contiguous: the kernels index rows with stride L (a strided view of a
+        B, L = noisy.shape            # [B, 2, L] batch would silently pair the wrong rows)
         plan = eng.plan(B, L)
         ws = plan.workspace(noisy.device)
         s = self._scratch(B, L, noisy.device)
@@ -112,13 +116,22 @@ class FlatAdam:
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
+        _dist.broadcast_from_rank0_(self.engine, process_group)            # like DDP: replicas start from rank 0's weights
+        self.engine.backwards_since_step = 0
 
     def zero_grad(self, set_to_none=True):
+        if not set_to_none:
+            raise RuntimeError("FlatAdam reads the model's flat gradient buffer, which holds the LAST backward only: "
+                               "zero_grad(set_to_none=False) / gradient accumulation is not supported")
         for p in self.model.parameters():
             p.grad = None
 
     def step(self):
         eng = self.engine
+        if eng.backwards_since_step != 1:
+            raise RuntimeError(f"FlatAdam.step(): {eng.backwards_since_step} backward passes since the last step; the flat "
+                               "gradient buffer holds exactly one (no accumulation, trainer.py:35-37 runs one per step)")
+        eng.backwards_since_step = 0
         if eng.flat.data_ptr() != self.exp_avg.data_ptr() and eng.flat.numel() != self.exp_avg.numel():
             raise RuntimeError("FlatAdam: the model's parameter layout changed")
         gscale = _dist.allreduce_sum_(eng.flat_grad, self.pg)

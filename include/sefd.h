@@ -189,6 +189,29 @@ int sefd_crn_backward(const sefd_plan* plan, const float* params, const float* d
 int sefd_crn_backward_spec(const sefd_plan* plan, const float* params, const float* d_wav, const float* d_est_mags,
                            float* grads, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- model level: FullSubNet.forward / autograd backward (models.py:568-682; SequenceModel tools_for_model.py:726-795,
+ * BaseModel.unfold :806-837, offline_laplace_norm :997-1011).  Same opaque plan type (workspace_bytes, param_floats,
+ * num_params, entry_info, tensor_info, plan_destroy serve it); state_dict keys are the reference's
+ * (fb_model.sequence_model.weight_ih_l0, ..., sb_model.fc_output_layer.bias).  Configuration of config.py:71-80:
+ * 15 sub-band neighbours, 0 full-band neighbours, look-ahead 2, LSTM 257 -> 512 -> 512 -> Linear 257 + ReLU (full band),
+ * LSTM 32 -> 384 -> 384 -> Linear 2 (sub band), offline_laplace_norm.
+ *   noisy_mag [B][257][frames] (tools.mag_phase of tools.stft, or sefd_fsn_features) -> crm [B][257][frames][2].
+ * nn.LSTM(dropout = 0.8) between the stacked layers (tools_for_model.py:746) is active when train != 0 and dropout_p > 0:
+ * mask_fb [T][B][512] / mask_sb [T][B*257][384] (T = frames + 2) are optional injected multipliers (0 or 1 / (1 - p));
+ * when NULL the masks come from Philox4x32-10 keyed by `seed` (the backward regenerates them; injected masks must stay
+ * alive until the backward has run). */
+sefd_plan* sefd_fsn_plan_create(int B, int frames);
+int sefd_fsn_forward(const sefd_plan* plan, const float* params, const float* noisy_mag, int train, float dropout_p,
+                     const float* mask_fb, const float* mask_sb, unsigned long long seed, float* crm, void* ws, size_t ws_bytes,
+                     void* stream);
+/* the inter-layer dropout op by itself: y = x * m, m = mask[i] when mask != NULL, else 0 or 1 / (1 - p) from
+ * Philox4x32-10(counter = (i / 4, stream_id), key = seed); n must be a multiple of 4; x == y is allowed */
+int sefd_dropout_forward(const float* x, float* y, long long n, float p, const float* mask, unsigned long long seed,
+                         unsigned int stream_id, void* stream);
+/* d_crm [B][257][frames][2] -> grads (flat, same layout as params; every entry is overwritten) */
+int sefd_fsn_backward(const sefd_plan* plan, const float* params, const float* d_crm, float* grads, void* ws, size_t ws_bytes,
+                      void* stream);
+
 /* ---- measurement support (bench.py): CUDA-event timing per kernel category on the launching stream.
  * categories: 0 tap-GEMM (conv/convT/linear fwd + dgrad), 1 weight gradients, 2 BN+PReLU passes,
  * 3 LSTM recurrence, 4 STFT/ISTFT/loss, 5 packing/reductions/Adam, 6 CUDA-core kernels of the 2-channel layers

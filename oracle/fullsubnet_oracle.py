@@ -16,7 +16,8 @@ fixed inter-layer mask to restate the train-mode arithmetic (inverted dropout, s
 
 Parity status: PINNED.  tests/golden/make_golden.py (mode `fullsubnet`) imports the unmodified reference FullSubNet in the
 build container and stores inputs / cIRM / cRM / loss / gradients under tests/golden/fullsubnet_golden.npz;
-tests/test_fullsubnet_oracle.py checks this module against them.  The CUDA path for this row is NOT built yet.
+tests/test_fullsubnet_oracle.py checks this module against them; tests/test_fullsubnet_gpu.py checks the CUDA path
+(csrc/fsnet.cu, lstm_seq.cu, lstm_step_tc.cu) against this module and the same fixtures.
 
 Only tests/, __graft_entry__.smoke() and bench.py may import this module; the product never does.
 """
@@ -154,20 +155,22 @@ def sequence_model(sd, prefix: str, x: torch.Tensor, activation: Optional[str], 
     return o.permute(0, 2, 1)
 
 
-def fullsubnet_forward(sd, noisy_mag: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
-    """FullSubNet.forward (models.py:626-672), dropout inactive: noisy_mag [B, 257, T] -> cRM [B, 257, T, 2]."""
+def fullsubnet_forward(sd, noisy_mag: torch.Tensor, taps: Optional[dict] = None, dropout_masks=None) -> torch.Tensor:
+    """FullSubNet.forward (models.py:626-672): noisy_mag [B, 257, T] -> cRM [B, 257, T, 2].  Dropout inactive unless
+    `dropout_masks` = (fb [B, T+2, 512], sb [B*257, T+2, 384]) multipliers (0 or 1 / (1 - p)) are injected."""
+    mfb, msb = dropout_masks if dropout_masks is not None else (None, None)
     x = noisy_mag[:, None] if noisy_mag.dim() == 3 else noisy_mag
     x = F.pad(x, [0, LOOK_AHEAD])
     B, C, Fq, T = x.shape
     fb_in = offline_laplace_norm(x).reshape(B, C * Fq, T)
-    fb_out = sequence_model(sd, "fb_model", fb_in, "ReLU").reshape(B, 1, Fq, T)
+    fb_out = sequence_model(sd, "fb_model", fb_in, "ReLU", mfb).reshape(B, 1, Fq, T)
     fb_unf = unfold(fb_out, FB_NEIGHBORS).reshape(B, Fq, FB_NEIGHBORS * 2 + 1, T)
     nm_unf = unfold(x, SB_NEIGHBORS).reshape(B, Fq, SB_NEIGHBORS * 2 + 1, T)
     sb_in = offline_laplace_norm(torch.cat([nm_unf, fb_unf], dim=2))
     if taps is not None:
         taps["fb_out"], taps["sb_in"] = fb_out.detach(), sb_in.detach()
     sb_in = sb_in.reshape(B * Fq, (SB_NEIGHBORS * 2 + 1) + (FB_NEIGHBORS * 2 + 1), T)
-    sb_mask = sequence_model(sd, "sb_model", sb_in, None)
+    sb_mask = sequence_model(sd, "sb_model", sb_in, None, msb)
     sb_mask = sb_mask.reshape(B, Fq, 2, T).permute(0, 2, 1, 3)
     return sb_mask[:, :, :, LOOK_AHEAD:].permute(0, 2, 3, 1)
 

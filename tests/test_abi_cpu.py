@@ -72,8 +72,12 @@ def test_dropin_refuses_cpu_and_unbuilt_configs():
         crn(torch.zeros(1, 4000))
     with pytest.raises(NotImplementedError):
         models.CRN(masking_mode="Direct(None make)")
-    with pytest.raises(NotImplementedError):
-        models.FullSubNet()
+    fsn = models.FullSubNet()                  # built: CUDA only as well
+    with pytest.raises(RuntimeError, match="CUDA"):
+        fsn(torch.zeros(1, 257, 5))
+    plan = D.Plan(2, 11, None, family="fsn")
+    assert [n for n, _, _, _ in plan.params] == [k for k, _ in fsn.named_parameters()]
+    assert sum(n for _, _, n, _ in plan.params) == 5637635
 
 
 def test_crn_dropin_layout_and_init_match_reference():

@@ -1,5 +1,6 @@
 """FullSubNet: the oracle restatement against fixtures of the unmodified reference
-(tests/golden/make_golden.py fullsubnet).  The CUDA path of this row is not built yet; the drop-in raises."""
+(tests/golden/make_golden.py fullsubnet), and the feature / target kernels.  The model's CUDA path is checked in
+tests/test_fullsubnet_gpu.py."""
 import os
 
 import numpy as np
@@ -70,10 +71,21 @@ def test_forward_loss_and_gradients(fs_golden):
         np.testing.assert_allclose(g.numpy(), r, atol=2e-3 * max(float(np.abs(r).max()), 1e-8), err_msg=k)
 
 
-def test_dropin_still_raises_for_fullsubnet():
+def test_dropin_layout_matches_reference_and_refuses_cpu(fs_golden):
+    """The drop-in constructs with the reference's state_dict keys / shapes / initial values for a torch seed (it consumes
+    the RNG like nn.LSTM + nn.Linear do) and refuses to run without CUDA (no CPU fallback)."""
     import models
+    torch.manual_seed(0)
+    m = models.FullSubNet()
+    sd = m.state_dict()
+    ref = FS.init_state(0)
+    assert list(sd.keys()) == list(ref.keys())
+    for k in ref:
+        assert sd[k].shape == ref[k].shape and torch.equal(sd[k], ref[k]), k
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 257, 5))
     with pytest.raises(NotImplementedError):
-        models.FullSubNet()
+        models.FullSubNet(sb_model_hidden_size=256)
 
 
 @pytest.mark.gpu
