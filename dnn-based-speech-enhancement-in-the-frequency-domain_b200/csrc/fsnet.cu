@@ -26,7 +26,7 @@ constexpr float NORM_EPS = 1e-5f;
 struct FsnLayer {
     int I_real, I, H;
     long long w_ih, w_hh, b_ih, b_hh;                    // parameter offsets
-    size_t Wih_nk, Wih_kn, Whh_nk, Whh_kn, bias;         // packed operands (workspace, floats)
+    size_t Wih_nk, Wih_kn, Whh_nk, Whh_kn, bias, Wcat;   // packed operands (workspace, floats); Whh_kn follows Wih_kn directly
     size_t gates, h, c;                                  // [T][rows][4H'], [T][rows][H] x2
 };
 struct FsnStack {
@@ -59,6 +59,7 @@ namespace {
 SeqLstmWeights weights_of(const FsnLayer& L, const float* ws) {
     SeqLstmWeights w;
     w.Wih_nk = ws + L.Wih_nk; w.Wih_kn = ws + L.Wih_kn; w.Whh_nk = ws + L.Whh_nk; w.Whh_kn = ws + L.Whh_kn; w.bias = ws + L.bias;
+    w.Wcat_nk = ws + L.Wcat;
     w.I = L.I; w.H = L.H;
     return w;
 }
@@ -393,6 +394,7 @@ int pack_stack(const FsnStack& S, const float* prm, float* ws, int tf, cudaStrea
         p.w_ih = prm + L.w_ih; p.w_hh = prm + L.w_hh; p.b_ih = prm + L.b_ih; p.b_hh = prm + L.b_hh;
         p.I_real = L.I_real; p.I = L.I; p.H = L.H;
         p.Wih_nk = ws + L.Wih_nk; p.Wih_kn = ws + L.Wih_kn; p.Whh_nk = ws + L.Whh_nk; p.Whh_kn = ws + L.Whh_kn; p.bias = ws + L.bias;
+        p.Wcat_nk = ws + L.Wcat;
         p.round_tf32 = tf;
         SEFD_TRY(sefd_seqlstm_pack(p, st));
     }
@@ -407,7 +409,8 @@ int stack_forward(const FsnExt& E, const FsnStack& S, float* ws, const float* x,
         p.x = l == 0 ? x : (E.drop_on ? ws + S.h0d : ws + S.l[0].h);
         p.w = weights_of(L, ws);
         p.gates = ws + L.gates; p.h = ws + L.h; p.c = ws + L.c;
-        p.rows = S.rows; p.T = T; p.round_h = tf;
+        p.rows = S.rows; p.T = T; p.round_h = tf; p.h_zero_slot = 1;
+        cudaMemsetAsync(ws + L.h - (size_t)S.rows * L.H, 0, sizeof(float) * S.rows * L.H, st);     // h_{-1} = 0
         SEFD_TRY(sefd_seqlstm_forward(p, st));
         if (l == 0 && E.drop_on)
             SEFD_TRY(sefd_dropout_apply(ws + L.h, ws + S.h0d, (long long)T * S.rows * L.H, E.drop_p, mask, E.seed, stream_id, tf, st));
@@ -420,7 +423,6 @@ int stack_forward(const FsnExt& E, const FsnStack& S, float* ws, const float* x,
 int stack_backward(const FsnExt& E, const FsnStack& S, float* ws, const float* x, int T, int tf, const float* mask, unsigned int stream_id,
                    float* dx0, float* grads, cudaStream_t st) {
     const int rows = S.rows;
-    const int nblk = sefd_seqlstm_bias_blocks(rows);
     for (int l = 1; l >= 0; --l) {
         const FsnLayer& L = S.l[l];
         const int N = 4 * L.H;
@@ -429,6 +431,8 @@ int stack_backward(const FsnExt& E, const FsnStack& S, float* ws, const float* x
         p.gates = ws + L.gates; p.c = ws + L.c; p.dh_out = ws + S.dh[l];
         p.dh_rec = ws + E.dh_rec; p.dc = ws + E.dc; p.bias_part = ws + E.bias_part;
         p.rows = rows; p.T = T; p.round_tf32 = tf;
+        p.dx = l == 1 ? ws + S.dh[0] : dx0;
+        p.dx_done = 0;
         SEFD_TRY(sefd_seqlstm_backward(p, st));
         const float* dG = ws + L.gates;
         const float* xin = l == 0 ? x : (E.drop_on ? ws + S.h0d : ws + S.l[0].h);
@@ -443,10 +447,10 @@ int stack_backward(const FsnExt& E, const FsnStack& S, float* ws, const float* x
         } else {
             cudaMemsetAsync(grads + L.w_hh, 0, sizeof(float) * N * L.H, st);
         }
-        SEFD_TRY(sefd_seqlstm_fold_bias(ws + E.bias_part, nblk, L.H, grads + L.b_ih, grads + L.b_hh, st));
+        SEFD_TRY(sefd_seqlstm_fold_bias(ws + E.bias_part, p.bias_blocks, L.H, grads + L.b_ih, grads + L.b_hh, st));
         float* dx = l == 1 ? ws + S.dh[0] : dx0;
         if (dx) {
-            SEFD_TRY(gemm_all_steps(dG, N, dx, L.I, rows, T, L.Wih_nk + ws, L.Wih_kn + ws, nullptr, 0, st));
+            if (!p.dx_done) SEFD_TRY(gemm_all_steps(dG, N, dx, L.I, rows, T, L.Wih_nk + ws, L.Wih_kn + ws, nullptr, 0, st));
             if (l == 1 && E.drop_on)
                 SEFD_TRY(sefd_dropout_apply(dx, dx, (long long)T * rows * L.I, E.drop_p, mask, E.seed, stream_id, 0, st));
         }
@@ -476,11 +480,14 @@ void carve_stack(FsnStack& S, Carver& w, int rows, int T) {
     for (int l = 0; l < 2; ++l) {
         FsnLayer& L = S.l[l];
         const size_t N = 4 * (size_t)L.H;
-        L.Wih_nk = w.floats(N * L.I); L.Wih_kn = w.floats(N * L.I);
-        L.Whh_nk = w.floats(N * L.H); L.Whh_kn = w.floats(N * L.H);
+        L.Wih_nk = w.floats(N * L.I);
+        L.Whh_nk = w.floats(N * L.H);
+        L.Whh_kn = w.floats(N * (L.I + L.H));        // [H][4H'] immediately followed by [I][4H'] = the backward's [W_hh^T ; W_ih^T]
+        L.Wih_kn = L.Whh_kn + N * L.H;
+        L.Wcat = w.floats(N * (L.I + L.H));
         L.bias = w.floats(N);
         L.gates = w.floats((size_t)T * rows * N);
-        L.h = w.floats((size_t)T * rows * L.H);
+        L.h = w.floats((size_t)(T + 1) * rows * L.H) + (size_t)rows * L.H;     // one zero step in front (h_{-1})
         L.c = w.floats((size_t)T * rows * L.H);
         S.dh[l] = w.floats((size_t)T * rows * L.H);
     }

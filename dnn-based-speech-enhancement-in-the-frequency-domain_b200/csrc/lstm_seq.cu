@@ -35,6 +35,7 @@ __global__ void pack_kernel(const SeqLstmPackParams p) {
             const int np = interleave(n, p.H);
             p.Wih_nk[(long long)np * p.I + k] = v;
             p.Wih_kn[(long long)k * N + np] = v;
+            if (p.Wcat_nk) p.Wcat_nk[(long long)np * (p.I + p.H) + k] = v;
         } else if (e < nih + nhh) {
             const long long r = e - nih;
             const int n = (int)(r / p.H), k = (int)(r % p.H);
@@ -43,6 +44,7 @@ __global__ void pack_kernel(const SeqLstmPackParams p) {
             const int np = interleave(n, p.H);
             p.Whh_nk[(long long)np * p.H + k] = v;
             p.Whh_kn[(long long)k * N + np] = v;
+            if (p.Wcat_nk) p.Wcat_nk[(long long)np * (p.I + p.H) + p.I + k] = v;
         } else {
             const int n = (int)(e - nih - nhh);
             p.bias[interleave(n, p.H)] = p.b_ih[n] + p.b_hh[n];
@@ -276,16 +278,14 @@ int sefd_seqlstm_fold_bias(const float* part, int nblk, int H, float* db_ih, flo
     return sefd_check_launch("seqlstm_fold_bias");
 }
 
-int sefd_seqlstm_bias_blocks(int rows) {
-    const int a = (rows + RB - 1) / RB, b = sefd_lstm_step_bias_blocks(rows);
-    return a > b ? a : b;
-}
+int sefd_seqlstm_bias_blocks(int rows) { return (rows + RB - 1) / RB + sefd_lstm_step_bias_blocks(rows); }
 
 int sefd_seqlstm_forward(const SeqLstmFwdParams& p, cudaStream_t st) {
     const int H = p.w.H, N = 4 * H, I = p.w.I;
     SEFD_REQUIRE(H % 64 == 0 && H <= 512 && p.rows > 0 && p.T > 0, "seqlstm_forward: H=%d rows=%d T=%d unsupported", H, p.rows, p.T);
     const bool tc = sefd_get_engine_internal() == 1;
-    if (tc && sefd_seqlstm_fused_enabled() && sefd_lstm_step_tc_eligible(I, H)) return sefd_lstm_step_tc_forward(p, st);
+    if (tc && sefd_seqlstm_fused_enabled() && p.w.Wcat_nk && p.h_zero_slot && sefd_lstm_step_tc_eligible(I, H))
+        return sefd_lstm_step_tc_forward(p, st);
     // ---- generic path: input projections of all steps as ONE GEMM, then per step [recurrent GEMM (+=) ; cell kernel] ----
     {
         TapGemmParams g = step_gemm(p.x, I, p.gates, N, p.rows, p.w.Wih_kn, p.w.Wih_nk, 0, 0);
@@ -313,11 +313,8 @@ int sefd_seqlstm_forward(const SeqLstmFwdParams& p, cudaStream_t st) {
     return 0;
 }
 
-int sefd_seqlstm_backward(const SeqLstmBwdParams& p, cudaStream_t st) {
+int sefd_seqlstm_cell_bwd_step(SeqLstmBwdParams& p, int t, int* nblk_out, cudaStream_t st) {
     const int H = p.w.H, N = 4 * H;
-    SEFD_REQUIRE(H % 64 == 0 && H <= 512 && p.rows > 0 && p.T > 0, "seqlstm_backward: H=%d rows=%d T=%d unsupported", H, p.rows, p.T);
-    const bool tc = sefd_get_engine_internal() == 1;
-    if (tc && sefd_seqlstm_fused_enabled() && sefd_lstm_step_tc_eligible(p.w.I, H)) return sefd_lstm_step_tc_backward(p, st);
     const int nblk = (p.rows + RB - 1) / RB, nthr = cell_threads(H);
     const size_t smem = sizeof(float) * (nthr / (H / 4)) * N;
     static bool attr = false;
@@ -325,24 +322,34 @@ int sefd_seqlstm_backward(const SeqLstmBwdParams& p, cudaStream_t st) {
         cudaFuncSetAttribute(cell_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         attr = true;
     }
+    CellBwd c;
+    c.gates = p.gates + (long long)t * p.rows * N;
+    c.c = p.c + (long long)t * p.rows * H;
+    c.c_prev = t > 0 ? p.c + (long long)(t - 1) * p.rows * H : nullptr;
+    c.dh_out = p.dh_out + (long long)t * p.rows * H;
+    c.dh_rec = t == p.T - 1 ? nullptr : p.dh_rec;
+    c.dc = p.dc;
+    c.bias_part = p.bias_part;
+    c.rows = p.rows; c.H = H; c.first = t == p.T - 1; c.round_tf32 = p.round_tf32;
+    SefdProfScope prof(SEFD_PROF_LSTM, 0, 4.0 * p.rows * (2.0 * N + 5.0 * H), st);
+    cell_bwd_kernel<<<nblk, nthr, smem, st>>>(c);
+    if (nblk_out) *nblk_out = nblk;
+    return sefd_check_launch("seqlstm_cell_bwd");
+}
+
+int sefd_seqlstm_backward(const SeqLstmBwdParams& p0, cudaStream_t st) {
+    SeqLstmBwdParams& p = const_cast<SeqLstmBwdParams&>(p0);
+    p.dx_done = 0;
+    const int H = p.w.H, N = 4 * H;
+    SEFD_REQUIRE(H % 64 == 0 && H <= 512 && p.rows > 0 && p.T > 0, "seqlstm_backward: H=%d rows=%d T=%d unsupported", H, p.rows, p.T);
+    const bool tc = sefd_get_engine_internal() == 1;
+    if (tc && sefd_seqlstm_fused_enabled() && sefd_lstm_step_tc_has_backward() && p.w.Wih_kn == p.w.Whh_kn + (long long)H * N &&
+        sefd_lstm_step_tc_eligible(p.w.I, H))
+        return sefd_lstm_step_tc_backward(p, st);
     for (int t = p.T - 1; t >= 0; --t) {
-        float* gt = p.gates + (long long)t * p.rows * N;
-        CellBwd c;
-        c.gates = gt;
-        c.c = p.c + (long long)t * p.rows * H;
-        c.c_prev = t > 0 ? p.c + (long long)(t - 1) * p.rows * H : nullptr;
-        c.dh_out = p.dh_out + (long long)t * p.rows * H;
-        c.dh_rec = t == p.T - 1 ? nullptr : p.dh_rec;
-        c.dc = p.dc;
-        c.bias_part = p.bias_part;
-        c.rows = p.rows; c.H = H; c.first = t == p.T - 1; c.round_tf32 = p.round_tf32;
-        {
-            SefdProfScope prof(SEFD_PROF_LSTM, 0, 4.0 * p.rows * (2.0 * N + 5.0 * H), st);
-            cell_bwd_kernel<<<nblk, nthr, smem, st>>>(c);
-            SEFD_TRY(sefd_check_launch("seqlstm_cell_bwd"));
-        }
+        SEFD_TRY(sefd_seqlstm_cell_bwd_step(p, t, &p.bias_blocks, st));
         if (t > 0) {   // dh_rec = dG_t W_hh  (contraction over the 4H' gate columns)
-            TapGemmParams g = step_gemm(gt, N, p.dh_rec, H, p.rows, p.w.Whh_nk, p.w.Whh_kn, 0, 0);
+            TapGemmParams g = step_gemm(p.gates + (long long)t * p.rows * N, N, p.dh_rec, H, p.rows, p.w.Whh_nk, p.w.Whh_kn, 0, 0);
             SEFD_TRY(sefd_tapgemm(g, st));
         }
     }

@@ -16,6 +16,8 @@ struct SeqLstmWeights {
     const float* Whh_nk;   // [4H'][H]
     const float* Whh_kn;   // [H][4H']
     const float* bias;     // [4H'] = b_ih + b_hh
+    const float* Wcat_nk;  // [4H'][I + H] = [W_ih | W_hh] rows (operand of the fused forward step kernel) or null
+    // the fused backward step kernel reads [W_hh^T ; W_ih^T] = [(H + I)][4H']: Wih_kn must FOLLOW Whh_kn directly in memory
     int I, H;              // I = input width as stored (padded to a multiple of 32)
 };
 
@@ -23,6 +25,7 @@ struct SeqLstmPackParams {
     const float *w_ih, *w_hh, *b_ih, *b_hh;   // reference layouts: [4H][I_real], [4H][H], [4H], [4H]
     int I_real, I, H;
     float *Wih_nk, *Wih_kn, *Whh_nk, *Whh_kn, *bias;
+    float* Wcat_nk;        // optional
     int round_tf32;
 };
 int sefd_seqlstm_pack(const SeqLstmPackParams& p, cudaStream_t st);
@@ -41,6 +44,7 @@ struct SeqLstmFwdParams {
     float* c;              // [T][rows][H]
     int rows, T;
     int round_h;           // h feeds tensor-core GEMMs: round to tf32 while writing
+    int h_zero_slot;       // h is preceded by one all-zero step ([-1] = h_{-1} = 0): the fused kernel reads h_{t-1} uniformly
 };
 int sefd_seqlstm_forward(const SeqLstmFwdParams& p, cudaStream_t st);
 
@@ -52,10 +56,15 @@ struct SeqLstmBwdParams {
     float* dh_rec;         // [rows][H] scratch: recurrent gradient
     float* dc;             // [rows][H] scratch: cell-state gradient carried backwards
     float* bias_part;      // [sefd_seqlstm_bias_blocks(rows)][4H'] per-block column sums of dG over all steps
+    int bias_blocks;       // out: how many of those slots the path that ran has written (sefd_seqlstm_fold_bias sums them)
+    float* dx;             // optional [T][rows][I]: gradient w.r.t. the layer input; when the fused kernel runs it is
+    int dx_done;           // written by the step epilogue and dx_done is set (else the caller computes it from dG)
     int rows, T;
     int round_tf32;        // dG feeds tensor-core GEMMs
 };
 int sefd_seqlstm_bias_blocks(int rows);
+// the generic cell backward of ONE step (t = T - 1: no recurrent gradient, initialises dc and the bias slots); *nblk = slots used
+int sefd_seqlstm_cell_bwd_step(SeqLstmBwdParams& p, int t, int* nblk, cudaStream_t st);
 int sefd_seqlstm_backward(const SeqLstmBwdParams& p, cudaStream_t st);
 
 // nn.LSTM(dropout = p) between stacked layers (tools_for_model.py:746): dst = src * m, m = 0 or 1 / (1 - p).

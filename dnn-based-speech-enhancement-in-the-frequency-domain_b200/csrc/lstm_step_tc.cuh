@@ -7,5 +7,6 @@
 
 bool sefd_lstm_step_tc_eligible(int I, int H);
 int sefd_lstm_step_bias_blocks(int rows);
+bool sefd_lstm_step_tc_has_backward();
 int sefd_lstm_step_tc_forward(const SeqLstmFwdParams& p, cudaStream_t st);
-int sefd_lstm_step_tc_backward(const SeqLstmBwdParams& p, cudaStream_t st);
+int sefd_lstm_step_tc_backward(SeqLstmBwdParams& p, cudaStream_t st);

@@ -140,3 +140,72 @@ class FlatAdam:
                                               ptr(self.exp_avg_sq), eng.flat.numel(), self.lr, self.betas[0],
                                               self.betas[1], self.eps, self.steps, gscale, stream()),
                    "adam_step")
+
+
+class FsnTrainStep:
+    """Autograd-free FullSubNet train step over the C ABI = the body of trainer.fullsubnet_train (trainer.py:97-112) with
+    cfg.loss = 'MSE' and torch.optim.Adam(lr): feature / target kernel (tools.stft x2 + mag_phase +
+    build_complex_ideal_ratio_mask fused) -> FullSubNet forward (train mode: Philox inter-layer dropout, p = 0.8 like
+    tools_for_model.py:746) -> MSE(cIRM, cRM) -> backward -> [all-reduce] -> fused Adam."""
+
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, process_group=None, dropout=None, seed=0):
+        self.model = model
+        self.engine = model._get_engine()
+        self.engine.sync()
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.dropout = model.dropout if dropout is None else float(dropout)
+        self.seed = int(seed)
+        self.exp_avg = torch.zeros_like(self.engine.flat)
+        self.exp_avg_sq = torch.zeros_like(self.engine.flat)
+        self.steps = 0
+        self.pg = process_group
+        self._bufs = {}
+        _dist.broadcast_from_rank0_(self.engine, self.pg)
+
+    def _scratch(self, B, L, dev):
+        key = (B, L)
+        if key not in self._bufs:
+            Tf = _lib.load().sefd_fsn_frames(L)
+            if Tf <= 0:
+                raise ValueError(f"FsnTrainStep: waveforms of {L} samples are too short for the centred STFT")
+            self._bufs[key] = dict(
+                Tf=Tf, mag=torch.empty(B, 257, Tf, device=dev), cirm=torch.empty(B, 257, Tf, 2, device=dev),
+                crm=torch.empty(B, 257, Tf, 2, device=dev), dcrm=torch.empty(B, 257, Tf, 2, device=dev),
+                loss=torch.empty(1, device=dev), coef=torch.empty(2 * B, device=dev),
+                red=torch.empty(8 * B, device=dev, dtype=torch.float64))
+        return self._bufs[key]
+
+    def forward_backward(self, noisy, clean):
+        lib = _lib.load()
+        eng = self.engine
+        eng.sync()
+        if noisy.dim() != 2 or noisy.shape != clean.shape:
+            raise ValueError(f"FsnTrainStep: expected noisy, clean of one shape [B, L], got {tuple(noisy.shape)} / {tuple(clean.shape)}")
+        _ops._req(noisy, clean)
+        B, L = noisy.shape
+        s = self._scratch(B, L, noisy.device)
+        plan = eng.plan(B, s["Tf"])
+        ws = plan.workspace(noisy.device)
+        st = stream()
+        n = 257 * s["Tf"] * 2
+        plan.generation += 1
+        _lib.check(lib.sefd_fsn_features(ptr(noisy), ptr(clean), B, L, ptr(s["mag"]), ptr(s["cirm"]), st), "fsn_features")
+        _lib.check(lib.sefd_fsn_forward(plan.handle, ptr(eng.flat), ptr(s["mag"]), 1, self.dropout, None, None,
+                                        self.seed + self.steps, ptr(s["crm"]), ptr(ws), plan.ws_bytes, st), "fsn_forward")
+        _lib.check(lib.sefd_loss_forward(ptr(s["crm"]), ptr(s["cirm"]), B, n, LOSSES["MSE"], ptr(s["red"]), ptr(s["loss"]),
+                                         ptr(s["coef"]), st), "loss_forward")
+        _lib.check(lib.sefd_loss_backward(ptr(s["crm"]), ptr(s["cirm"]), ptr(s["coef"]), None, ptr(s["dcrm"]), B, n, st),
+                   "loss_backward")
+        _lib.check(lib.sefd_fsn_backward(plan.handle, ptr(eng.flat), ptr(s["dcrm"]), ptr(eng.flat_grad), ptr(ws),
+                                         plan.ws_bytes, st), "fsn_backward")
+        return s["loss"]
+
+    def step(self, noisy, clean):
+        loss = self.forward_backward(noisy, clean)
+        eng = self.engine
+        gscale = _dist.allreduce_sum_(eng.flat_grad, self.pg)
+        self.steps += 1
+        _lib.check(_lib.load().sefd_adam_step(ptr(eng.flat), ptr(eng.flat_grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                                              eng.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.steps,
+                                              gscale, stream()), "adam_step")
+        return loss
