@@ -76,6 +76,9 @@ struct WgradParams {
     int ntaps;
     int a_off[SEFD_MAX_TAPS], g_off[SEFD_MAX_TAPS], dt[SEFD_MAX_TAPS], wslab[SEFD_MAX_TAPS];
     int rows_per_cta;    // (b,j) rows handled by one CTA
+    // g_tiled = 1: G is TILE-MAJOR [Fg][Tg / 128 tiles][C / 32][128][32] (lstm_step_tc.cu: 128-position tiles whose
+    // 32-channel blocks are contiguous 16 KB TMA boxes) instead of channels-last; tensor-core engine only, B = 1
+    int g_tiled;
 };
 
 int sefd_tapgemm_simt(const TapGemmParams& p, cudaStream_t st);

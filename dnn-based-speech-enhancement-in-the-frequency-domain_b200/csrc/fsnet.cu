@@ -13,6 +13,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "fsnet.cuh"
 #include "lstm_seq.cuh"
 #include "plan.cuh"
@@ -27,7 +29,8 @@ struct FsnLayer {
     int I_real, I, H;
     long long w_ih, w_hh, b_ih, b_hh;                    // parameter offsets
     size_t Wih_nk, Wih_kn, Whh_nk, Whh_kn, bias, Wcat;   // packed operands (workspace, floats); Whh_kn follows Wih_kn directly
-    size_t gates, h, c;                                  // [T][rows][4H'], [T][rows][H] x2
+    size_t gates, h, c;                                  // gates / c sized for rows rounded up to 128 (tile-major in the fused path)
+    mutable int tiled = 0;                               // layout the last forward left gates / c in (lstm_seq.cuh)
 };
 struct FsnStack {
     FsnLayer l[2];
@@ -375,12 +378,13 @@ int gemm_all_steps(const float* a, int K, float* out, int N, int rows, int T, co
     return sefd_tapgemm(g, st);
 }
 // partial[s][k][n] = sum over steps j < J and rows of a[j][r][k] g[j][r][n]
-int wgrad_all_steps(const float* a, int K, const float* g, int N, int rows, int J, float* part, long long cap, int* nsplit,
+int wgrad_all_steps(const float* a, int K, const float* g, int N, int rows, int J, int g_tiled, float* part, long long cap, int* nsplit,
                     long long* sstride, cudaStream_t st) {
     WgradParams w;
     memset(&w, 0, sizeof(w));
     w.a[0] = tm_src(a, rows, J, K);
     w.g = tm_src(g, rows, J, N);
+    w.g_tiled = g_tiled;
     w.B = 1; w.J = J; w.Tg = rows; w.Fa = J; w.Ta = rows; w.Fg = J;
     w.a_mul = 1; w.g_mul = 1; w.ntaps = 1;
     w.rows_per_cta = 1;
@@ -412,6 +416,7 @@ int stack_forward(const FsnExt& E, const FsnStack& S, float* ws, const float* x,
         p.rows = S.rows; p.T = T; p.round_h = tf; p.h_zero_slot = 1;
         cudaMemsetAsync(ws + L.h - (size_t)S.rows * L.H, 0, sizeof(float) * S.rows * L.H, st);     // h_{-1} = 0
         SEFD_TRY(sefd_seqlstm_forward(p, st));
+        L.tiled = p.tiled;
         if (l == 0 && E.drop_on)
             SEFD_TRY(sefd_dropout_apply(ws + L.h, ws + S.h0d, (long long)T * S.rows * L.H, E.drop_p, mask, E.seed, stream_id, tf, st));
     }
@@ -433,16 +438,18 @@ int stack_backward(const FsnExt& E, const FsnStack& S, float* ws, const float* x
         p.rows = rows; p.T = T; p.round_tf32 = tf;
         p.dx = l == 1 ? ws + S.dh[0] : dx0;
         p.dx_done = 0;
+        p.tiled = L.tiled;
         SEFD_TRY(sefd_seqlstm_backward(p, st));
+        const long long step_stride = L.tiled ? (long long)((rows + 127) / 128) * 128 * N : (long long)rows * N;
         const float* dG = ws + L.gates;
         const float* xin = l == 0 ? x : (E.drop_on ? ws + S.h0d : ws + S.l[0].h);
         int nsplit = 1;
         long long sstride = 0;
         float* part = ws + E.wpart;
-        SEFD_TRY(wgrad_all_steps(xin, L.I, dG, N, rows, T, part, E.wpart_floats, &nsplit, &sstride, st));
+        SEFD_TRY(wgrad_all_steps(xin, L.I, dG, N, rows, T, L.tiled, part, E.wpart_floats, &nsplit, &sstride, st));
         SEFD_TRY(sefd_seqlstm_fold_wgrad(part, nsplit, sstride, L.I, L.I_real, L.H, grads + L.w_ih, st));
         if (T > 1) {
-            SEFD_TRY(wgrad_all_steps(ws + L.h, L.H, dG + (long long)rows * N, N, rows, T - 1, part, E.wpart_floats, &nsplit, &sstride, st));
+            SEFD_TRY(wgrad_all_steps(ws + L.h, L.H, dG + step_stride, N, rows, T - 1, L.tiled, part, E.wpart_floats, &nsplit, &sstride, st));
             SEFD_TRY(sefd_seqlstm_fold_wgrad(part, nsplit, sstride, L.H, L.H, L.H, grads + L.w_hh, st));
         } else {
             cudaMemsetAsync(grads + L.w_hh, 0, sizeof(float) * N * L.H, st);
@@ -450,7 +457,10 @@ int stack_backward(const FsnExt& E, const FsnStack& S, float* ws, const float* x
         SEFD_TRY(sefd_seqlstm_fold_bias(ws + E.bias_part, p.bias_blocks, L.H, grads + L.b_ih, grads + L.b_hh, st));
         float* dx = l == 1 ? ws + S.dh[0] : dx0;
         if (dx) {
-            if (!p.dx_done) SEFD_TRY(gemm_all_steps(dG, N, dx, L.I, rows, T, L.Wih_nk + ws, L.Wih_kn + ws, nullptr, 0, st));
+            if (!p.dx_done) {
+                SEFD_REQUIRE(!L.tiled, "fsn backward: the input gradient must come from the fused step kernel when dG is tile-major");
+                SEFD_TRY(gemm_all_steps(dG, N, dx, L.I, rows, T, L.Wih_nk + ws, L.Wih_kn + ws, nullptr, 0, st));
+            }
             if (l == 1 && E.drop_on)
                 SEFD_TRY(sefd_dropout_apply(dx, dx, (long long)T * rows * L.I, E.drop_p, mask, E.seed, stream_id, 0, st));
         }
@@ -486,9 +496,10 @@ void carve_stack(FsnStack& S, Carver& w, int rows, int T) {
         L.Wih_kn = L.Whh_kn + N * L.H;
         L.Wcat = w.floats(N * (L.I + L.H));
         L.bias = w.floats(N);
-        L.gates = w.floats((size_t)T * rows * N);
+        const size_t rpad = (size_t)(rows + 127) / 128 * 128;
+        L.gates = w.floats((size_t)T * rpad * N);
         L.h = w.floats((size_t)(T + 1) * rows * L.H) + (size_t)rows * L.H;     // one zero step in front (h_{-1})
-        L.c = w.floats((size_t)T * rows * L.H);
+        L.c = w.floats((size_t)T * rpad * L.H);
         S.dh[l] = w.floats((size_t)T * rows * L.H);
     }
     S.h0d = w.floats((size_t)T * rows * S.l[0].H);
@@ -532,8 +543,9 @@ sefd_plan* sefd_fsn_plan_create_impl(int B, int Tf) {
     E->dsb_in = w.floats((size_t)T * R * SB_I);
     carve_stack(E->fb, w, B, T);
     carve_stack(E->sb, w, R, T);
-    E->dh_rec = w.floats((size_t)R * FB_H);      // >= max(R * 384, B * 512)
-    E->dc = w.floats((size_t)R * FB_H);
+    const size_t state = std::max((size_t)(R + 127) / 128 * 128 * SB_H, (size_t)(B + 127) / 128 * 128 * FB_H);
+    E->dh_rec = w.floats(state);
+    E->dc = w.floats(state);
     const int nblk = sefd_seqlstm_bias_blocks(R);
     E->bias_part = w.floats((size_t)nblk * 4 * FB_H);
     E->wpart_floats = 32ll * 4 * FB_H * FB_H;
@@ -637,7 +649,7 @@ int sefd_fsn_backward_impl(const sefd_plan* P, const float* prm, const float* d_
         int nsplit = 1;
         long long sstride = 0;
         float* part = ws + E.wpart;
-        SEFD_TRY(wgrad_all_steps(ws + E.fb.l[1].h, FB_H, ws + E.dfb_lin, FPAD, B, T, part, E.wpart_floats, &nsplit, &sstride, st));
+        SEFD_TRY(wgrad_all_steps(ws + E.fb.l[1].h, FB_H, ws + E.dfb_lin, FPAD, B, T, 0, part, E.wpart_floats, &nsplit, &sstride, st));
         fold_linear_kernel<<<dim3(FPAD / 32, FB_H / 32), dim3(32, 8), 0, st>>>(part, nsplit, sstride, FB_H, FPAD, FBINS, grads + E.fb.fc_w);
         SEFD_TRY(sefd_check_launch("fsn_fold_linear"));
         SEFD_TRY(sefd_colsum2(ws + E.dfb_lin, 1, 0, (long long)T * B, FPAD, FPAD, wsd + E.red, ws + E.bl, st));   // bl is free after the forward

@@ -16,7 +16,7 @@ constexpr int RB = 32;   // rows per CTA of the cell kernels (one bias-gradient 
 
 __device__ __forceinline__ int interleave(int n, int H) {   // reference column n = gate * H + u -> stored column n'
     const int g = n / H, u = n - g * H;
-    return (u >> 6) * 256 + g * 64 + (u & 63);
+    return (u >> 3) * 32 + g * 8 + (u & 7);
 }
 __device__ __forceinline__ float sigmoid_(float x) { return 1.f / (1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_(float x) {
@@ -68,9 +68,9 @@ __global__ void fold_wgrad_kernel(const float* __restrict__ part, int nsplit, lo
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int np = n0 + r, k = k0 + threadIdx.x;
-        // inverse of the interleave: n' = q * 256 + g * 64 + u6
-        const int q = np >> 8, g = (np >> 6) & 3, u6 = np & 63;
-        const int n = g * H + q * 64 + u6;
+        // inverse of the interleave: n' = ub * 32 + g * 8 + i
+        const int ub = np >> 5, g = (np >> 3) & 3, i8 = np & 7;
+        const int n = g * H + ub * 8 + i8;
         if (k < K_real) dW[(long long)n * K_real + k] = tile[threadIdx.x][r];
     }
 }
@@ -97,12 +97,12 @@ __global__ void cell_fwd_kernel(const CellFwd p) {
     const int H4 = p.H >> 2;
     const int u4 = threadIdx.x % H4, rl = threadIdx.x / H4, rstep = blockDim.x / H4;
     const int u = u4 * 4;
-    const int col = (u >> 6) * 256 + (u & 63);
+    const int col = (u >> 3) * 32 + (u & 7);      // gate g of these 4 units sits at col + 8 g
     const int r1 = min(p.rows, (int)(blockIdx.x + 1) * RB);
     for (int r = blockIdx.x * RB + rl; r < r1; r += rstep) {
         float* g = p.gates + (long long)r * 4 * p.H + col;
-        float4 gi = *reinterpret_cast<float4*>(g), gf = *reinterpret_cast<float4*>(g + 64);
-        float4 gg = *reinterpret_cast<float4*>(g + 128), go = *reinterpret_cast<float4*>(g + 192);
+        float4 gi = *reinterpret_cast<float4*>(g), gf = *reinterpret_cast<float4*>(g + 8);
+        float4 gg = *reinterpret_cast<float4*>(g + 16), go = *reinterpret_cast<float4*>(g + 24);
         float4 cp = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.c_prev) cp = *reinterpret_cast<const float4*>(p.c_prev + (long long)r * p.H + u);
         float4 c, h;
@@ -113,8 +113,8 @@ __global__ void cell_fwd_kernel(const CellFwd p) {
         CELL(x) CELL(y) CELL(z) CELL(w)
 #undef CELL
         if (p.round_h) { h.x = tf32_rn(h.x); h.y = tf32_rn(h.y); h.z = tf32_rn(h.z); h.w = tf32_rn(h.w); }
-        *reinterpret_cast<float4*>(g) = gi; *reinterpret_cast<float4*>(g + 64) = gf;
-        *reinterpret_cast<float4*>(g + 128) = gg; *reinterpret_cast<float4*>(g + 192) = go;
+        *reinterpret_cast<float4*>(g) = gi; *reinterpret_cast<float4*>(g + 8) = gf;
+        *reinterpret_cast<float4*>(g + 16) = gg; *reinterpret_cast<float4*>(g + 24) = go;
         *reinterpret_cast<float4*>(p.c + (long long)r * p.H + u) = c;
         *reinterpret_cast<float4*>(p.h + (long long)r * p.H + u) = h;
     }
@@ -132,13 +132,13 @@ __global__ void cell_bwd_kernel(const CellBwd p) {
     const int H4 = p.H >> 2;
     const int u4 = threadIdx.x % H4, rl = threadIdx.x / H4, rstep = blockDim.x / H4;
     const int u = u4 * 4;
-    const int col = (u >> 6) * 256 + (u & 63);
+    const int col = (u >> 3) * 32 + (u & 7);      // gate g of these 4 units sits at col + 8 g
     const int r1 = min(p.rows, (int)(blockIdx.x + 1) * RB);
     float4 si = make_float4(0.f, 0.f, 0.f, 0.f), sf = si, sg = si, so = si;
     for (int r = blockIdx.x * RB + rl; r < r1; r += rstep) {
         float* g = p.gates + (long long)r * 4 * p.H + col;
-        const float4 gi = *reinterpret_cast<float4*>(g), gf = *reinterpret_cast<float4*>(g + 64);
-        const float4 gg = *reinterpret_cast<float4*>(g + 128), go = *reinterpret_cast<float4*>(g + 192);
+        const float4 gi = *reinterpret_cast<float4*>(g), gf = *reinterpret_cast<float4*>(g + 8);
+        const float4 gg = *reinterpret_cast<float4*>(g + 16), go = *reinterpret_cast<float4*>(g + 24);
         const long long o = (long long)r * p.H + u;
         const float4 ct = *reinterpret_cast<const float4*>(p.c + o);
         float4 cp = make_float4(0.f, 0.f, 0.f, 0.f), dcn = cp;
@@ -171,14 +171,14 @@ __global__ void cell_bwd_kernel(const CellBwd p) {
             RND(di) RND(df) RND(dg) RND(d_o)
 #undef RND
         }
-        *reinterpret_cast<float4*>(g) = di; *reinterpret_cast<float4*>(g + 64) = df;
-        *reinterpret_cast<float4*>(g + 128) = dg; *reinterpret_cast<float4*>(g + 192) = d_o;
+        *reinterpret_cast<float4*>(g) = di; *reinterpret_cast<float4*>(g + 8) = df;
+        *reinterpret_cast<float4*>(g + 16) = dg; *reinterpret_cast<float4*>(g + 24) = d_o;
         *reinterpret_cast<float4*>(p.dc + o) = dcc;
     }
     // column sums of this CTA's rows -> its own slot (fixed order: deterministic, no atomics)
     float* mine = s_red + (long long)rl * 4 * p.H + col;
-    *reinterpret_cast<float4*>(mine) = si; *reinterpret_cast<float4*>(mine + 64) = sf;
-    *reinterpret_cast<float4*>(mine + 128) = sg; *reinterpret_cast<float4*>(mine + 192) = so;
+    *reinterpret_cast<float4*>(mine) = si; *reinterpret_cast<float4*>(mine + 8) = sf;
+    *reinterpret_cast<float4*>(mine + 16) = sg; *reinterpret_cast<float4*>(mine + 24) = so;
     __syncthreads();
     for (int n = threadIdx.x; n < 4 * p.H; n += blockDim.x) {
         float s = 0.f;
@@ -280,12 +280,17 @@ int sefd_seqlstm_fold_bias(const float* part, int nblk, int H, float* db_ih, flo
 
 int sefd_seqlstm_bias_blocks(int rows) { return (rows + RB - 1) / RB + sefd_lstm_step_bias_blocks(rows); }
 
-int sefd_seqlstm_forward(const SeqLstmFwdParams& p, cudaStream_t st) {
+int sefd_seqlstm_forward(const SeqLstmFwdParams& p0, cudaStream_t st) {
+    SeqLstmFwdParams& p = const_cast<SeqLstmFwdParams&>(p0);
+    p.tiled = 0;
     const int H = p.w.H, N = 4 * H, I = p.w.I;
     SEFD_REQUIRE(H % 64 == 0 && H <= 512 && p.rows > 0 && p.T > 0, "seqlstm_forward: H=%d rows=%d T=%d unsupported", H, p.rows, p.T);
     const bool tc = sefd_get_engine_internal() == 1;
-    if (tc && sefd_seqlstm_fused_enabled() && p.w.Wcat_nk && p.h_zero_slot && sefd_lstm_step_tc_eligible(I, H))
+    if (tc && sefd_seqlstm_fused_enabled() && p.w.Wcat_nk && p.h_zero_slot && p.w.Wih_kn == p.w.Whh_kn + (long long)H * N &&
+        sefd_lstm_step_tc_eligible(I, H)) {
+        p.tiled = 1;
         return sefd_lstm_step_tc_forward(p, st);
+    }
     // ---- generic path: input projections of all steps as ONE GEMM, then per step [recurrent GEMM (+=) ; cell kernel] ----
     {
         TapGemmParams g = step_gemm(p.x, I, p.gates, N, p.rows, p.w.Wih_kn, p.w.Wih_nk, 0, 0);
@@ -342,10 +347,11 @@ int sefd_seqlstm_backward(const SeqLstmBwdParams& p0, cudaStream_t st) {
     p.dx_done = 0;
     const int H = p.w.H, N = 4 * H;
     SEFD_REQUIRE(H % 64 == 0 && H <= 512 && p.rows > 0 && p.T > 0, "seqlstm_backward: H=%d rows=%d T=%d unsupported", H, p.rows, p.T);
-    const bool tc = sefd_get_engine_internal() == 1;
-    if (tc && sefd_seqlstm_fused_enabled() && sefd_lstm_step_tc_has_backward() && p.w.Wih_kn == p.w.Whh_kn + (long long)H * N &&
-        sefd_lstm_step_tc_eligible(p.w.I, H))
+    if (p.tiled) {
+        SEFD_REQUIRE(sefd_get_engine_internal() == 1 && p.w.Wih_kn == p.w.Whh_kn + (long long)H * N && sefd_lstm_step_tc_eligible(p.w.I, H),
+                     "seqlstm_backward: the forward ran fused (tile-major state) but the fused backward cannot run");
         return sefd_lstm_step_tc_backward(p, st);
+    }
     for (int t = p.T - 1; t >= 0; --t) {
         SEFD_TRY(sefd_seqlstm_cell_bwd_step(p, t, &p.bias_blocks, st));
         if (t > 0) {   // dh_rec = dG_t W_hh  (contraction over the 4H' gate columns)

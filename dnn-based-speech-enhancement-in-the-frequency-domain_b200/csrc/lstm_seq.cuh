@@ -3,10 +3,18 @@
 //
 // Layout: every per-step tensor is [T][rows][C] (time-major), so that step t of ALL sequences is one dense
 // [rows x C] matrix: the recurrence h_{t-1} W_hh^T is a plain GEMM per step and the tile of a GEMM CTA is 128
-// consecutive sequences.  The 4H gate columns are stored INTERLEAVED in chunks of 64 hidden units,
-//     n' = (u / 64) * 256 + gate * 64 + (u % 64)        (reference order n = gate * H + u, gates i, f, g, o)
-// so that one 256-column accumulator tile of the recurrent GEMM holds i, f, g, o of the same 64 units and the LSTM
-// cell can run in the GEMM epilogue (lstm_step_tc.cu); packed weights / bias use the same column order.
+// consecutive sequences.  The 4H gate columns are stored INTERLEAVED in blocks of 8 hidden units,
+//     n' = (u / 8) * 32 + gate * 8 + (u % 8)        (reference order n = gate * H + u, gates i, f, g, o)
+// so that every 32-column block (= one 128-byte TMA / MMA k-block) holds i, f, g, o of the same 8 units: a 256-column
+// accumulator tile of the recurrent GEMM covers 64 units with all their gates and the LSTM cell can run in the GEMM
+// epilogue (lstm_step_tc.cu); packed weights / bias use the same column order.
+//
+// The fused kernels keep the per-step state they alone touch TILE-MAJOR (`tiled` flag below): rows are cut into tiles of
+// 128 and each 32-column block of a tile is one contiguous 16 KB box,
+//     gates / dG : [T][row tiles][4H / 32][128][32]        c : [T][row tiles][H / 8][128][8]        dc : [row tiles][H / 8][128][8]
+// so that a thread-per-row epilogue reads / writes whole 128-byte lines that are contiguous across the warp (the row-major
+// form made every access a 32-byte sector at a 6 KB stride: DRAM ran at a third of its rate) and the backward's A operand
+// dG_t is fetched by TMA as contiguous boxes.  Buffers must be sized for rows rounded up to a multiple of 128.
 #pragma once
 #include "common.cuh"
 
@@ -45,6 +53,7 @@ struct SeqLstmFwdParams {
     int rows, T;
     int round_h;           // h feeds tensor-core GEMMs: round to tf32 while writing
     int h_zero_slot;       // h is preceded by one all-zero step ([-1] = h_{-1} = 0): the fused kernel reads h_{t-1} uniformly
+    int tiled;             // out: gates / c were written tile-major (the fused path ran); the backward must be told
 };
 int sefd_seqlstm_forward(const SeqLstmFwdParams& p, cudaStream_t st);
 
@@ -61,6 +70,7 @@ struct SeqLstmBwdParams {
     int dx_done;           // written by the step epilogue and dx_done is set (else the caller computes it from dG)
     int rows, T;
     int round_tf32;        // dG feeds tensor-core GEMMs
+    int tiled;             // in: layout the forward reported (tile-major: the fused backward runs, dG stays tile-major)
 };
 int sefd_seqlstm_bias_blocks(int rows);
 // the generic cell backward of ONE step (t = T - 1: no recurrent gradient, initialises dc and the bias slots); *nblk = slots used

@@ -24,7 +24,8 @@
 //     step costs one chunk of MMA time instead of H / 64; h_t / dG_{t-1} are exchanged through L2 with a cluster-scope
 //     mbarrier hand-over (remote arrive on every peer's barrier) once per step.
 //
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue (thread = sequence row x column half).
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, then 8 (forward) / 16 (backward) epilogue warps (thread = sequence row,
+// the warps that share a TMEM lane quarter split the chunk's columns).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -35,7 +36,8 @@
 
 namespace {
 
-constexpr int TM = 128, KB = 32, NEPI = 8, NTHREADS = 64 + 32 * NEPI;
+constexpr int TM = 128, KB = 32;
+constexpr int NEPI_F = 8, NEPI_B = 12;          // epilogue warps: forward (MUFU-bound), backward (global-load-latency-bound: more warps in flight)
 constexpr int A_BYTES = TM * KB * 4;            // 16 KB: 128 rows x 32 k
 constexpr int MAXN = 256;                       // widest chunk (accumulator columns)
 constexpr int W_BYTES = MAXN * KB * 4;          // 32 KB slot for a chunk's weight tile (narrower chunks use a prefix)
@@ -154,7 +156,7 @@ struct Smem {
 };
 
 // ---- shared set-up / tear-down -----------------------------------------------------------------------------------------
-template <int CLM, int CLN>
+template <int CLM, int CLN, int NE>
 __device__ __forceinline__ uint32_t step_setup(unsigned char* smem, Smem* sb, int warp) {
     constexpr int CL = CLM * CLN;
     if (threadIdx.x == 0) {
@@ -165,9 +167,9 @@ __device__ __forceinline__ uint32_t step_setup(unsigned char* smem, Smem* sb, in
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&sb->tfull[a]), 1);
-            mbar_init(smem_u32(&sb->tempty[a]), NEPI);
+            mbar_init(smem_u32(&sb->tempty[a]), NE);
         }
-        mbar_init(smem_u32(&sb->ready), NEPI * CLN);
+        mbar_init(smem_u32(&sb->ready), NE * CLN);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -252,7 +254,7 @@ __device__ __forceinline__ void await_step(Smem* sb, uint32_t& phase) {
 // forward
 // =====================================================================================================================
 template <int CLM, int CLN>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(64 + 32 * NEPI_F, 1)
 lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH,
                    const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmW2, const StepParams p) {
     constexpr int CL = CLM * CLN;
@@ -263,8 +265,8 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
     const int mrank = CLM > 1 ? (int)rank : 0, nrank = CLN > 1 ? (int)rank : 0;
     const int row0 = (CLN > 1 ? blockIdx.x / CLN : blockIdx.x) * TM;
-    for (int i = threadIdx.x; i < 4 * p.H; i += NTHREADS) s_bias[i] = p.bias[i];
-    const uint32_t tmem_base = step_setup<CLM, CLN>(smem, sb, warp);
+    for (int i = threadIdx.x; i < 4 * p.H; i += 64 + 32 * NEPI_F) s_bias[i] = p.bias[i];
+    const uint32_t tmem_base = step_setup<CLM, CLN, NEPI_F>(smem, sb, warp);
     const uint32_t smem_base = smem_u32(smem);
     const uint16_t mc_mask = (uint16_t)((1u << CLM) - 1);
 
@@ -301,78 +303,74 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     } else if (warp == 1) {
         mma_role<CLM, CLN>(p, sb, smem_base, tmem_base, nrank, p.t1 - p.t0);
     } else {
-        // ================= epilogue: LSTM cell (thread = row x half of the chunk's units) =================
+        // ================= epilogue: LSTM cell (thread = row; the two warps of a lane quarter split the chunk's units) ======
         const int qd = warp & 3, half = (warp - 2) >> 2;
-        const int row = row0 + qd * 32 + lane;
+        const int rt = qd * 32 + lane;                     // row inside the tile
+        const int row = row0 + rt;
         const bool rv = row < p.rows;
-        const int H = p.H, N4 = 4 * H;
+        const int H = p.H, UB = H >> 3;
+        const long long mt = row0 / TM, MT = (p.rows + TM - 1) / TM;
+        const bool tile_ok = mt < MT;                      // a cluster may carry CTAs without a row tile: they only run the protocol
         int abuf = 0;
         uint32_t aphase = 0;
         for (int t = p.t0; t < p.t1; ++t) {
-            float* gt = p.gates + ((long long)t * p.rows + row) * N4;
-            const float* cp = p.c + ((long long)(t - 1) * p.rows + row) * H;       // read only when t > 0
-            float* ct = p.c + ((long long)t * p.rows + row) * H;
+            // tile-major state: gates [T][MT][UB][128][32], c [T][MT][UB][128][8]; h row-major [T + 1][rows][H]
+            float* gt = p.gates + (((long long)t * MT + mt) * UB * TM + rt) * 32;
+            const float* cp = p.c + (((long long)(t - 1) * MT + mt) * UB * TM + rt) * 8;       // read only when t > 0
+            float* ct = p.c + (((long long)t * MT + mt) * UB * TM + rt) * 8;
             float* ht = p.hbuf + ((long long)(t + 1) * p.rows + row) * H;
-            const bool have_c = t > 0 && rv;
             for (int q = nrank; q < p.nchunks; q += CLN) {
-                float cv[2][16];
+                float cv[4][8];
 #pragma unroll
-                for (int ss = 0; ss < 2; ++ss) {           // both c_{t-1} sub-blocks are in flight before the accumulator is
-                    const int u0 = q * 64 + 16 * (2 * half + ss);
-                    if (have_c) { ld_v8(cp + u0, cv[ss]); ld_v8(cp + u0 + 8, cv[ss] + 8); }
+                for (int b = 0; b < 4; ++b) {              // the c_{t-1} blocks are in flight before the accumulator is ready
+                    const int ub = q * 8 + 4 * half + b;
+                    if (t > 0 && tile_ok) ld_v8(cp + (long long)ub * TM * 8, cv[b]);
                     else {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) cv[ss][i] = 0.f;
+                        for (int i = 0; i < 8; ++i) cv[b][i] = 0.f;
                     }
                 }
                 mbar_wait(smem_u32(&sb->tfull[abuf]), aphase);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(abuf * MAXN);
 #pragma unroll
-                for (int ss = 0; ss < 2; ++ss) {
-                    const int s = 2 * half + ss;
-                    float gi[16], gf[16], gg[16], go[16];
-                    tmem_ld16(tacc + 0 * 64 + 16 * s, gi);
-                    tmem_ld16(tacc + 1 * 64 + 16 * s, gf);
-                    tmem_ld16(tacc + 2 * 64 + 16 * s, gg);
-                    tmem_ld16(tacc + 3 * 64 + 16 * s, go);
-                    tmem_ld_wait();
-                    if (ss == 1) {                     // this warp is done with the accumulator
+                for (int b = 0; b < 4; ++b) {
+                    const int ubl = 4 * half + b, ub = q * 8 + ubl;
+                    float v[32];                           // [gate][unit] of this 8-unit block
+                    tmem_ld32(tacc + (uint32_t)(ubl * 32), v);
+                    if (b == 3) {                          // this warp is done with the accumulator
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(smem_u32(&sb->tempty[abuf]));
                     }
-                    const float* bq = s_bias + q * 256 + 16 * s;
-                    float hv[16];
+                    const float* bq = s_bias + ub * 32;
+                    float hv[8];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
+                    for (int i = 0; i < 8; ++i) {
                         // sigmoid(x) = 1 / (1 + 2^(-x log2 e)), tanh(x) = 1 - 2 / (1 + 2^(2 x log2 e)); the four gate
                         // reciprocals share ONE rcp (arguments clamped so that the product of the four denominators stays
                         // finite: sigmoid(-20) = 2e-9, 1 - tanh(10) = 4e-9): 7 MUFU per hidden unit instead of 10
-                        const float A = 1.f + ex2f(fminf(-(gi[i] + bq[i]), 20.f) * LOG2E);
-                        const float Bf = 1.f + ex2f(fminf(-(gf[i] + bq[64 + i]), 20.f) * LOG2E);
-                        const float C = 1.f + ex2f(fminf(gg[i] + bq[128 + i], 10.f) * (2.f * LOG2E));
-                        const float D = 1.f + ex2f(fminf(-(go[i] + bq[192 + i]), 20.f) * LOG2E);
+                        const float A = 1.f + ex2f(fminf(-(v[i] + bq[i]), 20.f) * LOG2E);
+                        const float Bf = 1.f + ex2f(fminf(-(v[8 + i] + bq[8 + i]), 20.f) * LOG2E);
+                        const float C = 1.f + ex2f(fminf(v[16 + i] + bq[16 + i], 10.f) * (2.f * LOG2E));
+                        const float D = 1.f + ex2f(fminf(-(v[24 + i] + bq[24 + i]), 20.f) * LOG2E);
                         const float AB = A * Bf, CD = C * D;
                         const float r = rcpf(AB * CD);
                         const float rab = r * CD, rcd = r * AB;          // 1 / (A B), 1 / (C D)
                         const float a = rab * Bf, f = rab * A, o = rcd * C;
                         const float g = 1.f - 2.f * (rcd * D);
-                        const float c = fmaf(f, cv[ss][i], a * g);
+                        const float c = fmaf(f, cv[b][i], a * g);
                         float h = o * tanh_fast(c);
                         if (p.round_tf32) h = tf32_rn(h);
-                        gi[i] = a; gf[i] = f; gg[i] = g; go[i] = o; cv[ss][i] = c; hv[i] = h;
+                        v[i] = a; v[8 + i] = f; v[16 + i] = g; v[24 + i] = o; cv[b][i] = c; hv[i] = h;
                     }
-                    if (rv) {
-                        const int u0 = q * 64 + 16 * s;
-                        float* gq = gt + q * 256 + 16 * s;
-                        st_v8(gq, gi); st_v8(gq + 8, gi + 8);
-                        st_v8(gq + 64, gf); st_v8(gq + 72, gf + 8);
-                        st_v8(gq + 128, gg); st_v8(gq + 136, gg + 8);
-                        st_v8(gq + 192, go); st_v8(gq + 200, go + 8);
-                        st_v8(ct + u0, cv[ss]); st_v8(ct + u0 + 8, cv[ss] + 8);
-                        st_v8(ht + u0, hv); st_v8(ht + u0 + 8, hv + 8);
+                    // pad rows of the last tile hold finite values (zero inputs): the tile-major stores need no guard
+                    if (tile_ok) {
+                        float* gq = gt + (long long)ub * TM * 32;
+                        st_v8(gq, v); st_v8(gq + 8, v + 8); st_v8(gq + 16, v + 16); st_v8(gq + 24, v + 24);
+                        st_v8(ct + (long long)ub * TM * 8, cv[b]);
                     }
+                    if (rv) st_v8(ht + ub * 8, hv);
                 }
                 if (++abuf == 2) { abuf = 0; aphase ^= 1; }
             }
@@ -385,8 +383,71 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 // =====================================================================================================================
 // backward
 // =====================================================================================================================
+// cell backward of one 8-unit block of one row (thread = row): consumes dh (recurrent part in d[], zeros for the last step),
+// reads the tile-major gates / c / dc of step tc and the row-major dh_out, writes dG in place over the gates and the carried
+// dc; v[32] = [gate][unit] gradient values (zeros for rows beyond the end) for the bias column sums
+struct CellCtx {
+    float* gates_t;        // tile-major base of step tc for this (tile, row): + ub * 128 * 32
+    const float* c_t;      // + ub * 128 * 8
+    const float* c_tm1;    // null when tc == 0
+    const float* dh_out;   // row-major row of step tc (+ u0)
+    float* dc;             // + ub * 128 * 8
+    bool rv, first;        // first: step T - 1 (no carried dc yet)
+    int round_tf32;
+};
+__device__ __forceinline__ void cell_bwd_block(const CellCtx& x, int ub, const float* d, float* v) {
+    float gi[8], gf[8], gg[8], go[8], cc[8], cpv[8], dh[8], dcn[8];
+    float* gq = x.gates_t + (long long)ub * TM * 32;
+    ld_v8(gq, gi); ld_v8(gq + 8, gf); ld_v8(gq + 16, gg); ld_v8(gq + 24, go);
+    ld_v8(x.c_t + (long long)ub * TM * 8, cc);
+    if (x.c_tm1) ld_v8(x.c_tm1 + (long long)ub * TM * 8, cpv);
+    if (!x.first) ld_v8(x.dc + (long long)ub * TM * 8, dcn);
+    if (x.rv) ld_v8(x.dh_out + ub * 8, dh);
+    float dcc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float cprev = x.c_tm1 ? cpv[i] : 0.f;
+        const float dht = x.rv ? dh[i] + d[i] : 0.f;
+        const float tc = tanh_fast(cc[i]);
+        const float dcv = fmaf(dht * go[i], 1.f - tc * tc, x.first ? 0.f : dcn[i]);
+        v[i] = dcv * gg[i] * gi[i] * (1.f - gi[i]);
+        v[8 + i] = dcv * cprev * gf[i] * (1.f - gf[i]);
+        v[16 + i] = dcv * gi[i] * (1.f - gg[i] * gg[i]);
+        v[24 + i] = dht * tc * go[i] * (1.f - go[i]);
+        dcc[i] = dcv * gf[i];
+    }
+    if (!x.rv) {                   // pad rows: zeros (they are read as GEMM / weight-gradient operands)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dcc[i] = 0.f;
+    }
+    float o[8];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = x.round_tf32 ? tf32_rn(v[8 * g + i]) : v[8 * g + i];
+        st_v8(gq + 8 * g, o);
+    }
+    st_v8(x.dc + (long long)ub * TM * 8, dcc);
+}
+// column sums of v[32] over the warp's 32 rows (transposing butterfly: lane c ends with value index c) into the slot the
+// lane owns: s_bsum[quarter][ub * 32 + lane]
+__device__ __forceinline__ void bias_accumulate(float* v, float* bs, int ub, int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float sv = up ? v[i] : v[i + off], kv = up ? v[i + off] : v[i];
+            v[i] = kv + __shfl_xor_sync(0xffffffffu, sv, off);
+        }
+    }
+    bs[ub * 32 + lane] += v[0];
+}
+
 template <int CLM, int CLN>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(64 + 32 * NEPI_B, 1)
 lstm_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmG_unused,
                    const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmW2, const StepParams p) {
     constexpr int CL = CLM * CLN;
@@ -396,20 +457,22 @@ lstm_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constan
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
     const int mrank = CLM > 1 ? (int)rank : 0, nrank = CLN > 1 ? (int)rank : 0;
-    const int row0 = (CLN > 1 ? blockIdx.x / CLN : blockIdx.x) * TM;
-    const int H = p.H, N4 = 4 * H;
-    for (int i = threadIdx.x; i < 4 * N4; i += NTHREADS) s_bsum[i] = 0.f;
-    const uint32_t tmem_base = step_setup<CLM, CLN>(smem, sb, warp);
+    const int mt = CLN > 1 ? blockIdx.x / CLN : blockIdx.x;
+    const int row0 = mt * TM;
+    const int H = p.H, N4 = 4 * H, UB = H >> 3;
+    for (int i = threadIdx.x; i < 4 * N4; i += 64 + 32 * NEPI_B) s_bsum[i] = 0.f;
+    const uint32_t tmem_base = step_setup<CLM, CLN, NEPI_B>(smem, sb, warp);
     const uint32_t smem_base = smem_u32(smem);
     const uint16_t mc_mask = (uint16_t)((1u << CLM) - 1);
     const int nsteps = p.t1 - p.t0;
+    const bool prologue = p.t1 == p.T;        // this launch starts at the last step: dG_{T-1} is produced here first
 
     if (warp == 0) {
-        // ================= TMA producer: A = dG_t (all 4H' gate columns), B = rows of [W_hh^T ; W_ih^T] =================
+        // ================= TMA producer: A = dG_t (tile-major: contiguous 16 KB boxes), B = rows of [W_hh^T ; W_ih^T] ======
         int stage = 0;
         uint32_t phase = 0, rphase = 0;
         for (int t = p.t1 - 1; t >= p.t0; --t) {
-            if (p.persist && t < p.t1 - 1) await_step<CLN>(sb, rphase);          // dG_t was written by the previous iteration
+            if (t == p.t1 - 1 ? prologue : p.persist != 0) await_step<CLN>(sb, rphase);      // dG_t was written inside this launch
             for (int q = nrank; q < p.nchunks; q += CLN) {
                 const int wslice = p.chunk_n[q] / CLM;
                 const uint32_t bytes = (uint32_t)(A_BYTES + p.chunk_n[q] * KB * 4);
@@ -420,7 +483,7 @@ lstm_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constan
                     const uint32_t sa = smem_base + (uint32_t)(stage * STAGE_BYTES);
                     if (elect_one_sync()) {
                         mbar_expect_tx(fb, bytes);
-                        tma_load_4d(&tmG, fb, sa, 0, row0, kb, t);
+                        tma_load_5d(&tmG, fb, sa, 0, 0, kb, mt, t);
                         const uint32_t sw = sa + A_BYTES + (uint32_t)(mrank * wslice * KB * 4);
                         if (CLM > 1) tma_load_3d_multicast(wm, fb, sw, 0, p.chunk_row[q] + mrank * wslice, kb, mc_mask);
                         else tma_load_3d(wm, fb, sw, 0, p.chunk_row[q], kb);
@@ -434,94 +497,80 @@ lstm_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constan
         mma_role<CLM, CLN>(p, sb, smem_base, tmem_base, nrank, nsteps);
     } else {
         // ================= epilogue: dh columns -> cell backward of step t - 1 (dG_{t-1} in place); dx columns -> store ====
-        const int qd = warp & 3, half = (warp - 2) >> 2;
-        const int row = row0 + qd * 32 + lane;
+        constexpr int NPART = NEPI_B / 4;                 // warps per TMEM lane quarter: they split the chunk's columns
+        const int qd = warp & 3, part = (warp - 2) >> 2;
+        const int rt = qd * 32 + lane;
+        const int row = row0 + rt;
         const bool rv = row < p.rows;
+        const long long MT = (p.rows + TM - 1) / TM;
+        const bool tile_ok = mt < MT;                     // CTAs without a row tile only run the protocol
         float* bs = s_bsum + qd * N4;
         int abuf = 0;
         uint32_t aphase = 0;
+        auto ctx_for = [&](int tc) {                      // cell context of step tc for this thread's row
+            CellCtx x;
+            x.gates_t = p.gates + (((long long)tc * MT + mt) * UB * TM + rt) * 32;
+            x.c_t = p.c + (((long long)tc * MT + mt) * UB * TM + rt) * 8;
+            x.c_tm1 = tc > 0 ? p.c + (((long long)(tc - 1) * MT + mt) * UB * TM + rt) * 8 : nullptr;
+            x.dh_out = p.dh_out + ((long long)tc * p.rows + row) * H;
+            x.dc = p.dc + ((long long)mt * UB * TM + rt) * 8;
+            x.rv = rv; x.first = tc == p.T - 1; x.round_tf32 = p.round_tf32;
+            return x;
+        };
+        if (prologue) {
+            // step T - 1 has no recurrent gradient: cell backward of the dh chunks this CTA owns, straight from memory
+            const CellCtx x = ctx_for(p.T - 1);
+            float zero[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) zero[i] = 0.f;
+            for (int q = nrank; q < p.nchunks; q += CLN) {
+                if (p.chunk_row[q] >= H) break;
+                const int n_dh = min(p.chunk_n[q], H - p.chunk_row[q]) >> 3;
+#pragma unroll 1
+                for (int s = part; s < n_dh && tile_ok; s += NPART) {
+                    const int ub = (p.chunk_row[q] >> 3) + s;
+                    float v[32];
+                    cell_bwd_block(x, ub, zero, v);
+                    bias_accumulate(v, bs, ub, lane);
+                }
+            }
+            publish_step<CLN>(sb, lane);
+        }
         for (int t = p.t1 - 1; t >= p.t0; --t) {
-            float* gp = p.gates + ((long long)(t - 1) * p.rows + row) * N4;          // step t - 1 (used when t > 0)
-            const float* c1 = p.c + ((long long)(t - 1) * p.rows + row) * H;
-            const float* c2 = p.c + ((long long)(t - 2) * p.rows + row) * H;          // read only when t > 1
-            const float* dho = p.dh_out + ((long long)(t - 1) * p.rows + row) * H;
-            float* dcp = p.dc + (long long)row * H;
-            float* dxp = p.dx ? p.dx + ((long long)t * p.rows + row) * p.I : nullptr;
             const bool cell = t > 0;
+            const CellCtx x = ctx_for(cell ? t - 1 : 0);
+            float* dxp = p.dx ? p.dx + ((long long)t * p.rows + row) * p.I : nullptr;
             for (int q = nrank; q < p.nchunks; q += CLN) {
                 mbar_wait(smem_u32(&sb->tfull[abuf]), aphase);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(abuf * MAXN);
-                const int nsb = p.chunk_n[q] >> 4;            // 8-column sub-blocks of this warp's half
+                const int nsb_all = p.chunk_n[q] >> 3;        // 8-column sub-blocks, dealt round-robin to the NPART warps
+                const int nsb = (nsb_all - part + NPART - 1) / NPART;
+                if (nsb <= 0) {                               // nothing to do in a narrow chunk: still release the buffer
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&sb->tempty[abuf]));
+                }
 #pragma unroll 1
                 for (int s = 0; s < nsb; ++s) {
-                    const int cl0 = (half * nsb + s) * 8;     // column inside the chunk
+                    const int cl0 = (part + s * NPART) * 8;   // column inside the chunk
                     const int j0 = p.chunk_row[q] + cl0;      // output column: [0, H) = dh units, [H, H + I) = dx
                     float d[8];
                     tmem_ld8(tacc + (uint32_t)cl0, d);
-                    if (j0 >= H) {
-                        tmem_ld_wait();
-                        if (s == nsb - 1) {
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(smem_u32(&sb->tempty[abuf]));
-                        }
-                        if (rv && dxp) st_v8(dxp + (j0 - H), d);
-                        continue;
-                    }
-                    const int u0 = j0;
-                    const int gc = (u0 >> 6) * 256 + (u0 & 63);
-                    float gi[8], gf[8], gg[8], go[8], cc[8], cpv[8], dh[8], dcn[8];
-                    if (cell && rv) {
-                        ld_v8(gp + gc, gi); ld_v8(gp + gc + 64, gf); ld_v8(gp + gc + 128, gg); ld_v8(gp + gc + 192, go);
-                        ld_v8(c1 + u0, cc); ld_v8(dho + u0, dh); ld_v8(dcp + u0, dcn);
-                        if (t > 1) ld_v8(c2 + u0, cpv);
-                    }
                     tmem_ld_wait();
                     if (s == nsb - 1) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(smem_u32(&sb->tempty[abuf]));
                     }
-                    if (!cell) continue;                      // warp-uniform
+                    if (j0 >= H) {
+                        if (rv && dxp) st_v8(dxp + (j0 - H), d);
+                        continue;
+                    }
+                    if (!cell || !tile_ok) continue;          // warp-uniform
                     float v[32];
-                    if (rv) {
-                        float dcc[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float cprev = t > 1 ? cpv[i] : 0.f;
-                            const float dht = dh[i] + d[i];
-                            const float tc = tanh_fast(cc[i]);
-                            const float dcv = fmaf(dht * go[i], 1.f - tc * tc, dcn[i]);
-                            v[i] = dcv * gg[i] * gi[i] * (1.f - gi[i]);
-                            v[8 + i] = dcv * cprev * gf[i] * (1.f - gf[i]);
-                            v[16 + i] = dcv * gi[i] * (1.f - gg[i] * gg[i]);
-                            v[24 + i] = dht * tc * go[i] * (1.f - go[i]);
-                            dcc[i] = dcv * gf[i];
-                        }
-                        float o[8];
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) o[i] = p.round_tf32 ? tf32_rn(v[8 * g + i]) : v[8 * g + i];
-                            st_v8(gp + gc + 64 * g, o);
-                        }
-                        st_v8(dcp + u0, dcc);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = 0.f;
-                    }
-                    // column sums over the warp's 32 rows: transposing butterfly, lane c ends with value index c
-#pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) {
-                        const bool up = (lane & off) != 0;
-#pragma unroll
-                        for (int i = 0; i < off; ++i) {
-                            const float sv = up ? v[i] : v[i + off], kv = up ? v[i + off] : v[i];
-                            v[i] = kv + __shfl_xor_sync(0xffffffffu, sv, off);
-                        }
-                    }
-                    bs[gc + 64 * (lane >> 3) + (lane & 7)] += v[0];       // slot (quarter, column) is owned by this lane
+                    cell_bwd_block(x, j0 >> 3, d, v);
+                    bias_accumulate(v, bs, j0 >> 3, lane);
                 }
                 if (++abuf == 2) { abuf = 0; aphase ^= 1; }
                 // dG_{t-1} of this CTA is complete after its last chunk with dh columns: publish before the dx chunks, whose
@@ -531,9 +580,9 @@ lstm_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constan
             }
         }
         // per-CTA column sums -> this CTA's slot (columns it never touched stay zero)
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * NEPI) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * NEPI_B) : "memory");
         float* slot = p.bias_part + (long long)blockIdx.x * N4;
-        for (int i = threadIdx.x - 64; i < N4; i += 32 * NEPI)
+        for (int i = threadIdx.x - 64; i < N4; i += 32 * NEPI_B)
             slot[i] = (p.bias_accum ? slot[i] : 0.f) + ((s_bsum[i] + s_bsum[N4 + i]) + (s_bsum[2 * N4 + i] + s_bsum[3 * N4 + i]));
     }
     step_teardown<CL>(tmem_base, warp);
@@ -547,6 +596,14 @@ int make_seq_map(CUtensorMap* m, const float* base, int rows, int C, int steps) 
     cuuint64_t str[3] = {(cuuint64_t)C * 4, 128, (cuuint64_t)rows * C * 4};
     cuuint32_t box[4] = {32, TM, 1, 1};
     return make_map(m, base, 4, dims, str, box);
+}
+int make_tiled_map(CUtensorMap* m, const float* base, int rows, int C, int steps) {
+    // tile-major [steps][row tiles][C / 32][128][32]: one box = one contiguous 16 KB block
+    const int mt = (rows + TM - 1) / TM, kbn = C / 32;
+    cuuint64_t dims[5] = {32, TM, (cuuint64_t)kbn, (cuuint64_t)mt, (cuuint64_t)steps};
+    cuuint64_t str[4] = {128, 16384, (cuuint64_t)kbn * 16384, (cuuint64_t)mt * kbn * 16384};
+    cuuint32_t box[5] = {32, TM, 1, 1, 1};
+    return make_map(m, base, 5, dims, str, box);
 }
 int make_w_map3(CUtensorMap* m, const float* base, int nrows, int K, int box_rows) {
     // [nrows][K] K-major as (k_inner 32, row, k_block)
@@ -572,11 +629,11 @@ StepKernel kernel_for(bool fwd, Shape s) {
 #undef PICK
 }
 
-cudaLaunchConfig_t make_cfg(int grid, int cl, int smem, cudaStream_t st, cudaLaunchAttribute* attr) {
+cudaLaunchConfig_t make_cfg(int grid, int cl, int smem, cudaStream_t st, cudaLaunchAttribute* attr, int nthreads) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(NTHREADS);
+    cfg.blockDim = dim3(nthreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -602,7 +659,7 @@ Shape pick_shape(bool fwd, int m_tiles, int nsplit, int smem) {
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaLaunchAttribute attr[1];
         const int clusters = split ? 1 : (m_tiles + cl - 1) / cl;
-        cudaLaunchConfig_t cfg = make_cfg(clusters * cl, cl, smem, nullptr, attr);
+        cudaLaunchConfig_t cfg = make_cfg(clusters * cl, cl, smem, nullptr, attr, fwd ? 64 + 32 * NEPI_F : 64 + 32 * NEPI_B);
         int n = 0;
         if (cudaOccupancyMaxActiveClusters(&n, k, &cfg) == cudaSuccess && n >= clusters) return s;
         cudaGetLastError();
@@ -611,13 +668,13 @@ Shape pick_shape(bool fwd, int m_tiles, int nsplit, int smem) {
     return Shape{1, 1};
 }
 
-int launch_step(StepKernel k, Shape s, int m_tiles, int smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b,
+int launch_step(bool fwd, StepKernel k, Shape s, int m_tiles, int smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& b,
                 const CUtensorMap& c, const CUtensorMap& d, const StepParams& p, int* grid_out) {
     const int cl = s.clm * s.cln;
     const int grid = s.cln > 1 ? m_tiles * s.cln : (m_tiles + cl - 1) / cl * cl;
     if (grid_out) *grid_out = grid;
     cudaLaunchAttribute attr[1];
-    cudaLaunchConfig_t cfg = make_cfg(grid, cl, smem, st, attr);
+    cudaLaunchConfig_t cfg = make_cfg(grid, cl, smem, st, attr, fwd ? 64 + 32 * NEPI_F : 64 + 32 * NEPI_B);
     cudaError_t e = cudaLaunchKernelEx(&cfg, k, a, b, c, d, p);
     if (e != cudaSuccess) {
         sefd_set_error("lstm_step_tc launch: %s", cudaGetErrorString(e));
@@ -662,7 +719,7 @@ int sefd_lstm_step_tc_forward(const SeqLstmFwdParams& f, cudaStream_t st) {
         p.t0 = t0; p.t1 = t1; p.persist = t1 - t0 > 1;
         sefd_prof_label("lstm_fwd_tc rows%d I%d H%d steps%d clm%d cln%d", f.rows, I, H, t1 - t0, s.clm, s.cln);
         SefdProfScope prof(SEFD_PROF_LSTM, flops * (t1 - t0), bytes * (t1 - t0), st);
-        SEFD_TRY(launch_step(k, s, m_tiles, smem, st, mx, mh, mw, mw, p, nullptr));
+        SEFD_TRY(launch_step(true, k, s, m_tiles, smem, st, mx, mh, mw, mw, p, nullptr));
         return sefd_check_launch("lstm_fwd_tc");
     };
     if (persist_mode()) return go(0, f.T);
@@ -674,12 +731,8 @@ int sefd_lstm_step_tc_backward(SeqLstmBwdParams& b, cudaStream_t st) {
     const int H = b.w.H, I = b.w.I, N4 = 4 * H;
     SEFD_REQUIRE(sefd_lstm_step_tc_eligible(I, H), "lstm_step_tc: I=%d H=%d unsupported", I, H);
     SEFD_REQUIRE(b.w.Wih_kn == b.w.Whh_kn + (long long)H * N4, "lstm_step_tc backward: W_ih^T must follow W_hh^T in memory");
-    // step T - 1 has no recurrent gradient: the generic cell kernel produces dG_{T-1}, initialises dc and its bias slots
-    int nb0 = 0;
-    SEFD_TRY(sefd_seqlstm_cell_bwd_step(b, b.T - 1, &nb0, st));
-    b.bias_blocks = nb0;
+    const int nb0 = 0;      // step T - 1 (no recurrent gradient) is the prologue of the launch that contains it
     b.dx_done = 0;
-    if (b.T == 1) return 0;
     const int m_tiles = (b.rows + TM - 1) / TM, smem = smem_bytes(H);
     StepParams p;
     memset(&p, 0, sizeof(p));
@@ -718,7 +771,7 @@ int sefd_lstm_step_tc_backward(SeqLstmBwdParams& b, cudaStream_t st) {
     p.gates = b.gates; p.c = const_cast<float*>(b.c); p.dh_out = b.dh_out; p.dc = b.dc; p.dx = fuse_dx ? b.dx : nullptr;
     p.bias_part = b.bias_part + (long long)nb0 * N4;
     CUtensorMap mg, mw, mw2;
-    SEFD_TRY(make_seq_map(&mg, b.gates, b.rows, N4, b.T));
+    SEFD_TRY(make_tiled_map(&mg, b.gates, b.rows, N4, b.T));
     SEFD_TRY(make_w_map3(&mw, b.w.Whh_kn, Nout, N4, (wide < Nout ? wide : Nout) / s.clm));
     if (narrow) SEFD_TRY(make_w_map3(&mw2, b.w.Whh_kn, Nout, N4, narrow / s.clm));
     else mw2 = mw;
@@ -729,7 +782,7 @@ int sefd_lstm_step_tc_backward(SeqLstmBwdParams& b, cudaStream_t st) {
         p.t0 = t0; p.t1 = t1; p.persist = t1 - t0 > 1;
         sefd_prof_label("lstm_bwd_tc rows%d I%d H%d Nout%d steps%d clm%d cln%d", b.rows, I, H, Nout, t1 - t0, s.clm, s.cln);
         SefdProfScope prof(SEFD_PROF_LSTM, flops * (t1 - t0), bytes * (t1 - t0), st);
-        SEFD_TRY(launch_step(k, s, m_tiles, smem, st, mg, mg, mw, mw2, p, &grid));
+        SEFD_TRY(launch_step(false, k, s, m_tiles, smem, st, mg, mg, mw, mw2, p, &grid));
         return sefd_check_launch("lstm_bwd_tc");
     };
     // iteration t consumes dG_t and produces dG_{t-1} (t >= 1) and dx_t; the bias sums of all iterations share one slot set

@@ -46,6 +46,7 @@ struct WgParams {
     int nstage, stage_bytes;
     int a_sp;          // spacing of the A slots inside a stage, in 4 KB chunks (= min(4, K/32))
     int a_box;         // 32-channel blocks fetched by one A TMA instruction (divides a_sp and the source widths)
+    int g_tiled;       // G operand is tile-major (see WgradParams)
     long long units;
 };
 
@@ -136,7 +137,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                             const int g = op - nAb;
                             const int fg = j * p.g_mul + G.g_roff[g];
                             const uint32_t sg = sa + (uint32_t)(G.nA * p.a_sp * CHB);
-                            tma_load_5d(&tmG, fb, sg + (uint32_t)(g * NG * CHB), 0, t0, x.n0 / 32, fg, b);
+                            if (p.g_tiled) tma_load_5d(&tmG, fb, sg + (uint32_t)(g * NG * CHB), 0, t0 & 127, x.n0 / 32, t0 >> 7, fg);
+                            else tma_load_5d(&tmG, fb, sg + (uint32_t)(g * NG * CHB), 0, t0, x.n0 / 32, fg, b);
                         }
                     }
                     if (++stage == p.nstage) { stage = 0; phase ^= 1; }
@@ -473,7 +475,17 @@ int sefd_wgrad_tc(const WgradParams& w, float* partial, long long cap_floats, in
     SEFD_TRY(make_pos_map(&a0, w.a[0], w.Fa, w.Ta, w.B, p.a_box));
     if (w.a[1].C) SEFD_TRY(make_pos_map(&a1, w.a[1], w.Fa, w.Ta, w.B, p.a_box));
     else a1 = a0;
-    SEFD_TRY(make_pos_map(&g, w.g, w.Fg, w.Tg, w.B, BN / 32));
+    if (w.g_tiled) {
+        SEFD_REQUIRE(w.B == 1, "wgrad_tc: a tile-major gradient operand needs B = 1");
+        const int mt = (w.Tg + 127) / 128, kbn = N / 32;
+        cuuint64_t dims[5] = {32, 128, (cuuint64_t)kbn, (cuuint64_t)mt, (cuuint64_t)w.Fg};
+        cuuint64_t str[4] = {128, 16384, (cuuint64_t)kbn * 16384, (cuuint64_t)mt * kbn * 16384};
+        cuuint32_t box[5] = {32, (cuuint32_t)PB, (cuuint32_t)(BN / 32), 1, 1};
+        SEFD_TRY(make_map(&g, w.g.p, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+        p.g_tiled = 1;
+    } else {
+        SEFD_TRY(make_pos_map(&g, w.g, w.Fg, w.Tg, w.B, BN / 32));
+    }
     const double pos = (double)w.B * w.J * w.Tg;
     sefd_prof_label("wgrad_tc BN%d K%d N%d taps%d J%d groups%d stage%dK x%d splits%d units%lld", BN, K, N, w.ntaps, w.J,
                     p.ngroups, stage / 1024, p.nstage, p.splits, p.units);
@@ -493,6 +505,7 @@ int sefd_wgrad(const WgradParams& w, float* partial, long long cap_floats, int n
                long long* split_stride, cudaStream_t st) {
     if (sefd_get_engine_internal() == 1 && sefd_wgrad_tc_eligible(w))
         return sefd_wgrad_tc(w, partial, cap_floats, nslabs, nsplit, split_stride, st);
+    SEFD_REQUIRE(!w.g_tiled, "wgrad: a tile-major gradient operand needs the tensor-core engine");
     const long long one = (long long)nslabs * (w.a[0].C + w.a[1].C) * w.g.C;
     SEFD_REQUIRE(one <= cap_floats, "wgrad: gradient scratch too small");
     cudaMemsetAsync(partial, 0, sizeof(float) * one, st);
