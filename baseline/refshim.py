@@ -124,3 +124,29 @@ def load(model):
     except Exception as e:                      # a broken copy must not take the GPU measurement down with it
         sys.stderr.write(f"refshim: the reference in {REF_DIR} could not be imported ({type(e).__name__}: {e}); using the oracle port\n")
         return None
+
+
+def load_trainer():
+    """The UNMODIFIED reference trainer.py (baseline/_ref) imported against whatever `models` / `tools_for_model` modules are on
+    sys.path - i.e. the repo's drop-ins: the boundary test drives trainer.model_train / model_perceptual_train /
+    fullsubnet_train exactly as train_interface.py:63-77 would.  tools_for_estimate (PESQ.so / pystoi / oct2py, validation
+    only) is stubbed.  Returns None when baseline/_ref has not been populated."""
+    path = os.path.join(REF_DIR, "trainer.py")
+    if not os.path.exists(path):
+        return None
+    import importlib.util
+    est = types.ModuleType("tools_for_estimate")
+    est.cal_pesq = lambda *a, **k: 0.0
+    est.cal_stoi = lambda *a, **k: 0.0
+    saved = sys.modules.get("tools_for_estimate")
+    sys.modules["tools_for_estimate"] = est
+    try:
+        spec = importlib.util.spec_from_file_location("sefd_reference_trainer", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        if saved is None:
+            sys.modules.pop("tools_for_estimate", None)
+        else:
+            sys.modules["tools_for_estimate"] = saved
+    return mod

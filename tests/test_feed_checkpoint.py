@@ -106,3 +106,37 @@ def test_checkpoint_round_trip_with_flat_adam(tmp_path):
     assert l1 == pytest.approx(l2, rel=1e-6)
     for (n1, p1), (n2, p2) in zip(m.named_parameters(), m2.named_parameters()):
         assert torch.allclose(p1, p2, rtol=1e-5, atol=1e-7), n1
+
+
+@pytest.mark.gpu
+def test_feeder_into_train_step_and_strided_input_is_rejected():
+    """WaveFeeder -> TrainStep.step: the feeder hands out CONTIGUOUS [B, L] buffers (the kernels index rows with stride L), the
+    step on them equals the step on clones, and a strided view of a [B, 2, L] batch is refused instead of silently pairing
+    the wrong rows."""
+    import models
+    from oracle import dccrn_oracle as O
+    from sefd.train import TrainStep
+    models.cfg.loss = "SI-SNR"
+    rng = np.random.default_rng(1)
+    data = (rng.uniform(-0.1, 0.1, (6, 2, 4000))).astype(np.float32)
+    sd0 = O.init_state(0)
+    losses = []
+    for use_feeder in (True, False):
+        m = models.DCCRN(masking_mode="C"); m.load_state_dict(sd0); m = m.cuda().train()
+        ts = TrainStep(m, lr=1e-3, loss="SI-SNR")
+        if use_feeder:
+            f = feed.WaveFeeder(data, batch=2, shuffle=False, rank=0, world=1)
+            cur = []
+            for x, y in f:
+                assert x.is_contiguous() and y.is_contiguous()
+                cur.append(float(ts.step(x, y)))
+        else:
+            cur = [float(ts.step(torch.from_numpy(data[2 * i:2 * i + 2, 0]).cuda(), torch.from_numpy(data[2 * i:2 * i + 2, 1]).cuda()))
+                   for i in range(3)]
+        losses.append(cur)
+    assert losses[0] == pytest.approx(losses[1], rel=1e-6)
+    d = torch.from_numpy(data[:2]).cuda()
+    with pytest.raises(RuntimeError, match="contiguous"):
+        ts.step(d[:, 0], d[:, 1])
+    with pytest.raises(RuntimeError, match="float32"):
+        ts.step(d[:, 0].contiguous().double(), d[:, 1].contiguous().double())
