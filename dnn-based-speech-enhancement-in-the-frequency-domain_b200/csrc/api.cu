@@ -339,6 +339,12 @@ int sefd_dccrn_backward(const sefd_plan* plan, const float* params, const float*
     return sefd_backward_impl(plan, params, d_wav, nullptr, nullptr, grads, ws, ws_bytes, ST);
 }
 
+int sefd_dccrn_backward_overlap(const sefd_plan* plan, const float* params, const float* d_wav, float* grads, void* ws,
+                                size_t ws_bytes, void* stream, void* tail_ready_event) {
+    SEFD_REQUIRE(plan && params && d_wav && grads && ws, "dccrn_backward_overlap: null argument");
+    return sefd_backward_impl(plan, params, d_wav, nullptr, nullptr, grads, ws, ws_bytes, ST, (cudaEvent_t)tail_ready_event);
+}
+
 int sefd_dccrn_backward_spec(const sefd_plan* plan, const float* params, const float* d_wav, const float* d_out_real,
                              const float* d_out_imag, float* grads, void* ws, size_t ws_bytes, void* stream) {
     SEFD_REQUIRE(plan && params && grads && ws, "dccrn_backward_spec: null argument");

@@ -397,7 +397,7 @@ int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const 
 
 // ------------------------------------------------------------------------------------------------
 int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, const float* dreal, const float* dimag,
-                       float* grads, void* wsv, size_t ws_bytes, cudaStream_t st) {
+                       float* grads, void* wsv, size_t ws_bytes, cudaStream_t st, cudaEvent_t tail_ready) {
     SEFD_REQUIRE(ws_bytes >= P->ws_bytes, "backward: workspace too small");
     float* ws = (float*)wsv;
     double* wsd = (double*)wsv;
@@ -645,6 +645,13 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
         }
     }
 
+    // every decoder / projection / LSTM gradient (the tail of the flat buffer, sefd_dccrn_grad_split) is final once the side
+    // stream has drained up to here: their all-reduce can run beside the encoder backward
+    if (tail_ready) {
+        fork();
+        cudaEventRecord(tail_ready, sx);
+    }
+
     // ---- encoder backward ----
     for (int i = NL - 1; i >= 0; --i) {
         const ConvLayer& c = P->enc[i];
@@ -709,6 +716,7 @@ void sefd_dccrn_plan_destroy(sefd_plan* plan) {
     delete plan;
 }
 size_t sefd_dccrn_workspace_bytes(const sefd_plan* plan) { return plan ? plan->ws_bytes : 0; }
+long long sefd_dccrn_grad_split(const sefd_plan* plan) { return plan && plan->kind == 0 ? plan->dec[0].wr : 0; }
 long long sefd_dccrn_param_floats(const sefd_plan* plan) { return plan ? plan->n_param_floats : 0; }
 long long sefd_dccrn_buffer_floats(const sefd_plan* plan) { return plan ? plan->n_buffer_floats : 0; }
 int sefd_dccrn_num_params(const sefd_plan* plan) { return plan ? (int)plan->params.size() : 0; }

@@ -67,6 +67,14 @@ SIGNATURES = {
     "sefd_fsn_forward": (_i, [_vp, _vp, _vp, _i, _f, _vp, _vp, C.c_ulonglong, _vp, _vp, _sz, _vp]),
     "sefd_fsn_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sefd_dropout_forward": (_i, [_vp, _vp, _ll, _f, _vp, C.c_ulonglong, C.c_uint, _vp]),
+    "sefd_dccrn_grad_split": (_ll, [_vp]),
+    "sefd_dccrn_backward_overlap": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "sefd_nccl_unique_id_bytes": (_i, []),
+    "sefd_nccl_unique_id": (_i, [_vp]),
+    "sefd_nccl_init": (_vp, [_i, _i, _vp]),
+    "sefd_nccl_allreduce": (_i, [_vp, _vp, _ll, _vp]),
+    "sefd_nccl_world": (_i, [_vp]),
+    "sefd_nccl_destroy": (None, [_vp]),
     "sefd_set_engine": (_i, [_i]),
     "sefd_get_engine": (_i, []),
     "sefd_launch_count": (_ll, []),

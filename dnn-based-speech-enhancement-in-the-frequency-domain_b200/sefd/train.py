@@ -5,6 +5,8 @@ trainer.model_train loop (trainer.py:27-37) with torch.optim.Adam(lr) (train_int
 Data-parallel semantics: utterances are sharded by batch, weights replicated, BatchNorm uses
 per-rank statistics (standard DDP), gradients are summed over ranks and scaled by 1/world inside Adam.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -35,6 +37,16 @@ class TrainStep:
             self.world = torch.distributed.get_world_size(process_group)
         self._bufs = {}
         _dist.broadcast_from_rank0_(self.engine, self.pg)                 # every replica starts from rank 0's weights
+        # data-parallel overlap: the decoder / LSTM / projection gradients (the tail of the flat buffer, 76 %
+        # of it) are final before the encoder backward starts; their all-reduce runs on a side stream beside it, the encoder
+        # slice is reduced when the backward ends.  SEFD_DP_OVERLAP=0 falls back to one all-reduce after the backward.
+        self.overlap = (self.world > 1 and self.engine.family == "dccrn" and os.environ.get("SEFD_DP_OVERLAP", "1") != "0")
+        self._tail_pending = False
+        if self.overlap:
+            self._comm_stream = torch.cuda.Stream()
+            self._tail_event = torch.cuda.Event()
+            self._tail_event.record()                                      # materialises the cudaEvent_t handle
+            self._split = int(_lib.load().sefd_dccrn_grad_split(self.engine._layout.handle))
 
     def _scratch(self, B, L, dev):
         key = (B, L)
@@ -44,8 +56,9 @@ class TrainStep:
                 loss=torch.empty(1, device=dev), coef=torch.empty(2 * B, device=dev))
         return self._bufs[key]
 
-    def forward_backward(self, noisy, clean):
-        """Fills engine.flat_grad with this rank's gradient; returns the loss tensor (1 element, device)."""
+    def forward_backward(self, noisy, clean, reduce_tail=False):
+        """Fills engine.flat_grad with this rank's gradient; returns the loss tensor (1 element, device).  reduce_tail (used by
+        step()): with the data-parallel overlap on, the tail slice of the gradient is already being all-reduced on return."""
         lib = _lib.load()
         eng = self.engine
         eng.sync()
@@ -84,14 +97,27 @@ class TrainStep:
         else:
             _lib.check(lib.sefd_loss_backward(ptr(s["wav"]), ptr(clean), ptr(s["coef"]), None, ptr(s["dwav"]), B, L, st),
                        "loss_backward")
-        _lib.check(bwd(plan.handle, ptr(eng.flat), ptr(s["dwav"]), ptr(eng.flat_grad), ptr(ws),
-                       plan.ws_bytes, st), eng.family + "_backward")
+        if self.overlap and reduce_tail:
+            _lib.check(lib.sefd_dccrn_backward_overlap(plan.handle, ptr(eng.flat), ptr(s["dwav"]), ptr(eng.flat_grad), ptr(ws),
+                                                       plan.ws_bytes, st, self._tail_event.cuda_event), "dccrn_backward_overlap")
+            self._comm_stream.wait_event(self._tail_event)
+            with torch.cuda.stream(self._comm_stream):
+                _dist.allreduce_sum_(eng.flat_grad[self._split:], self.pg)
+            self._tail_pending = True
+        else:
+            _lib.check(bwd(plan.handle, ptr(eng.flat), ptr(s["dwav"]), ptr(eng.flat_grad), ptr(ws),
+                           plan.ws_bytes, st), eng.family + "_backward")
         return s["loss"]
 
     def step(self, noisy, clean):
-        loss = self.forward_backward(noisy, clean)
+        loss = self.forward_backward(noisy, clean, reduce_tail=True)
         eng = self.engine
-        gscale = _dist.allreduce_sum_(eng.flat_grad, self.pg)              # single flat 14.7 MB buffer
+        if self._tail_pending:                                             # head slice now, tail slice already in flight
+            gscale = _dist.allreduce_sum_(eng.flat_grad[:self._split], self.pg)
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+            self._tail_pending = False
+        else:
+            gscale = _dist.allreduce_sum_(eng.flat_grad, self.pg)          # single flat 14.7 MB buffer
         self.steps += 1
         _lib.check(_lib.load().sefd_adam_step(ptr(eng.flat), ptr(eng.flat_grad), ptr(self.exp_avg),
                                               ptr(self.exp_avg_sq), eng.flat.numel(), self.lr, self.betas[0],

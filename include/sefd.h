@@ -164,6 +164,13 @@ int sefd_dccrn_forward(const sefd_plan* plan, const float* params, float* bn_buf
 /* d_wav [B][L] -> grads (flat, same layout as params; every entry is overwritten) */
 int sefd_dccrn_backward(const sefd_plan* plan, const float* params, const float* d_wav, float* grads, void* ws,
                         size_t ws_bytes, void* stream);
+/* same as sefd_dccrn_backward, for data-parallel steps: `tail_ready_event` (a cudaEvent_t, may be NULL) is recorded as soon as
+ * every gradient at flat offset >= sefd_dccrn_grad_split(plan) is final (decoder, projection and LSTM parameters: 76 % of
+ * the buffer, finished before the encoder backward starts), so that slice can be all-reduced on another stream while the
+ * encoder backward runs; the head slice [0, split) is final when the call's work on `stream` is. */
+long long sefd_dccrn_grad_split(const sefd_plan* plan);
+int sefd_dccrn_backward_overlap(const sefd_plan* plan, const float* params, const float* d_wav, float* grads, void* ws,
+                                size_t ws_bytes, void* stream, void* tail_ready_event);
 /* same, with an additional gradient arriving at the masked spectrum out_real / out_imag [B][257][T] (perceptual losses,
  * models.py:305-312); d_wav or the pair (d_out_real, d_out_imag) may be NULL */
 int sefd_dccrn_backward_spec(const sefd_plan* plan, const float* params, const float* d_wav, const float* d_out_real,
@@ -211,6 +218,18 @@ int sefd_dropout_forward(const float* x, float* y, long long n, float p, const f
 /* d_crm [B][257][frames][2] -> grads (flat, same layout as params; every entry is overwritten) */
 int sefd_fsn_backward(const sefd_plan* plan, const float* params, const float* d_crm, float* grads, void* ws, size_t ws_bytes,
                       void* stream);
+
+/* ---- data-parallel plumbing without torch: one NCCL communicator per process / GPU; the only collective on
+ * the path is a sum all-reduce of (slices of) the flat fp32 gradient buffer.  libnccl.so.2 is bound at run time (dlopen;
+ * SEFD_NCCL_LIB overrides the name).  Rank 0 creates the 128-byte id with sefd_nccl_unique_id and hands it to the other ranks
+ * by any host-side channel (file, MPI, torchrun's store, ...). */
+typedef struct sefd_comm sefd_comm;
+int sefd_nccl_unique_id_bytes(void);
+int sefd_nccl_unique_id(void* out128);
+sefd_comm* sefd_nccl_init(int rank, int world, const void* unique_id128);
+int sefd_nccl_allreduce(sefd_comm* comm, float* buf, long long n, void* stream);   /* in place, sum, asynchronous on stream */
+int sefd_nccl_world(const sefd_comm* comm);
+void sefd_nccl_destroy(sefd_comm* comm);
 
 /* ---- measurement support (bench.py): CUDA-event timing per kernel category on the launching stream.
  * categories: 0 tap-GEMM (conv/convT/linear fwd + dgrad), 1 weight gradients, 2 BN+PReLU passes,

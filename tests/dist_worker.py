@@ -48,6 +48,18 @@ def main():
     got = eng.flat_grad.double() * scale
     err = float((got - mean).abs().max() / (mean.abs().max() + 1e-30))
     assert err < 1e-6, f"rank {rank}: reduced gradient vs mean of shard gradients: rel err {err}"
+    # the overlapped reduction (tail slice all-reduced on a side stream beside the encoder backward, head slice after it) yields
+    # the same gradient as one all-reduce after the backward (compared on the gradient itself: Adam turns rounding-level noise
+    # of near-zero gradients into +-lr updates, so parameters after a few steps are not a usable comparison)
+    assert ts.overlap, "the tail-slice all-reduce overlap should be on for a multi-rank DCCRN step"
+    ts.forward_backward(xn, xc, reduce_tail=True)
+    assert ts._tail_pending
+    sdist.allreduce_sum_(eng.flat_grad[:ts._split])
+    torch.cuda.current_stream().wait_stream(ts._comm_stream)
+    ts._tail_pending = False
+    got2 = eng.flat_grad.double() * scale
+    err2 = float((got2 - mean).abs().max() / (mean.abs().max() + 1e-30))
+    assert err2 < 1e-6, f"rank {rank}: overlapped reduction vs mean of shard gradients: rel err {err2}"
     for _ in range(3):
         ts.step(xn, xc)
     same_everywhere(eng.flat, "parameters after 3 data-parallel steps")
