@@ -269,6 +269,11 @@ int pick_rows(int rows2) {
 }  // namespace
 
 int sefd_lstm_fwd_launch(const LstmFwdParams& p, cudaStream_t st) {
+    if (const int RC = sefd_lstm_cluster_rows(p.rows, p.nl ? p.nl : 2)) {
+        sefd_prof_label("lstm_cluster_fwd rows%d T%d R%d", p.rows, p.T, RC);
+        SefdProfScope prof(SEFD_PROF_LSTM, 4.0 * p.rows * p.T * 512.0 * 128.0, 4.0 * 2 * p.rows * p.T * (2 * 512.0 + 256.0), st);
+        return sefd_lstm_cluster_fwd(p, RC, st);
+    }
     const int R = pick_rows(p.rows * (p.nl ? p.nl : 2));
     sefd_prof_label("lstm_fwd rows%d T%d R%d", p.rows, p.T, R);
     SefdProfScope prof(SEFD_PROF_LSTM, 4.0 * p.rows * p.T * 512.0 * 128.0, 4.0 * 2 * p.rows * p.T * (2 * 512.0 + 256.0), st);
@@ -278,6 +283,11 @@ int sefd_lstm_fwd_launch(const LstmFwdParams& p, cudaStream_t st) {
 }
 
 int sefd_lstm_bwd_launch(const LstmBwdParams& p, cudaStream_t st) {
+    if (const int RC = sefd_lstm_cluster_rows(p.rows, p.nl ? p.nl : 2)) {
+        sefd_prof_label("lstm_cluster_bwd rows%d T%d R%d", p.rows, p.T, RC);
+        SefdProfScope prof(SEFD_PROF_LSTM, 4.0 * p.rows * p.T * 512.0 * 128.0, 4.0 * 2 * p.rows * p.T * (2 * 512.0 + 384.0), st);
+        return sefd_lstm_cluster_bwd(p, RC, st);
+    }
     const int R = pick_rows(p.rows * (p.nl ? p.nl : 2));
     sefd_prof_label("lstm_bwd rows%d T%d R%d", p.rows, p.T, R);
     SefdProfScope prof(SEFD_PROF_LSTM, 4.0 * p.rows * p.T * 512.0 * 128.0, 4.0 * 2 * p.rows * p.T * (2 * 512.0 + 384.0), st);

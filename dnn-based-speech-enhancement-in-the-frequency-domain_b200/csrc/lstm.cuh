@@ -23,3 +23,8 @@ struct LstmBwdParams {
 };
 int sefd_lstm_fwd_launch(const LstmFwdParams& p, cudaStream_t st);
 int sefd_lstm_bwd_launch(const LstmBwdParams& p, cudaStream_t st);
+
+// cluster-split variant (lstm_cluster.cu): rows per cluster (4 or 8) when it applies to (rows, nl), else 0
+int sefd_lstm_cluster_rows(int rows, int nl);
+int sefd_lstm_cluster_fwd(const LstmFwdParams& p, int R, cudaStream_t st);
+int sefd_lstm_cluster_bwd(const LstmBwdParams& p, int R, cudaStream_t st);
