@@ -55,8 +55,12 @@ struct Unit {
 };
 __device__ __forceinline__ Unit decode_unit(const WgParams& p, long long u, int BN) {
     Unit x;
-    x.split = (int)(u % p.splits);
-    u /= p.splits;
+    // tile index fastest: the ~148 units in flight at any time are ALL (tap group, m, n) tiles of the same few row splits,
+    // so the activation / gradient rows they stream are shared through L2 instead of being re-read from HBM once per tile
+    // (split-fastest order measured 1.86x the algorithmic DRAM bytes)
+    const long long tiles = (long long)p.ngroups * p.m_tiles * p.n_tiles;
+    x.split = (int)(u / tiles);
+    u %= tiles;
     x.n0 = (int)(u % p.n_tiles) * BN;
     u /= p.n_tiles;
     x.m0 = (int)(u % p.m_tiles) * WM;
