@@ -224,7 +224,7 @@ def run_workload(name, args, env, peaks, primary):
     else:
         models.cfg.loss = "SI-SNR"
         model = models.DCCRN(masking_mode="C").to(dev).train()
-        ts = TrainStep(model, lr=1e-3, loss="SI-SNR", perceptual=perceptual)
+        ts = TrainStep(model, lr=1e-3, loss="SI-SNR", perceptual=perceptual, graph=not args.no_graph)
         models.cfg.perceptual = perceptual if perceptual else False
     noisy, clean = synthetic(B, 1234 + rank, dev)
 
@@ -245,6 +245,7 @@ def run_workload(name, args, env, peaks, primary):
     for _ in range(5 if fsn else 25):       # ~0.5 s of extra untimed steps on EVERY rank (same count: each holds an all-reduce)
         ts.step(noisy, clean)
     barrier()
+    graphed = bool(getattr(ts, "graph", False))
     n0 = lib.sefd_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -253,6 +254,12 @@ def run_workload(name, args, env, peaks, primary):
     e1.record()
     torch.cuda.synchronize()
     launches = lib.sefd_launch_count() - n0
+    if graphed:                 # the kernels were launched by graph replays: count the nodes of one eagerly issued step
+        n0 = lib.sefd_launch_count()
+        ts._step_eager(noisy, clean)
+        ts.steps += 1
+        torch.cuda.synchronize()
+        launches = (lib.sefd_launch_count() - n0) * steps
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -322,7 +329,11 @@ def run_workload(name, args, env, peaks, primary):
     if rank == 0:
         lib.sefd_prof_reset()
         lib.sefd_prof_enable(1)
-    ts.step(noisy, clean)
+    if graphed:                      # the profiled step is issued kernel by kernel (events around every launch)
+        ts._step_eager(noisy, clean)
+        ts.steps += 1
+    else:
+        ts.step(noisy, clean)
     torch.cuda.synchronize()
     lib.sefd_prof_enable(0)
     if rank == 0:
@@ -395,6 +406,8 @@ def run_workload(name, args, env, peaks, primary):
                         "sefd.train.FlatAdam") if fsn else "models.DCCRN + model.loss + backward + sefd.train.FlatAdam",
                 "h2d": "pinned -> device every step, double-buffered on a copy stream (overlaps the previous step)"},
         "gpu_launches": int(launches),
+        "launch_mode": ("one CUDA graph replay per step (gpu_launches = kernel nodes per graph x steps)" if graphed
+                        else "every kernel launched from the host"),
         "roofline": roofline,
         "kernel_breakdown_ms": breakdown,
     }
@@ -415,6 +428,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="utterances per GPU (default: the config's own, 32 / 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs (other_configs)")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel of the DCCRN step from the host instead of replaying one CUDA graph")
     ap.add_argument("--perceptual", default=None, choices=["PMSQE"],
                     help="headline = the perceptual train step (SI-SNR + PMSQE) / 2 of BASELINE configs[3] (per-GPU slice of 32)")
     args = ap.parse_args()

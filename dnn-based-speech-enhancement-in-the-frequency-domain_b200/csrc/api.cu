@@ -316,6 +316,12 @@ int sefd_adam_step(float* params, const float* grads, float* exp_avg, float* exp
     return sefd_adam(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, gscale, ST);
 }
 
+int sefd_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                       float beta1, float beta2, float eps, int* step_dev, float* bc_scratch2, float gscale, void* stream) {
+    SEFD_REQUIRE(params && grads && exp_avg && exp_avg_sq && step_dev && bc_scratch2, "adam_step_dev: null argument");
+    return sefd_adam_dev(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step_dev, bc_scratch2, gscale, ST);
+}
+
 // ---- model level ------------------------------------------------------------------------------
 sefd_plan* sefd_dccrn_plan_create(int B, int L, int masking_mode) { return sefd_plan_create_impl(B, L, masking_mode, 0); }
 sefd_plan* sefd_dccrn_plan_create_ex(int B, int L, int masking_mode, int flags) {

@@ -424,6 +424,29 @@ __global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, 
     }
 }
 
+// device-resident step counter (CUDA-graph friendly: nothing host-computed changes between steps): one thread bumps the
+// counter and derives the bias corrections in double, like the host path does
+__global__ void adam_prep_kernel(int* step, float* bc, double b1, double b2) {
+    const int t = *step + 1;
+    *step = t;
+    bc[0] = (float)(1.0 - pow(b1, (double)t));
+    bc[1] = (float)sqrt(1.0 - pow(b2, (double)t));
+}
+__global__ void adam_dev_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                                const float* __restrict__ bc, float gscale) {
+    const float bc1 = bc[0], bc2_sqrt = bc[1];
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const float gr = g[e] * gscale;
+        const float mm = b1 * m[e] + (1.f - b1) * gr;
+        const float vv = b2 * v[e] + (1.f - b2) * gr * gr;
+        m[e] = mm;
+        v[e] = vv;
+        const float denom = sqrtf(vv) / bc2_sqrt + eps;
+        w[e] -= (lr / bc1) * (mm / denom);
+    }
+}
+
 inline int grid_for(long long n, int block = 256, int cap = 148 * 16) {
     long long g = (n + block - 1) / block;
     if (g > cap) g = cap;
@@ -525,6 +548,15 @@ int sefd_clstm_combine_bwd(const float* dX, float* dH, long long n, cudaStream_t
     SefdProfScope prof(SEFD_PROF_MISC, 0, 0, st);
     clstm_combine_bwd_kernel<<<grid_for(n), 256, 0, st>>>(dX, dH, n);
     return sefd_check_launch("clstm_combine_bwd");
+}
+
+int sefd_adam_dev(float* w, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                  int* step_dev, float* bc_dev, float gscale, cudaStream_t st) {
+    SefdProfScope prof(SEFD_PROF_MISC, 0, 0, st);
+    adam_prep_kernel<<<1, 1, 0, st>>>(step_dev, bc_dev, (double)b1, (double)b2);
+    SEFD_TRY(sefd_check_launch("adam_prep"));
+    adam_dev_kernel<<<grid_for(n), 256, 0, st>>>(w, g, m, v, n, lr, b1, b2, eps, bc_dev, gscale);
+    return sefd_check_launch("adam_dev");
 }
 
 int sefd_adam(float* w, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,

@@ -89,5 +89,7 @@ int sefd_colsum2(const float* x, int nO, long long sO, long long nI, long long s
                  cudaStream_t st);
 int sefd_clstm_combine(const float* H, float* X, long long n, int round_tf32, cudaStream_t st);
 int sefd_clstm_combine_bwd(const float* dX, float* dH, long long n, cudaStream_t st);
+int sefd_adam_dev(float* w, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                  int* step_dev, float* bc_dev, float gscale, cudaStream_t st);
 int sefd_adam(float* w, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
               int step, float gscale, cudaStream_t st);

@@ -64,6 +64,8 @@ def load_checkpoint(path, model, optimizer=None, map_location="cpu"):
             optimizer.exp_avg.copy_(m)
             optimizer.exp_avg_sq.copy_(v)
             optimizer.steps = step
+            if hasattr(optimizer, "_step_dev"):          # TrainStep keeps the Adam step count on the device
+                optimizer._step_dev.fill_(int(step))
         else:
             optimizer.load_state_dict(ck["optimizer"])
     return ck["epoch"] + 1

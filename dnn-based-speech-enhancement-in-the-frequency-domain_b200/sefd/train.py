@@ -16,9 +16,16 @@ from .ops import LOSSES, ptr, stream
 
 
 class TrainStep:
-    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, loss="SI-SNR", process_group=None, perceptual=False):
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, loss="SI-SNR", process_group=None, perceptual=False,
+                 graph=False):
         """perceptual = 'PMSQE': the step of trainer.model_perceptual_train (trainer.py:44-70) with r1 = r2 = 1,
-        loss = (main + PMSQE(out_wav, clean)) / 2 (BASELINE configs[3])."""
+        loss = (main + PMSQE(out_wav, clean)) / 2 (BASELINE configs[3]).
+        graph = True: step() replays ONE CUDA graph per (input buffers, shape): the ~200 kernel launches of a step (forward,
+        loss, backward with its side-stream folds, all-reduce, Adam) become one host call.  The first call with a new pair of
+        input buffers runs eagerly (it initialises plans / workspaces), the second captures, later ones replay; the Adam step
+        count lives on the device.  Inputs must then be written INTO the same device buffers every step (e.g. WaveFeeder slots)."""
+        self.graph = bool(graph)
+        self._graphs, self._seen = {}, set()
         if perceptual not in (False, None, "PMSQE"):
             raise NotImplementedError(f"TrainStep: perceptual={perceptual!r} (built here: 'PMSQE'; LMS runs through the "
                                       "autograd drop-in, models.DCCRN.loss(..., perceptual=True))")
@@ -31,6 +38,8 @@ class TrainStep:
         self.exp_avg = torch.zeros_like(self.engine.flat)
         self.exp_avg_sq = torch.zeros_like(self.engine.flat)
         self.steps = 0
+        self._step_dev = torch.zeros(1, dtype=torch.int32, device=self.engine.flat.device)
+        self._bc_dev = torch.zeros(2, device=self.engine.flat.device)
         self.pg = process_group
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
@@ -109,7 +118,7 @@ class TrainStep:
                            plan.ws_bytes, st), eng.family + "_backward")
         return s["loss"]
 
-    def step(self, noisy, clean):
+    def _step_eager(self, noisy, clean):
         loss = self.forward_backward(noisy, clean, reduce_tail=True)
         eng = self.engine
         if self._tail_pending:                                             # head slice now, tail slice already in flight
@@ -118,12 +127,31 @@ class TrainStep:
             self._tail_pending = False
         else:
             gscale = _dist.allreduce_sum_(eng.flat_grad, self.pg)          # single flat 14.7 MB buffer
-        self.steps += 1
-        _lib.check(_lib.load().sefd_adam_step(ptr(eng.flat), ptr(eng.flat_grad), ptr(self.exp_avg),
-                                              ptr(self.exp_avg_sq), eng.flat.numel(), self.lr, self.betas[0],
-                                              self.betas[1], self.eps, self.steps, gscale, stream()),
-                   "adam_step")
+        # the step count lives on the device (same arithmetic as the host-side sefd_adam_step: corrections in double)
+        _lib.check(_lib.load().sefd_adam_step_dev(ptr(eng.flat), ptr(eng.flat_grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                                                  eng.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
+                                                  ptr(self._step_dev), ptr(self._bc_dev), gscale, stream()), "adam_step_dev")
         return loss
+
+    def step(self, noisy, clean):
+        self.steps += 1
+        if not self.graph:
+            return self._step_eager(noisy, clean)
+        key = (noisy.data_ptr(), clean.data_ptr(), tuple(noisy.shape))
+        g = self._graphs.get(key)
+        if g is None:
+            if key not in self._seen:                  # first sight of these buffers: eager (initialises plans, workspaces, streams)
+                self._seen.add(key)
+                return self._step_eager(noisy, clean)
+            self.engine.sync()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):                  # records the step (nothing executes yet)
+                self._graph_loss = self._step_eager(noisy, clean)
+            self._graphs[key] = g
+            self.launches_per_graph = None
+        g.replay()
+        return self._graph_loss
 
 
 class FlatAdam:

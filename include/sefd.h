@@ -136,6 +136,12 @@ int sefd_lstm_backward(const float* w_hh, const float* gates, const float* c, co
 int sefd_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                    float beta1, float beta2, float eps, int step, float gscale, void* stream);
 
+/* same update with the step count kept ON THE DEVICE (step_dev: 1 int, starts at 0 and is incremented by the call;
+ * bc_scratch2: 2 floats of scratch): no host-computed value changes from step to step, so a whole train step can be captured
+ * in one CUDA graph and replayed. */
+int sefd_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                       float beta1, float beta2, float eps, int* step_dev, float* bc_scratch2, float gscale, void* stream);
+
 /* ---- model level: DCCRN.forward / autograd backward (models.py:176-284) ---------------------- */
 sefd_plan* sefd_dccrn_plan_create(int B, int L, int masking_mode);
 /* flags: SEFD_PLAN_NO_SKIP builds the decoder of cfg.skip_type = False (models.py:138-169, 227-230): the transposed

@@ -270,3 +270,28 @@ def test_batch32_properties():
         _, _, w32 = m(noisy)
         _, _, w2 = m(noisy[5:7].contiguous())
     assert float((w32[5:7] - w2).abs().max()) < 1e-5     # utterances are independent in eval mode
+
+
+@pytest.mark.gpu
+def test_graphed_train_step_equals_eager(sd0):
+    """TrainStep(graph=True): the CUDA-graph replay of a step (device-resident Adam step count) produces the same losses and
+    parameters as the eager step, call for call (first call eager, second captures + replays, later ones replay)."""
+    import models
+    from oracle import dccrn_oracle as O
+    from sefd.train import TrainStep
+    models.cfg.loss = "SI-SNR"
+    noisy, clean = O.synthetic_batch(2, 4000)
+    noisy, clean = noisy.cuda(), clean.cuda()
+    out = []
+    for graph in (False, True):
+        m = models.DCCRN(masking_mode="C"); m.load_state_dict(sd0); m = m.cuda().train()
+        ts = TrainStep(m, lr=1e-3, loss="SI-SNR", graph=graph)
+        losses = [float(ts.step(noisy, clean)) for _ in range(5)]
+        torch.cuda.synchronize()
+        out.append((losses, ts.engine.flat.clone(), int(ts._step_dev)))
+    assert out[0][2] == out[1][2] == 5
+    # same trajectory; not bit-identical: Adam turns rounding-level differences of near-zero gradients (the small-shape weight
+    # gradients accumulate with atomics) into steps of at most lr, which the next losses see at the 1e-4 level
+    assert out[0][0][:2] == pytest.approx(out[1][0][:2], rel=2e-6)
+    assert out[0][0] == pytest.approx(out[1][0], rel=5e-4)
+    assert float((out[0][1] - out[1][1]).abs().max()) <= 5 * 1e-3 + 1e-6
