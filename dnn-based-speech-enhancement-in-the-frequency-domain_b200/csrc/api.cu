@@ -325,8 +325,8 @@ int sefd_adam_step_dev(float* params, const float* grads, float* exp_avg, float*
 // ---- model level ------------------------------------------------------------------------------
 sefd_plan* sefd_dccrn_plan_create(int B, int L, int masking_mode) { return sefd_plan_create_impl(B, L, masking_mode, 0); }
 sefd_plan* sefd_dccrn_plan_create_ex(int B, int L, int masking_mode, int flags) {
-    if (flags & ~SEFD_PLAN_NO_SKIP) {
-        sefd_set_error("plan: unknown flag bits 0x%x", flags & ~SEFD_PLAN_NO_SKIP);
+    if (flags & ~(SEFD_PLAN_NO_SKIP | SEFD_PLAN_REAL_LSTM)) {
+        sefd_set_error("plan: unknown flag bits 0x%x", flags & ~(SEFD_PLAN_NO_SKIP | SEFD_PLAN_REAL_LSTM));
         return nullptr;
     }
     return sefd_plan_create_impl(B, L, masking_mode, flags);

@@ -7,7 +7,39 @@
 #include "fsnet.cuh"
 #include "plan.cuh"
 #include "prof.cuh"
+#include "seqstack.cuh"
 #include "taps.cuh"
+
+// cfg.lstm = 'real' (models.py:96-105, 213-218): self.enhance = nn.LSTM(1024 -> 256, 2 layers), self.tranform = Linear(256 -> 1024)
+// on the [T, B, C * D] view of the encoder output.  Runs on the time-major layer engine (lstm_seq.cuh; B rows <= 128: the
+// chunks of the one row tile are split over a cluster).  The LSTM input is stored as D = 4 blocks of C = 256 channels
+// (k' = d * 256 + c instead of the reference's c * 4 + d): the packed W_ih columns are permuted to match.
+struct RealLstmExt {
+    SeqStack st;
+    SeqScratch sc;
+    long long w_tr, b_tr;                  // tranform.weight [1024][256], tranform.bias [1024]
+    size_t x_tm, dx_tm;                    // [T][B][1024]
+    size_t Wtrp, WtrT, btrp;               // [d][k][c], [d][c][k], [d][c]
+};
+
+namespace {
+constexpr int RL_I = 1024, RL_H = 256, RL_C = 256, RL_D = 4;
+
+// x_tm[t][b][d * 256 + c] = z[b][d][t][c]  (forward) / the inverse scatter (backward)
+__global__ void real_lstm_gather_kernel(const float* __restrict__ z, float* __restrict__ x, int B, int T, int scatter) {
+    const long long n4 = (long long)B * RL_D * T * RL_C / 4;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n4; e += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(e % (RL_C / 4));
+        long long r = e / (RL_C / 4);
+        const int t = (int)(r % T);
+        r /= T;
+        const int d = (int)(r % RL_D), b = (int)(r / RL_D);
+        const long long xi = (((long long)t * B + b) * RL_D + d) * (RL_C / 4) + c4;
+        if (scatter) reinterpret_cast<float4*>(const_cast<float*>(z))[e] = reinterpret_cast<const float4*>(x)[xi];
+        else reinterpret_cast<float4*>(x)[xi] = reinterpret_cast<const float4*>(z)[e];
+    }
+}
+}  // namespace
 
 // ------------------------------------------------------------------------------------------------
 sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode, int flags) {
@@ -71,7 +103,25 @@ sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode, int flags) {
             c.gamma = c.beta = c.alpha = c.rmean = c.rvar = -1;
         }
     }
-    for (int l = 0; l < 2; ++l) {
+    const bool real_lstm = (flags & SEFD_PLAN_REAL_LSTM) != 0;
+    if (real_lstm) {
+        RealLstmExt* R = new RealLstmExt();
+        P->rl = R;
+        for (int l = 0; l < 2; ++l) {
+            SeqLayer& Lr = R->st.l[l];
+            Lr.I_real = Lr.I = l == 0 ? RL_I : RL_H;
+            Lr.H = RL_H;
+            Lr.kd = l == 0 ? RL_D : 1;
+            const std::string sfx = "_l" + std::to_string(l);
+            add_param(P, "enhance.weight_ih" + sfx, pc, &Lr.w_ih, {4ll * RL_H, Lr.I_real});
+            add_param(P, "enhance.weight_hh" + sfx, pc, &Lr.w_hh, {4ll * RL_H, RL_H});
+            add_param(P, "enhance.bias_ih" + sfx, pc, &Lr.b_ih, {4ll * RL_H});
+            add_param(P, "enhance.bias_hh" + sfx, pc, &Lr.b_hh, {4ll * RL_H});
+        }
+        add_param(P, "tranform.weight", pc, &R->w_tr, {RL_I, RL_H});
+        add_param(P, "tranform.bias", pc, &R->b_tr, {RL_I});
+    }
+    for (int l = 0; l < (real_lstm ? 0 : 2); ++l) {
         const long long I = l == 0 ? 512 : 128;
         const char* part[2] = {"real", "imag"};
         for (int p = 0; p < 2; ++p) {
@@ -174,6 +224,16 @@ sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode, int flags) {
     P->dX = w.floats(2 * Bz * T * RNN_H);
     P->dH = w.floats(2 * 2 * Bz * T * RNN_H);
     P->dG = w.floats(2 * 2 * Bz * T * G4);
+    if (P->rl) {
+        RealLstmExt& R = *P->rl;
+        R.x_tm = w.floats(T * Bz * RL_I);
+        R.dx_tm = w.floats(T * Bz * RL_I);
+        R.Wtrp = w.floats((size_t)RL_D * RL_H * RL_C);
+        R.WtrT = w.floats((size_t)RL_D * RL_H * RL_C);
+        R.btrp = w.floats((size_t)RL_D * RL_C);
+        carve_stack(R.st, w, B, (int)T);
+        carve_seq_scratch(R.sc, w, (size_t)(B + 127) / 128 * 128 * RL_H, B, RL_H, RL_I);
+    }
     P->ws_bytes = align_up(w.cur, 256);
     return P;
 }
@@ -195,6 +255,20 @@ static int pack_weights(const sefd_plan* P, const float* prm, float* ws, int par
     }
     if (!part) return 0;
     const int tf = sefd_get_engine_internal() == 1;
+    if (P->rl) {
+        const RealLstmExt& R = *P->rl;
+        SEFD_TRY(pack_stack(R.st, prm, ws, tf, st));
+        Permute3Params q;
+        q.src = prm + R.w_tr; q.na = RL_D; q.nb = RL_H; q.nc = RL_C; q.accumulate = 0; q.nsplit = 1; q.split_stride = 0; q.round_tf32 = tf;
+        // W_tr [c * 4 + d][k] -> Wtrp[d][k][c]
+        q.dst = ws + R.Wtrp; q.sa = RL_H; q.sb = 1; q.sc = (long long)RL_D * RL_H; q.da = (long long)RL_H * RL_C; q.db = RL_C; q.dc = 1;
+        SEFD_TRY(sefd_permute3p(q, st));
+        // -> WtrT[d][c][k]
+        q.dst = ws + R.WtrT; q.nb = RL_C; q.nc = RL_H; q.sb = (long long)RL_D * RL_H; q.sc = 1; q.da = (long long)RL_C * RL_H; q.db = RL_H;
+        SEFD_TRY(sefd_permute3p(q, st));
+        SEFD_TRY(sefd_permute3(prm + R.b_tr, ws + R.btrp, 1, RL_D, RL_C, 0, 1, RL_D, 0, st));
+        return 0;
+    }
     auto perm = [&](const float* src, float* dst, int na, int nb, int nc, long long sa, long long sb, long long sc,
                     long long da, long long db, long long dc) -> int {
         Permute3Params q;
@@ -299,9 +373,32 @@ int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const 
     }
 
     if (sx != st) cudaStreamWaitEvent(st, P->ev_join, 0);      // packed LSTM / projection / decoder operands are ready
+    if (P->rl) {
+        // ---- cfg.lstm = 'real': one 2-layer nn.LSTM on [T, B, 1024] + tranform (models.py:213-218) ----
+        const RealLstmExt& R = *P->rl;
+        const int tf = sefd_get_engine_internal() == 1;
+        real_lstm_gather_kernel<<<148 * 4, 256, 0, st>>>(ws + P->enc[NL - 1].z, ws + R.x_tm, B, T, 0);
+        SEFD_TRY(sefd_check_launch("real_lstm_gather"));
+        SEFD_TRY(stack_forward(R.sc, R.st, ws, ws + R.x_tm, T, tf, nullptr, 0u, st));
+        // out[t][b][c * 4 + d] -> U[b][d][t][c]: four output rows d, the source is time-major h1 [T][B][256]
+        TapGemmParams g;
+        memset(&g, 0, sizeof(g));
+        g.a[0].p = ws + R.st.l[1].h; g.a[0].sB = RL_H; g.a[0].sF = 0; g.a[0].sT = (long long)B * RL_H; g.a[0].C = RL_H;
+        g.a[1] = no_src();
+        g.o[0] = dst4(ws + P->U, RL_D, T, RL_C, RL_C);
+        g.o[1] = no_dst();
+        g.W = ws + R.Wtrp; g.wJ = (long long)RL_H * RL_C;
+        g.Wnk = ws + R.WtrT; g.nslabs = RL_D; g.wJ_slabs = 1;
+        g.round_out[0] = tf;                                    // U feeds decoder 0
+        g.bias = ws + R.btrp; g.bJ = RL_C;
+        g.B = B; g.J = RL_D; g.Tout = T; g.Fin = 1; g.Tin = T;
+        g.fi_mul = 0; g.fo_mul = 1; g.fo_off = 0;
+        g.ntaps = 1;
+        SEFD_TRY(sefd_tapgemm(g, st));
+    }
     // ---- complex LSTM x2 (tools_for_model.py:162-177) ----
     const size_t rowsz = (size_t)T * G4;
-    for (int l = 0; l < 2; ++l) {
+    for (int l = 0; l < (P->rl ? 0 : 2); ++l) {
         for (int p = 0; p < 2; ++p)
             for (int q = 0; q < 2; ++q) {
                 TapGemmParams g;
@@ -337,7 +434,7 @@ int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const 
                                     sefd_get_engine_internal() == 1, st));
     }
     // projection r_trans / i_trans (Linear 128 -> 512), output feature c*4+d -> U[b][d][t][q*128+c]
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < (P->rl ? 0 : 2); ++q) {
         TapGemmParams g;
         memset(&g, 0, sizeof(g));
         g.a[0] = src4(ws + P->X2 + (size_t)q * B * T * RNN_H, 1, T, RNN_H, RNN_H);
@@ -520,9 +617,55 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
         SEFD_TRY(sefd_tapgemm(g, st));
     }
 
+    if (P->rl) {
+        // ---- cfg.lstm = 'real': tranform backward, LSTM stack backward, gradient back into the encoder layout ----
+        const RealLstmExt& R = *P->rl;
+        const int tf = sefd_get_engine_internal() == 1;
+        join();
+        {   // d h1[t][b][k] = sum_d sum_c dU[b][d][t][c] W_d[k][c]
+            TapGemmParams g;
+            memset(&g, 0, sizeof(g));
+            g.a[0] = src4(ws + P->dU, RL_D, T, RL_C, RL_C);
+            g.a[1] = no_src();
+            g.o[0].p = ws + R.st.dh[1]; g.o[0].sB = RL_H; g.o[0].sF = 0; g.o[0].sT = (long long)B * RL_H; g.o[0].N = RL_H;
+            g.o[1] = no_dst();
+            g.W = ws + R.WtrT; g.Wnk = ws + R.Wtrp; g.nslabs = RL_D;
+            g.B = B; g.J = 1; g.Tout = T; g.Fin = RL_D; g.Tin = T;
+            g.fi_mul = 0; g.fo_mul = 1;
+            g.ntaps = RL_D;
+            for (int d = 0; d < RL_D; ++d) { g.df[d] = d; g.dt[d] = 0; g.wslab[d] = d; }
+            SEFD_TRY(sefd_tapgemm(g, st));
+        }
+        {   // dW_tr[c * 4 + d][k] = sum dU[b][d][t][c] h1[t][b][k]
+            WgradParams wg;
+            memset(&wg, 0, sizeof(wg));
+            wg.a[0].p = ws + R.st.l[1].h; wg.a[0].sB = RL_H; wg.a[0].sF = 0; wg.a[0].sT = (long long)B * RL_H; wg.a[0].C = RL_H;
+            wg.a[1] = no_src();
+            wg.g = src4(ws + P->dU, RL_D, T, RL_C, RL_C);
+            wg.dW = dWs;
+            wg.B = B; wg.J = 1; wg.Tg = T; wg.Fa = 1; wg.Ta = T; wg.Fg = RL_D;
+            wg.a_mul = 0; wg.g_mul = 0; wg.ntaps = RL_D;
+            for (int d = 0; d < RL_D; ++d) { wg.a_off[d] = 0; wg.g_off[d] = d; wg.dt[d] = 0; wg.wslab[d] = d; }
+            SEFD_TRY(sefd_wgrad(wg, dWs, (long long)P->dWs_floats, RL_D, &nsplit, &sstride, st));
+            // dWs[d][k][c] -> grads[c][d][k]
+            Permute3Params q;
+            q.src = dWs; q.dst = grads + R.w_tr; q.na = RL_C; q.nb = RL_D; q.nc = RL_H;
+            q.sa = 1; q.sb = (long long)RL_H * RL_C; q.sc = RL_C;
+            q.da = (long long)RL_D * RL_H; q.db = RL_H; q.dc = 1;
+            q.accumulate = 0; q.nsplit = nsplit; q.split_stride = sstride; q.round_tf32 = 0;
+            SEFD_TRY(sefd_permute3p(q, st));
+            for (int d = 0; d < RL_D; ++d)
+                SEFD_TRY(sefd_colsum2(ws + P->dU + (size_t)d * T * RL_C, B, (long long)RL_D * T * RL_C, T, RL_C, RL_C, wsd + P->red,
+                                      ws + P->dbs + d * RL_C, st));
+            SEFD_TRY(sefd_permute3(ws + P->dbs, grads + R.b_tr, 1, RL_C, RL_D, 0, 1, RL_C, 0, st));    // dbs[d][c] -> grads[c * 4 + d]
+        }
+        SEFD_TRY(stack_backward(R.sc, R.st, ws, ws + R.x_tm, T, tf, nullptr, 0u, ws + R.dx_tm, grads, st));
+        real_lstm_gather_kernel<<<148 * 4, 256, 0, st>>>(ws + (P->skip ? P->enc[NL - 1].dz2 : P->enc[NL - 1].dz), ws + R.dx_tm, B, T, 1);
+        SEFD_TRY(sefd_check_launch("real_lstm_scatter"));
+    }
     // ---- projection backward ----
     const long long nX = (long long)B * T * RNN_H;
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < (P->rl ? 0 : 2); ++q) {
         TapGemmParams g;
         memset(&g, 0, sizeof(g));
         g.a[0] = src4(ws + P->dU + q * 128, 4, T, 256, 128);
@@ -553,17 +696,17 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
         SEFD_TRY(unperm(dWs, grads + P->w_tr[q], 128, 4, 128, 1, 128 * 128, 128, 0));
         side_done();
     }
-    fork();
+    if (!P->rl) fork();
     // db_tr[q][c*4+d] = sum_{b,t} dU[b][d][t][q*128+c]
-    for (int d = 0; d < 4; ++d)
+    for (int d = 0; d < (P->rl ? 0 : 4); ++d)
         SEFD_TRY(sefd_colsum2(ws + P->dU + (size_t)d * T * 256, B, (long long)4 * T * 256, T, 256, 256,
                               red_side, ws + P->dbs + d * 256, sx));
-    for (int q = 0; q < 2; ++q)   // dbs[d][q*128+c] -> grads[c*4+d]
+    for (int q = 0; q < (P->rl ? 0 : 2); ++q)   // dbs[d][q*128+c] -> grads[c*4+d]
         SEFD_TRY(sefd_permute3(ws + P->dbs + q * 128, grads + P->b_tr[q], 1, 128, 4, 0, 1, 256, 0, sx));
-    side_done();
+    if (!P->rl) side_done();
 
     // ---- LSTM backward (layer 1 then layer 0) ----
-    for (int l = 1; l >= 0; --l) {
+    for (int l = P->rl ? -1 : 1; l >= 0; --l) {
         join();                                            // side kernels of the previous layer still read dG
         SEFD_TRY(sefd_clstm_combine_bwd(ws + P->dX, ws + P->dH, nX, st));
         LstmBwdParams lb;
@@ -713,6 +856,7 @@ void sefd_dccrn_plan_destroy(sefd_plan* plan) {
         cudaEventDestroy(plan->ev_join);
     }
     if (plan && plan->fsn) sefd_fsn_plan_free_ext(plan);
+    if (plan && plan->rl) delete plan->rl;
     delete plan;
 }
 size_t sefd_dccrn_workspace_bytes(const sefd_plan* plan) { return plan ? plan->ws_bytes : 0; }

@@ -19,53 +19,27 @@
 #include "lstm_seq.cuh"
 #include "plan.cuh"
 #include "prof.cuh"
+#include "seqstack.cuh"
 
 namespace {
 
 constexpr int FBINS = 257, FPAD = 288, SB_N = 15, SB_I = 32, LOOK = 2, FB_H = 512, SB_H = 384;
 constexpr float NORM_EPS = 1e-5f;
 
-struct FsnLayer {
-    int I_real, I, H;
-    long long w_ih, w_hh, b_ih, b_hh;                    // parameter offsets
-    size_t Wih_nk, Wih_kn, Whh_nk, Whh_kn, bias, Wcat;   // packed operands (workspace, floats); Whh_kn follows Wih_kn directly
-    size_t gates, h, c;                                  // gates / c sized for rows rounded up to 128 (tile-major in the fused path)
-    mutable int tiled = 0;                               // layout the last forward left gates / c in (lstm_seq.cuh)
-};
-struct FsnStack {
-    FsnLayer l[2];
-    int rows;
-    size_t h0d;                                          // inter-layer dropout output [T][rows][H]
-    size_t dh[2];                                        // gradient arriving at h of layer l from above [T][rows][H]
-    long long fc_w, fc_b;
-};
-
 }  // namespace
 
 struct FsnExt {
     int B, Tf, T, R;
-    FsnStack fb, sb;
+    SeqStack fb, sb;
     size_t rowsum /*double [B][257]*/, wsum /*double [B]*/, sum2 /*double [B]*/, Sred /*double [B]*/, inv /*float [2][B]*/;
     size_t fb_in, fb_lin, dfb_lin, Wl_nk, Wl_kn, bl, sb_in, dsb_in;
-    size_t dh_rec, dc, bias_part, wpart, hpart, red /*double*/;
-    long long wpart_floats;
+    size_t hpart, red /*double*/;
+    mutable SeqScratch sc;      // scratch of the LSTM stacks + dropout state of the last forward (needed by the backward)
     int head_blocks;
-    // state of the last forward (needed by the backward)
-    mutable int drop_on = 0;
-    mutable float drop_p = 0.f;
-    mutable unsigned long long seed = 0;
     mutable const float *mask_fb = nullptr, *mask_sb = nullptr;
 };
 
 namespace {
-
-SeqLstmWeights weights_of(const FsnLayer& L, const float* ws) {
-    SeqLstmWeights w;
-    w.Wih_nk = ws + L.Wih_nk; w.Wih_kn = ws + L.Wih_kn; w.Whh_nk = ws + L.Whh_nk; w.Whh_kn = ws + L.Whh_kn; w.bias = ws + L.bias;
-    w.Wcat_nk = ws + L.Wcat;
-    w.I = L.I; w.H = L.H;
-    return w;
-}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // feature normalisation / sub-band unfolding
@@ -354,124 +328,10 @@ __global__ void fold_linear_kernel(const float* __restrict__ part, int nsplit, l
 // ---------------------------------------------------------------------------------------------------------------------
 // host helpers
 // ---------------------------------------------------------------------------------------------------------------------
-TapSrc tm_src(const float* p, int rows, int T, int C) {      // time-major [T][rows][C] as [B = 1][F = T]["T" = rows][C]
-    TapSrc s;
-    s.p = p; s.sT = C; s.sF = (long long)rows * C; s.sB = (long long)T * rows * C; s.C = C;
-    return s;
-}
-TapDst tm_dst(float* p, int rows, int T, int N) {
-    TapDst d;
-    d.p = p; d.sT = N; d.sF = (long long)rows * N; d.sB = (long long)T * rows * N; d.N = N;
-    return d;
-}
-// out[t][r][:] = a[t][r][:] W + bias over all steps
-int gemm_all_steps(const float* a, int K, float* out, int N, int rows, int T, const float* Wkn, const float* Wnk, const float* bias,
-                   int round_out, cudaStream_t st) {
-    TapGemmParams g;
-    memset(&g, 0, sizeof(g));
-    g.a[0] = tm_src(a, rows, T, K);
-    g.o[0] = tm_dst(out, rows, T, N);
-    g.W = Wkn; g.Wnk = Wnk; g.nslabs = 1; g.bias = bias;
-    g.B = 1; g.J = T; g.Tout = rows; g.Fin = T; g.Tin = rows;
-    g.fi_mul = 1; g.fo_mul = 1; g.fo_off = 0; g.ntaps = 1;
-    g.round_out[0] = round_out;
-    return sefd_tapgemm(g, st);
-}
-// partial[s][k][n] = sum over steps j < J and rows of a[j][r][k] g[j][r][n]
-int wgrad_all_steps(const float* a, int K, const float* g, int N, int rows, int J, int g_tiled, float* part, long long cap, int* nsplit,
-                    long long* sstride, cudaStream_t st) {
-    WgradParams w;
-    memset(&w, 0, sizeof(w));
-    w.a[0] = tm_src(a, rows, J, K);
-    w.g = tm_src(g, rows, J, N);
-    w.g_tiled = g_tiled;
-    w.B = 1; w.J = J; w.Tg = rows; w.Fa = J; w.Ta = rows; w.Fg = J;
-    w.a_mul = 1; w.g_mul = 1; w.ntaps = 1;
-    w.rows_per_cta = 1;
-    return sefd_wgrad(w, part, cap, 1, nsplit, sstride, st);
-}
-
-int pack_stack(const FsnStack& S, const float* prm, float* ws, int tf, cudaStream_t st) {
-    for (int l = 0; l < 2; ++l) {
-        const FsnLayer& L = S.l[l];
-        SeqLstmPackParams p;
-        p.w_ih = prm + L.w_ih; p.w_hh = prm + L.w_hh; p.b_ih = prm + L.b_ih; p.b_hh = prm + L.b_hh;
-        p.I_real = L.I_real; p.I = L.I; p.H = L.H;
-        p.Wih_nk = ws + L.Wih_nk; p.Wih_kn = ws + L.Wih_kn; p.Whh_nk = ws + L.Whh_nk; p.Whh_kn = ws + L.Whh_kn; p.bias = ws + L.bias;
-        p.Wcat_nk = ws + L.Wcat;
-        p.round_tf32 = tf;
-        SEFD_TRY(sefd_seqlstm_pack(p, st));
-    }
-    return 0;
-}
-
-int stack_forward(const FsnExt& E, const FsnStack& S, float* ws, const float* x, int T, int tf, const float* mask, unsigned int stream_id,
-                  cudaStream_t st) {
-    for (int l = 0; l < 2; ++l) {
-        const FsnLayer& L = S.l[l];
-        SeqLstmFwdParams p;
-        p.x = l == 0 ? x : (E.drop_on ? ws + S.h0d : ws + S.l[0].h);
-        p.w = weights_of(L, ws);
-        p.gates = ws + L.gates; p.h = ws + L.h; p.c = ws + L.c;
-        p.rows = S.rows; p.T = T; p.round_h = tf; p.h_zero_slot = 1;
-        cudaMemsetAsync(ws + L.h - (size_t)S.rows * L.H, 0, sizeof(float) * S.rows * L.H, st);     // h_{-1} = 0
-        SEFD_TRY(sefd_seqlstm_forward(p, st));
-        L.tiled = p.tiled;
-        if (l == 0 && E.drop_on)
-            SEFD_TRY(sefd_dropout_apply(ws + L.h, ws + S.h0d, (long long)T * S.rows * L.H, E.drop_p, mask, E.seed, stream_id, tf, st));
-    }
-    return 0;
-}
-
-// backward through the two layers; dh[1] holds the gradient arriving at h1.  dx0 (gradient w.r.t. the stack input) is
-// written when non-null.
-int stack_backward(const FsnExt& E, const FsnStack& S, float* ws, const float* x, int T, int tf, const float* mask, unsigned int stream_id,
-                   float* dx0, float* grads, cudaStream_t st) {
-    const int rows = S.rows;
-    for (int l = 1; l >= 0; --l) {
-        const FsnLayer& L = S.l[l];
-        const int N = 4 * L.H;
-        SeqLstmBwdParams p;
-        p.w = weights_of(L, ws);
-        p.gates = ws + L.gates; p.c = ws + L.c; p.dh_out = ws + S.dh[l];
-        p.dh_rec = ws + E.dh_rec; p.dc = ws + E.dc; p.bias_part = ws + E.bias_part;
-        p.rows = rows; p.T = T; p.round_tf32 = tf;
-        p.dx = l == 1 ? ws + S.dh[0] : dx0;
-        p.dx_done = 0;
-        p.tiled = L.tiled;
-        SEFD_TRY(sefd_seqlstm_backward(p, st));
-        const long long step_stride = L.tiled ? (long long)((rows + 127) / 128) * 128 * N : (long long)rows * N;
-        const float* dG = ws + L.gates;
-        const float* xin = l == 0 ? x : (E.drop_on ? ws + S.h0d : ws + S.l[0].h);
-        int nsplit = 1;
-        long long sstride = 0;
-        float* part = ws + E.wpart;
-        SEFD_TRY(wgrad_all_steps(xin, L.I, dG, N, rows, T, L.tiled, part, E.wpart_floats, &nsplit, &sstride, st));
-        SEFD_TRY(sefd_seqlstm_fold_wgrad(part, nsplit, sstride, L.I, L.I_real, L.H, grads + L.w_ih, st));
-        if (T > 1) {
-            SEFD_TRY(wgrad_all_steps(ws + L.h, L.H, dG + step_stride, N, rows, T - 1, L.tiled, part, E.wpart_floats, &nsplit, &sstride, st));
-            SEFD_TRY(sefd_seqlstm_fold_wgrad(part, nsplit, sstride, L.H, L.H, L.H, grads + L.w_hh, st));
-        } else {
-            cudaMemsetAsync(grads + L.w_hh, 0, sizeof(float) * N * L.H, st);
-        }
-        SEFD_TRY(sefd_seqlstm_fold_bias(ws + E.bias_part, p.bias_blocks, L.H, grads + L.b_ih, grads + L.b_hh, st));
-        float* dx = l == 1 ? ws + S.dh[0] : dx0;
-        if (dx) {
-            if (!p.dx_done) {
-                SEFD_REQUIRE(!L.tiled, "fsn backward: the input gradient must come from the fused step kernel when dG is tile-major");
-                SEFD_TRY(gemm_all_steps(dG, N, dx, L.I, rows, T, L.Wih_nk + ws, L.Wih_kn + ws, nullptr, 0, st));
-            }
-            if (l == 1 && E.drop_on)
-                SEFD_TRY(sefd_dropout_apply(dx, dx, (long long)T * rows * L.I, E.drop_p, mask, E.seed, stream_id, 0, st));
-        }
-    }
-    return 0;
-}
-
-void add_stack_params(sefd_plan* P, FsnStack& S, const char* name, int I, int O, int H, long long& pc) {
+void add_stack_params(sefd_plan* P, SeqStack& S, const char* name, int I, int O, int H, long long& pc) {
     const std::string pre = std::string(name) + ".sequence_model.";
     for (int l = 0; l < 2; ++l) {
-        FsnLayer& L = S.l[l];
+        SeqLayer& L = S.l[l];
         L.I_real = l == 0 ? I : H;
         L.I = (L.I_real + 31) / 32 * 32;
         L.H = H;
@@ -483,26 +343,6 @@ void add_stack_params(sefd_plan* P, FsnStack& S, const char* name, int I, int O,
     }
     add_param(P, std::string(name) + ".fc_output_layer.weight", pc, &S.fc_w, {O, H});
     add_param(P, std::string(name) + ".fc_output_layer.bias", pc, &S.fc_b, {O});
-}
-
-void carve_stack(FsnStack& S, Carver& w, int rows, int T) {
-    S.rows = rows;
-    for (int l = 0; l < 2; ++l) {
-        FsnLayer& L = S.l[l];
-        const size_t N = 4 * (size_t)L.H;
-        L.Wih_nk = w.floats(N * L.I);
-        L.Whh_nk = w.floats(N * L.H);
-        L.Whh_kn = w.floats(N * (L.I + L.H));        // [H][4H'] immediately followed by [I][4H'] = the backward's [W_hh^T ; W_ih^T]
-        L.Wih_kn = L.Whh_kn + N * L.H;
-        L.Wcat = w.floats(N * (L.I + L.H));
-        L.bias = w.floats(N);
-        const size_t rpad = (size_t)(rows + 127) / 128 * 128;
-        L.gates = w.floats((size_t)T * rpad * N);
-        L.h = w.floats((size_t)(T + 1) * rows * L.H) + (size_t)rows * L.H;     // one zero step in front (h_{-1})
-        L.c = w.floats((size_t)T * rpad * L.H);
-        S.dh[l] = w.floats((size_t)T * rows * L.H);
-    }
-    S.h0d = w.floats((size_t)T * rows * S.l[0].H);
 }
 
 }  // namespace
@@ -544,12 +384,7 @@ sefd_plan* sefd_fsn_plan_create_impl(int B, int Tf) {
     carve_stack(E->fb, w, B, T);
     carve_stack(E->sb, w, R, T);
     const size_t state = std::max((size_t)(R + 127) / 128 * 128 * SB_H, (size_t)(B + 127) / 128 * 128 * FB_H);
-    E->dh_rec = w.floats(state);
-    E->dc = w.floats(state);
-    const int nblk = sefd_seqlstm_bias_blocks(R);
-    E->bias_part = w.floats((size_t)nblk * 4 * FB_H);
-    E->wpart_floats = 32ll * 4 * FB_H * FB_H;
-    E->wpart = w.floats((size_t)E->wpart_floats);
+    carve_seq_scratch(E->sc, w, state, R, FB_H, FB_H);
     E->head_blocks = 148 * 4;
     E->hpart = w.floats((size_t)E->head_blocks * (2 * SB_H + 2));
     P->ws_bytes = align_up(w.cur, 256);
@@ -573,8 +408,8 @@ int sefd_fsn_forward_impl(const sefd_plan* P, const float* prm, const float* noi
     double* wsd = (double*)wsv;
     const int B = E.B, Tf = E.Tf, T = E.T, R = E.R;
     const int tf = sefd_get_engine_internal() == 1;
-    E.drop_on = train && dropout_p > 0.f;
-    E.drop_p = dropout_p; E.seed = seed; E.mask_fb = mask_fb; E.mask_sb = mask_sb;
+    E.sc.drop_on = train && dropout_p > 0.f;
+    E.sc.drop_p = dropout_p; E.sc.seed = seed; E.mask_fb = mask_fb; E.mask_sb = mask_sb;
 
     // ---- packed operands ----
     SEFD_TRY(pack_stack(E.fb, prm, ws, tf, st));
@@ -592,7 +427,7 @@ int sefd_fsn_forward_impl(const sefd_plan* P, const float* prm, const float* noi
         fsn_fb_in_kernel<<<dim3((T + 31) / 32, FPAD / 32, B), dim3(32, 8), 0, st>>>(noisy_mag, ws + E.inv, B, Tf, T, ws + E.fb_in, tf);
         SEFD_TRY(sefd_check_launch("fsn_fb_in"));
     }
-    SEFD_TRY(stack_forward(E, E.fb, ws, ws + E.fb_in, T, tf, mask_fb, 1u, st));
+    SEFD_TRY(stack_forward(E.sc, E.fb, ws, ws + E.fb_in, T, tf, mask_fb, 1u, st));
     SEFD_TRY(gemm_all_steps(ws + E.fb.l[1].h, FB_H, ws + E.fb_lin, FPAD, B, T, ws + E.Wl_kn, ws + E.Wl_nk, ws + E.bl, 0, st));
 
     // ---- sub-band input (models.py:649-664) ----
@@ -606,7 +441,7 @@ int sefd_fsn_forward_impl(const sefd_plan* P, const float* prm, const float* noi
         SEFD_TRY(sefd_check_launch("fsn_unfold"));
     }
     // ---- sub-band model (models.py:667) ----
-    SEFD_TRY(stack_forward(E, E.sb, ws, ws + E.sb_in, T, tf, mask_sb, 2u, st));
+    SEFD_TRY(stack_forward(E.sc, E.sb, ws, ws + E.sb_in, T, tf, mask_sb, 2u, st));
     {
         SefdProfScope prof(SEFD_PROF_MISC, 4.0 * T * R * SB_H, 4.0 * T * R * SB_H, st);
         sb_head_fwd_kernel<SB_H><<<148 * 8, 256, 0, st>>>(ws + E.sb.l[1].h, prm + E.sb.fc_w, prm + E.sb.fc_b, crm, T, R, Tf);
@@ -634,7 +469,7 @@ int sefd_fsn_backward_impl(const sefd_plan* P, const float* prm, const float* d_
         SEFD_TRY(sefd_check_launch("fsn_sb_head_fold"));
     }
     // ---- sub-band LSTMs ----
-    SEFD_TRY(stack_backward(E, E.sb, ws, ws + E.sb_in, T, tf, E.mask_sb, 2u, ws + E.dsb_in, grads, st));
+    SEFD_TRY(stack_backward(E.sc, E.sb, ws, ws + E.sb_in, T, tf, E.mask_sb, 2u, ws + E.dsb_in, grads, st));
     // ---- normalisation / unfold backward: only the full-band output carries a gradient (models.py:649-658) ----
     {
         SefdProfScope prof(SEFD_PROF_STFT, 0, 8.0 * T * R * SB_I, st);
@@ -648,8 +483,8 @@ int sefd_fsn_backward_impl(const sefd_plan* P, const float* prm, const float* d_
     {
         int nsplit = 1;
         long long sstride = 0;
-        float* part = ws + E.wpart;
-        SEFD_TRY(wgrad_all_steps(ws + E.fb.l[1].h, FB_H, ws + E.dfb_lin, FPAD, B, T, 0, part, E.wpart_floats, &nsplit, &sstride, st));
+        float* part = ws + E.sc.wpart;
+        SEFD_TRY(wgrad_all_steps(ws + E.fb.l[1].h, FB_H, ws + E.dfb_lin, FPAD, B, T, 0, part, E.sc.wpart_floats, &nsplit, &sstride, st));
         fold_linear_kernel<<<dim3(FPAD / 32, FB_H / 32), dim3(32, 8), 0, st>>>(part, nsplit, sstride, FB_H, FPAD, FBINS, grads + E.fb.fc_w);
         SEFD_TRY(sefd_check_launch("fsn_fold_linear"));
         SEFD_TRY(sefd_colsum2(ws + E.dfb_lin, 1, 0, (long long)T * B, FPAD, FPAD, wsd + E.red, ws + E.bl, st));   // bl is free after the forward
@@ -657,7 +492,7 @@ int sefd_fsn_backward_impl(const sefd_plan* P, const float* prm, const float* d_
         SEFD_TRY(gemm_all_steps(ws + E.dfb_lin, FPAD, ws + E.fb.dh[1], FB_H, B, T, ws + E.Wl_nk, ws + E.Wl_kn, nullptr, 0, st));
     }
     // ---- full-band LSTMs (the input is data: no dx) ----
-    SEFD_TRY(stack_backward(E, E.fb, ws, ws + E.fb_in, T, tf, E.mask_fb, 1u, nullptr, grads, st));
+    SEFD_TRY(stack_backward(E.sc, E.fb, ws, ws + E.fb_in, T, tf, E.mask_fb, 1u, nullptr, grads, st));
     return 0;
 }
 
@@ -676,10 +511,10 @@ int sefd_fsn_tensor_info(const sefd_plan* P, const char* name, long long* off, i
     if (n == "sb_in") return set(E.sb_in, T, R, SB_I);
     if (n == "dsb_in") return set(E.dsb_in, T, R, SB_I);
     if (n.size() == 6 && (n.compare(0, 3, "fb.") == 0 || n.compare(0, 3, "sb.") == 0)) {
-        const FsnStack& S = n[0] == 'f' ? E.fb : E.sb;
+        const SeqStack& S = n[0] == 'f' ? E.fb : E.sb;
         const int l = n[5] - '0';
         SEFD_REQUIRE(l == 0 || l == 1, "tensor_info: bad name %s", name);
-        const FsnLayer& L = S.l[l];
+        const SeqLayer& L = S.l[l];
         if (n[3] == 'h' && n[4] == '.') return set(L.h, T, S.rows, L.H);          // "sb.h.1"
         if (n[3] == 'c' && n[4] == '.') return set(L.c, T, S.rows, L.H);
         if (n[3] == 'g' && n[4] == '.') return set(L.gates, T, S.rows, 4 * L.H);

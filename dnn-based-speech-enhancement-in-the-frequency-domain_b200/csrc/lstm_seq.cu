@@ -30,7 +30,8 @@ __global__ void pack_kernel(const SeqLstmPackParams p) {
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nih + nhh + N; e += (long long)gridDim.x * blockDim.x) {
         if (e < nih) {
             const int n = (int)(e / p.I), k = (int)(e % p.I);
-            float v = k < p.I_real ? p.w_ih[(long long)n * p.I_real + k] : 0.f;
+            const int ks = p.kd > 1 ? (k % (p.I_real / p.kd)) * p.kd + k / (p.I_real / p.kd) : k;     // reference column of stored column k
+            float v = k < p.I_real ? p.w_ih[(long long)n * p.I_real + ks] : 0.f;
             if (p.round_tf32) v = tf32_rn(v);
             const int np = interleave(n, p.H);
             p.Wih_nk[(long long)np * p.I + k] = v;
@@ -53,7 +54,7 @@ __global__ void pack_kernel(const SeqLstmPackParams p) {
 }
 
 __global__ void fold_wgrad_kernel(const float* __restrict__ part, int nsplit, long long split_stride, int K, int K_real, int H,
-                                  float* __restrict__ dW) {
+                                  float* __restrict__ dW, int kd) {
     // tile transpose: read [k][n'] coalesced over n', write [n][k] coalesced over k
     __shared__ float tile[32][33];
     const int N = 4 * H;
@@ -71,7 +72,8 @@ __global__ void fold_wgrad_kernel(const float* __restrict__ part, int nsplit, lo
         // inverse of the interleave: n' = ub * 32 + g * 8 + i
         const int ub = np >> 5, g = (np >> 3) & 3, i8 = np & 7;
         const int n = g * H + ub * 8 + i8;
-        if (k < K_real) dW[(long long)n * K_real + k] = tile[threadIdx.x][r];
+        const int ks = kd > 1 ? (k % (K_real / kd)) * kd + k / (K_real / kd) : k;
+        if (k < K_real) dW[(long long)n * K_real + ks] = tile[threadIdx.x][r];
     }
 }
 
@@ -265,10 +267,10 @@ int sefd_seqlstm_pack(const SeqLstmPackParams& p, cudaStream_t st) {
 }
 
 int sefd_seqlstm_fold_wgrad(const float* part, int nsplit, long long split_stride, int K, int K_real, int H, float* dW,
-                            cudaStream_t st) {
+                            cudaStream_t st, int kd) {
     SefdProfScope prof(SEFD_PROF_MISC, 0, 0, st);
     dim3 grid(4 * H / 32, (K + 31) / 32), block(32, 8);
-    fold_wgrad_kernel<<<grid, block, 0, st>>>(part, nsplit, split_stride, K, K_real, H, dW);
+    fold_wgrad_kernel<<<grid, block, 0, st>>>(part, nsplit, split_stride, K, K_real, H, dW, kd);
     return sefd_check_launch("seqlstm_fold_wgrad");
 }
 

@@ -35,12 +35,14 @@ struct SeqLstmPackParams {
     float *Wih_nk, *Wih_kn, *Whh_nk, *Whh_kn, *bias;
     float* Wcat_nk;        // optional
     int round_tf32;
+    int kd;                // input-column permutation of layer 0 (0 / 1: none): the stored column k' = d * (I / kd) + c holds the
+                           // reference's column c * kd + d (DCCRN's [T, B, C * D] LSTM input read as D blocks of C channels)
 };
 int sefd_seqlstm_pack(const SeqLstmPackParams& p, cudaStream_t st);
 
 // dW[n][k] (reference layout [4H][K_real]) = sum_s part[s][k][n'(n)]   (partials [nsplit][K][4H'] of sefd_wgrad)
 int sefd_seqlstm_fold_wgrad(const float* part, int nsplit, long long split_stride, int K, int K_real, int H, float* dW,
-                            cudaStream_t st);
+                            cudaStream_t st, int kd = 1);
 // db_ih[n] = db_hh[n] = sum_blk part[blk][n'(n)]
 int sefd_seqlstm_fold_bias(const float* part, int nblk, int H, float* db_ih, float* db_hh, cudaStream_t st);
 

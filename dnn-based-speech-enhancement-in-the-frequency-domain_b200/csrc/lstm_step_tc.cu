@@ -690,7 +690,7 @@ bool persist_mode() {
 
 }  // namespace
 
-bool sefd_lstm_step_tc_eligible(int I, int H) { return I % 32 == 0 && H % 64 == 0 && H <= 512 && I >= 32 && I <= 512; }
+bool sefd_lstm_step_tc_eligible(int I, int H) { return I % 32 == 0 && H % 64 == 0 && H <= 512 && I >= 32 && I <= 1024; }
 bool sefd_lstm_step_tc_has_backward() { return true; }
 
 int sefd_lstm_step_bias_blocks(int rows) { return (rows + TM - 1) / TM + 8; }

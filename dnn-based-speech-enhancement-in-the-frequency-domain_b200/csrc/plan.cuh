@@ -38,11 +38,13 @@ struct ConvLayer {
 }  // namespace
 
 struct FsnExt;               // fsnet.cu
+struct RealLstmExt;          // dccrn.cu: cfg.lstm = 'real'
 
 struct sefd_plan {
     int kind;                 // 0: DCCRN (complex), 1: CRN (real), 2: FullSubNet (fsnet.cu; everything below except the
                               // parameter list / workspace size lives in `fsn`)
     FsnExt* fsn = nullptr;
+    RealLstmExt* rl = nullptr; // non-null: the recurrent part is one 2-layer nn.LSTM(1024 -> 256) + Linear (models.py:96-105)
     int B, L, T, mask_mode;
     int skip = 1;             // 1: decoder convs read complex_cat(out, encoder skip) (cfg.skip_type, models.py:107-169)
     int ch[NL + 1], Fe[NL + 1];

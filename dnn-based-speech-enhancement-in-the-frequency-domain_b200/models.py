@@ -31,8 +31,8 @@ class DCCRN(nn.Module):
             unsupported.append(f"window {win_type!r} (built: periodic Hann)")
         if kernel_num != _d.KERNEL_NUM or kernel_size != 5:
             unsupported.append(f"kernel_num {kernel_num} / kernel_size {kernel_size}")
-        if rnn_layers != 2 or rnn_units != 256 or cfg.lstm != "complex":
-            unsupported.append(f"rnn_layers={rnn_layers}, rnn_units={rnn_units}, lstm={cfg.lstm!r} (built: 2 x complex LSTM 256)")
+        if rnn_layers != 2 or rnn_units != 256 or cfg.lstm not in ("complex", "real"):
+            unsupported.append(f"rnn_layers={rnn_layers}, rnn_units={rnn_units}, lstm={cfg.lstm!r} (built: 2 layers, 256 units, 'complex' / 'real')")
         if use_cbn:
             unsupported.append("use_cbn=True (ComplexBatchNorm, tools_for_model.py:430-603)")
         if masking_mode not in _ops.MODES:
@@ -55,12 +55,18 @@ class DCCRN(nn.Module):
             self.encoder.append(nn.Sequential(_d.ComplexConvParams(kn[i], kn[i + 1], transposed=False),
                                               _d.BatchNormParams(kn[i + 1]), _d.PReLUParams()))
         hidden_dim = fft_len // (2 ** len(kn))
-        rnns = []
-        for i in range(rnn_layers):                                      # models.py:83-95
-            rnns.append(_d.ComplexLSTMParams(
-                input_size=hidden_dim * kn[-1] if i == 0 else rnn_units, hidden_size=rnn_units,
-                projection_dim=hidden_dim * kn[-1] if i == rnn_layers - 1 else None))
-        self.enhance = nn.Sequential(*rnns)
+        self.lstm_type = cfg.lstm
+        if cfg.lstm == "complex":
+            rnns = []
+            for i in range(rnn_layers):                                  # models.py:83-95
+                rnns.append(_d.ComplexLSTMParams(
+                    input_size=hidden_dim * kn[-1] if i == 0 else rnn_units, hidden_size=rnn_units,
+                    projection_dim=hidden_dim * kn[-1] if i == rnn_layers - 1 else None))
+            self.enhance = nn.Sequential(*rnns)
+        else:                                                            # models.py:96-105: nn.LSTM(1024 -> 256, 2 layers) + Linear
+            from sefd.fullsubnet import StackedLSTMParams
+            self.enhance = StackedLSTMParams(hidden_dim * kn[-1], rnn_units, num_layers=2, dropout=0.0)
+            self.tranform = _d.LinearParams(rnn_units, hidden_dim * kn[-1])
         for idx in range(len(kn) - 1, 0, -1):                            # models.py:107-137
             mods = [_d.ComplexConvParams(kn[idx] * (2 if self.skip_type else 1), kn[idx - 1], transposed=True)]   # :138-169 without skip
             if idx != 1:
@@ -73,7 +79,7 @@ class DCCRN(nn.Module):
     def _get_engine(self):
         eng = self.__dict__.get("_engine")
         if eng is None:
-            eng = _d.Engine(self, self.masking_mode, skip=self.skip_type)
+            eng = _d.Engine(self, self.masking_mode, skip=self.skip_type, real_lstm=self.lstm_type == "real")
             self.__dict__["_engine"] = eng
         return eng
 

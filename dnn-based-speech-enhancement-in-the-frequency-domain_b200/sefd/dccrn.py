@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .ops import LOSSES, MODES, PLAN_NO_SKIP, ptr, stream
+from .ops import LOSSES, MODES, PLAN_NO_SKIP, PLAN_REAL_LSTM, ptr, stream
 
 KERNEL_NUM = [32, 64, 128, 256, 256, 256]
 
@@ -136,16 +136,17 @@ class STFTBuffers(nn.Module):
 # plan + workspace cache
 # --------------------------------------------------------------------------------------------------
 class Plan:
-    def __init__(self, B, L, mode, family="dccrn", skip=True):
+    def __init__(self, B, L, mode, family="dccrn", skip=True, real_lstm=False):
         lib = _lib.load()
         self.family = family
         self.skip = skip
+        self.real_lstm = real_lstm
         if family == "crn":
             self.handle = lib.sefd_crn_plan_create(B, L)
         elif family == "fsn":                      # L = number of STFT frames of noisy_mag
             self.handle = lib.sefd_fsn_plan_create(B, L)
         else:
-            self.handle = lib.sefd_dccrn_plan_create_ex(B, L, MODES[mode], 0 if skip else PLAN_NO_SKIP)
+            self.handle = lib.sefd_dccrn_plan_create_ex(B, L, MODES[mode], (0 if skip else PLAN_NO_SKIP) | (PLAN_REAL_LSTM if real_lstm else 0))
         if not self.handle:
             raise RuntimeError("sefd plan: " + lib.sefd_last_error().decode())
         self.B, self.L, self.T, self.mode = B, L, (L + 2 if family == "fsn" else L // 100 + 3), mode
@@ -286,21 +287,22 @@ class Engine:
     """Owns the flat parameter / gradient / BN-statistics buffers of one DCCRN / CRN module and keeps the module's
     nn.Parameters aliased onto them."""
 
-    def __init__(self, module, mode, family="dccrn", skip=True):
+    def __init__(self, module, mode, family="dccrn", skip=True, real_lstm=False):
         self.module = module
         self.mode = mode
         self.family = family
         self.skip = skip
+        self.real_lstm = real_lstm
         self.plans = {}
         self.flat = self.flat_grad = self.flat_buf = None
-        self._layout = Plan(1, 1 if family == "fsn" else 100, mode, family, skip)  # layout is independent of (B, L)
+        self._layout = Plan(1, 1 if family == "fsn" else 100, mode, family, skip, real_lstm)  # layout is independent of (B, L)
         self.param_list = None
         self.backwards_since_step = 0       # autograd backwards that wrote flat_grad since the last FlatAdam.step()
 
     def plan(self, B, L):
         key = (B, L)
         if key not in self.plans:
-            self.plans[key] = Plan(B, L, self.mode, self.family, self.skip)
+            self.plans[key] = Plan(B, L, self.mode, self.family, self.skip, self.real_lstm)
         return self.plans[key]
 
     def _named(self):

@@ -147,6 +147,10 @@ sefd_plan* sefd_dccrn_plan_create(int B, int L, int masking_mode);
 /* flags: SEFD_PLAN_NO_SKIP builds the decoder of cfg.skip_type = False (models.py:138-169, 227-230): the transposed
  * convolutions read the previous output only (Cin = kernel_num[idx], no complex_cat with the encoder output) */
 #define SEFD_PLAN_NO_SKIP 1
+/* SEFD_PLAN_REAL_LSTM: cfg.lstm = 'real' (models.py:96-105, 213-218): the recurrent part is self.enhance = nn.LSTM(1024 -> 256,
+ * 2 layers) + self.tranform = Linear(256 -> 1024) on the [T, B, C * D] view of the encoder output (state_dict keys
+ * enhance.weight_ih_l0 ... tranform.bias) instead of the two NavieComplexLSTM layers */
+#define SEFD_PLAN_REAL_LSTM 2
 sefd_plan* sefd_dccrn_plan_create_ex(int B, int L, int masking_mode, int flags);
 void sefd_dccrn_plan_destroy(sefd_plan* plan);
 size_t sefd_dccrn_workspace_bytes(const sefd_plan* plan);
