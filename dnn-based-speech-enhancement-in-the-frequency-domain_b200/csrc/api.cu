@@ -85,6 +85,50 @@ int sefd_mask_istft_forward(const float* spec, const float* mask, int mode, int 
     return sefd_mask_istft_launch(m, ST);
 }
 
+// ---- either transform geometry (config.py:55-61) ------------------------------------------------------------------
+static int geometry(int nfft, int L, int* T, int* nbin) {
+    SEFD_REQUIRE(nfft == 512 || nfft == 1024, "fft length %d is not built (512: win 400 / hop 100, 1024: win 800 / hop 200)", nfft);
+    const int hop = nfft == 512 ? 100 : 200;
+    SEFD_REQUIRE(L > 0 && L % hop == 0, "L=%d must be a positive multiple of the hop (%d)", L, hop);
+    *T = L / hop + 3;
+    *nbin = nfft / 2 + 1;
+    return 0;
+}
+
+int sefd_stft_forward_n(const float* wav, float* spec, int B, int L, int nfft, void* stream) {
+    int T, F;
+    SEFD_TRY(geometry(nfft, L, &T, &F));
+    return sefd_stft_launch_n(wav, spec, B, L, nfft, ST);
+}
+
+int sefd_mask_istft_forward_n(const float* spec, const float* mask, int mode, int B, int L, int nfft, float* out_wav,
+                              void* stream) {
+    int T, F;
+    SEFD_TRY(geometry(nfft, L, &T, &F));
+    SEFD_REQUIRE(mode == SEFD_MASK_NONE || (mode >= SEFD_MASK_E && mode <= SEFD_MASK_R) || mode == SEFD_MASK_DIRECT,
+                 "mask mode %d unsupported", mode);
+    MaskIstftParams m;
+    memset(&m, 0, sizeof(m));
+    m.spec = spec; m.mask = mask; m.mode = mode; m.B = B; m.L = L; m.T = T;
+    m.mT = 2; m.mF = (long long)T * 2; m.mB = (long long)(F - 1) * T * 2;
+    m.out_wav = out_wav;
+    return sefd_mask_istft_launch_n(m, nullptr, nfft, ST);
+}
+
+int sefd_stft_mask_istft_fused(const float* wav, const float* mask, int mode, int B, int L, int nfft, float* out_wav,
+                               void* stream) {
+    int T, F;
+    SEFD_TRY(geometry(nfft, L, &T, &F));
+    SEFD_REQUIRE((mode >= SEFD_MASK_E && mode <= SEFD_MASK_R), "fused STFT-mask-ISTFT: mask mode %d unsupported", mode);
+    SEFD_REQUIRE(wav != out_wav, "fused STFT-mask-ISTFT: in-place operation is not supported (frames overlap across CTAs)%s", "");
+    MaskIstftParams m;
+    memset(&m, 0, sizeof(m));
+    m.mask = mask; m.mode = mode; m.B = B; m.L = L; m.T = T;
+    m.mT = 2; m.mF = (long long)T * 2; m.mB = (long long)(F - 1) * T * 2;
+    m.out_wav = out_wav;
+    return sefd_mask_istft_launch_n(m, wav, nfft, ST);
+}
+
 int sefd_mask_istft_backward(const float* dwav, const float* raw_wav, const float* spec, const float* mask, int mode,
                              int B, int L, float* dmask, void* stream) {
     CHECK_L(L);

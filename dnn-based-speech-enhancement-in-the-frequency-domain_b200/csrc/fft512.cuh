@@ -54,37 +54,44 @@ FFT_HD void dft8(float2* v) {
     }
 }
 
+// Shared-memory placement of logical element i.  The three exchanges read / write the buffer at strides 1, 8 and 64;
+// stored linearly the stride-8 and stride-64 patterns put a half-warp's sixteen 8-byte accesses on 2 - 8 words of the same
+// banks (measured on stft_fwd_kernel: 5x the ideal shared wavefronts, short_scoreboard the top stall).  XOR-ing index bits
+// 3..6 into bits 0..3 makes all six patterns conflict-free; every access to a transform buffer, inside this file or in a
+// caller that packs / unpacks frames, goes through fft_at().
+FFT_HD int fft_at(int i) { return i ^ ((i >> 3) & 15); }
+
 // The three passes, each split into "gather + compute" and "scatter" so that a barrier can sit between
-// them.  s: 512 complex values (shared memory on the device); tw[j] = exp(-2*pi*i*j/512), j < 512.
+// them.  s: 512 complex values (shared memory on the device), element i stored at fft_at(i); tw[j] = exp(-2*pi*i*j/512), j < 512.
 template <bool INV>
 FFT_HD void fft512_pass1(const float2* s, const float2* tw, int tid, float2* v) {
-    for (int n2 = 0; n2 < 8; ++n2) v[n2] = s[64 * n2 + tid];
+    for (int n2 = 0; n2 < 8; ++n2) v[n2] = s[fft_at(64 * n2 + tid)];
     dft8<INV>(v);
     const int n1 = tid >> 3;
     for (int k0 = 1; k0 < 8; ++k0) v[k0] = c_mul(v[k0], c_tw<INV>(tw[8 * n1 * k0]));
 }
 FFT_HD void fft512_scatter1(float2* s, int tid, const float2* v) {
-    for (int k0 = 0; k0 < 8; ++k0) s[64 * k0 + tid] = v[k0];      // A[k0][n1][n0], tid = 8 n1 + n0
+    for (int k0 = 0; k0 < 8; ++k0) s[fft_at(64 * k0 + tid)] = v[k0];      // A[k0][n1][n0], tid = 8 n1 + n0
 }
 template <bool INV>
 FFT_HD void fft512_pass2(const float2* s, const float2* tw, int tid, float2* v) {
     const int k0 = tid >> 3, n0 = tid & 7;
-    for (int n1 = 0; n1 < 8; ++n1) v[n1] = s[64 * k0 + 8 * n1 + n0];
+    for (int n1 = 0; n1 < 8; ++n1) v[n1] = s[fft_at(64 * k0 + 8 * n1 + n0)];
     dft8<INV>(v);
     for (int k1 = 0; k1 < 8; ++k1) v[k1] = c_mul(v[k1], c_tw<INV>(tw[n0 * (k0 + 8 * k1)]));
 }
 FFT_HD void fft512_scatter2(float2* s, int tid, const float2* v) {
     const int k0 = tid >> 3, n0 = tid & 7;
-    for (int k1 = 0; k1 < 8; ++k1) s[64 * k0 + 8 * k1 + n0] = v[k1];   // B[k0][k1][n0]
+    for (int k1 = 0; k1 < 8; ++k1) s[fft_at(64 * k0 + 8 * k1 + n0)] = v[k1];   // B[k0][k1][n0]
 }
 template <bool INV>
 FFT_HD void fft512_pass3(const float2* s, int tid, float2* v) {
-    for (int n0 = 0; n0 < 8; ++n0) v[n0] = s[8 * tid + n0];             // tid = 8 k0 + k1
+    for (int n0 = 0; n0 < 8; ++n0) v[n0] = s[fft_at(8 * tid + n0)];             // tid = 8 k0 + k1
     dft8<INV>(v);
 }
 FFT_HD void fft512_scatter3(float2* s, int tid, const float2* v) {
     const int k0 = tid >> 3, k1 = tid & 7;
-    for (int k2 = 0; k2 < 8; ++k2) s[k0 + 8 * k1 + 64 * k2] = v[k2];
+    for (int k2 = 0; k2 < 8; ++k2) s[fft_at(k0 + 8 * k1 + 64 * k2)] = v[k2];
 }
 
 #ifdef __CUDACC__

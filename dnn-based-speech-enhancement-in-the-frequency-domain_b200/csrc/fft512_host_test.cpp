@@ -26,13 +26,14 @@ int main() {
     for (int j = 0; j < N; ++j) x[j] = make_float2(rand() / (float)RAND_MAX - 0.5f, rand() / (float)RAND_MAX - 0.5f);
     double worst = 0;
     for (int inv = 0; inv < 2; ++inv) {
-        std::vector<float2> s = x;
+        std::vector<float2> s(N);
+        for (int j = 0; j < N; ++j) s[fft_at(j)] = x[j];
         if (inv) run<true>(s, tw); else run<false>(s, tw);
         for (int k = 0; k < N; ++k) {
             std::complex<double> acc = 0;
             for (int n = 0; n < N; ++n)
                 acc += std::complex<double>(x[n].x, x[n].y) * std::polar(1.0, (inv ? 2 : -2) * M_PI * ((long)n * k % N) / N);
-            double e = std::abs(acc - std::complex<double>(s[k].x, s[k].y));
+            double e = std::abs(acc - std::complex<double>(s[fft_at(k)].x, s[fft_at(k)].y));
             if (e > worst) worst = e;
         }
     }

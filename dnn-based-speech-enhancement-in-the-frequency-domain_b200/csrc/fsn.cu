@@ -74,12 +74,12 @@ __global__ void __launch_bounds__(256) fsn_stft_kernel(const float* __restrict__
                 if (MODE == 0) { if (ta < T) y = __ldg(wb + reflect(ta * FHOP + n - NF / 2, L)); }
                 else if (tb < T) y = __ldg(wa + reflect(tb * FHOP + n - NF / 2, L));
             }
-            s[n] = make_float2(w * x, w * y);
+            s[fft_at(n)] = make_float2(w * x, w * y);
         }
         __syncthreads();
         fft512_cta<false>(s, sm.tw, t64);
         for (int k = t64; k <= 256; k += 64) {
-            const float2 z = s[k], zc = s[(NF - k) & (NF - 1)];
+            const float2 z = s[fft_at(k)], zc = s[fft_at((NF - k) & (NF - 1))];
             const float2 xa = make_float2(0.5f * (z.x + zc.x), 0.5f * (z.y - zc.y));      // spectrum of the real part
             const float2 xb = make_float2(0.5f * (z.y + zc.y), -0.5f * (z.x - zc.x));     // spectrum of the imaginary part
             if (MODE == 0) {
@@ -168,10 +168,10 @@ __global__ void __launch_bounds__(256) fsn_istft_kernel(const float* __restrict_
                 if (vb) b = sp[base + fb];
             }
             if (k == 0 || k == 256) {
-                s[k] = make_float2(a.x, b.x);
+                s[fft_at(k)] = make_float2(a.x, b.x);
             } else {
-                s[k] = make_float2(a.x - b.y, a.y + b.x);
-                s[NF - k] = make_float2(a.x + b.y, -a.y + b.x);
+                s[fft_at(k)] = make_float2(a.x - b.y, a.y + b.x);
+                s[fft_at(NF - k)] = make_float2(a.x + b.y, -a.y + b.x);
             }
         }
         __syncthreads();
@@ -181,8 +181,8 @@ __global__ void __launch_bounds__(256) fsn_istft_kernel(const float* __restrict_
             for (int i = 0; i < 8; ++i) {
                 const int n = t64 + 64 * i;
                 const float w = sm.win[n] * (1.f / NF);
-                sm.fr[j0][n] = va ? w * s[n].x : 0.f;
-                if (j0 + 1 < IH + 4) sm.fr[j0 + 1][n] = vb ? w * s[n].y : 0.f;
+                sm.fr[j0][n] = va ? w * s[fft_at(n)].x : 0.f;
+                if (j0 + 1 < IH + 4) sm.fr[j0 + 1][n] = vb ? w * s[fft_at(n)].y : 0.f;
             }
         }
         __syncthreads();

@@ -91,12 +91,12 @@ __global__ void __launch_bounds__(256) pmsqe_stft_kernel(const float* __restrict
         for (int i = 0; i < 8; ++i) {
             const int n = t64 + 64 * i;
             const float xa = fa < PF ? __ldg(w + PHOP * fa + n) : 0.f, xb = fb < PF ? __ldg(w + PHOP * fb + n) : 0.f;
-            s[n] = make_float2(sm.win[n] * xa, sm.win[n] * xb);
+            s[fft_at(n)] = make_float2(sm.win[n] * xa, sm.win[n] * xb);
         }
         __syncthreads();
         fft512_cta<false>(s, sm.tw, t64);
         for (int k = t64; k <= 256; k += 64) {            // unpack the two real transforms
-            const float2 z = s[k], zc = s[(NF - k) & (NF - 1)];
+            const float2 z = s[fft_at(k)], zc = s[fft_at((NF - k) & (NF - 1))];
             const float sc = bin_scale(k);
             float2 xa = make_float2(sc * 0.5f * (z.x + zc.x), sc * 0.5f * (z.y - zc.y));
             float2 xb = make_float2(sc * 0.5f * (z.y + zc.y), -sc * 0.5f * (z.x - zc.x));
@@ -387,11 +387,11 @@ __global__ void __launch_bounds__(256) pmsqe_mag_istft_bwd_kernel(int L, int S, 
             // Re sum_{k=0}^{256} G_k e^{+i theta k n}  =  inverse transform of the Hermitian H: H_0 = Re G_0, H_256 = Re G_256,
             // H_k = G_k / 2, H_{512-k} = conj(G_k) / 2; two frames ride one complex transform as H_a + i H_b
             if (k == 0 || k == 256) {
-                s[k] = make_float2(ga.x, gb.x);
+                s[fft_at(k)] = make_float2(ga.x, gb.x);
             } else {
                 ga.x *= 0.5f; ga.y *= 0.5f; gb.x *= 0.5f; gb.y *= 0.5f;
-                s[k] = make_float2(ga.x - gb.y, ga.y + gb.x);
-                s[NF - k] = make_float2(ga.x + gb.y, -ga.y + gb.x);
+                s[fft_at(k)] = make_float2(ga.x - gb.y, ga.y + gb.x);
+                s[fft_at(NF - k)] = make_float2(ga.x + gb.y, -ga.y + gb.x);
             }
         }
         __syncthreads();
@@ -399,8 +399,8 @@ __global__ void __launch_bounds__(256) pmsqe_mag_istft_bwd_kernel(int L, int S, 
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int n = t64 + 64 * i;
-            if (fa < PF) sm.fr[fa][n] = sm.win[n] * s[n].x;
-            if (fb < PF) sm.fr[fb][n] = sm.win[n] * s[n].y;
+            if (fa < PF) sm.fr[fa][n] = sm.win[n] * s[fft_at(n)].x;
+            if (fb < PF) sm.fr[fb][n] = sm.win[n] * s[fft_at(n)].y;
         }
         __syncthreads();
     }

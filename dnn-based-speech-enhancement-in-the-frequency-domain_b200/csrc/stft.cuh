@@ -41,6 +41,10 @@ int sefd_stft_launch(const float* wav, float* spec, int B, int L, int T, cudaStr
 int sefd_spec_mag_launch(const float* spec, float* mag, long long n, cudaStream_t st);
 int sefd_mask_istft_launch(const MaskIstftParams& p, cudaStream_t st);
 int sefd_mask_istft_bwd_launch(const MaskIstftBwdParams& p, cudaStream_t st);
+// either transform geometry of config.py:55-61 (nfft 512: win 400 / hop 100 / 257 bins; nfft 1024: win 800 / hop 200 / 513 bins);
+// spec [B][nfft/2+1][T][2], T = L / hop + 3.  fused_wav != null: wave -> STFT -> mask -> ISTFT in one kernel (p.spec unused).
+int sefd_stft_launch_n(const float* wav, float* spec, int B, int L, int nfft, cudaStream_t st);
+int sefd_mask_istft_launch_n(const MaskIstftParams& p, const float* fused_wav, int nfft, cudaStream_t st);
 int sefd_loss_fwd_launch(const float* est, const float* tgt, int B, int L, int kind, double* dots, int dots_ready,
                          float* loss, float* coef, cudaStream_t st);
 int sefd_loss_bwd_launch(const float* est, const float* tgt, const float* coef, const float* gout, float* dest,

@@ -18,6 +18,9 @@ SIGNATURES = {
     "sefd_istft_forward": (_i, [_vp, _vp, _i, _i, _vp]),
     "sefd_istft_backward": (_i, [_vp, _vp, _i, _i, _vp]),
     "sefd_mask_istft_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "sefd_stft_forward_n": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "sefd_mask_istft_forward_n": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "sefd_stft_mask_istft_fused": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "sefd_mask_istft_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "sefd_loss_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "sefd_loss_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),

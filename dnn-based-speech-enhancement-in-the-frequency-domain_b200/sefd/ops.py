@@ -84,6 +84,55 @@ def mask_istft(spec, mask, mode, L, want_spec=True):
     return o_r, o_i, wav, raw
 
 
+# ---- either transform geometry of config.py:55-61 (nfft 512: 400/100, 257 bins; nfft 1024: 800/200, 513 bins) ----
+def _geometry(nfft, L):
+    if nfft not in (512, 1024):
+        raise ValueError(f"fft length {nfft} is not built (512 or 1024)")
+    hop = 100 if nfft == 512 else 200
+    return nfft // 2 + 1, L // hop + 3
+
+
+def stft_n(wav, nfft):
+    """ConvSTFT 'complex' for win = 25/32 nfft, hop = win/4: wav [B,L] -> spec [B,nfft/2+1,T,2]."""
+    wav = wav.contiguous()
+    _req(wav)
+    B, L = wav.shape
+    F, T = _geometry(nfft, L)
+    spec = torch.empty(B, F, T, 2, device=wav.device, dtype=torch.float32)
+    _lib.check(_lib.load().sefd_stft_forward_n(ptr(wav), ptr(spec), B, L, nfft, stream()), "stft_forward_n")
+    return spec
+
+
+def mask_istft_n(spec, mask, mode, L, nfft):
+    """mask apply (mode None: plain ISTFT) + ConviSTFT + clamp for either geometry: -> wav [B,L]."""
+    spec = spec.contiguous()
+    _req(spec)
+    B = spec.shape[0]
+    F, T = _geometry(nfft, L)
+    assert spec.shape[1:] == (F, T, 2), spec.shape
+    if mask is not None:
+        mask = mask.contiguous()
+        _req(mask)
+        assert mask.shape == (B, F - 1, T, 2), mask.shape
+    wav = torch.empty(B, L, device=spec.device, dtype=torch.float32)
+    _lib.check(_lib.load().sefd_mask_istft_forward_n(ptr(spec), ptr(mask), MODES[mode] if mask is not None else 0, B, L,
+                                                     nfft, ptr(wav), stream()), "mask_istft_forward_n")
+    return wav
+
+
+def stft_mask_istft(wav, mask, mode, nfft):
+    """wave -> STFT -> mask -> ISTFT -> clamp in one kernel (the spectrum never reaches HBM)."""
+    wav, mask = wav.contiguous(), mask.contiguous()
+    _req(wav, mask)
+    B, L = wav.shape
+    F, T = _geometry(nfft, L)
+    assert mask.shape == (B, F - 1, T, 2), mask.shape
+    out = torch.empty_like(wav)
+    _lib.check(_lib.load().sefd_stft_mask_istft_fused(ptr(wav), ptr(mask), MODES[mode], B, L, nfft, ptr(out), stream()),
+               "stft_mask_istft_fused")
+    return out
+
+
 def mask_istft_backward(dwav, raw, spec, mask, mode):
     _req(dwav, raw, spec, mask)
     B, L = dwav.shape

@@ -46,6 +46,18 @@ int sefd_mask_istft_forward(const float* spec, const float* mask, int mode, int 
 int sefd_mask_istft_backward(const float* dwav, const float* raw_wav, const float* spec, const float* mask, int mode,
                              int B, int L, float* dmask, void* stream);
 
+/* The same three ops for either transform geometry the reference's config allows (config.py:55-61; init_kernels
+ * tools_for_model.py:16-33 is generic in win_len / win_inc / fft_len): nfft = 512 -> win 400 / hop 100 / F = 257 bins,
+ * nfft = 1024 -> win 800 / hop 200 / F = 513 bins; T = L / hop + 3; spec [B][F][T][2]; mask [B][F-1][T][2] (DC mask zero).
+ * sefd_mask_istft_forward_n: mode 0 = plain ISTFT of spec (mask unused), output clamped to [-1, 1] like the model's.
+ * sefd_stft_mask_istft_fused: wave -> STFT -> mask -> ISTFT -> wave in ONE kernel, the spectrum never leaves the SM
+ * (BASELINE configs[4]'s fused form: 8 (F-1) + 8 hop bytes per frame); wav and out_wav must not alias. */
+int sefd_stft_forward_n(const float* wav, float* spec, int B, int L, int nfft, void* stream);
+int sefd_mask_istft_forward_n(const float* spec, const float* mask, int mode, int B, int L, int nfft, float* out_wav,
+                              void* stream);
+int sefd_stft_mask_istft_fused(const float* wav, const float* mask, int mode, int B, int L, int nfft, float* out_wav,
+                               void* stream);
+
 /* DCCRN.loss, non-perceptual branch (models.py:315-323; tools_for_loss.py:29-94).
  * scratch: 8*B doubles; coef: 2*B floats (kept for the backward); loss: 1 float. */
 int sefd_loss_forward(const float* est, const float* target, int B, int L, int kind, double* scratch, float* loss,

@@ -57,6 +57,90 @@ def test_istft_matches_conv_istft_on_arbitrary_spectra(bases, B, L):
     _close(got, ref, atol=2e-5, rtol=1e-5, name="istft")
 
 
+# ---- both transform geometries of config.py:55-61 through the warp-FFT kernels ----------------------------------------
+GEOMETRIES = {512: (400, 100), 1024: (800, 200)}
+
+
+def _bases_n(nfft):
+    win, _ = GEOMETRIES[nfft]
+    k_a, k_s, w = O.stft_bases(win, nfft)
+    return torch.from_numpy(k_a).float(), torch.from_numpy(k_s).float(), torch.from_numpy(w).float()
+
+
+def _apply_mask_ref(spec_ref, mask, mode, F):
+    """models.py:253-276 on the oracle layout: spec_ref [B,2F,T], mask [B,F-1,T,2] (DC bin padded with zero)."""
+    real, imag = spec_ref[:, :F], spec_ref[:, F:]
+    mr = torch.nn.functional.pad(mask[..., 0], [0, 0, 1, 0])
+    mi = torch.nn.functional.pad(mask[..., 1], [0, 0, 1, 0])
+    if mode == "C":
+        r, i = real * mr - imag * mi, real * mi + imag * mr
+    elif mode == "R":
+        r, i = real * mr, imag * mi
+    else:
+        mags, phase = torch.sqrt(real ** 2 + imag ** 2 + 1e-8), torch.atan2(imag, real)
+        mm = (mr ** 2 + mi ** 2) ** 0.5
+        est_phase = phase + torch.atan2(mi / (mm + 1e-8), mr / (mm + 1e-8))
+        em = torch.tanh(mm) * mags
+        r, i = em * torch.cos(est_phase), em * torch.sin(est_phase)
+    return torch.cat([r, i], 1)
+
+
+@pytest.mark.parametrize("nfft", [512, 1024])
+@pytest.mark.parametrize("B,frames_", [(1, 1), (2, 37), (3, 240)])
+def test_stft_both_geometries(nfft, B, frames_):
+    from sefd import ops
+    win, hop = GEOMETRIES[nfft]
+    L, F = hop * frames_, nfft // 2 + 1
+    k_a, _, _ = _bases_n(nfft)
+    g = torch.Generator().manual_seed(31)
+    wav = torch.randn(B, L, generator=g)
+    ref = O.conv_stft(wav, k_a, win, hop)
+    got = ops.stft_n(wav.to(DEV), nfft)
+    got = torch.cat([got[..., 0], got[..., 1]], 1)
+    assert got.shape[1] == 2 * F
+    _close(got, ref, atol=3e-4, rtol=1e-5, name=f"stft{nfft}")      # |X| up to ~90 on N(0,1) input at 800 taps
+
+
+@pytest.mark.parametrize("nfft", [512, 1024])
+@pytest.mark.parametrize("B,frames_", [(1, 1), (2, 37), (2, 240)])
+def test_istft_both_geometries_on_arbitrary_spectra(nfft, B, frames_):
+    """Off-manifold spectra exercise the pinv synthesis; scaled so that the clamp of the _n entry point stays inactive."""
+    from sefd import ops
+    win, hop = GEOMETRIES[nfft]
+    L, F = hop * frames_, nfft // 2 + 1
+    T = L // hop + 3
+    _, k_s, w = _bases_n(nfft)
+    g = torch.Generator().manual_seed(32)
+    spec = torch.randn(B, 2 * F, T, generator=g)
+    ref = O.conv_istft(spec, k_s, w, win, hop)
+    scale = 0.5 / float(ref.abs().max())
+    spec, ref = spec * scale, ref * scale
+    sp = torch.stack([spec[:, :F], spec[:, F:]], -1).contiguous()
+    got = ops.mask_istft_n(sp.to(DEV), None, None, L, nfft)
+    _close(got, ref, atol=1e-6, rtol=1e-5, name=f"istft{nfft}")
+
+
+@pytest.mark.parametrize("nfft", [512, 1024])
+@pytest.mark.parametrize("mode", ["C", "E", "R"])
+def test_fused_stft_mask_istft_matches_the_three_reference_steps(nfft, mode):
+    """wave -> ConvSTFT -> mask (models.py:253-276) -> ConviSTFT -> clamp, against the oracle's three separate steps; the
+    split pair of kernels must give the same waveform as the fused one."""
+    from sefd import ops
+    win, hop = GEOMETRIES[nfft]
+    B, L, F = 2, hop * 75, nfft // 2 + 1
+    T = L // hop + 3
+    k_a, k_s, w = _bases_n(nfft)
+    g = torch.Generator().manual_seed(33)
+    wav = torch.randn(B, L, generator=g) * 0.3
+    mask = torch.randn(B, F - 1, T, 2, generator=g) * 0.7
+    ref = O.conv_istft(_apply_mask_ref(O.conv_stft(wav, k_a, win, hop), mask, mode, F), k_s, w, win, hop).clamp(-1, 1)
+    fused = ops.stft_mask_istft(wav.to(DEV), mask.to(DEV), mode, nfft)
+    split = ops.mask_istft_n(ops.stft_n(wav.to(DEV), nfft), mask.to(DEV), mode, L, nfft)
+    tol = 2e-5 if mode != "E" else 1e-4          # E: atan2 / sincos on fp32 spectra
+    _close(fused, ref, atol=tol, rtol=1e-5, name=f"fused{nfft}{mode}")
+    _close(split, ref, atol=tol, rtol=1e-5, name=f"split{nfft}{mode}")
+
+
 def test_istft_adjoint_matches_autograd(bases):
     from sefd import ops
     B, L = 2, 4000
