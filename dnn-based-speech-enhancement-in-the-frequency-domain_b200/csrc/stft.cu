@@ -442,7 +442,8 @@ struct Geo {
 constexpr int WF = 16;                  // frames per round of a CTA (8 warps x 2)
 constexpr int OUT_PITCH = 18;           // float2 per bin row of the frame-contiguous staging tile: 16-byte aligned pairs,
                                         // 36-word stride = conflict-free for the 16-byte column writes and the row reads
-constexpr int LU = 8;                   // tile elements whose global loads a thread keeps in flight together
+constexpr int LU = 17;                  // tile elements whose global loads a thread keeps in flight together: all 17 bin rows of
+                                        // its column for 257 bins (one DRAM latency per round), two batches for 513
 constexpr int TILE_PITCH = 17;          // float2 per bin row of the synthesis tile: conflict-free 8-byte column reads
 
 template <int NFFT>
@@ -523,7 +524,7 @@ struct StftWSmem {
 
 // STFT forward: wav [B][L] -> spec [B][NBIN][T][2]; persistent over (utterance, 16-frame chunk) units
 template <int NFFT>
-__global__ void __launch_bounds__(256, 2) stft_fwd_w_kernel(const float* __restrict__ wav, float* __restrict__ spec,
+__global__ void __launch_bounds__(256, NFFT == 512 ? 3 : 2) stft_fwd_w_kernel(const float* __restrict__ wav, float* __restrict__ spec,
                                                             int B, int L, int T) {
     using G = Geo<NFFT>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -674,7 +675,7 @@ __device__ __forceinline__ void finish_chunk(const MaskIstftParams& p, const flo
 // mask apply + ISTFT + clamp (+ loss dot products): spec [B][NBIN][T][2], mask as MaskIstftParams describes.
 // MODE >= 0: the mask mode is a compile-time constant (the common modes: straight-line code), -1: p.mode at run time.
 template <int NFFT, int MODE>
-__global__ void __launch_bounds__(256, 2) mask_istft_fwd_w_kernel(const MaskIstftParams p) {
+__global__ void __launch_bounds__(256, NFFT == 512 ? 3 : 2) mask_istft_fwd_w_kernel(const MaskIstftParams p) {
     using G = Geo<NFFT>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     IstftWSmem<NFFT>& S = *reinterpret_cast<IstftWSmem<NFFT>*>(smem_raw);
