@@ -366,6 +366,16 @@ int sefd_adam_step_dev(float* params, const float* grads, float* exp_avg, float*
     return sefd_adam_dev(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step_dev, bc_scratch2, gscale, ST);
 }
 
+int sefd_axpby(float* y, const float* x, float a, float b, long long n, void* stream) {
+    SEFD_REQUIRE(y && x && n >= 0, "axpby: null argument or negative length%s", "");
+    return sefd_axpby_launch(y, x, a, b, n, ST);
+}
+
+int sefd_counters_inc(long long* const* counters_dev, int n, long long inc, void* stream) {
+    SEFD_REQUIRE(counters_dev && n >= 0, "counters_inc: null argument or negative count%s", "");
+    return sefd_counters_inc_launch(counters_dev, n, inc, ST);
+}
+
 // ---- model level ------------------------------------------------------------------------------
 sefd_plan* sefd_dccrn_plan_create(int B, int L, int masking_mode) { return sefd_plan_create_impl(B, L, masking_mode, 0); }
 sefd_plan* sefd_dccrn_plan_create_ex(int B, int L, int masking_mode, int flags) {

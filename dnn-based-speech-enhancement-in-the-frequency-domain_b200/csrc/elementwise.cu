@@ -567,3 +567,29 @@ int sefd_adam(float* w, const float* g, float* m, float* v, long long n, float l
     adam_kernel<<<grid_for(n), 256, 0, st>>>(w, g, m, v, n, lr, b1, b2, eps, (float)bc1, (float)sqrt(bc2), gscale);
     return sefd_check_launch("adam");
 }
+
+// ---- small step glue that used to run as eager framework kernels ------------------------------------------------------
+namespace {
+__global__ void axpby_kernel(float* __restrict__ y, const float* __restrict__ x, float a, float b, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = fmaf(a, x[i], b * y[i]);
+}
+__global__ void counters_inc_kernel(long long* const* __restrict__ ptrs, int n, long long inc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) *ptrs[i] += inc;
+}
+}  // namespace
+
+int sefd_axpby_launch(float* y, const float* x, float a, float b, long long n, cudaStream_t st) {
+    if (n <= 0) return 0;
+    long long g = (n + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    axpby_kernel<<<(int)g, 256, 0, st>>>(y, x, a, b, n);
+    return sefd_check_launch("axpby");
+}
+
+int sefd_counters_inc_launch(long long* const* ptrs, int n, long long inc, cudaStream_t st) {
+    if (n <= 0) return 0;
+    counters_inc_kernel<<<(n + 127) / 128, 128, 0, st>>>(ptrs, n, inc);
+    return sefd_check_launch("counters_inc");
+}

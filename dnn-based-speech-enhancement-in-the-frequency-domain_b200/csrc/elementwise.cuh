@@ -93,3 +93,8 @@ int sefd_adam_dev(float* w, const float* g, float* m, float* v, long long n, flo
                   int* step_dev, float* bc_dev, float gscale, cudaStream_t st);
 int sefd_adam(float* w, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
               int step, float gscale, cudaStream_t st);
+
+// y = a x + b y (the perceptual step's gradient / loss mixing, trainer.py:166-169)
+int sefd_axpby_launch(float* y, const float* x, float a, float b, long long n, cudaStream_t st);
+// *ptrs[i] += inc for n device counters (BatchNorm num_batches_tracked of every layer in one launch)
+int sefd_counters_inc_launch(long long* const* ptrs, int n, long long inc, cudaStream_t st);

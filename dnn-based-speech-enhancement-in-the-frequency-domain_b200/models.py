@@ -91,9 +91,7 @@ class DCCRN(nn.Module):
         tgt = targets if torch.is_tensor(targets) and targets.shape == inputs.shape else None
         out_real, out_imag, out_wav = eng.forward(inputs, tgt, self.training)
         if self.training:
-            for m in self.modules():
-                if isinstance(m, _d.BatchNormParams):
-                    m.num_batches_tracked += 1
+            _d.bump_batches_tracked(self)
         self.__dict__["_last"] = (out_wav, tgt)
         if self.masking_mode == "Direct(None make)":                     # spectral mapping, models.py:232-250
             if tgt is None:
@@ -180,9 +178,7 @@ class CRN(nn.Module):
         tgt = targets if torch.is_tensor(targets) and targets.shape == inputs.shape else None
         est_mags, target_mags, out_wav = eng.forward(inputs, tgt, self.training)
         if self.training:
-            for m in self.modules():
-                if isinstance(m, _d.BatchNormParams):
-                    m.num_batches_tracked += 1
+            _d.bump_batches_tracked(self)
         return est_mags, target_mags, out_wav
 
     get_params = DCCRN.get_params

@@ -34,6 +34,8 @@ SIGNATURES = {
     "sefd_lstm_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "sefd_lstm_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "sefd_adam_step": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _i, _f, _vp]),
+    "sefd_axpby": (_i, [_vp, _vp, _f, _f, _ll, _vp]),
+    "sefd_counters_inc": (_i, [_vp, _i, _ll, _vp]),
     "sefd_adam_step_dev": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _vp, _vp, _f, _vp]),
     "sefd_dccrn_plan_create": (_vp, [_i, _i, _i]),
     "sefd_dccrn_plan_create_ex": (_vp, [_i, _i, _i, _i]),

@@ -283,6 +283,23 @@ class _ForwardCRN(torch.autograd.Function):
         return (None, None, None, None) + grads
 
 
+def bump_batches_tracked(model):
+    """BatchNorm2d bookkeeping after a train-mode forward: every layer's num_batches_tracked += 1 (torch semantics), one
+    launch of the library's counter kernel for all layers; the device array of addresses is cached until a buffer moves."""
+    bns = [m for m in model.modules() if isinstance(m, BatchNormParams)]
+    if not bns:
+        return
+    addrs = tuple(m.num_batches_tracked.data_ptr() for m in bns)
+    dev = bns[0].num_batches_tracked.device
+    if dev.type != "cuda":
+        raise RuntimeError("sefd: the model's buffers must live on a CUDA device")
+    cache = model.__dict__.get("_nbt_cache")
+    if cache is None or cache[0] != addrs:
+        cache = (addrs, torch.tensor(addrs, dtype=torch.int64, device=dev))
+        model.__dict__["_nbt_cache"] = cache
+    _lib.check(_lib.load().sefd_counters_inc(cache[1].data_ptr(), len(addrs), 1, stream()), "counters_inc")
+
+
 class Engine:
     """Owns the flat parameter / gradient / BN-statistics buffers of one DCCRN / CRN module and keeps the module's
     nn.Parameters aliased onto them."""

@@ -10,6 +10,7 @@ import os
 import torch
 
 from . import _lib
+from . import dccrn as _dccrn
 from . import dist as _dist
 from . import ops as _ops
 from .ops import LOSSES, ptr, stream
@@ -84,6 +85,7 @@ class TrainStep:
                    (lib.sefd_dccrn_forward, lib.sefd_dccrn_backward)
         _lib.check(fwd(plan.handle, ptr(eng.flat), ptr(eng.flat_buf), ptr(noisy), ptr(clean), 1,
                        None, None, ptr(s["wav"]), ptr(ws), plan.ws_bytes, st), eng.family + "_forward")
+        _dccrn.bump_batches_tracked(eng.module)       # train-mode forward: BatchNorm2d.num_batches_tracked += 1
         _lib.check(lib.sefd_dccrn_loss(plan.handle, ptr(s["wav"]), ptr(clean), self.kind, 1, ptr(s["loss"]),
                                        ptr(s["coef"]), ptr(ws), st), "dccrn_loss")
         if self.perceptual == "PMSQE":
@@ -101,8 +103,8 @@ class TrainStep:
                                               st), "loss_backward")
             _lib.check(lib.sefd_pmsqe_backward(ptr(s["half"]), B, L, ptr(s["tables"]), ptr(s["pws"]), nb, ptr(s["dpw"]), st),
                        "pmsqe_backward")
-            s["dwav"].add_(s["dpw"])
-            s["loss"].add_(s["ploss"]).mul_(0.5)
+            _lib.check(lib.sefd_axpby(ptr(s["dwav"]), ptr(s["dpw"]), 1.0, 1.0, B * L, st), "axpby")
+            _lib.check(lib.sefd_axpby(ptr(s["loss"]), ptr(s["ploss"]), 0.5, 0.5, 1, st), "axpby")
         else:
             _lib.check(lib.sefd_loss_backward(ptr(s["wav"]), ptr(clean), ptr(s["coef"]), None, ptr(s["dwav"]), B, L, st),
                        "loss_backward")

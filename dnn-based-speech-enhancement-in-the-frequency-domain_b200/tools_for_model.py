@@ -197,14 +197,6 @@ class Bar(object):
         return item
 
 
-def _fullsubnet_only(name):
-    def f(*a, **k):
-        raise NotImplementedError(f"sefd: tools_for_model.{name} belongs to the FullSubNet path, which is not built "
-                                  "yet (SURVEY.md §8 a14)")
-    f.__name__ = name
-    return f
-
-
 def stft(y, n_fft=512, hop_length=300, win_length=400):
     """tools_for_model.py:628-648 (torch.stft, centred, reflect padding, periodic Hann): [B, L] -> complex [B, 257, T]."""
     if (n_fft, hop_length, win_length) != (512, 300, 400):

@@ -154,6 +154,13 @@ int sefd_adam_step(float* params, const float* grads, float* exp_avg, float* exp
 int sefd_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                        float beta1, float beta2, float eps, int* step_dev, float* bc_scratch2, float gscale, void* stream);
 
+/* y[i] = a x[i] + b y[i]: the mixing of the perceptual step, loss = (main + perceptual) / 2 and the matching sum of
+ * the two waveform gradients (trainer.py:166-169), as a kernel of this library instead of framework element-wise ops. */
+int sefd_axpby(float* y, const float* x, float a, float b, long long n, void* stream);
+/* *counters_dev[i] += inc for n int64 device counters whose addresses sit in a DEVICE array: BatchNorm2d's
+ * num_batches_tracked of every layer after a train-mode forward (torch BatchNorm semantics) in one launch. */
+int sefd_counters_inc(long long* const* counters_dev, int n, long long inc, void* stream);
+
 /* ---- model level: DCCRN.forward / autograd backward (models.py:176-284) ---------------------- */
 sefd_plan* sefd_dccrn_plan_create(int B, int L, int masking_mode);
 /* flags: SEFD_PLAN_NO_SKIP builds the decoder of cfg.skip_type = False (models.py:138-169, 227-230): the transposed

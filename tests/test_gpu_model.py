@@ -126,7 +126,7 @@ def test_small_forward_backward_every_tensor(golden, sd0, mode, engine):
                 g64, r64 = p.grad.detach().double().cpu().reshape(-1), ref.detach().double().reshape(-1)
                 cosv = float((g64 * r64).sum() / (g64.norm() * r64.norm() + 1e-30))
                 nr = float(g64.norm() / (r64.norm() + 1e-30))
-                ok = cosv > 0.99 and abs(nr - 1) < 0.05
+                ok = cosv > 0.999 and abs(nr - 1) < 0.01      # worst measured: cos 0.99924, norm ratio 0.9976
                 if name.endswith(".2.weight"):      # one cancelling global sum: TF32 noise does not cancel with it
                     ok = e <= 2e-2 * amax
                 _report(f"[{mode}/tf32] grad {name:40s} cos={cosv:.5f} |got|/|ref|={nr:.4f}")
@@ -288,8 +288,10 @@ def test_graphed_train_step_equals_eager(sd0):
         ts = TrainStep(m, lr=1e-3, loss="SI-SNR", graph=graph)
         losses = [float(ts.step(noisy, clean)) for _ in range(5)]
         torch.cuda.synchronize()
-        out.append((losses, ts.engine.flat.clone(), int(ts._step_dev)))
+        nbt = {int(v) for k, v in m.state_dict().items() if k.endswith("num_batches_tracked")}
+        out.append((losses, ts.engine.flat.clone(), int(ts._step_dev), nbt))
     assert out[0][2] == out[1][2] == 5
+    assert out[0][3] == out[1][3] == {5}          # BatchNorm2d bookkeeping: one increment per train-mode forward, graph or not
     # same trajectory; not bit-identical: Adam turns rounding-level differences of near-zero gradients (the small-shape weight
     # gradients accumulate with atomics) into steps of at most lr, which the next losses see at the 1e-4 level
     assert out[0][0][0] == pytest.approx(out[1][0][0], rel=2e-6)
