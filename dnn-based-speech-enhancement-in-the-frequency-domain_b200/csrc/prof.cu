@@ -32,6 +32,20 @@ cudaEvent_t get_event() {
 
 bool sefd_prof_on() { return g_on; }
 
+namespace {
+int g_stale = 0;
+char g_stale_msg[160] = "";
+}  // namespace
+void sefd_absorb_stale_error() {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        ++g_stale;
+        snprintf(g_stale_msg, sizeof(g_stale_msg), "%s (%s)", cudaGetErrorString(e), cudaGetErrorName(e));
+    }
+}
+extern "C" int sefd_stale_cuda_errors(void) { return g_stale; }
+extern "C" const char* sefd_last_stale_cuda_error(void) { return g_stale_msg; }
+
 void sefd_prof_label(const char* fmt, ...) {
     if (!g_on) return;
     va_list ap;

@@ -15,6 +15,11 @@ enum SefdProfCat {
 };
 
 bool sefd_prof_on();
+// cudaGetLastError() is per host thread and keeps a NON-sticky error (a failed launch configuration, a rejected attribute, a
+// query that returned "not ready") until somebody reads it: left pending by other code in the process it would be blamed on
+// the next kernel this library launches.  Every launch scope reads it first; a pending error is counted and kept
+// (sefd_stale_cuda_errors / sefd_last_stale_cuda_error) instead of failing an unrelated call.  Sticky errors are unaffected.
+void sefd_absorb_stale_error();
 void sefd_prof_push(int cat, double flops, double bytes, cudaStream_t st, bool begin);
 void sefd_prof_label(const char* fmt, ...);   // label for the NEXT pushed record (ignored when profiling is off)
 
@@ -23,6 +28,7 @@ struct SefdProfScope {
     cudaStream_t st;
     bool on;
     SefdProfScope(int c, double flops, double bytes, cudaStream_t s) : cat(c), st(s), on(sefd_prof_on()) {
+        sefd_absorb_stale_error();
         if (on) sefd_prof_push(cat, flops, bytes, st, true);
     }
     ~SefdProfScope() {

@@ -14,6 +14,8 @@ _vp, _i, _f, _ll, _sz = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t
 SIGNATURES = {
     "sefd_abi_version": (_i, []),
     "sefd_last_error": (C.c_char_p, []),
+    "sefd_stale_cuda_errors": (_i, []),
+    "sefd_last_stale_cuda_error": (C.c_char_p, []),
     "sefd_stft_forward": (_i, [_vp, _vp, _i, _i, _vp]),
     "sefd_istft_forward": (_i, [_vp, _vp, _i, _i, _vp]),
     "sefd_istft_backward": (_i, [_vp, _vp, _i, _i, _vp]),

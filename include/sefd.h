@@ -28,6 +28,12 @@ enum { SEFD_MSE = 0, SEFD_SDR = 1, SEFD_SI_SNR = 2, SEFD_SI_SDR = 3 };
 int sefd_abi_version(void);
 const char* sefd_last_error(void);
 
+/* Non-sticky CUDA errors that were pending in the calling thread when one of this library's launches began (left by
+ * other code in the process; cudaGetLastError semantics): they are absorbed and counted here instead of being reported
+ * as a failure of the unrelated kernel that happened to be launched next. */
+int sefd_stale_cuda_errors(void);
+const char* sefd_last_stale_cuda_error(void);
+
 /* ---- op level ------------------------------------------------------------------------------- */
 
 /* ConvSTFT.forward, 'complex' (tools_for_model.py:54-61).  wav [B][L] -> spec [B][257][T][2] (re, im). */

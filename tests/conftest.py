@@ -28,3 +28,16 @@ def engine(request):
     lib.sefd_set_engine(request.param)
     yield request.param
     lib.sefd_set_engine(1)
+
+
+def pytest_terminal_summary(terminalreporter):
+    """Report CUDA errors that were pending from outside the library when one of its launches began (include/sefd.h:
+    sefd_stale_cuda_errors): absorbed instead of failing an unrelated test, but never silently."""
+    mod = sys.modules.get("sefd._lib")
+    lib = getattr(mod, "_lib", None) if mod else None
+    try:
+        n = lib.sefd_stale_cuda_errors() if lib is not None else 0
+    except Exception:
+        n = 0
+    if n:
+        terminalreporter.write_line(f"sefd: {n} stale CUDA error(s) absorbed; last: {lib.sefd_last_stale_cuda_error().decode()}")
