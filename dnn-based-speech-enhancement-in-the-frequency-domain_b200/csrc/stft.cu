@@ -1,4 +1,5 @@
-// STFT, mask + ISTFT (+ clamp + loss dot products) and its adjoint, for win 400 / hop 100 / N 512.
+// STFT, mask + ISTFT (+ clamp + loss dot products), the fused wave -> STFT -> mask -> ISTFT kernel and the adjoint, for
+// win 400 / hop 100 / N 512 (every model) and win 800 / hop 200 / N 1024 (op level).
 //
 // Reference semantics reproduced (file:line relative to the reference checkout):
 //  * ConvSTFT  (tools_for_model.py:54-61): zero-pad 300|300, frames of 400 x periodic Hann, zero-padded at
@@ -9,131 +10,18 @@
 //        frame[n] = w[n]/256 * ( y[n] - P_{n mod 2}/456 ),  P_q = sum_{n = q mod 2} y[n]
 //    overlap-add, divide by coff = sum of 4 shifted w^2 + 1e-8, trim 300|300.
 //  * DC mask bin is zero (models.py:255-256), mask modes C/E/R (models.py:258-276), clamp (models.py:282).
-// Two real frames share one complex 512-point FFT (fft512.cuh).
-#include "fft512.cuh"
+// Two real frames share one complex transform computed by one warp (fftw.cuh).
 #include "fftw.cuh"
 #include "stft.cuh"
 #include "prof.cuh"
 
 namespace {
 
-constexpr int WIN = 400, HOP = 100, NFFT = 512, NBIN = 257, PAD = 300;
-constexpr float INV_HALF_N = 1.0f / 256.0f, INV_PAR = 1.0f / 456.0f;   // N/2 and N/2 + win/2
-
-__device__ __forceinline__ void init_tables(float2* tw, float* win, float* coff) {
-    for (int j = threadIdx.x; j < NFFT; j += blockDim.x) {
-        float s, c;
-        sincospif(2.0f * j / NFFT, &s, &c);
-        tw[j] = make_float2(c, -s);
-    }
-    for (int n = threadIdx.x; n < WIN; n += blockDim.x) win[n] = 0.5f - 0.5f * cospif(2.0f * n / WIN);
-    if (coff) {
-        __syncthreads();
-        for (int m = threadIdx.x; m < HOP; m += blockDim.x) {
-            float a = 0.f;
-            for (int r = 0; r < WIN / HOP; ++r) a += win[m + HOP * r] * win[m + HOP * r];
-            coff[m] = a + 1e-8f;
-        }
-    }
-    __syncthreads();   // tables are read by every thread right after this returns
-}
-
-// sums over the even-n and odd-n samples of one 64-thread group; thread parity == sample parity.
-// scratch: 4 floats per group.
-__device__ __forceinline__ float2 group_parity_sums(float a, float b, float* scratch, int tid64) {
-    // reduce across lanes of equal parity inside the warp
-#pragma unroll
-    for (int o = 16; o >= 2; o >>= 1) {
-        a += __shfl_xor_sync(0xffffffffu, a, o);
-        b += __shfl_xor_sync(0xffffffffu, b, o);
-    }
-    // lanes 0 (even) and 1 (odd) of each of the two warps hold partials
-    const int lane = tid64 & 31, w = tid64 >> 5;
-    __syncthreads();
-    if (lane < 2) {
-        scratch[(w * 2 + lane) * 2 + 0] = a;
-        scratch[(w * 2 + lane) * 2 + 1] = b;
-    }
-    __syncthreads();
-    const int par = tid64 & 1;
-    return make_float2(scratch[(0 * 2 + par) * 2 + 0] + scratch[(1 * 2 + par) * 2 + 0],
-                       scratch[(0 * 2 + par) * 2 + 1] + scratch[(1 * 2 + par) * 2 + 1]);
-}
+constexpr int HOP = 100, NBIN = 257;      // the models' geometry (fft 512); the kernels themselves are templates over the fft length
 
 // ------------------------------------------------------------------------------------------------
-// STFT forward: wav [B][L] -> spec [B][257][T][2]
+// mask application (models.py:253-276) and its Jacobian
 // ------------------------------------------------------------------------------------------------
-constexpr int SF = 16;                                  // frames per CTA
-constexpr int SEG = (SF - 1) * HOP + WIN;               // 1900 samples
-
-struct StftSmem {
-    float2 fft[4][NFFT];
-    float2 tw[NFFT];
-    float2 out[NBIN][SF];
-    float win[WIN];
-    float seg[SEG];
-    float scratch[4][8];
-    float coff[HOP];
-};
-
-__global__ void __launch_bounds__(256) stft_fwd_kernel(const float* __restrict__ wav, float* __restrict__ spec,
-                                                       int B, int L, int T) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    StftSmem& S = *reinterpret_cast<StftSmem*>(smem_raw);
-    const int b = blockIdx.y, t0 = blockIdx.x * SF;
-    const int tid = threadIdx.x, g = tid >> 6, tid64 = tid & 63;
-    init_tables(S.tw, S.win, nullptr);
-    const float* w = wav + (long long)b * L;
-    for (int i = tid; i < SEG; i += 256) {
-        const int n = t0 * HOP + i - PAD;
-        S.seg[i] = (n >= 0 && n < L) ? __ldg(w + n) : 0.f;
-    }
-    __syncthreads();
-    for (int r = 0; r < SF / 8; ++r) {
-        const int fa = 8 * r + 2 * g;                   // local frame index of the pair (fa, fa+1)
-        float2* s = S.fft[g];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int n = tid64 + 64 * i;
-            float2 v = make_float2(0.f, 0.f);
-            if (n < WIN) v = make_float2(S.win[n] * S.seg[fa * HOP + n], S.win[n] * S.seg[(fa + 1) * HOP + n]);
-            s[fft_at(n)] = v;
-        }
-        __syncthreads();
-        fft512_cta<false>(s, S.tw, tid64);
-        // unpack the two real transforms: XA = (Z[k] + conj Z[N-k])/2, XB = (Z[k] - conj Z[N-k])/(2i)
-        for (int k = tid64; k <= 256; k += 64) {
-            const float2 z = s[fft_at(k)], zc = s[fft_at((NFFT - k) & (NFFT - 1))];
-            S.out[k][fa] = make_float2(0.5f * (z.x + zc.x), 0.5f * (z.y - zc.y));
-            S.out[k][fa + 1] = make_float2(0.5f * (z.y + zc.y), -0.5f * (z.x - zc.x));
-        }
-        __syncthreads();
-    }
-    float2* o = reinterpret_cast<float2*>(spec) + (long long)b * NBIN * T;
-    for (int e = tid; e < NBIN * SF; e += 256) {
-        const int k = e / SF, f = e % SF;
-        if (t0 + f < T) o[(long long)k * T + t0 + f] = S.out[k][f];
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// mask apply + ISTFT + clamp (+ <est,tgt>, <tgt,tgt>, <est,est>)
-// ------------------------------------------------------------------------------------------------
-constexpr int IF = 32;                  // frames per CTA
-constexpr int IHB = IF - 3;             // hop blocks of output produced per CTA (29)
-constexpr int OLA = (IF + 3) * HOP;     // 3500
-
-struct IstftSmem {
-    float2 fft[4][NFFT];
-    float2 tw[NFFT];
-    float win[WIN];
-    float coff[HOP];
-    float fr[8][WIN];
-    float ola[OLA];
-    float scratch[4][8];
-    float red[3][8];
-};
-
 __device__ __forceinline__ float2 apply_mask(int mode, float2 x, float2 m) {
     if (mode == SEFD_MASK_C) return make_float2(x.x * m.x - x.y * m.y, x.x * m.y + x.y * m.x);
     if (mode == SEFD_MASK_R) return make_float2(x.x * m.x, x.y * m.y);
@@ -159,141 +47,6 @@ __device__ __forceinline__ float2 apply_mask(int mode, float2 x, float2 m) {
     }
     return x;   // SEFD_MASK_NONE: plain ISTFT of `spec`
 }
-__device__ __forceinline__ float2 load_mask(const MaskIstftParams& p, int b, int k, int t) {
-    const float* q = p.mask + b * p.mB + (long long)(k - 1) * p.mF + (long long)(t + p.m_tshift) * p.mT;
-    if (p.mode == SEFD_MASK_MAG) return make_float2(__ldg(q), 0.f);
-    return __ldg(reinterpret_cast<const float2*>(q));
-}
-
-__global__ void __launch_bounds__(256) mask_istft_fwd_kernel(const MaskIstftParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    IstftSmem& S = *reinterpret_cast<IstftSmem*>(smem_raw);
-    const int b = blockIdx.y, c = blockIdx.x;
-    const int tid = threadIdx.x, g = tid >> 6, tid64 = tid & 63;
-    const int f0 = IHB * c;                                  // first frame held by this CTA
-    const int T = p.T, L = p.L;
-    init_tables(S.tw, S.win, S.coff);
-    for (int i = tid; i < OLA; i += 256) S.ola[i] = 0.f;
-    const float2* X = reinterpret_cast<const float2*>(p.spec) + (long long)b * NBIN * T;
-    __syncthreads();
-
-    for (int r = 0; r < IF / 8; ++r) {
-        const int la = 8 * r + 2 * g;                        // local frame pair (la, la+1)
-        const int ta = f0 + la, tb = ta + 1;
-        float2* s = S.fft[g];
-        const bool va = ta < T, vb = tb < T;
-        // ownership for the spectrum outputs: frames [f0+3, f0+3+IHB) plus frames 0..2 in the first CTA
-        const bool oa = va && (la >= 3 ? la < 3 + IHB : c == 0);
-        const bool ob = vb && (la + 1 >= 3 ? la + 1 < 3 + IHB : c == 0);
-        for (int k = tid64; k <= 256; k += 64) {
-            float2 sa = make_float2(0.f, 0.f), sb = sa;
-            float ema = 0.f, emb = 0.f;
-            if (va) {
-                const float2 x = __ldg(X + (long long)k * T + ta);
-                float2 m = make_float2(0.f, 0.f);
-                if (p.mode != SEFD_MASK_NONE && k >= 1) m = load_mask(p, b, k, ta);
-                if (p.mode == SEFD_MASK_MAG) ema = tanhf(m.x) * sqrtf(x.x * x.x + x.y * x.y);
-                sa = (p.mode != SEFD_MASK_NONE && k == 0) ? make_float2(0.f, 0.f) : apply_mask(p.mode, x, m);
-            }
-            if (vb) {
-                const float2 x = __ldg(X + (long long)k * T + tb);
-                float2 m = make_float2(0.f, 0.f);
-                if (p.mode != SEFD_MASK_NONE && k >= 1) m = load_mask(p, b, k, tb);
-                if (p.mode == SEFD_MASK_MAG) emb = tanhf(m.x) * sqrtf(x.x * x.x + x.y * x.y);
-                sb = (p.mode != SEFD_MASK_NONE && k == 0) ? make_float2(0.f, 0.f) : apply_mask(p.mode, x, m);
-            }
-            if (p.out_real) {
-                const long long o = ((long long)b * NBIN + k) * T;
-                if (p.mode == SEFD_MASK_MAG) {          // est_mags = tanh(mask) * |X| (models.py:521-522)
-                    if (oa) p.out_real[o + ta] = ema;
-                    if (ob) p.out_real[o + tb] = emb;
-                } else {
-                    if (oa) { p.out_real[o + ta] = sa.x; p.out_imag[o + ta] = sa.y; }
-                    if (ob) { p.out_real[o + tb] = sb.x; p.out_imag[o + tb] = sb.y; }
-                }
-            }
-            // Hermitian parts of the one-sided spectra, packed A + iB
-            if (k == 0 || k == 256) {
-                s[fft_at(k)] = make_float2(sa.x, sb.x);
-            } else {
-                s[fft_at(k)] = make_float2(0.5f * (sa.x - sb.y), 0.5f * (sa.y + sb.x));
-                s[fft_at(NFFT - k)] = make_float2(0.5f * (sa.x + sb.y), 0.5f * (sb.x - sa.y));
-            }
-        }
-        __syncthreads();
-        fft512_cta<true>(s, S.tw, tid64);
-        float ea = 0.f, eb = 0.f;
-#pragma unroll
-        for (int i = 0; i < 7; ++i) {
-            const int n = tid64 + 64 * i;
-            if (n < WIN) { const float2 e = s[fft_at(n)]; ea += e.x; eb += e.y; }
-        }
-        const float2 par = group_parity_sums(ea, eb, S.scratch[g], tid64);
-#pragma unroll
-        for (int i = 0; i < 7; ++i) {
-            const int n = tid64 + 64 * i;
-            if (n < WIN) {
-                const float wn = S.win[n] * INV_HALF_N;
-                S.fr[2 * g][n] = wn * (s[fft_at(n)].x - par.x * INV_PAR);
-                S.fr[2 * g + 1][n] = wn * (s[fft_at(n)].y - par.y * INV_PAR);
-            }
-        }
-        __syncthreads();
-        // overlap-add of the 8 frames of this round (fixed order -> deterministic)
-        const int base = 8 * r * HOP;
-        for (int q = tid; q < 7 * HOP + WIN; q += 256) {
-            float a = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int n = q - j * HOP;
-                if (n >= 0 && n < WIN) a += S.fr[j][n];
-            }
-            S.ola[base + q] += a;
-        }
-        __syncthreads();
-    }
-
-    // finalize hop blocks [3, 3+IHB): sample index n = f0*HOP + q - PAD
-    float d12 = 0.f, d22 = 0.f, d11 = 0.f;
-    for (int q = PAD + tid; q < PAD + IHB * HOP; q += 256) {
-        const int n = f0 * HOP + q - PAD;
-        if (n < L) {
-            const float raw = S.ola[q] / S.coff[q % HOP];
-            const float v = fminf(fmaxf(raw, -1.f), 1.f);
-            const long long o = (long long)b * L + n;
-            p.out_wav[o] = v;
-            if (p.raw_wav) p.raw_wav[o] = raw;
-            if (p.target) {
-                const float tg = __ldg(p.target + o);
-                d12 += v * tg; d22 += tg * tg; d11 += v * v;
-            }
-        }
-    }
-    if (p.target) {
-        d12 = warp_sum(d12); d22 = warp_sum(d22); d11 = warp_sum(d11);
-        if ((tid & 31) == 0) { S.red[0][tid >> 5] = d12; S.red[1][tid >> 5] = d22; S.red[2][tid >> 5] = d11; }
-        __syncthreads();
-        if (tid < 3) {
-            float a = 0.f;
-            for (int i = 0; i < 8; ++i) a += S.red[tid][i];
-            atomicAdd(p.dots + b * 8 + tid, (double)a);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// adjoint: d wav -> d mask   (ISTFT^T, then the mask-apply Jacobian; no gradient to the noisy spectrum)
-// ------------------------------------------------------------------------------------------------
-struct IstftBwdSmem {
-    float2 fft[4][NFFT];
-    float2 tw[NFFT];
-    float2 out[NBIN][SF];
-    float win[WIN];
-    float coff[HOP];
-    float seg[SEG];
-    float scratch[4][8];
-};
-
 __device__ __forceinline__ float2 mask_bwd(int mode, float2 x, float2 m, float2 ds) {
     if (mode == SEFD_MASK_C) return make_float2(x.x * ds.x + x.y * ds.y, -x.y * ds.x + x.x * ds.y);
     if (mode == SEFD_MASK_R) return make_float2(x.x * ds.x, x.y * ds.y);
@@ -331,106 +84,8 @@ __device__ __forceinline__ float2 mask_bwd(int mode, float2 x, float2 m, float2 
     return ds;   // NONE: gradient with respect to the spectrum itself
 }
 
-__global__ void __launch_bounds__(256) mask_istft_bwd_kernel(const MaskIstftBwdParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    IstftBwdSmem& S = *reinterpret_cast<IstftBwdSmem*>(smem_raw);
-    const int b = blockIdx.y, t0 = blockIdx.x * SF;
-    const int tid = threadIdx.x, g = tid >> 6, tid64 = tid & 63;
-    const int T = p.T, L = p.L;
-    init_tables(S.tw, S.win, S.coff);
-    for (int i = tid; i < SEG; i += 256) {
-        const int P = t0 * HOP + i, n = P - PAD;
-        float v = 0.f;
-        if (n >= 0 && n < L) {
-            const long long o = (long long)b * L + n;
-            v = p.dwav ? __ldg(p.dwav + o) : 0.f;
-            if (p.raw_wav) {
-                const float raw = __ldg(p.raw_wav + o);
-                if (!(raw >= -1.f && raw <= 1.f)) v = 0.f;
-            }
-            v /= S.coff[P % HOP];
-        }
-        S.seg[i] = v;
-    }
-    __syncthreads();
-    for (int r = 0; r < SF / 8; ++r) {
-        const int fa = 8 * r + 2 * g;
-        float2* s = S.fft[g];
-        float ga[7], gb[7];
-        float ea = 0.f, eb = 0.f;
-#pragma unroll
-        for (int i = 0; i < 7; ++i) {
-            const int n = tid64 + 64 * i;
-            ga[i] = gb[i] = 0.f;
-            if (n < WIN) {
-                const float wn = S.win[n] * INV_HALF_N;
-                ga[i] = wn * S.seg[fa * HOP + n];
-                gb[i] = wn * S.seg[(fa + 1) * HOP + n];
-                ea += ga[i]; eb += gb[i];
-            }
-        }
-        const float2 par = group_parity_sums(ea, eb, S.scratch[g], tid64);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int n = tid64 + 64 * i;
-            float2 v = make_float2(0.f, 0.f);
-            if (i < 7 && n < WIN) v = make_float2(ga[i] - par.x * INV_PAR, gb[i] - par.y * INV_PAR);
-            s[fft_at(n)] = v;
-        }
-        __syncthreads();
-        fft512_cta<false>(s, S.tw, tid64);
-        for (int k = tid64; k <= 256; k += 64) {
-            const float2 z = s[fft_at(k)], zc = s[fft_at((NFFT - k) & (NFFT - 1))];
-            S.out[k][fa] = make_float2(0.5f * (z.x + zc.x), 0.5f * (z.y - zc.y));
-            S.out[k][fa + 1] = make_float2(0.5f * (z.y + zc.y), -0.5f * (z.x - zc.x));
-        }
-        __syncthreads();
-    }
-    const float2* X = reinterpret_cast<const float2*>(p.spec) + (long long)b * NBIN * T;
-    const int k_lo = (p.mode == SEFD_MASK_NONE) ? 0 : 1;
-    for (int e = tid; e < NBIN * SF; e += 256) {
-        const int k = e / SF, f = e % SF, t = t0 + f;
-        if (t >= T || k < k_lo) continue;
-        float2 ds = S.out[k][f];
-        float dmag = 0.f;                 // SEFD_MASK_MAG: gradient arriving at est_mags = tanh(mask) |X|
-        if (p.dreal) {
-            const long long o = ((long long)b * NBIN + k) * T + t;
-            if (p.mode == SEFD_MASK_MAG) {
-                dmag = __ldg(p.dreal + o);
-            } else {
-                ds.x += __ldg(p.dreal + o);
-                ds.y += __ldg(p.dimag + o);
-            }
-        }
-        float2 x = make_float2(0.f, 0.f), m = x;
-        if (p.mode != SEFD_MASK_NONE) {
-            x = __ldg(X + (long long)k * T + t);
-            const float* mq = p.mask + b * p.mB + (long long)(k - 1) * p.mF + (long long)(t + p.m_tshift) * p.mT;
-            if (p.mode == SEFD_MASK_E) m = __ldg(reinterpret_cast<const float2*>(mq));
-            if (p.mode == SEFD_MASK_MAG) m.x = __ldg(mq);
-        }
-        float2 dm = mask_bwd(p.mode, x, m, ds);
-        if (p.mode == SEFD_MASK_MAG && p.dreal) {
-            const float th = tanhf(m.x);
-            dm.x += dmag * (1.f - th * th) * sqrtf(x.x * x.x + x.y * x.y);
-        }
-        float* dq = p.dmask + b * p.mB + (long long)(k - k_lo) * p.mF + (long long)(t + p.m_tshift) * p.mT;
-        if (p.mode == SEFD_MASK_MAG) *dq = dm.x;
-        else *reinterpret_cast<float2*>(dq) = dm;
-    }
-    // frames in front of the shift (the decoder's dropped look-ahead frame) get zero gradient
-    if (blockIdx.x == 0 && p.m_tshift > 0) {
-        for (int e = tid; e < (NBIN - k_lo) * p.m_tshift; e += 256) {
-            const int k = e / p.m_tshift, t = e % p.m_tshift;
-            float* dq = p.dmask + b * p.mB + (long long)k * p.mF + (long long)t * p.mT;
-            if (p.mode == SEFD_MASK_MAG) *dq = 0.f;
-            else *reinterpret_cast<float2*>(dq) = make_float2(0.f, 0.f);
-        }
-    }
-}
-
 // ================================================================================================
-// Warp-FFT kernels (fftw.cuh): one warp = one complex transform = two real frames; CTA = 8 warps = 16 frames per round.
+// The kernels (fftw.cuh): one warp = one complex transform = two real frames; CTA = 8 warps = 16 frames per round.
 // Both transform geometries of the reference's config (config.py:55-61): NFFT 512 (win 400 / hop 100, 257 bins) and
 // NFFT 1024 (win 800 / hop 200, 513 bins); in both win = 4 hop and the zero padding is win - hop on either side.
 // ================================================================================================
@@ -827,6 +482,119 @@ __global__ void __launch_bounds__(256, 2) stft_mask_istft_w_kernel(const float* 
 }
 
 // ------------------------------------------------------------------------------------------------
+// adjoint: d wav -> d mask   (ISTFT^T, then the mask-apply Jacobian; no gradient to the noisy spectrum).
+// ISTFT^T of a frame = forward transform of w[n] / (N/2) * (g[n] - parity means of it), g = d wav / coff gated by the
+// clamp: the same analysis structure as the STFT kernel (one warp per frame pair, staging tile aliasing the buffers).
+// ------------------------------------------------------------------------------------------------
+template <int NFFT>
+struct IstftBwdWSmem {
+    static constexpr int FFT_LEN = 8 * fftw::Buf<NFFT>::LEN, OUT_LEN = Geo<NFFT>::NBIN * OUT_PITCH;
+    float2 buf[FFT_LEN > OUT_LEN ? FFT_LEN : OUT_LEN];
+    float win[Geo<NFFT>::WIN];
+    float coff[Geo<NFFT>::HOP];
+};
+
+template <int NFFT>
+__global__ void __launch_bounds__(256, 2) mask_istft_bwd_w_kernel(const MaskIstftBwdParams p) {
+    using G = Geo<NFFT>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    IstftBwdWSmem<NFFT>& S = *reinterpret_cast<IstftBwdWSmem<NFFT>*>(smem_raw);
+    const int b = blockIdx.y, t0 = blockIdx.x * WF;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int T = p.T, L = p.L;
+    fftw::Twiddles<NFFT> tw;
+    tw.init(lane);
+    init_window<NFFT>(S.win, S.coff);
+    float2* s = S.buf + warp * fftw::Buf<NFFT>::LEN;
+    const int fa = t0 + 2 * warp;
+    // g[n] of frame f: d wav at sample f hop + n - pad (zero outside the signal or where the clamp was active) / coff
+    auto grad_at = [&](int P) {
+        const int n = P - G::PAD;
+        float v = 0.f;
+        if (n >= 0 && n < L) {
+            const long long o = (long long)b * L + n;
+            v = p.dwav ? __ldg(p.dwav + o) : 0.f;
+            if (p.raw_wav) {
+                const float raw = __ldg(p.raw_wav + o);
+                if (!(raw >= -1.f && raw <= 1.f)) v = 0.f;
+            }
+            v /= S.coff[P % G::HOP];
+        }
+        return v;
+    };
+    float2 v[G::R1];
+    float ea = 0.f, eb = 0.f;
+#pragma unroll
+    for (int n1 = 0; n1 < G::R1; ++n1) {
+        const int n = 32 * n1 + lane;
+        v[n1] = make_float2(0.f, 0.f);
+        if (32 * n1 < G::WIN && n < G::WIN) {
+            const float wn = S.win[n] * G::INV_HALF;
+            v[n1] = make_float2(wn * grad_at(fa * G::HOP + n), wn * grad_at((fa + 1) * G::HOP + n));
+            ea += v[n1].x; eb += v[n1].y;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o >= 2; o >>= 1) {                     // sums over the lanes (= samples) of this lane's parity
+        ea += __shfl_xor_sync(0xffffffffu, ea, o);
+        eb += __shfl_xor_sync(0xffffffffu, eb, o);
+    }
+#pragma unroll
+    for (int n1 = 0; n1 < G::R1; ++n1) {
+        const int n = 32 * n1 + lane;
+        if (32 * n1 < G::WIN && n < G::WIN) { v[n1].x -= ea * G::INV_PARITY; v[n1].y -= eb * G::INV_PARITY; }
+    }
+    fftw::fft_warp<NFFT, false>(v, s, tw, lane);
+    float4 o[NFFT / 64 + 1];
+    unpack_pair<NFFT>(s, o, lane);
+    __syncthreads();
+    stage_pair<NFFT>(S.buf, o, 2 * warp, lane);
+    __syncthreads();
+
+    const float2* X = reinterpret_cast<const float2*>(p.spec) + (long long)b * G::NBIN * T;
+    const int k_lo = (p.mode == SEFD_MASK_NONE) ? 0 : 1;
+    for (int e = tid; e < G::NBIN * WF; e += 256) {
+        const int k = e >> 4, f = e & 15, t = t0 + f;
+        if (t >= T || k < k_lo) continue;
+        float2 ds = S.buf[k * OUT_PITCH + f];
+        float dmag = 0.f;                 // SEFD_MASK_MAG: gradient arriving at est_mags = tanh(mask) |X|
+        if (p.dreal) {
+            const long long o2 = ((long long)b * G::NBIN + k) * T + t;
+            if (p.mode == SEFD_MASK_MAG) {
+                dmag = __ldg(p.dreal + o2);
+            } else {
+                ds.x += __ldg(p.dreal + o2);
+                ds.y += __ldg(p.dimag + o2);
+            }
+        }
+        float2 x = make_float2(0.f, 0.f), m = x;
+        if (p.mode != SEFD_MASK_NONE) {
+            x = __ldg(X + (long long)k * T + t);
+            const float* mq = p.mask + b * p.mB + (long long)(k - 1) * p.mF + (long long)(t + p.m_tshift) * p.mT;
+            if (p.mode == SEFD_MASK_E) m = __ldg(reinterpret_cast<const float2*>(mq));
+            if (p.mode == SEFD_MASK_MAG) m.x = __ldg(mq);
+        }
+        float2 dm = mask_bwd(p.mode, x, m, ds);
+        if (p.mode == SEFD_MASK_MAG && p.dreal) {
+            const float th = tanhf(m.x);
+            dm.x += dmag * (1.f - th * th) * sqrtf(x.x * x.x + x.y * x.y);
+        }
+        float* dq = p.dmask + b * p.mB + (long long)(k - k_lo) * p.mF + (long long)(t + p.m_tshift) * p.mT;
+        if (p.mode == SEFD_MASK_MAG) *dq = dm.x;
+        else *reinterpret_cast<float2*>(dq) = dm;
+    }
+    // frames in front of the shift (the decoder's dropped look-ahead frame) get zero gradient
+    if (blockIdx.x == 0 && p.m_tshift > 0) {
+        for (int e = tid; e < (G::NBIN - k_lo) * p.m_tshift; e += 256) {
+            const int k = e / p.m_tshift, t = e % p.m_tshift;
+            float* dq = p.dmask + b * p.mB + (long long)k * p.mF + (long long)t * p.mT;
+            if (p.mode == SEFD_MASK_MAG) *dq = 0.f;
+            else *reinterpret_cast<float2*>(dq) = make_float2(0.f, 0.f);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // losses (tools_for_loss.py:29-94; selection models.py:315-323).  dots[b][8] (double):
 //   0 <E,G>  1 <G,G>  2 <E,E>  3 sum res^2  4 sum res*G      res = E - c_b G
 // coef[b][2]: d loss / d E[b,n] = coef[b][0] * E[b,n] + coef[b][1] * G[b,n]
@@ -965,11 +733,6 @@ int sefd_spec_mag_launch(const float* spec, float* mag, long long n, cudaStream_
     return sefd_check_launch("spec_mag");
 }
 
-static bool legacy_fft() {
-    static const int v = [] { const char* e = getenv("SEFD_STFT_LEGACY"); return e && e[0] == '1' ? 1 : 0; }();
-    return v != 0;
-}
-
 template <int NFFT>
 static int stft_launch_w(const float* wav, float* spec, int B, int L, cudaStream_t st) {
     using G = Geo<NFFT>;
@@ -1020,16 +783,7 @@ static int mask_istft_launch_w(const MaskIstftParams& p, const float* fused_wav,
 
 int sefd_stft_launch(const float* wav, float* spec, int B, int L, int T, cudaStream_t st) {
     SEFD_REQUIRE(L % HOP == 0 && T == L / HOP + 3, "stft: L=%d must be a multiple of %d and T=%d == L/hop+3", L, HOP, T);
-    if (!legacy_fft()) return stft_launch_w<512>(wav, spec, B, L, st);
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(stft_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StftSmem));
-        attr = true;
-    }
-    dim3 grid((T + SF - 1) / SF, B);
-    SefdProfScope prof(SEFD_PROF_STFT, 0, 4.0 * B * L + 8.0 * B * NBIN * T, st);
-    stft_fwd_kernel<<<grid, 256, sizeof(StftSmem), st>>>(wav, spec, B, L, T);
-    return sefd_check_launch("stft_fwd");
+    return stft_launch_w<512>(wav, spec, B, L, st);
 }
 
 int sefd_stft_launch_n(const float* wav, float* spec, int B, int L, int nfft, cudaStream_t st) {
@@ -1042,32 +796,18 @@ int sefd_mask_istft_launch_n(const MaskIstftParams& p, const float* fused_wav, i
     return nfft == 512 ? mask_istft_launch_w<512>(p, fused_wav, st) : mask_istft_launch_w<1024>(p, fused_wav, st);
 }
 
-int sefd_mask_istft_launch(const MaskIstftParams& p, cudaStream_t st) {
-    SEFD_REQUIRE(p.L % HOP == 0 && p.T == p.L / HOP + 3, "istft: L=%d / T=%d inconsistent", p.L, p.T);
-    if (!legacy_fft()) return mask_istft_launch_w<512>(p, nullptr, st);
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(mask_istft_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IstftSmem));
-        attr = true;
-    }
-    if (p.target) cudaMemsetAsync(p.dots, 0, sizeof(double) * 8 * p.B, st);
-    const int chunks = (p.L / HOP + IHB - 1) / IHB;
-    dim3 grid(chunks, p.B);
-    SefdProfScope prof(SEFD_PROF_STFT, 0, 8.0 * p.B * NBIN * p.T * (p.mode != SEFD_MASK_NONE ? 2 : 1) +
-                       4.0 * p.B * p.L * (p.target ? 3 : 2) + (p.out_real ? 8.0 * p.B * NBIN * p.T : 0.0), st);
-    mask_istft_fwd_kernel<<<grid, 256, sizeof(IstftSmem), st>>>(p);
-    return sefd_check_launch("mask_istft_fwd");
-}
+int sefd_mask_istft_launch(const MaskIstftParams& p, cudaStream_t st) { return mask_istft_launch_w<512>(p, nullptr, st); }
 
 int sefd_mask_istft_bwd_launch(const MaskIstftBwdParams& p, cudaStream_t st) {
+    SEFD_REQUIRE(p.L > 0 && p.L % HOP == 0 && p.T == p.L / HOP + 3, "istft backward: L=%d / T=%d inconsistent", p.L, p.T);
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(mask_istft_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IstftBwdSmem));
+        cudaFuncSetAttribute(mask_istft_bwd_w_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IstftBwdWSmem<512>));
         attr = true;
     }
-    dim3 grid((p.T + SF - 1) / SF, p.B);
+    dim3 grid((p.T + WF - 1) / WF, p.B);
     SefdProfScope prof(SEFD_PROF_STFT, 0, 8.0 * p.B * NBIN * p.T * 2 + 8.0 * p.B * p.L, st);
-    mask_istft_bwd_kernel<<<grid, 256, sizeof(IstftBwdSmem), st>>>(p);
+    mask_istft_bwd_w_kernel<512><<<grid, 256, sizeof(IstftBwdWSmem<512>), st>>>(p);
     return sefd_check_launch("mask_istft_bwd");
 }
 
