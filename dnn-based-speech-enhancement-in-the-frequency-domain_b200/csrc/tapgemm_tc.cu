@@ -19,6 +19,7 @@
 // (ncu, round 1: with one TMA instruction per 16-24 KB the single producer thread was ~64 % busy issuing and the
 //  small-tile layers sat at a 0.3 ms floor; hence the multi-block boxes.)
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -50,6 +51,11 @@ struct TcParams {
     int it_slab_lo[SEFD_MAX_TAPS], it_wbox[SEFD_MAX_TAPS];   // first weight slab / slabs (1, 2 or 4) of the item's box
     // per tap of an item: weight sub-tile inside the box, activation row offset (0/1), accumulator (output-row phase)
     int it_wt[SEFD_MAX_TAPS][4], it_roff[SEFD_MAX_TAPS][4], it_acc[SEFD_MAX_TAPS][4];
+    // merged item (two output rows per tile): its four taps are (phase 0 | phase 1) x (frame shift a | b) on ONE activation
+    // tile; the weight box lands as [shift][k-block][phase][n][k], so that the two phases' tiles of one shift are 2 BN
+    // consecutive operand rows and ONE MMA of width 2 BN feeds both accumulators (adjacent in TMEM): the A operand is read
+    // from shared memory once per shift instead of once per tap.  it_mroff[it][s]: activation row offset of shift s.
+    int it_merge[SEFD_MAX_TAPS], it_mroff[SEFD_MAX_TAPS][2];
     int C0, C1, N, wJ_slabs;
     int t_tiles, n_tiles;
     long long total_tiles;
@@ -84,7 +90,7 @@ template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
-                  const __grid_constant__ CUtensorMap tmW4, const TcParams p) {
+                  const __grid_constant__ CUtensorMap tmW4, const __grid_constant__ CUtensorMap tmWm, const TcParams p) {
     using C = Cfg<BN>;
     // declared alignment keeps every derived pointer in the shared address space (LDS/STS/ATOMS, not generic)
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -148,7 +154,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                             mbar_expect_tx(fb, bytes);
                             if (kg < kg0) tma_load_5d(&tmA0, fb, sa, 0, tin, kg * p.kbs, fi, tc.b);
                             else tma_load_5d(&tmA1, fb, sa, 0, tin, (kg - kg0) * p.kbs, fi, tc.b);
-                            if (wbox == 4) tma_load_4d(&tmW4, fb, sa + p.a_bytes, 0, tc.n0, kg * p.kbs, slab);
+                            if (p.it_merge[it]) tma_load_5d(&tmWm, fb, sa + p.a_bytes, 0, tc.n0, slab >> 1, kg * p.kbs, 0);
+                            else if (wbox == 4) tma_load_4d(&tmW4, fb, sa + p.a_bytes, 0, tc.n0, kg * p.kbs, slab);
                             else if (wbox == 2) tma_load_4d(&tmW2, fb, sa + p.a_bytes, 0, tc.n0, kg * p.kbs, slab);
                             else tma_load_4d(&tmW1, fb, sa + p.a_bytes, 0, tc.n0, kg * p.kbs, slab);
                         }
@@ -163,6 +170,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         {
             // instruction descriptor: D fp32, A/B tf32, both K-major, N = BN, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN > 256 ? 256 : 2 * BN) >> 3) << 17) |
+                                    ((uint32_t)(TM >> 4) << 24);                                    // N = 2 BN (merged items, BN <= 128)
             int stage = 0, abuf = 0;
             uint32_t phase = 0, aphase = 0;
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -179,6 +188,21 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                         mbar_wait(smem_u32(&full[stage]), phase);
                         tc_fence_after();
                         const uint32_t sa = smem_base + (uint32_t)(stage * p.stage_bytes);
+                        if (p.it_merge[it]) {
+                            // both accumulators in one MMA of width 2 BN per frame shift (they start together: merged items
+                            // come first in the item list, so acc0 == acc1 here)
+                            for (int sh = 0; sh < 2; ++sh) {
+                                for (int kb = 0; kb < p.kbs; ++kb) {
+                                    const uint64_t ad = make_desc(sa + (uint32_t)(kb * C::A_TILE + p.it_mroff[it][sh] * 128));
+                                    const uint64_t bd = make_desc(sa + (uint32_t)(p.a_bytes + (sh * p.kbs + kb) * 2 * C::B_BYTES));
+#pragma unroll
+                                    for (int k8 = 0; k8 < KB / 8; ++k8) {
+                                        if (elect_one_sync()) tc_mma_tf32(d_tmem, ad + 2 * k8, bd + 2 * k8, idesc2, acc0);
+                                        acc0 = acc1 = 1;
+                                    }
+                                }
+                            }
+                        } else
                         for (int w = 0; w < n; ++w) {
                             const int a = p.it_acc[it][w];
                             const uint32_t dt = d_tmem + (uint32_t)(a * BN);
@@ -329,7 +353,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
 template <int BN>
 int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w1, const CUtensorMap& w2, const CUtensorMap& w4,
-           const TcParams& p, int smem, cudaStream_t st) {
+           const CUtensorMap& wm, const TcParams& p, int smem, cudaStream_t st) {
     static int cur = 0;
     if (smem > cur) {
         cudaFuncSetAttribute(tapgemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -342,7 +366,7 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w1, 
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const int grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
-    tapgemm_tc_kernel<BN><<<grid, NTHREADS, smem, st>>>(a0, a1, w1, w2, w4, p);
+    tapgemm_tc_kernel<BN><<<grid, NTHREADS, smem, st>>>(a0, a1, w1, w2, w4, wm, p);
     return sefd_check_launch("tapgemm_tc");
 }
 
@@ -353,6 +377,16 @@ int make_w_map(CUtensorMap* m, const TapGemmParams& g, int K, int N, int BN, int
                          (cuuint64_t)(g.w_slab_stride ? g.w_slab_stride : (long long)K * N) * 4};
     cuuint32_t box[4] = {32, (cuuint32_t)BN, (cuuint32_t)kbs, (cuuint32_t)nslab_box};
     return make_map(m, g.Wnk, 4, dims, str, box);
+}
+
+int make_w_map_merged(CUtensorMap* m, const TapGemmParams& g, int K, int N, int BN, int kbs) {
+    // slab = 4 m + 2 phase + shift: (k_inner 32, n, q = 2 m + phase [stride 2 slabs], k_block, shift [stride 1 slab]); the box
+    // {32, BN, 2, kbs, 2} lands in shared memory as [shift][k-block][phase][n][k]
+    const cuuint64_t slab_bytes = (cuuint64_t)(g.w_slab_stride ? g.w_slab_stride : (long long)K * N) * 4;
+    cuuint64_t dims[5] = {32, (cuuint64_t)N, (cuuint64_t)(g.nslabs / 2), (cuuint64_t)(K / 32), 2};
+    cuuint64_t str[4] = {(cuuint64_t)(g.w_ldk ? g.w_ldk : K) * 4, 2 * slab_bytes, 128, slab_bytes};
+    cuuint32_t box[5] = {32, (cuuint32_t)BN, 2, (cuuint32_t)kbs, 2};
+    return make_map(m, g.Wnk, 5, dims, str, box);
 }
 
 template <int BN>
@@ -386,12 +420,16 @@ int run(const TapGemmParams& g, TcParams& p, cudaStream_t st) {
     else w2 = w1;
     if (wmax >= 4) SEFD_TRY(make_w_map(&w4, g, K, N, BN, kbs, 4));
     else w4 = w1;
+    CUtensorMap wm = w1;
+    bool any_merge = false;
+    for (int it = 0; it < p.nitems; ++it) any_merge = any_merge || p.it_merge[it];
+    if (any_merge) SEFD_TRY(make_w_map_merged(&wm, g, K, N, BN, kbs));
     const double pos = (double)g.B * g.J * g.Tout;
     sefd_prof_label("tapgemm_tc BN%d K%d N%d taps%d items%d acc%d kbs%d x%d J%d Tout%d tiles%lld", BN, K, N, g.ntaps, p.nitems,
                     p.nacc, kbs, p.nstage, g.J, g.Tout, p.total_tiles);
     SefdProfScope prof(SEFD_PROF_TAPGEMM, 2.0 * pos * N * K * g.ntaps,
                        4.0 * ((double)g.B * g.J * (g.fi_mul > 1 ? g.fi_mul : 1) * g.Tin * K + pos * N * p.nacc), st);
-    return launch<BN>(a0, a1, w1, w2, w4, p, smem, st);
+    return launch<BN>(a0, a1, w1, w2, w4, wm, p, smem, st);
 }
 
 }  // namespace
@@ -433,6 +471,7 @@ int sefd_tapgemm_tc(const TapGemmParams& g, cudaStream_t st) {
     p.nacc = g.nacc == 2 ? 2 : 1;
     SEFD_REQUIRE(p.nacc == 1 || BN <= 128, "tapgemm_tc: two output rows per tile need N <= 128");
     const bool pair = BN <= 128;
+    static const bool merge_ok = getenv("SEFD_TAPGEMM_MERGE") == nullptr || atoi(getenv("SEFD_TAPGEMM_MERGE")) != 0;
     bool used[SEFD_MAX_TAPS] = {false};
     p.nitems = 0;
     for (int i = 0; i < g.ntaps; ++i) {
@@ -466,6 +505,25 @@ int sefd_tapgemm_tc(const TapGemmParams& g, cudaStream_t st) {
             p.it_roff[it][w] = g.dt[tp] - dt_lo;
             p.it_wt[it][w] = g.wslab[tp] - s_lo;
             p.it_acc[it][w] = p.nacc == 2 ? g.tap_acc[tp] : 0;
+        }
+        // merged form: slabs s_lo + 2 phase + shift with s_lo a multiple of 4, both shifts present for both phases, the two
+        // phases of a shift reading the activation tile at the same row offset
+        p.it_merge[it] = 0;
+        if (merge_ok && p.nacc == 2 && nm == 4 && s_lo % 4 == 0 && g.wJ_slabs == 0 && g.nslabs % 2 == 0) {
+            int roff[2][2] = {{-1, -1}, {-1, -1}};
+            bool ok = true;
+            for (int w = 0; w < 4; ++w) {
+                const int rel = p.it_wt[it][w], ph = rel >> 1, sh = rel & 1;
+                ok = ok && p.it_acc[it][w] == ph && roff[ph][sh] < 0;
+                roff[ph][sh] = p.it_roff[it][w];
+            }
+            ok = ok && roff[0][0] == roff[1][0] && roff[0][1] == roff[1][1] && roff[0][0] >= 0 && roff[0][1] >= 0;
+            for (int e = 0; e < it; ++e) ok = ok && p.it_merge[e];      // merged items must come first (common accumulate flag)
+            if (ok) {
+                p.it_merge[it] = 1;
+                p.it_mroff[it][0] = roff[0][0];
+                p.it_mroff[it][1] = roff[0][1];
+            }
         }
     }
     p.vec8 = 1;
