@@ -343,3 +343,22 @@ def test_adam_matches_torch_optim():
         opt.step()
         ops.adam_step(wd, grad.to(DEV), m, v, step)
         _close(wd, ref, atol=2e-7, rtol=1e-6, name=f"adam step {step}")
+
+
+def test_step_glue_kernels():
+    """sefd_axpby (the perceptual step's mixing, trainer.py:166-169) and sefd_counters_inc (BatchNorm2d.num_batches_tracked of
+    every layer in one launch) against the obvious torch expressions (axpby within a rounding, the counters exactly)."""
+    from sefd import _lib
+    from sefd.ops import ptr, stream
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(41)
+    x, y = torch.randn(100003, generator=g).to(DEV), torch.randn(100003, generator=g).to(DEV)
+    ref = torch.addcmul(0.25 * y, x, torch.full_like(x, 0.75))       # fma(a, x, b * y) has one rounding less than a*x + b*y
+    _lib.check(lib.sefd_axpby(ptr(y), ptr(x), 0.75, 0.25, y.numel(), stream()), "axpby")
+    assert float((y - ref).abs().max()) <= 1e-6 * float(ref.abs().max())
+    counters = [torch.tensor(i, dtype=torch.int64, device=DEV) for i in range(7)]
+    table = torch.tensor([c.data_ptr() for c in counters], dtype=torch.int64, device=DEV)
+    for _ in range(3):
+        _lib.check(lib.sefd_counters_inc(ptr(table), len(counters), 2, stream()), "counters_inc")
+    assert [int(c) for c in counters] == [i + 6 for i in range(7)]
+    assert lib.sefd_stale_cuda_errors() >= 0 and isinstance(lib.sefd_last_stale_cuda_error(), bytes)
