@@ -81,6 +81,9 @@ struct WgradParams {
     int g_tiled;
 };
 
+// > 0: the tensor-core weight gradient uses at most n CTAs (and sizes its row splits for them), leaving SMs free for a kernel
+// that runs beside it on another stream; 0 restores the whole device
+void sefd_wgrad_tc_set_cta_limit(int n);
 int sefd_tapgemm_simt(const TapGemmParams& p, cudaStream_t st);
 bool sefd_tapgemm_tc_eligible(const TapGemmParams& p);
 int sefd_tapgemm_tc(const TapGemmParams& p, cudaStream_t st);

@@ -468,18 +468,48 @@ int sefd_fsn_backward_impl(const sefd_plan* P, const float* prm, const float* d_
         sb_head_fold_kernel<<<(2 * SB_H + 2 + 127) / 128, 128, 0, st>>>(ws + E.hpart, E.head_blocks, SB_H, grads + E.sb.fc_w, grads + E.sb.fc_b);
         SEFD_TRY(sefd_check_launch("fsn_sb_head_fold"));
     }
-    // ---- sub-band LSTMs ----
-    SEFD_TRY(stack_backward(E.sc, E.sb, ws, ws + E.sb_in, T, tf, E.mask_sb, 2u, ws + E.dsb_in, grads, st));
+    // The full-band chain (unfold backward -> Linear data gradient -> two recurrences of ONE 128-row tile: 8 CTAs for ~9 ms,
+    // latency-bound) depends only on the sub-band RECURRENCES; the sub-band weight gradients (~16 ms on all SMs) depend on
+    // nothing after them.  With the tensor-core engine the chain therefore runs on a side stream BESIDE the sub-band weight
+    // gradients, which leave 8 SMs to it; the full-band weight gradients (they share the partial buffer) follow the join.
+    static const bool overlap_on = getenv("SEFD_FSN_OVERLAP") == nullptr || atoi(getenv("SEFD_FSN_OVERLAP")) != 0;
+    const bool overlap = overlap_on && tf && E.sb.l[0].tiled && E.sb.l[1].tiled;
+    if (overlap && !P->side) {
+        SEFD_REQUIRE(cudaStreamCreateWithFlags(&P->side, cudaStreamNonBlocking) == cudaSuccess, "fsn_backward: side stream");
+        cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&P->ev_join, cudaEventDisableTiming);
+    }
+    // ---- sub-band LSTMs: recurrences (and, without the overlap, their weight gradients) ----
+    SEFD_TRY(stack_backward(E.sc, E.sb, ws, ws + E.sb_in, T, tf, E.mask_sb, 2u, ws + E.dsb_in, grads, st, overlap ? 1 : 3));
+    cudaStream_t sc = st;                      // stream of the full-band chain
+    if (overlap) {
+        cudaEventRecord(P->ev_fork, st);
+        cudaStreamWaitEvent(P->side, P->ev_fork, 0);
+        sc = P->side;
+    }
     // ---- normalisation / unfold backward: only the full-band output carries a gradient (models.py:649-658) ----
     {
-        SefdProfScope prof(SEFD_PROF_STFT, 0, 8.0 * T * R * SB_I, st);
-        cudaMemsetAsync(wsd + E.Sred, 0, sizeof(double) * B, st);
-        fsn_unfold_bwd_reduce_kernel<<<dim3(T, B), 256, 0, st>>>(ws + E.dsb_in, ws + E.sb_in, B, wsd + E.Sred);
+        SefdProfScope prof(SEFD_PROF_STFT, 0, 8.0 * T * R * SB_I, sc);
+        cudaMemsetAsync(wsd + E.Sred, 0, sizeof(double) * B, sc);
+        fsn_unfold_bwd_reduce_kernel<<<dim3(T, B), 256, 0, sc>>>(ws + E.dsb_in, ws + E.sb_in, B, wsd + E.Sred);
         SEFD_TRY(sefd_check_launch("fsn_unfold_bwd_reduce"));
-        fsn_unfold_bwd_kernel<<<148 * 4, 256, 0, st>>>(ws + E.dsb_in, ws + E.fb_lin, wsd + E.Sred, ws + E.inv + B, B, T, ws + E.dfb_lin, tf);
+        fsn_unfold_bwd_kernel<<<148 * 4, 256, 0, sc>>>(ws + E.dsb_in, ws + E.fb_lin, wsd + E.Sred, ws + E.inv + B, B, T, ws + E.dfb_lin, tf);
         SEFD_TRY(sefd_check_launch("fsn_unfold_bwd"));
     }
-    // ---- full-band Linear (+ ReLU, folded into d lin) ----
+    // ---- full-band Linear (+ ReLU, folded into d lin): data gradient, then the recurrences (the input is data: no dx) ----
+    SEFD_TRY(gemm_all_steps(ws + E.dfb_lin, FPAD, ws + E.fb.dh[1], FB_H, B, T, ws + E.Wl_nk, ws + E.Wl_kn, nullptr, 0, sc));
+    SEFD_TRY(stack_backward(E.sc, E.fb, ws, ws + E.fb_in, T, tf, E.mask_fb, 1u, nullptr, grads, sc, overlap ? 1 : 3));
+    if (overlap) {
+        cudaEventRecord(P->ev_join, sc);
+        // meanwhile, on the main stream: the sub-band weight gradients on all SMs but the 8 of the full-band cluster
+        sefd_wgrad_tc_set_cta_limit(148 - 8);
+        const int rc = stack_backward(E.sc, E.sb, ws, ws + E.sb_in, T, tf, E.mask_sb, 2u, ws + E.dsb_in, grads, st, 2);
+        sefd_wgrad_tc_set_cta_limit(0);
+        SEFD_TRY(rc);
+        cudaStreamWaitEvent(st, P->ev_join, 0);
+        SEFD_TRY(stack_backward(E.sc, E.fb, ws, ws + E.fb_in, T, tf, E.mask_fb, 1u, nullptr, grads, st, 2));
+    }
+    // ---- full-band Linear: weight and bias gradients ----
     {
         int nsplit = 1;
         long long sstride = 0;
@@ -489,10 +519,7 @@ int sefd_fsn_backward_impl(const sefd_plan* P, const float* prm, const float* d_
         SEFD_TRY(sefd_check_launch("fsn_fold_linear"));
         SEFD_TRY(sefd_colsum2(ws + E.dfb_lin, 1, 0, (long long)T * B, FPAD, FPAD, wsd + E.red, ws + E.bl, st));   // bl is free after the forward
         cudaMemcpyAsync(grads + E.fb.fc_b, ws + E.bl, sizeof(float) * FBINS, cudaMemcpyDeviceToDevice, st);
-        SEFD_TRY(gemm_all_steps(ws + E.dfb_lin, FPAD, ws + E.fb.dh[1], FB_H, B, T, ws + E.Wl_nk, ws + E.Wl_kn, nullptr, 0, st));
     }
-    // ---- full-band LSTMs (the input is data: no dx) ----
-    SEFD_TRY(stack_backward(E.sc, E.fb, ws, ws + E.fb_in, T, tf, E.mask_fb, 1u, nullptr, grads, st));
     return 0;
 }
 

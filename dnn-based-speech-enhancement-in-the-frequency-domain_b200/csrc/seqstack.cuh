@@ -114,44 +114,52 @@ int stack_forward(const SeqScratch& E, const SeqStack& S, float* ws, const float
 
 // backward through the two layers; dh[1] holds the gradient arriving at h1.  dx0 (gradient w.r.t. the stack input) is
 // written when non-null.
+// phases: 1 = the recurrences (LSTM backward kernels of both layers, bias folds, input gradients, dropout backward), 2 = the
+// weight gradients (two wgrad calls + folds per layer; they only read what phase 1 left: dG in the gates buffers, the layer
+// inputs and h), 3 = both in the reference order.  Phase 2 may run later and on another stream than phase 1 (fsnet.cu
+// overlaps the sub-band weight gradients with the full-band recurrences); it owns E.wpart, phase 1 owns dh_rec / dc / bias_part.
 int stack_backward(const SeqScratch& E, const SeqStack& S, float* ws, const float* x, int T, int tf, const float* mask, unsigned int stream_id,
-                   float* dx0, float* grads, cudaStream_t st) {
+                   float* dx0, float* grads, cudaStream_t st, int phases = 3) {
     const int rows = S.rows;
     for (int l = 1; l >= 0; --l) {
         const SeqLayer& L = S.l[l];
         const int N = 4 * L.H;
-        SeqLstmBwdParams p;
-        p.w = weights_of(L, ws);
-        p.gates = ws + L.gates; p.c = ws + L.c; p.dh_out = ws + S.dh[l];
-        p.dh_rec = ws + E.dh_rec; p.dc = ws + E.dc; p.bias_part = ws + E.bias_part;
-        p.rows = rows; p.T = T; p.round_tf32 = tf;
-        p.dx = l == 1 ? ws + S.dh[0] : dx0;
-        p.dx_done = 0;
-        p.tiled = L.tiled;
-        SEFD_TRY(sefd_seqlstm_backward(p, st));
-        const long long step_stride = L.tiled ? (long long)((rows + 127) / 128) * 128 * N : (long long)rows * N;
-        const float* dG = ws + L.gates;
-        const float* xin = l == 0 ? x : (E.drop_on ? ws + S.h0d : ws + S.l[0].h);
-        int nsplit = 1;
-        long long sstride = 0;
-        float* part = ws + E.wpart;
-        SEFD_TRY(wgrad_all_steps(xin, L.I, dG, N, rows, T, L.tiled, part, E.wpart_floats, &nsplit, &sstride, st));
-        SEFD_TRY(sefd_seqlstm_fold_wgrad(part, nsplit, sstride, L.I, L.I_real, L.H, grads + L.w_ih, st, L.kd));
-        if (T > 1) {
-            SEFD_TRY(wgrad_all_steps(ws + L.h, L.H, dG + step_stride, N, rows, T - 1, L.tiled, part, E.wpart_floats, &nsplit, &sstride, st));
-            SEFD_TRY(sefd_seqlstm_fold_wgrad(part, nsplit, sstride, L.H, L.H, L.H, grads + L.w_hh, st));
-        } else {
-            cudaMemsetAsync(grads + L.w_hh, 0, sizeof(float) * N * L.H, st);
-        }
-        SEFD_TRY(sefd_seqlstm_fold_bias(ws + E.bias_part, p.bias_blocks, L.H, grads + L.b_ih, grads + L.b_hh, st));
-        float* dx = l == 1 ? ws + S.dh[0] : dx0;
-        if (dx) {
-            if (!p.dx_done) {
-                SEFD_REQUIRE(!L.tiled, "fsn backward: the input gradient must come from the fused step kernel when dG is tile-major");
-                SEFD_TRY(gemm_all_steps(dG, N, dx, L.I, rows, T, L.Wih_nk + ws, L.Wih_kn + ws, nullptr, 0, st));
+        if (phases & 1) {
+            SeqLstmBwdParams p;
+            p.w = weights_of(L, ws);
+            p.gates = ws + L.gates; p.c = ws + L.c; p.dh_out = ws + S.dh[l];
+            p.dh_rec = ws + E.dh_rec; p.dc = ws + E.dc; p.bias_part = ws + E.bias_part;
+            p.rows = rows; p.T = T; p.round_tf32 = tf;
+            p.dx = l == 1 ? ws + S.dh[0] : dx0;
+            p.dx_done = 0;
+            p.tiled = L.tiled;
+            SEFD_TRY(sefd_seqlstm_backward(p, st));
+            SEFD_TRY(sefd_seqlstm_fold_bias(ws + E.bias_part, p.bias_blocks, L.H, grads + L.b_ih, grads + L.b_hh, st));
+            float* dx = l == 1 ? ws + S.dh[0] : dx0;
+            if (dx) {
+                if (!p.dx_done) {
+                    SEFD_REQUIRE(!L.tiled, "fsn backward: the input gradient must come from the fused step kernel when dG is tile-major");
+                    SEFD_TRY(gemm_all_steps(ws + L.gates, N, dx, L.I, rows, T, L.Wih_nk + ws, L.Wih_kn + ws, nullptr, 0, st));
+                }
+                if (l == 1 && E.drop_on)
+                    SEFD_TRY(sefd_dropout_apply(dx, dx, (long long)T * rows * L.I, E.drop_p, mask, E.seed, stream_id, 0, st));
             }
-            if (l == 1 && E.drop_on)
-                SEFD_TRY(sefd_dropout_apply(dx, dx, (long long)T * rows * L.I, E.drop_p, mask, E.seed, stream_id, 0, st));
+        }
+        if (phases & 2) {
+            const long long step_stride = L.tiled ? (long long)((rows + 127) / 128) * 128 * N : (long long)rows * N;
+            const float* dG = ws + L.gates;
+            const float* xin = l == 0 ? x : (E.drop_on ? ws + S.h0d : ws + S.l[0].h);
+            int nsplit = 1;
+            long long sstride = 0;
+            float* part = ws + E.wpart;
+            SEFD_TRY(wgrad_all_steps(xin, L.I, dG, N, rows, T, L.tiled, part, E.wpart_floats, &nsplit, &sstride, st));
+            SEFD_TRY(sefd_seqlstm_fold_wgrad(part, nsplit, sstride, L.I, L.I_real, L.H, grads + L.w_ih, st, L.kd));
+            if (T > 1) {
+                SEFD_TRY(wgrad_all_steps(ws + L.h, L.H, dG + step_stride, N, rows, T - 1, L.tiled, part, E.wpart_floats, &nsplit, &sstride, st));
+                SEFD_TRY(sefd_seqlstm_fold_wgrad(part, nsplit, sstride, L.H, L.H, L.H, grads + L.w_hh, st));
+            } else {
+                cudaMemsetAsync(grads + L.w_hh, 0, sizeof(float) * N * L.H, st);
+            }
         }
     }
     return 0;

@@ -249,6 +249,8 @@ int make_pos_map(CUtensorMap* m, const TapSrc& s, int F, int T, int B, int nblk)
     return make_act_map5(m, s, F, T, B, PB, nblk, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
 }
 
+int g_cta_limit = 0;      // > 0: use at most this many CTAs (the caller keeps SMs free for a kernel on another stream)
+
 template <int BN>
 int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& g, const WgParams& p, int smem, cudaStream_t st) {
     static int cur = 0;
@@ -262,7 +264,8 @@ int launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& g, c
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    const int grid = (int)(p.units < sms ? p.units : sms);
+    const int ctas = g_cta_limit > 0 && g_cta_limit < sms ? g_cta_limit : sms;
+    const int grid = (int)(p.units < ctas ? p.units : ctas);
     wgrad_tc_kernel<BN><<<grid, NTHREADS, smem, st>>>(a0, a1, g, p);
     return sefd_check_launch("wgrad_tc");
 }
@@ -414,6 +417,8 @@ int build_groups(const WgradParams& w, int BN, int K, int nAc, WgParams& p) {
 
 }  // namespace
 
+void sefd_wgrad_tc_set_cta_limit(int n) { g_cta_limit = n; }
+
 bool sefd_wgrad_tc_eligible(const WgradParams& p) {
     if (p.a[0].C % 32 || p.a[1].C % 32 || p.a[0].C == 0 || p.g.C % 32 || p.g.C == 0) return false;
     const TapSrc* v[3] = {&p.a[0], &p.a[1], &p.g};
@@ -461,11 +466,12 @@ int sefd_wgrad_tc(const WgradParams& w, float* partial, long long cap_floats, in
     const long long one = (long long)nslabs * K * N;
     // units = tiles x splits are dealt round-robin to the 148 persistent CTAs: aim for just UNDER two full rounds
     // (300 units made three rounds, the third 3 % full: 2.03 rounds of work in the time of 3)
-    long long splits = (2 * 148) / tiles;
+    const int ctas = g_cta_limit > 0 && g_cta_limit < 148 ? g_cta_limit : 148;
+    long long splits = (2 * ctas) / tiles;
     if (splits < 1) splits = 1;
     if (splits > rows) splits = rows;
     if (splits > cap_floats / one) splits = cap_floats / one;
-    if (splits > 2 * 148) splits = 2 * 148;
+    if (splits > 2 * ctas) splits = 2 * ctas;
     SEFD_REQUIRE(splits >= 1, "wgrad_tc: partial buffer too small");
     p.rows_per_split = (int)((rows + splits - 1) / splits);
     p.splits = (rows + p.rows_per_split - 1) / p.rows_per_split;
