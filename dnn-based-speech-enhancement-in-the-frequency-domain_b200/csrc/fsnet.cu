@@ -473,7 +473,8 @@ int sefd_fsn_backward_impl(const sefd_plan* P, const float* prm, const float* d_
     // nothing after them.  With the tensor-core engine the chain therefore runs on a side stream BESIDE the sub-band weight
     // gradients, which leave 8 SMs to it; the full-band weight gradients (they share the partial buffer) follow the join.
     static const bool overlap_on = getenv("SEFD_FSN_OVERLAP") == nullptr || atoi(getenv("SEFD_FSN_OVERLAP")) != 0;
-    const bool overlap = overlap_on && tf && E.sb.l[0].tiled && E.sb.l[1].tiled;
+    // (not while per-launch profiling is on: event timings of kernels that share the device with another stream are meaningless)
+    const bool overlap = overlap_on && !sefd_prof_on() && tf && E.sb.l[0].tiled && E.sb.l[1].tiled;
     if (overlap && !P->side) {
         SEFD_REQUIRE(cudaStreamCreateWithFlags(&P->side, cudaStreamNonBlocking) == cudaSuccess, "fsn_backward: side stream");
         cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming);
