@@ -76,7 +76,7 @@ def conv_istft(spec: torch.Tensor, k_s: torch.Tensor, window: torch.Tensor,
 # parameter construction in the reference's RNG order (models.py:17-170)
 # --------------------------------------------------------------------------------------
 def init_state(seed: int = 0, kernel_num: Optional[List[int]] = None, skip_type: bool = True,
-               lstm: str = "complex") -> Dict[str, torch.Tensor]:
+               lstm: str = "complex", use_cbn: bool = False) -> Dict[str, torch.Tensor]:
     """State dict with the reference's keys/shapes and, for a given torch seed, its values.
 
     Built by instantiating torch.nn modules in the same order as DCCRN.__init__
@@ -99,6 +99,21 @@ def init_state(seed: int = 0, kernel_num: Optional[List[int]] = None, skip_type:
         sd[prefix + "imag_conv.bias"] = torch.zeros_like(ic.bias.data)
 
     def bn_prelu(prefix_bn, prefix_act, c):
+        if use_cbn:                                      # ComplexBatchNorm(c) (tools_for_model.py:430-491): c // 2 complex features;
+            h = c // 2                                   # reset_parameters draws Wri ~ U(-0.9, 0.9) from the global RNG
+            sd[prefix_bn + "Wrr"] = torch.ones(h)
+            sd[prefix_bn + "Wri"] = torch.empty(h).uniform_(-.9, +.9)
+            sd[prefix_bn + "Wii"] = torch.ones(h)
+            sd[prefix_bn + "Br"] = torch.zeros(h)
+            sd[prefix_bn + "Bi"] = torch.zeros(h)
+            sd[prefix_bn + "RMr"] = torch.zeros(h)
+            sd[prefix_bn + "RMi"] = torch.zeros(h)
+            sd[prefix_bn + "RVrr"] = torch.ones(h)
+            sd[prefix_bn + "RVri"] = torch.zeros(h)
+            sd[prefix_bn + "RVii"] = torch.ones(h)
+            sd[prefix_bn + "num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+            sd[prefix_act + "weight"] = torch.full((1,), 0.25)
+            return
         sd[prefix_bn + "weight"] = torch.ones(c)
         sd[prefix_bn + "bias"] = torch.zeros(c)
         sd[prefix_bn + "running_mean"] = torch.zeros(c)
@@ -148,7 +163,7 @@ def init_state(seed: int = 0, kernel_num: Optional[List[int]] = None, skip_type:
 
 def trainable_keys(sd: Dict[str, torch.Tensor]) -> List[str]:
     """Keys that are nn.Parameters in the reference (everything but BN/STFT buffers)."""
-    skip = ("running_mean", "running_var", "num_batches_tracked")
+    skip = ("running_mean", "running_var", "num_batches_tracked", ".RMr", ".RMi", ".RVrr", ".RVri", ".RVii")
     return [k for k in sd if not k.endswith(skip) and not k.startswith(("stft.", "istft."))]
 
 
@@ -190,6 +205,40 @@ def batch_norm_train(x, gamma, beta):
 def batch_norm_eval(x, gamma, beta, rmean, rvar):
     s = gamma * torch.rsqrt(rvar + BN_EPS)
     return (x - rmean[None, :, None, None]) * s[None, :, None, None] + beta[None, :, None, None]
+
+
+def complex_batch_norm(x, Wrr, Wri, Wii, Br, Bi, stats=None):
+    """ComplexBatchNorm.forward (tools_for_model.py:492-599) on x [B, C, F, T] whose first C/2 channels are the real and the
+    last C/2 the imaginary parts: 2x2 whitening with the inverse square root of the covariance (eps 1e-5 on its diagonal),
+    then the affine map [[Wrr, Wri], [Wri, Wii]] and bias.  stats = None: batch statistics (train mode), returned as
+    (Mr, Mi, Vrr, Vri, Vii) WITHOUT eps - what the reference lerps into its running buffers; stats = the five running buffers:
+    eval mode.  The reference line 567 calls torch.addcmul with the pre-1.5 positional `value` (addcmul(t, -1, a, b) =
+    t - a * b), which current torch rejects; the arithmetic restated here is that expression."""
+    xr, xi = torch.chunk(x, 2, dim=1)
+    v = lambda t: t[None, :, None, None]
+    if stats is None:
+        Mr, Mi = xr.mean(dim=(0, 2, 3)), xi.mean(dim=(0, 2, 3))
+    else:
+        Mr, Mi = stats[0], stats[1]
+    xr, xi = xr - v(Mr), xi - v(Mi)
+    if stats is None:
+        Vrr, Vri, Vii = (xr * xr).mean(dim=(0, 2, 3)), (xr * xi).mean(dim=(0, 2, 3)), (xi * xi).mean(dim=(0, 2, 3))
+        out_stats = (Mr, Mi, Vrr, Vri, Vii)
+    else:
+        Vrr, Vri, Vii = stats[2], stats[3], stats[4]
+        out_stats = None
+    Vrr_e, Vii_e = Vrr + BN_EPS, Vii + BN_EPS
+    tau = Vrr_e + Vii_e
+    delta = Vrr_e * Vii_e - Vri * Vri
+    s = delta.sqrt()
+    t = (tau + 2 * s).sqrt()
+    rst = (s * t).reciprocal()
+    Urr, Uii, Uri = (s + Vii_e) * rst, (s + Vrr_e) * rst, -Vri * rst
+    Zrr, Zri = Wrr * Urr + Wri * Uri, Wrr * Uri + Wri * Uii
+    Zir, Zii = Wri * Urr + Wii * Uri, Wri * Uri + Wii * Uii
+    yr = v(Zrr) * xr + v(Zri) * xi + v(Br)
+    yi = v(Zir) * xr + v(Zii) * xi + v(Bi)
+    return torch.cat([yr, yi], 1), out_stats
 
 
 def prelu(x, alpha):
@@ -274,6 +323,15 @@ def dccrn_forward(sd: Dict[str, torch.Tensor], wav: torch.Tensor, masking_mode: 
         taps["bn_stats"] = {}
 
     def norm_act(x, pbn, pact):
+        if pbn + "Wrr" in sd:                                          # use_cbn = True (models.py:76, 120, 151)
+            aff = [sd[pbn + k] for k in ("Wrr", "Wri", "Wii", "Br", "Bi")]
+            if train:
+                y, st = complex_batch_norm(x, *aff)
+                if taps is not None:
+                    taps["bn_stats"][pbn] = tuple(t.detach() for t in st)
+            else:
+                y, _ = complex_batch_norm(x, *aff, stats=[sd[pbn + k] for k in ("RMr", "RMi", "RVrr", "RVri", "RVii")])
+            return prelu(y, sd[pact + "weight"])
         if train:
             y, m, v = batch_norm_train(x, sd[pbn + "weight"], sd[pbn + "bias"])
             if taps is not None:
@@ -482,7 +540,13 @@ class OracleTrainer:
         loss = dccrn_loss(wav, clean, self.loss_name)
         loss.backward()
         with torch.no_grad():                          # BN running stats, momentum 0.1 (models.py:76)
-            for pbn, (m, v) in t["bn_stats"].items():
+            for pbn, st in t["bn_stats"].items():
+                if len(st) == 5:                       # ComplexBatchNorm: lerp_ of the five buffers (tools_for_model.py:527-550)
+                    for k, val in zip(("RMr", "RMi", "RVrr", "RVri", "RVii"), st):
+                        self.sd[pbn + k].lerp_(val.to(self.sd[pbn + k].dtype), BN_MOMENTUM)
+                    self.sd[pbn + "num_batches_tracked"] += 1
+                    continue
+                m, v = st
                 self.sd[pbn + "running_mean"].mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * m)
                 self.sd[pbn + "running_var"].mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * v)
                 self.sd[pbn + "num_batches_tracked"] += 1

@@ -415,8 +415,56 @@ def main_reallstm():
     print("wrote reallstm_golden.npz", out["loss"], len(out["param_names"]))
 
 
+def main_cbn():
+    """use_cbn = True (models.py:26, 76, 120, 151; ComplexBatchNorm tools_for_model.py:430-603).  The reference module calls
+    torch.addcmul with the positional `value` argument of torch < 1.5 (line 567), which current torch rejects, so it cannot run
+    as is; the ONLY change made here is a shim that accepts that legacy call form (addcmul(t, value, a, b) = t + value * a * b) -
+    the reference files themselves are imported unmodified."""
+    cfg, models, tfl = import_reference()
+    torch.set_num_threads(8)
+    _addcmul = torch.addcmul
+
+    def addcmul_legacy(inp, *args, **kw):
+        if len(args) == 3 and not torch.is_tensor(args[0]):
+            return _addcmul(inp, args[1], args[2], value=args[0])
+        return _addcmul(inp, *args, **kw)
+
+    torch.addcmul = addcmul_legacy
+    out = {}
+    noisy, clean = speechlike(2, 4000)
+    torch.manual_seed(0)
+    m = models.DCCRN(masking_mode="C", use_cbn=True).train()
+    sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    out["state_keys"] = np.array(list(sd0.keys()))
+    o_r, o_i, wav = m(noisy, clean)
+    loss = m.loss(wav, clean)
+    loss.backward()
+    out["loss"] = np.array(loss.item())
+    out["wav"], out["out_real"] = wav.detach().numpy(), o_r.detach().numpy()
+    out["param_names"] = np.array([n for n, _ in m.named_parameters()])
+    out["param_shapes"] = np.array([str(tuple(p.shape)) for _, p in m.named_parameters()])
+    out["gnorm"] = np.array([float(p.grad.double().norm()) for _, p in m.named_parameters()])
+    for n, p in m.named_parameters():
+        gflat = p.grad.reshape(-1)
+        out["grad:" + n] = (gflat if gflat.numel() <= 4096 else gflat[::997]).numpy().copy()
+    for k in ("encoder.0.1.Wri", "encoder.3.1.Wri", "decoder.2.1.Wri", "decoder.0.0.real_conv.weight", "enhance.1.imag_lstm.weight_hh_l0"):
+        out["init:" + k] = sd0[k].reshape(-1)[::7].numpy().copy()
+    for k, v in m.state_dict().items():                      # running buffers after one train-mode forward
+        if k.split(".")[-1] in ("RMr", "RMi", "RVrr", "RVri", "RVii", "num_batches_tracked"):
+            out["buf:" + k] = v.detach().numpy().copy()
+    m.eval()
+    with torch.no_grad():
+        _, _, wav_e = m(noisy, clean)
+    out["wav_eval"] = wav_e.numpy()
+    torch.addcmul = _addcmul
+    np.savez_compressed(os.path.join(HERE, "cbn_golden.npz"), **out)
+    print("wrote cbn_golden.npz", out["loss"], len(out["param_names"]))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "reallstm":
+    if len(sys.argv) > 1 and sys.argv[1] == "cbn":
+        main_cbn()
+    elif len(sys.argv) > 1 and sys.argv[1] == "reallstm":
         main_reallstm()
     elif len(sys.argv) > 1 and sys.argv[1] == "fullsubnet":
         main_fullsubnet()
