@@ -379,8 +379,8 @@ int sefd_counters_inc(long long* const* counters_dev, int n, long long inc, void
 // ---- model level ------------------------------------------------------------------------------
 sefd_plan* sefd_dccrn_plan_create(int B, int L, int masking_mode) { return sefd_plan_create_impl(B, L, masking_mode, 0); }
 sefd_plan* sefd_dccrn_plan_create_ex(int B, int L, int masking_mode, int flags) {
-    if (flags & ~(SEFD_PLAN_NO_SKIP | SEFD_PLAN_REAL_LSTM)) {
-        sefd_set_error("plan: unknown flag bits 0x%x", flags & ~(SEFD_PLAN_NO_SKIP | SEFD_PLAN_REAL_LSTM));
+    if (flags & ~(SEFD_PLAN_NO_SKIP | SEFD_PLAN_REAL_LSTM | SEFD_PLAN_CBN)) {
+        sefd_set_error("plan: unknown flag bits 0x%x", flags & ~(SEFD_PLAN_NO_SKIP | SEFD_PLAN_REAL_LSTM | SEFD_PLAN_CBN));
         return nullptr;
     }
     return sefd_plan_create_impl(B, L, masking_mode, flags);

@@ -58,6 +58,31 @@ sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode, int flags) {
     P->T = L / HOP + 3;
     P->mask_mode = mask_mode;
     P->skip = (flags & SEFD_PLAN_NO_SKIP) ? 0 : 1;
+    P->cbn = (flags & SEFD_PLAN_CBN) ? 1 : 0;
+    // BatchNorm2d(C): weight, bias + running_mean, running_var; ComplexBatchNorm(C): Wrr, Wri, Wii, Br, Bi + RMr, RMi, RVrr, RVri,
+    // RVii over C / 2 complex features (tools_for_model.py:444-470), in the reference's registration order
+    auto add_norm = [&](ConvLayer& c, const std::string& pre, long long& pc, long long& bc) {
+        if (!P->cbn) {
+            add_param(P, pre + ".1.weight", pc, &c.gamma, {c.Cout});
+            add_param(P, pre + ".1.bias", pc, &c.beta, {c.Cout});
+            add_param(P, pre + ".2.weight", pc, &c.alpha, {1});
+            add_buffer(P, pre + ".1.running_mean", bc, &c.rmean, c.Cout);
+            add_buffer(P, pre + ".1.running_var", bc, &c.rvar, c.Cout);
+            return;
+        }
+        const int h = c.Cout / 2;
+        add_param(P, pre + ".1.Wrr", pc, &c.gamma, {h});
+        add_param(P, pre + ".1.Wri", pc, &c.wri, {h});
+        add_param(P, pre + ".1.Wii", pc, &c.wii, {h});
+        add_param(P, pre + ".1.Br", pc, &c.beta, {h});
+        add_param(P, pre + ".1.Bi", pc, &c.bi2, {h});
+        add_param(P, pre + ".2.weight", pc, &c.alpha, {1});
+        add_buffer(P, pre + ".1.RMr", bc, &c.rmean, h);
+        add_buffer(P, pre + ".1.RMi", bc, &c.rmi, h);
+        add_buffer(P, pre + ".1.RVrr", bc, &c.rvar, h);
+        add_buffer(P, pre + ".1.RVri", bc, &c.rvri, h);
+        add_buffer(P, pre + ".1.RVii", bc, &c.rvii, h);
+    };
     const int kn[NL + 1] = {2, 32, 64, 128, 256, 256, 256};
     for (int i = 0; i <= NL; ++i) {
         P->ch[i] = kn[i];
@@ -75,11 +100,7 @@ sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode, int flags) {
         add_param(P, pre + ".0.real_conv.bias", pc, &c.br, {c.Cout / 2});
         add_param(P, pre + ".0.imag_conv.weight", pc, &c.wi, {c.Cout / 2, c.Cin / 2, 5, 2});
         add_param(P, pre + ".0.imag_conv.bias", pc, &c.bi, {c.Cout / 2});
-        add_param(P, pre + ".1.weight", pc, &c.gamma, {c.Cout});
-        add_param(P, pre + ".1.bias", pc, &c.beta, {c.Cout});
-        add_param(P, pre + ".2.weight", pc, &c.alpha, {1});
-        add_buffer(P, pre + ".1.running_mean", bc, &c.rmean, c.Cout);
-        add_buffer(P, pre + ".1.running_var", bc, &c.rvar, c.Cout);
+        add_norm(c, pre, pc, bc);
     }
     for (int j = 0; j < NL; ++j) {
         ConvLayer& c = P->dec[j];
@@ -94,11 +115,7 @@ sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode, int flags) {
         add_param(P, pre + ".0.imag_conv.weight", pc, &c.wi, {c.Cin / 2, c.Cout / 2, 5, 2});
         add_param(P, pre + ".0.imag_conv.bias", pc, &c.bi, {c.Cout / 2});
         if (j != NL - 1) {
-            add_param(P, pre + ".1.weight", pc, &c.gamma, {c.Cout});
-            add_param(P, pre + ".1.bias", pc, &c.beta, {c.Cout});
-            add_param(P, pre + ".2.weight", pc, &c.alpha, {1});
-            add_buffer(P, pre + ".1.running_mean", bc, &c.rmean, c.Cout);
-            add_buffer(P, pre + ".1.running_var", bc, &c.rvar, c.Cout);
+            add_norm(c, pre, pc, bc);
         } else {
             c.gamma = c.beta = c.alpha = c.rmean = c.rvar = -1;
         }
@@ -168,7 +185,7 @@ sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode, int flags) {
         c.Wf = w.floats(10ull * c.Cin * c.Cout);
         c.Wt = w.floats(10ull * c.Cin * c.Cout);
         c.bias = w.floats(c.Cout);
-        c.save = w.floats(2 * c.Cout);
+        c.save = w.floats(5 * c.Cout);           // BatchNorm: [2][C]; ComplexBatchNorm: [9][C / 2]
         c.stats = sc;
         sc += 2 * c.Cout;
         if (n > max_y) max_y = n;
@@ -184,7 +201,7 @@ sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode, int flags) {
         c.Wf = w.floats(10ull * c.Cin * c.Cout);
         c.Wt = w.floats(10ull * c.Cin * c.Cout);
         c.bias = w.floats(c.Cout);
-        c.save = w.floats(2 * c.Cout + 4);
+        c.save = w.floats(5 * c.Cout + 4);
         if (j != NL - 1) {
             c.stats = sc;
             sc += 2 * c.Cout;
@@ -219,8 +236,11 @@ sefd_plan* sefd_plan_create_impl(int B, int L, int mask_mode, int flags) {
     P->dWs_floats = 16 * max_w;                   // room for the split partials of the tensor-core wgrad
     P->dWs = w.floats(16 * max_w);
     P->dbs = w.floats(1024);
-    P->red = w.doubles(2 * 512 + 8);
+    P->red = w.doubles(2 * 512 + 8);             // BatchNorm backward: 2 C + 1; ComplexBatchNorm backward: 3 C + 1 (C <= 256)
     P->red2 = w.doubles(2 * 512 + 8);
+    P->cbn_coef = w.floats(9 * 128);
+    for (int i = 0; i < NL; ++i) P->enc[i].cstats = w.doubles(5 * 128);
+    for (int j = 0; j < NL; ++j) P->dec[j].cstats = w.doubles(5 * 128);
     P->dX = w.floats(2 * Bz * T * RNN_H);
     P->dH = w.floats(2 * 2 * Bz * T * RNN_H);
     P->dG = w.floats(2 * 2 * Bz * T * G4);
@@ -334,6 +354,25 @@ int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const 
     SEFD_TRY(sefd_stft_launch(noisy, ws + P->spec, B, L, T, st));
 
     auto bn = [&](const ConvLayer& c, int Ty, int tshift) -> int {
+        if (P->cbn) {
+            CbnPreluFwdParams b;
+            memset(&b, 0, sizeof(b));
+            b.y = ws + c.y; b.z = ws + c.z;
+            b.BF = B * c.Fout; b.Ty = Ty; b.T = T; b.tshift = tshift; b.C = c.Cout;
+            b.stats = wsd + c.cstats; b.n_stat = (double)B * c.Fout * Ty;
+            b.W[0] = prm + c.gamma; b.W[1] = prm + c.wri; b.W[2] = prm + c.wii;
+            b.B2[0] = prm + c.beta; b.B2[1] = prm + c.bi2; b.alpha = prm + c.alpha;
+            b.save = ws + c.save;
+            if (bnbuf) {
+                b.RM[0] = bnbuf + c.rmean; b.RM[1] = bnbuf + c.rmi;
+                b.RV[0] = bnbuf + c.rvar; b.RV[1] = bnbuf + c.rvri; b.RV[2] = bnbuf + c.rvii;
+            }
+            b.momentum = BN_MOM; b.eps = BN_EPS;
+            b.use_running = !train;
+            b.round_tf32 = sefd_get_engine_internal() == 1;
+            if (!train) SEFD_REQUIRE(bnbuf != nullptr, "forward: eval mode needs the ComplexBatchNorm running statistics");
+            return sefd_cbn_prelu_fwd(b, st);
+        }
         BnPreluFwdParams b;
         memset(&b, 0, sizeof(b));
         b.y = ws + c.y; b.z = ws + c.z;
@@ -502,6 +541,21 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
     float* dWs = ws + P->dWs;
 
     auto bn_bwd = [&](const ConvLayer& c, int Ty, int tshift, bool two) -> int {
+        if (P->cbn) {
+            CbnPreluBwdParams b;
+            memset(&b, 0, sizeof(b));
+            b.y = ws + c.y; b.dz = ws + c.dz; b.dy = ws + c.dy;
+            b.dz2 = two ? ws + c.dz2 : nullptr;
+            b.BF = B * c.Fout; b.Ty = Ty; b.T = T; b.tshift = tshift; b.C = c.Cout;
+            b.n_stat = (double)B * c.Fout * Ty;
+            b.W[0] = prm + c.gamma; b.W[1] = prm + c.wri; b.W[2] = prm + c.wii;
+            b.B2[0] = prm + c.beta; b.B2[1] = prm + c.bi2; b.alpha = prm + c.alpha; b.save = ws + c.save;
+            b.red = wsd + P->red; b.coef = ws + P->cbn_coef;
+            b.dW[0] = grads + c.gamma; b.dW[1] = grads + c.wri; b.dW[2] = grads + c.wii;
+            b.dB2[0] = grads + c.beta; b.dB2[1] = grads + c.bi2; b.dalpha = grads + c.alpha;
+            b.round_tf32 = sefd_get_engine_internal() == 1;
+            return sefd_cbn_prelu_bwd(b, st);
+        }
         BnPreluBwdParams b;
         memset(&b, 0, sizeof(b));
         b.y = ws + c.y; b.dz = ws + c.dz; b.dy = ws + c.dy;

@@ -28,6 +28,45 @@ struct BnPreluBwdParams {
     int round_tf32;        // dy feeds tensor-core GEMMs
 };
 
+// ComplexBatchNorm + PReLU (cbn.cu; use_cbn = True, tools_for_model.py:430-603): C = 2 h channels, real parts in [0, h),
+// imaginary parts in [h, 2 h) of every channels-last row
+struct CbnPreluFwdParams {
+    const float* y;        // [BF][Ty][C] raw conv output
+    float* z;              // [BF][T][C]  z[bf, t] = prelu(cbn(y[bf, t + tshift]))
+    int BF, Ty, T, tshift, C;
+    double* stats;         // [5][h] scratch of the moment pass (train mode)
+    double n_stat;
+    const float* W[3];     // Wrr, Wri, Wii [h]
+    const float* B2[2];    // Br, Bi [h]
+    const float* alpha;
+    float* save;           // [9][h]: Mr, Mi, Zrr, Zri, Zir, Zii, Vrr + eps, Vri, Vii + eps (kept for the backward)
+    float* RM[2];          // RMr, RMi: updated in train mode when non-null; read when use_running
+    float* RV[3];          // RVrr, RVri, RVii
+    float momentum, eps;
+    int use_running;       // eval mode
+    int round_tf32;
+};
+
+struct CbnPreluBwdParams {
+    const float* y;        // [BF][Ty][C]
+    const float* dz;       // [BF][T][C]
+    const float* dz2;      // optional second gradient source (skip connection) or nullptr
+    float* dy;             // [BF][Ty][C]
+    int BF, Ty, T, tshift, C;
+    double n_stat;
+    const float* W[3];
+    const float* B2[2];
+    const float *alpha, *save;
+    double* red;           // [6 h + 1] scratch
+    float* coef;           // [9][h] scratch
+    float* dW[3];          // d Wrr, d Wri, d Wii
+    float* dB2[2];         // d Br, d Bi
+    float* dalpha;
+    int round_tf32;
+};
+int sefd_cbn_prelu_fwd(const CbnPreluFwdParams& p, cudaStream_t st);
+int sefd_cbn_prelu_bwd(const CbnPreluBwdParams& p, cudaStream_t st);
+
 struct CconvPackParams {
     const float *wr, *wi, *br, *bi;
     int Ci2, Co2;          // complex channel counts (half of the real channel counts)

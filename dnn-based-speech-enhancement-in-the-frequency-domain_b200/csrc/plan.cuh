@@ -31,6 +31,9 @@ struct ConvLayer {
     int Fin, Fout;
     long long wr, br, wi, bi, gamma, beta, alpha;   // param offsets (gamma < 0: no BN/PReLU)
     long long rmean, rvar;                           // bn buffer offsets
+    // use_cbn (SEFD_PLAN_CBN): gamma / beta hold the offsets of Wrr / Br, rmean / rvar those of RMr / RVrr; the others:
+    long long wri, wii, bi2, rmi, rvri, rvii;
+    size_t cstats /*doubles: 5 * Cout / 2 moments of the ComplexBatchNorm statistics pass*/;
     // workspace offsets (floats)
     size_t y, z, Wf, Wt, bias, stats /*doubles*/, save, dz, dz2, dy;
 };
@@ -47,6 +50,8 @@ struct sefd_plan {
     RealLstmExt* rl = nullptr; // non-null: the recurrent part is one 2-layer nn.LSTM(1024 -> 256) + Linear (models.py:96-105)
     int B, L, T, mask_mode;
     int skip = 1;             // 1: decoder convs read complex_cat(out, encoder skip) (cfg.skip_type, models.py:107-169)
+    int cbn = 0;              // 1: ComplexBatchNorm instead of BatchNorm2d (use_cbn, models.py:76, 120, 151; cbn.cu)
+    size_t cbn_coef = 0;      // floats: [9][128] coefficients of the ComplexBatchNorm backward apply pass
     int ch[NL + 1], Fe[NL + 1];
     ConvLayer enc[NL], dec[NL];
     // LSTM parameter offsets [layer][lstm]

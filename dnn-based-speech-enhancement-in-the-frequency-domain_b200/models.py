@@ -33,8 +33,6 @@ class DCCRN(nn.Module):
             unsupported.append(f"kernel_num {kernel_num} / kernel_size {kernel_size}")
         if rnn_layers != 2 or rnn_units != 256 or cfg.lstm not in ("complex", "real"):
             unsupported.append(f"rnn_layers={rnn_layers}, rnn_units={rnn_units}, lstm={cfg.lstm!r} (built: 2 layers, 256 units, 'complex' / 'real')")
-        if use_cbn:
-            unsupported.append("use_cbn=True (ComplexBatchNorm, tools_for_model.py:430-603)")
         if masking_mode not in _ops.MODES:
             unsupported.append(f"masking_mode {masking_mode!r} (built: E, C, R, Direct(None make))")
         if unsupported:
@@ -45,6 +43,8 @@ class DCCRN(nn.Module):
         self.kernel_num = [2] + kernel_num
         self.masking_mode = masking_mode
         self.skip_type = bool(cfg.skip_type)
+        self.use_cbn = bool(use_cbn)
+        norm = _d.ComplexBatchNormParams if use_cbn else _d.BatchNormParams      # models.py:76, 120, 151
 
         self.stft = _d.STFTBuffers(win_len, fft_len, inverse=False)
         self.istft = _d.STFTBuffers(win_len, fft_len, inverse=True)
@@ -53,7 +53,7 @@ class DCCRN(nn.Module):
         kn = self.kernel_num
         for i in range(len(kn) - 1):                                     # models.py:63-80
             self.encoder.append(nn.Sequential(_d.ComplexConvParams(kn[i], kn[i + 1], transposed=False),
-                                              _d.BatchNormParams(kn[i + 1]), _d.PReLUParams()))
+                                              norm(kn[i + 1]), _d.PReLUParams()))
         hidden_dim = fft_len // (2 ** len(kn))
         self.lstm_type = cfg.lstm
         if cfg.lstm == "complex":
@@ -70,7 +70,7 @@ class DCCRN(nn.Module):
         for idx in range(len(kn) - 1, 0, -1):                            # models.py:107-137
             mods = [_d.ComplexConvParams(kn[idx] * (2 if self.skip_type else 1), kn[idx - 1], transposed=True)]   # :138-169 without skip
             if idx != 1:
-                mods += [_d.BatchNormParams(kn[idx - 1]), _d.PReLUParams()]
+                mods += [norm(kn[idx - 1]), _d.PReLUParams()]
             self.decoder.append(nn.Sequential(*mods))
         self._engine = None
         self._last = None
@@ -79,7 +79,7 @@ class DCCRN(nn.Module):
     def _get_engine(self):
         eng = self.__dict__.get("_engine")
         if eng is None:
-            eng = _d.Engine(self, self.masking_mode, skip=self.skip_type, real_lstm=self.lstm_type == "real")
+            eng = _d.Engine(self, self.masking_mode, skip=self.skip_type, real_lstm=self.lstm_type == "real", cbn=self.use_cbn)
             self.__dict__["_engine"] = eng
         return eng
 

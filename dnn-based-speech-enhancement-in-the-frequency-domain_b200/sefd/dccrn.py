@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .ops import LOSSES, MODES, PLAN_NO_SKIP, PLAN_REAL_LSTM, ptr, stream
+from .ops import LOSSES, MODES, PLAN_CBN, PLAN_NO_SKIP, PLAN_REAL_LSTM, ptr, stream
 
 KERNEL_NUM = [32, 64, 128, 256, 256, 256]
 
@@ -56,6 +56,27 @@ class BatchNormParams(nn.Module):
         self.bias = nn.Parameter(torch.zeros(c))
         self.register_buffer("running_mean", torch.zeros(c))
         self.register_buffer("running_var", torch.ones(c))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+
+
+class ComplexBatchNormParams(BatchNormParams):
+    """ComplexBatchNorm(c) (tools_for_model.py:430-491): c // 2 complex features; reset_parameters draws Wri ~ U(-0.9, 0.9) from
+    the global RNG at construction (same stream position as the reference).  A BatchNormParams subclass only so that the
+    bookkeeping that looks for normalisation layers (num_batches_tracked) finds it; it owns none of BatchNorm2d's tensors."""
+
+    def __init__(self, c):
+        nn.Module.__init__(self)
+        h = c // 2
+        self.Wrr = nn.Parameter(torch.ones(h))
+        self.Wri = nn.Parameter(torch.empty(h).uniform_(-.9, +.9))
+        self.Wii = nn.Parameter(torch.ones(h))
+        self.Br = nn.Parameter(torch.zeros(h))
+        self.Bi = nn.Parameter(torch.zeros(h))
+        self.register_buffer("RMr", torch.zeros(h))
+        self.register_buffer("RMi", torch.zeros(h))
+        self.register_buffer("RVrr", torch.ones(h))
+        self.register_buffer("RVri", torch.zeros(h))
+        self.register_buffer("RVii", torch.ones(h))
         self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
 
 
@@ -136,17 +157,19 @@ class STFTBuffers(nn.Module):
 # plan + workspace cache
 # --------------------------------------------------------------------------------------------------
 class Plan:
-    def __init__(self, B, L, mode, family="dccrn", skip=True, real_lstm=False):
+    def __init__(self, B, L, mode, family="dccrn", skip=True, real_lstm=False, cbn=False):
         lib = _lib.load()
         self.family = family
         self.skip = skip
         self.real_lstm = real_lstm
+        self.cbn = cbn
         if family == "crn":
             self.handle = lib.sefd_crn_plan_create(B, L)
         elif family == "fsn":                      # L = number of STFT frames of noisy_mag
             self.handle = lib.sefd_fsn_plan_create(B, L)
         else:
-            self.handle = lib.sefd_dccrn_plan_create_ex(B, L, MODES[mode], (0 if skip else PLAN_NO_SKIP) | (PLAN_REAL_LSTM if real_lstm else 0))
+            self.handle = lib.sefd_dccrn_plan_create_ex(B, L, MODES[mode], (0 if skip else PLAN_NO_SKIP) | (PLAN_REAL_LSTM if real_lstm else 0) |
+                                                        (PLAN_CBN if cbn else 0))
         if not self.handle:
             raise RuntimeError("sefd plan: " + lib.sefd_last_error().decode())
         self.B, self.L, self.T, self.mode = B, L, (L + 2 if family == "fsn" else L // 100 + 3), mode
@@ -304,22 +327,23 @@ class Engine:
     """Owns the flat parameter / gradient / BN-statistics buffers of one DCCRN / CRN module and keeps the module's
     nn.Parameters aliased onto them."""
 
-    def __init__(self, module, mode, family="dccrn", skip=True, real_lstm=False):
+    def __init__(self, module, mode, family="dccrn", skip=True, real_lstm=False, cbn=False):
         self.module = module
         self.mode = mode
         self.family = family
         self.skip = skip
         self.real_lstm = real_lstm
+        self.cbn = cbn
         self.plans = {}
         self.flat = self.flat_grad = self.flat_buf = None
-        self._layout = Plan(1, 1 if family == "fsn" else 100, mode, family, skip, real_lstm)  # layout is independent of (B, L)
+        self._layout = Plan(1, 1 if family == "fsn" else 100, mode, family, skip, real_lstm, cbn)  # layout is independent of (B, L)
         self.param_list = None
         self.backwards_since_step = 0       # autograd backwards that wrote flat_grad since the last FlatAdam.step()
 
     def plan(self, B, L):
         key = (B, L)
         if key not in self.plans:
-            self.plans[key] = Plan(B, L, self.mode, self.family, self.skip, self.real_lstm)
+            self.plans[key] = Plan(B, L, self.mode, self.family, self.skip, self.real_lstm, self.cbn)
         return self.plans[key]
 
     def _named(self):

@@ -10,6 +10,7 @@ from . import _lib
 MODES = {"E": 1, "C": 2, "R": 3, "Direct(None make)": 5}
 PLAN_NO_SKIP = 1          # include/sefd.h: SEFD_PLAN_NO_SKIP
 PLAN_REAL_LSTM = 2        # include/sefd.h: SEFD_PLAN_REAL_LSTM (cfg.lstm = 'real')
+PLAN_CBN = 4              # include/sefd.h: SEFD_PLAN_CBN (DCCRN(use_cbn=True): ComplexBatchNorm)
 LOSSES = {"MSE": 0, "SDR": 1, "SI-SNR": 2, "SI-SDR": 3}
 
 

@@ -176,6 +176,10 @@ sefd_plan* sefd_dccrn_plan_create(int B, int L, int masking_mode);
  * 2 layers) + self.tranform = Linear(256 -> 1024) on the [T, B, C * D] view of the encoder output (state_dict keys
  * enhance.weight_ih_l0 ... tranform.bias) instead of the two NavieComplexLSTM layers */
 #define SEFD_PLAN_REAL_LSTM 2
+/* SEFD_PLAN_CBN: DCCRN(use_cbn=True) (models.py:26, 76, 120, 151): every BatchNorm2d(C) becomes ComplexBatchNorm(C)
+ * (tools_for_model.py:430-603) - parameters .1.Wrr / Wri / Wii / Br / Bi and buffers .1.RMr / RMi / RVrr / RVri / RVii over
+ * C / 2 complex features (2x2 whitening + affine), train and eval mode, forward and backward (csrc/cbn.cu). */
+#define SEFD_PLAN_CBN 4
 sefd_plan* sefd_dccrn_plan_create_ex(int B, int L, int masking_mode, int flags);
 void sefd_dccrn_plan_destroy(sefd_plan* plan);
 size_t sefd_dccrn_workspace_bytes(const sefd_plan* plan);

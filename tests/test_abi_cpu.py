@@ -65,8 +65,9 @@ def test_dropin_refuses_cpu_and_unbuilt_configs():
     models.DCCRN(masking_mode="Direct(None make)")          # spectral mapping is built
     with pytest.raises(NotImplementedError):
         models.DCCRN(masking_mode="X")
-    with pytest.raises(NotImplementedError):
-        models.DCCRN(use_cbn=True)
+    cbn = models.DCCRN(use_cbn=True)           # ComplexBatchNorm is built (plan flag SEFD_PLAN_CBN); CUDA only as well
+    with pytest.raises(RuntimeError, match="CUDA"):
+        cbn(torch.zeros(1, 4000))
     crn = models.CRN()                         # built; like DCCRN it has no CPU path
     with pytest.raises(RuntimeError, match="CUDA"):
         crn(torch.zeros(1, 4000))

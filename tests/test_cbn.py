@@ -56,3 +56,69 @@ def test_cbn_oracle(gold):
     with torch.no_grad():                                   # eval mode reads the running buffers
         _, _, wav_e = O.dccrn_forward(tr.sd, noisy, "C", train=False)
     np.testing.assert_allclose(wav_e.numpy(), gold["wav_eval"], atol=5e-6)
+
+
+def test_dropin_layout_for_cbn():
+    import models
+    torch.manual_seed(0)
+    m = models.DCCRN(masking_mode="C", use_cbn=True)
+    ref = O.init_state(0, use_cbn=True)
+    sd = m.state_dict()
+    assert set(sd.keys()) == set(ref.keys())
+    for k in ref:
+        assert sd[k].shape == ref[k].shape, k
+        if sd[k].is_floating_point() and not k.startswith(("stft.", "istft.")):
+            assert torch.equal(sd[k], ref[k]), k            # same RNG stream as the reference constructor (Wri ~ U(-0.9, 0.9))
+    assert [n for n, _ in m.named_parameters() if n.startswith("encoder.0.")] == [
+        "encoder.0.0.real_conv.weight", "encoder.0.0.real_conv.bias", "encoder.0.0.imag_conv.weight", "encoder.0.0.imag_conv.bias",
+        "encoder.0.1.Wrr", "encoder.0.1.Wri", "encoder.0.1.Wii", "encoder.0.1.Br", "encoder.0.1.Bi", "encoder.0.2.weight"]
+
+
+@pytest.mark.gpu
+def test_cbn_gpu(engine, gold):
+    """Drop-in DCCRN(use_cbn=True) through the C ABI (plan flag SEFD_PLAN_CBN, csrc/cbn.cu): waveform, loss, every gradient and the
+    running buffers against the oracle and the reference's own fixture values; then the eval-mode forward."""
+    import models
+    models.cfg.loss = "SI-SNR"
+    sd0 = O.init_state(0, use_cbn=True)
+    noisy, clean = _speech()
+    tr = O.OracleTrainer(sd0, masking_mode="C", loss="SI-SNR")
+    loss_ref, wav_ref = tr.forward_backward(noisy, clean)
+    m = models.DCCRN(masking_mode="C", use_cbn=True)
+    m.load_state_dict(sd0)
+    m = m.cuda().train()
+    _, _, wav = m(noisy.cuda(), clean.cuda())
+    loss = m.loss(wav, clean.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    tf = engine == 1
+    rmse = float((wav.detach().cpu() - wav_ref).pow(2).mean().sqrt())
+    assert rmse < (1e-4 if tf else 2e-6), rmse
+    np.testing.assert_allclose(wav.detach().cpu().numpy(), gold["wav"], atol=2e-3 if tf else 2e-5)
+    assert float(loss.detach()) == pytest.approx(float(gold["loss"]), rel=5e-3 if tf else 2e-4)
+    grads = tr.grads()
+    amax = max(float(v.abs().max()) for n, v in grads.items() if n.endswith(".2.weight"))
+    for k, p in m.named_parameters():
+        if k.endswith("_conv.bias") and not k.startswith("decoder.5"):
+            continue                      # zero by the mean removal
+        g, r = p.grad.detach().cpu().double().reshape(-1), grads[k].double().reshape(-1)
+        if k.endswith(".2.weight"):       # the single PReLU slope: one cancelling global sum
+            assert abs(float(g[0] - r[0])) <= 2e-2 * amax, k
+            continue
+        cos = float((g * r).sum() / (g.norm() * r.norm() + 1e-30))
+        nr = float(g.norm() / (r.norm() + 1e-30))
+        assert cos > (0.99 if tf else 0.9995) and abs(nr - 1) < (0.05 if tf else 0.02), (k, cos, nr)
+    sd = m.state_dict()
+    for k in sd:                                            # running buffers after one train-mode forward
+        if k.split(".")[-1] in BUFS:
+            ref = tr.sd[k].numpy()                          # means / covariances of TF32 conv outputs: error relative to the buffer's scale
+            tol = dict(rtol=5e-3, atol=2e-3 * float(np.abs(ref).max())) if tf else dict(rtol=1e-4, atol=1e-6)
+            np.testing.assert_allclose(sd[k].cpu().numpy(), ref, err_msg=k, **tol)
+            np.testing.assert_allclose(sd[k].cpu().numpy(), gold["buf:" + k], err_msg=k, **tol)
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == 1
+    m.eval()
+    with torch.no_grad():
+        _, _, wav_e = m(noisy.cuda(), clean.cuda())
+        _, _, wav_eo = O.dccrn_forward(tr.sd, noisy, "C", train=False)
+    assert float((wav_e.cpu() - wav_eo).pow(2).mean().sqrt()) < (2e-4 if tf else 5e-6)
