@@ -62,7 +62,7 @@ def test_noskip_plan_layout(noskip_golden):
     assert [str(tuple(e[3])) for e in p.params] == shapes
     from sefd import _lib
     lib = _lib.load()
-    assert not lib.sefd_dccrn_plan_create_ex(1, 100, 2, 6)              # unknown flag bits are an error, not ignored
+    assert not lib.sefd_dccrn_plan_create_ex(1, 100, 2, 8)              # unknown flag bits are an error, not ignored
     assert b"flag" in lib.sefd_last_error()
 
 
