@@ -120,6 +120,9 @@ __global__ void fsn_cirm_kernel(const float2* __restrict__ noisy, const float2* 
         out[i] = make_float2(compress((x.x * c.x + x.y * c.y) / den), compress((x.x * c.y - x.y * c.x) / den));
     }
 }
+__global__ void fsn_compress_kernel(const float* __restrict__ m, long long n, float* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = compress(m[i]);
+}
 __global__ void fsn_decompress_kernel(const float* __restrict__ m, long long n, float* __restrict__ out) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float v = m[i];
@@ -265,6 +268,11 @@ int sefd_fsn_istft(const float* spec_or_mag, const float* phase, int B, int T, i
     if (phase) fsn_istft_kernel<true><<<grid, 256, sizeof(IfsnSmem), st>>>(spec_or_mag, phase, T, len, wav);
     else fsn_istft_kernel<false><<<grid, 256, sizeof(IfsnSmem), st>>>(spec_or_mag, nullptr, T, len, wav);
     return sefd_check_launch("fsn_istft");
+}
+int sefd_fsn_compress_cirm(const float* mask, long long n, float* out, void* stream) {
+    SEFD_REQUIRE(mask && out && n > 0, "fsn_compress_cirm: bad argument");
+    fsn_compress_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(mask, n, out);
+    return sefd_check_launch("fsn_compress_cirm");
 }
 int sefd_fsn_decompress_cirm(const float* mask, long long n, float* out, void* stream) {
     SEFD_REQUIRE(mask && out && n > 0, "fsn_decompress_cirm: bad argument");

@@ -61,6 +61,7 @@ SIGNATURES = {
     "sefd_fsn_mag_phase": (_i, [_vp, C.c_longlong, _vp, _vp, _vp]),
     "sefd_fsn_cirm": (_i, [_vp, _vp, C.c_longlong, _vp, _vp]),
     "sefd_fsn_decompress_cirm": (_i, [_vp, C.c_longlong, _vp, _vp]),
+    "sefd_fsn_compress_cirm": (_i, [_vp, C.c_longlong, _vp, _vp]),
     "sefd_fsn_istft": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "sefd_pmsqe_table_floats": (_i, []),
     "sefd_pmsqe_workspace_bytes": (C.c_size_t, [_i, _i]),

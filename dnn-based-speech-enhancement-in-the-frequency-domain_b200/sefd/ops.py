@@ -492,6 +492,14 @@ def fsn_cirm(noisy, clean):
     return out
 
 
+def fsn_compress_cirm(mask):
+    m = mask.contiguous().float()
+    _req(m)
+    out = torch.empty_like(m)
+    _lib.check(_lib.load().sefd_fsn_compress_cirm(ptr(m), m.numel(), ptr(out), stream()), "fsn_compress_cirm")
+    return out
+
+
 def fsn_decompress_cirm(mask):
     m = mask.contiguous().float()
     _req(m)

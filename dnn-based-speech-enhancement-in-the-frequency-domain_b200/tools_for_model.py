@@ -10,11 +10,34 @@ Anything else raises NotImplementedError (there is no PyTorch fallback).
 import sys
 import time
 
+import numpy as np
+
 import torch
 import torch.nn as nn
 
 from sefd import dccrn as _d
 from sefd import ops as _ops
+
+EPSILON = np.finfo(np.float32).eps                 # tools_for_model.py: module constant
+
+
+def init_kernels(win_len, win_inc, fft_len, win_type=None, invers=False):
+    """tools_for_model.py:16-33: the windowed rFFT basis [2 F, 1, win] (or, invers=True, the transposed pseudo-inverse of the
+    un-windowed basis times the window) and the window [1, win, 1], built on the host exactly as the reference builds them.  The
+    CUDA kernels never read these matrices (they evaluate the same sums as FFTs, csrc/stft.cu); the function exists for code
+    that wants the reference's buffers (checkpoints, analysis)."""
+    if win_type == 'None' or win_type is None:
+        window = np.ones(win_len)
+    else:
+        from scipy.signal import get_window
+        window = get_window(win_type, win_len, fftbins=True)
+    basis = np.fft.rfft(np.eye(fft_len))[:win_len]
+    kernel = np.concatenate([np.real(basis), np.imag(basis)], 1).T
+    if invers:
+        kernel = np.linalg.pinv(kernel).T
+    kernel = (kernel * window)[:, None, :]
+    return torch.from_numpy(kernel.astype(np.float32)), torch.from_numpy(window[None, :, None].astype(np.float32))
+
 
 
 def _check_stft(win_len, win_inc, fft_len, win_type, feature_type):
@@ -212,6 +235,17 @@ def mag_phase(complex_tensor):
 def build_complex_ideal_ratio_mask(noisy, clean):
     """tools_for_model.py:686-705 (+ compress_cIRM :708-717): complex [B, F, T] x2 -> [B, F, T, 2]."""
     return _ops.fsn_cirm(noisy, clean)
+
+
+def compress_cIRM(mask, K=10, C=0.1):
+    """tools_for_model.py:707-717: (-inf, +inf) -> [-K, K].  Tensors run the library's kernel; numpy arrays take the
+    reference's own numpy branch (host data stays on the host)."""
+    if not torch.is_tensor(mask):
+        mask = -100 * (mask <= -100) + mask * (mask > -100)
+        return K * (1 - np.exp(-C * mask)) / (1 + np.exp(-C * mask))
+    if (K, C) != (10, 0.1):
+        raise NotImplementedError("sefd: compress_cIRM is built for K = 10, C = 0.1")
+    return _ops.fsn_compress_cirm(mask)
 
 
 def decompress_cIRM(mask, K=10, limit=9.9):

@@ -111,6 +111,8 @@ int sefd_fsn_stft(const float* wav, int B, int L, float* spec, void* stream);
 int sefd_fsn_mag_phase(const float* spec, long long n, float* mag, float* phase, void* stream);
 int sefd_fsn_cirm(const float* noisy_spec, const float* clean_spec, long long n, float* cirm, void* stream);
 int sefd_fsn_decompress_cirm(const float* mask, long long n, float* out, void* stream);
+/* compress_cIRM (tools_for_model.py:707-717, K = 10, C = 0.1) by itself: out = K (1 - e^{-C m}) / (1 + e^{-C m}), m clipped at -100 */
+int sefd_fsn_compress_cirm(const float* mask, long long n, float* out, void* stream);
 /* tools.istft (tools_for_model.py:651-679, torch.istft 512 / 300 / 400, centred, Hann): spec [B][257][T][2], or magnitude and
  * phase [B][257][T] when phase != NULL (use_mag_phase=True), -> wav [B][len] */
 int sefd_fsn_istft(const float* spec_or_mag, const float* phase, int B, int T, int len, float* wav, void* stream);

@@ -137,3 +137,17 @@ def test_host_side_guards_of_the_later_additions():
         pass
     with pytest.raises(NotImplementedError):
         TrainStep(_M(), perceptual="LMS")
+
+
+def test_init_kernels_matches_the_oracle_bases():
+    """tools_for_model.init_kernels (reference :16-33) on the host: same matrices as the oracle's float64 bases; numpy branch of
+    compress_cIRM (:715-716)."""
+    import tools_for_model as T
+    from oracle import dccrn_oracle as O
+    k_a, k_s, w = O.stft_bases()
+    k, win = T.init_kernels(400, 100, 512, "hann")
+    assert k.shape == (514, 1, 400) and win.shape == (1, 400, 1)
+    assert float(np.abs(k[:, 0].numpy() - k_a).max()) < 1e-6 and float(np.abs(win.reshape(-1).numpy() - w).max()) < 1e-7
+    ki, _ = T.init_kernels(400, 100, 512, "hann", invers=True)
+    assert float(np.abs(ki[:, 0].numpy() - k_s).max()) < 1e-8
+    np.testing.assert_allclose(T.compress_cIRM(np.array([-200.0, 0.0, 1.0])), [10 * (1 - np.exp(10)) / (1 + np.exp(10)), 0.0, 10 * np.tanh(0.05)], rtol=1e-12)

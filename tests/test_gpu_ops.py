@@ -362,3 +362,18 @@ def test_step_glue_kernels():
         _lib.check(lib.sefd_counters_inc(ptr(table), len(counters), 2, stream()), "counters_inc")
     assert [int(c) for c in counters] == [i + 6 for i in range(7)]
     assert lib.sefd_stale_cuda_errors() >= 0 and isinstance(lib.sefd_last_stale_cuda_error(), bytes)
+
+
+def test_compress_decompress_cirm():
+    """tools.compress_cIRM (tools_for_model.py:707-717) as a kernel, and its inverse decompress_cIRM (:720-723)."""
+    import tools_for_model as T
+    g = torch.Generator().manual_seed(43)
+    m = torch.randn(3, 257, 40, 2, generator=g) * 20.0
+    m[0, 0, 0, 0] = -500.0                                       # clipped at -100 before the squash
+    ref = -100 * (m <= -100) + m * (m > -100)
+    ref = 10 * (1 - torch.exp(-0.1 * ref)) / (1 + torch.exp(-0.1 * ref))
+    got = T.compress_cIRM(m.to(DEV))
+    _close(got, ref, atol=2e-6, rtol=1e-6, name="compress_cIRM")
+    small = torch.randn(1000, generator=g) * 3.0                  # |compressed| < 9.9: the round trip is the identity
+    back = T.decompress_cIRM(T.compress_cIRM(small.to(DEV)))
+    _close(back, small, atol=2e-5, rtol=1e-5, name="decompress(compress)")
