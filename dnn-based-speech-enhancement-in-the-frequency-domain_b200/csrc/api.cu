@@ -339,6 +339,43 @@ int sefd_bn_prelu_backward(const float* y, const float* dz, float* dy, long long
     return sefd_bn_prelu_bwd(b, ST);
 }
 
+// ComplexBatchNorm (+ PReLU with the given slope; a slope of 1 is the bare module) on channels-last rows [rows][C]
+int sefd_cbn_prelu_forward(const float* y, float* z, long long rows, int C, const float* w3h, const float* b2h, const float* alpha,
+                           float* save, float* running5h, int use_running, double* scratch, void* stream) {
+    SEFD_REQUIRE(y && z && w3h && b2h && alpha && save && (use_running ? running5h != nullptr : scratch != nullptr) && rows > 0,
+                 "cbn_prelu_forward: bad argument%s", "");
+    const int h = C / 2;
+    CbnPreluFwdParams b;
+    memset(&b, 0, sizeof(b));
+    b.y = y; b.z = z; b.BF = 1; b.Ty = (int)rows; b.T = (int)rows; b.C = C;
+    b.stats = scratch; b.n_stat = (double)rows;
+    for (int i = 0; i < 3; ++i) b.W[i] = w3h + i * h;
+    for (int i = 0; i < 2; ++i) b.B2[i] = b2h + i * h;
+    b.alpha = alpha; b.save = save;
+    if (running5h) {
+        b.RM[0] = running5h; b.RM[1] = running5h + h;
+        for (int i = 0; i < 3; ++i) b.RV[i] = running5h + (2 + i) * h;
+    }
+    b.momentum = 0.1f; b.eps = 1e-5f; b.use_running = use_running;
+    return sefd_cbn_prelu_fwd(b, ST);
+}
+
+int sefd_cbn_prelu_backward(const float* y, const float* dz, float* dy, long long rows, int C, const float* w3h, const float* b2h,
+                            const float* alpha, const float* save, float* dw3h, float* db2h, float* dalpha, double* scratch,
+                            float* coef, void* stream) {
+    SEFD_REQUIRE(y && dz && dy && w3h && b2h && alpha && save && dw3h && db2h && dalpha && scratch && coef && rows > 0,
+                 "cbn_prelu_backward: bad argument%s", "");
+    const int h = C / 2;
+    CbnPreluBwdParams b;
+    memset(&b, 0, sizeof(b));
+    b.y = y; b.dz = dz; b.dy = dy; b.BF = 1; b.Ty = (int)rows; b.T = (int)rows; b.C = C;
+    b.n_stat = (double)rows;
+    for (int i = 0; i < 3; ++i) { b.W[i] = w3h + i * h; b.dW[i] = dw3h + i * h; }
+    for (int i = 0; i < 2; ++i) { b.B2[i] = b2h + i * h; b.dB2[i] = db2h + i * h; }
+    b.alpha = alpha; b.save = save; b.red = scratch; b.coef = coef; b.dalpha = dalpha;
+    return sefd_cbn_prelu_bwd(b, ST);
+}
+
 int sefd_lstm_forward(const float* w_hh, float* gates, float* h, float* c, int rows, int T, void* stream) {
     LstmFwdParams p;
     memset(&p, 0, sizeof(p));

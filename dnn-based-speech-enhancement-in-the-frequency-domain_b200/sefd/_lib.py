@@ -33,6 +33,8 @@ SIGNATURES = {
     "sefd_cconvT2d_backward": (_i, [_vp] * 11 + [_i] * 5 + [_vp, _vp]),
     "sefd_bn_prelu_forward": (_i, [_vp, _vp, _ll, _i] + [_vp] * 8),
     "sefd_bn_prelu_backward": (_i, [_vp, _vp, _vp, _ll, _i] + [_vp] * 9),
+    "sefd_cbn_prelu_forward": (_i, [_vp, _vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "sefd_cbn_prelu_backward": (_i, [_vp, _vp, _vp, _ll, _i] + [_vp] * 10),
     "sefd_lstm_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "sefd_lstm_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "sefd_adam_step": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _i, _f, _vp]),

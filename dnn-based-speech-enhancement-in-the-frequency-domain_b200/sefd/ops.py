@@ -266,6 +266,44 @@ def bn_prelu_backward(y, dz, gamma, beta, alpha, save):
     return dy, dg, db, da
 
 
+class _Cbn(torch.autograd.Function):
+    """ComplexBatchNorm on channels-last rows [rows, C] (sefd_cbn_prelu_forward / backward with a PReLU slope of 1)."""
+
+    @staticmethod
+    def forward(ctx, y, w3h, b2h, running5h, train):
+        _req(y, w3h, b2h, running5h)
+        rows, Cc = y.shape
+        h = Cc // 2
+        z = torch.empty_like(y)
+        save = torch.empty(9 * h, device=y.device)
+        one = torch.ones(1, device=y.device)
+        scratch = torch.empty(6 * h + 1, device=y.device, dtype=torch.float64)
+        _lib.check(_lib.load().sefd_cbn_prelu_forward(ptr(y), ptr(z), rows, Cc, ptr(w3h), ptr(b2h), ptr(one), ptr(save),
+                                                      ptr(running5h), 0 if train else 1, ptr(scratch), stream()), "cbn_prelu_forward")
+        ctx.save_for_backward(y, w3h, b2h, save, one)
+        ctx.train = train
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        if not ctx.train:
+            raise RuntimeError("sefd: ComplexBatchNorm backward is built for train mode (batch statistics)")
+        y, w3h, b2h, save, one = ctx.saved_tensors
+        dz = dz.contiguous()
+        rows, Cc = y.shape
+        h = Cc // 2
+        dy, dw, db, da = torch.empty_like(y), torch.empty_like(w3h), torch.empty_like(b2h), torch.empty_like(one)
+        scratch = torch.empty(6 * h + 1, device=y.device, dtype=torch.float64)
+        coef = torch.empty(9 * h, device=y.device)
+        _lib.check(_lib.load().sefd_cbn_prelu_backward(ptr(y), ptr(dz), ptr(dy), rows, Cc, ptr(w3h), ptr(b2h), ptr(one), ptr(save),
+                                                       ptr(dw), ptr(db), ptr(da), ptr(scratch), ptr(coef), stream()), "cbn_prelu_backward")
+        return dy, dw, db, None, None
+
+
+def complex_batch_norm(y, w3h, b2h, running5h, train):
+    return _Cbn.apply(y, w3h, b2h, running5h, train)
+
+
 # ---- LSTM recurrence ------------------------------------------------------------------------------
 def lstm_forward(w_hh, pregates):
     """w_hh [2,512,128]; pregates [2,rows,T,512] (consumed: overwritten with the activated gates)."""

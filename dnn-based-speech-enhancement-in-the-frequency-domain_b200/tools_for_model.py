@@ -182,6 +182,40 @@ class ComplexConvTranspose2d(nn.Module):
         return _CConvT.apply(inputs, self.real_conv.weight, self.real_conv.bias, self.imag_conv.weight, self.imag_conv.bias)
 
 
+class ComplexBatchNorm(nn.Module):
+    """tools_for_model.py:430-603 as a stand-alone layer on [B, C, F, T] (C = num_features channels: the real parts of the C / 2
+    complex features in the first half of the channel axis, the imaginary parts in the second): same parameter / buffer names,
+    initial values and RNG use as the reference.
+    Inside models.DCCRN(use_cbn=True) the layer is fused with the PReLU that follows it (csrc/cbn.cu)."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True, complex_axis=1):
+        super().__init__()
+        if (eps, momentum, affine, track_running_stats, complex_axis) != (1e-5, 0.1, True, True, 1) or num_features % 8:
+            raise NotImplementedError("sefd ComplexBatchNorm: built for eps 1e-5, momentum 0.1, affine, running statistics, "
+                                      "complex_axis 1 and a multiple of 8 features")
+        p = _d.ComplexBatchNormParams(num_features)
+        self.num_features = num_features // 2
+        for k in ("Wrr", "Wri", "Wii", "Br", "Bi"):
+            setattr(self, k, getattr(p, k))
+        for k in ("RMr", "RMi", "RVrr", "RVri", "RVii", "num_batches_tracked"):
+            self.register_buffer(k, getattr(p, k))
+
+    def forward(self, inputs):
+        x = _to_cl(inputs)
+        B, F, T, C = x.shape
+        w3h = torch.cat([self.Wrr, self.Wri, self.Wii])
+        b2h = torch.cat([self.Br, self.Bi])
+        running = torch.cat([self.RMr, self.RMi, self.RVrr, self.RVri, self.RVii])
+        z = _ops.complex_batch_norm(x.reshape(-1, C), w3h, b2h, running, self.training)
+        if self.training:
+            with torch.no_grad():
+                h = C // 2
+                for i, k in enumerate(("RMr", "RMi", "RVrr", "RVri", "RVii")):
+                    getattr(self, k).copy_(running[i * h:(i + 1) * h])
+                self.num_batches_tracked += 1
+        return _from_cl(z.reshape(B, F, T, C))
+
+
 class Bar(object):
     """Progress iterator used by the reference trainer loops (`for inputs, targets in tools.Bar(loader)`,
     trainer.py:23).  Own implementation: prints count, rate and ETA on one line."""

@@ -145,6 +145,17 @@ int sefd_bn_prelu_backward(const float* y, const float* dz, float* dy, long long
                            const float* beta, const float* alpha, const float* save, float* dgamma, float* dbeta,
                            float* dalpha, double* scratch, void* stream);
 
+/* ComplexBatchNorm (tools_for_model.py:430-603) + PReLU on channels-last rows [rows][C], C = 2 h: real parts in [0, h),
+ * imaginary parts in [h, 2 h).  w3h = Wrr | Wri | Wii, b2h = Br | Bi, running5h = RMr | RMi | RVrr | RVri | RVii (each h
+ * floats; train mode lerps the batch moments into it when non-NULL, use_running = 1 normalises with it); alpha: PReLU slope
+ * (1 float on the device; 1.0 gives the bare module); save: 9 h floats kept for the backward; scratch: 5 h doubles (forward),
+ * 6 h + 1 doubles (backward); coef: 9 h floats of backward scratch. */
+int sefd_cbn_prelu_forward(const float* y, float* z, long long rows, int C, const float* w3h, const float* b2h, const float* alpha,
+                           float* save, float* running5h, int use_running, double* scratch, void* stream);
+int sefd_cbn_prelu_backward(const float* y, const float* dz, float* dy, long long rows, int C, const float* w3h, const float* b2h,
+                            const float* alpha, const float* save, float* dw3h, float* db2h, float* dalpha, double* scratch,
+                            float* coef, void* stream);
+
 /* recurrent part of two nn.LSTM(H=128) run side by side (tools_for_model.py:147-150,167-170):
  * gates [2][rows][T][512] holds x W_ih^T + b_ih + b_hh on entry and the activated gates on exit. */
 int sefd_lstm_forward(const float* w_hh, float* gates, float* h, float* c, int rows, int T, void* stream);

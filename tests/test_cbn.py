@@ -122,3 +122,40 @@ def test_cbn_gpu(engine, gold):
         _, _, wav_e = m(noisy.cuda(), clean.cuda())
         _, _, wav_eo = O.dccrn_forward(tr.sd, noisy, "C", train=False)
     assert float((wav_e.cpu() - wav_eo).pow(2).mean().sqrt()) < (2e-4 if tf else 5e-6)
+
+
+@pytest.mark.gpu
+def test_standalone_complex_batch_norm_layer():
+    """tools_for_model.ComplexBatchNorm (the bare layer, op-level sefd_cbn_prelu_forward / backward with slope 1) against the
+    oracle's complex_batch_norm and its autograd: output, input / parameter gradients, running buffers, eval mode."""
+    import tools_for_model as T
+    torch.manual_seed(3)
+    layer = T.ComplexBatchNorm(32).cuda().train()
+    with torch.no_grad():
+        layer.Wrr.uniform_(0.5, 1.5); layer.Wii.uniform_(0.5, 1.5); layer.Br.normal_(); layer.Bi.normal_()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 32, 6, 9, generator=g)
+    x[:, 16:] = 0.5 * x[:, :16] + 0.7 * x[:, 16:]                 # correlated real / imaginary parts: Vri != 0
+    dz = torch.randn(2, 32, 6, 9, generator=g)
+    ref_p = [getattr(layer, k).detach().cpu().double().requires_grad_(True) for k in ("Wrr", "Wri", "Wii", "Br", "Bi")]
+    xr = x.double().requires_grad_(True)
+    y_ref, st = O.complex_batch_norm(xr, *ref_p)
+    (y_ref * dz.double()).sum().backward()
+    xg = x.cuda().requires_grad_(True)
+    y = layer(xg)
+    (y * dz.cuda()).sum().backward()
+    assert float((y.detach().cpu().double() - y_ref.detach()).abs().max()) < 2e-5
+    assert float((xg.grad.cpu().double() - xr.grad).abs().max()) < 2e-5 * float(xr.grad.abs().max()) + 1e-6
+    for k, r in zip(("Wrr", "Wri", "Wii", "Br", "Bi"), ref_p):
+        got = getattr(layer, k).grad.cpu().double()
+        assert float((got - r.grad).abs().max()) < 1e-4 * float(r.grad.abs().max()) + 1e-5, k
+    for k, v, init in zip(BUFS, st, (0.0, 0.0, 1.0, 0.0, 1.0)):
+        want = init + 0.1 * (v.detach() - init)
+        assert float((getattr(layer, k).cpu().double() - want).abs().max()) < 1e-5, k
+    assert int(layer.num_batches_tracked) == 1
+    layer.eval()
+    with torch.no_grad():
+        ye = layer(x.cuda())
+        ye_ref, _ = O.complex_batch_norm(x.double(), *[p.detach() for p in ref_p],
+                                         stats=[getattr(layer, k).cpu().double() for k in BUFS])
+    assert float((ye.cpu().double() - ye_ref).abs().max()) < 2e-5
