@@ -183,3 +183,39 @@ def test_reference_train_loop_body_and_adam():
         opt.step()
         losses.append(float(loss.detach()))
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+def test_bench_configuration_properties():
+    """BASELINE configs[2] itself (B = 64, 161 frames: 16 448 sub-band sequences = 129 row tiles, the multicast clusters, the
+    partial last tile, the backward's stream overlap) on the default engine, through properties that do not need a full-size
+    oracle run: (1) sequences are independent, so utterances 0 and 63 of the batch equal the ORACLE's result for those two
+    utterances alone; (2) the MSE gradient of the batch is the mean of the gradients of its two halves."""
+    B, Tf = 64, 161
+    g = torch.Generator().manual_seed(64)
+    mag = torch.rand(B, 257, Tf, generator=g) * (0.2 + torch.rand(B, 257, 1, generator=g))
+    cirm = torch.randn(B, 257, Tf, 2, generator=g)
+    sd = FS.init_state(0)
+    pick = [0, B - 1]
+    with torch.no_grad():
+        crm_ref = FS.fullsubnet_forward(sd, mag[pick])
+    m = _model(sd, train=True)
+    m.dropout = 0.0
+
+    def run(idx):
+        for p in m.parameters():
+            p.grad = None
+        crm = m(mag[idx].cuda())
+        loss = m.loss(cirm[idx].cuda(), crm)
+        loss.backward()
+        torch.cuda.synchronize()
+        return crm.detach().cpu(), float(loss.detach()), torch.cat([p.grad.detach().reshape(-1) for p in m.parameters()]).double().cpu()
+
+    crm, loss, grad = run(slice(0, B))
+    assert float((crm[pick] - crm_ref).abs().max()) < 5e-3                     # TF32 engine bar of this file
+    crm_a, loss_a, grad_a = run(slice(0, B // 2))
+    crm_b, loss_b, grad_b = run(slice(B // 2, B))
+    assert float((crm[:B // 2] - crm_a).abs().max()) < 1e-5 and float((crm[B // 2:] - crm_b).abs().max()) < 1e-5
+    assert loss == pytest.approx(0.5 * (loss_a + loss_b), rel=1e-5)
+    mean = 0.5 * (grad_a + grad_b)
+    cos = float((grad * mean).sum() / (grad.norm() * mean.norm()))
+    assert cos > 0.99999 and abs(float(grad.norm() / mean.norm()) - 1) < 1e-3, (cos, float(grad.norm() / mean.norm()))
