@@ -159,3 +159,35 @@ def test_standalone_complex_batch_norm_layer():
         ye_ref, _ = O.complex_batch_norm(x.double(), *[p.detach() for p in ref_p],
                                          stats=[getattr(layer, k).cpu().double() for k in BUFS])
     assert float((ye.cpu().double() - ye_ref).abs().max()) < 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("skip,lstm", [(False, "complex"), (True, "real"), (False, "real")])
+def test_plan_flag_combinations(skip, lstm):
+    """SEFD_PLAN_CBN together with SEFD_PLAN_NO_SKIP / SEFD_PLAN_REAL_LSTM (the flags are independent in the reference too: use_cbn,
+    cfg.skip_type, cfg.lstm): waveform, loss and the flat gradient of the drop-in against the oracle, default engine."""
+    import models
+    old = (models.cfg.skip_type, models.cfg.lstm, models.cfg.loss)
+    models.cfg.skip_type, models.cfg.lstm, models.cfg.loss = skip, lstm, "SI-SNR"
+    try:
+        sd0 = O.init_state(0, skip_type=skip, lstm=lstm, use_cbn=True)
+        noisy, clean = _speech()
+        tr = O.OracleTrainer(sd0, masking_mode="E", loss="SI-SNR")
+        loss_ref, wav_ref = tr.forward_backward(noisy, clean)
+        m = models.DCCRN(masking_mode="E", use_cbn=True)
+        m.load_state_dict(sd0)
+        m = m.cuda().train()
+        _, _, wav = m(noisy.cuda(), clean.cuda())
+        loss = m.loss(wav, clean.cuda())
+        loss.backward()
+        torch.cuda.synchronize()
+        assert float((wav.detach().cpu() - wav_ref).pow(2).mean().sqrt()) < 1e-4
+        assert float(loss.detach()) == pytest.approx(float(loss_ref), rel=5e-3, abs=5e-3)      # SI-SNR in dB, may sit near 0
+        grads = tr.grads()
+        keys = [k for k, _ in m.named_parameters() if not k.endswith(".2.weight") and not (k.endswith("_conv.bias") and not k.startswith("decoder.5"))]
+        got = torch.cat([dict(m.named_parameters())[k].grad.detach().cpu().double().reshape(-1) for k in keys])
+        ref = torch.cat([grads[k].double().reshape(-1) for k in keys])
+        cos = float((got * ref).sum() / (got.norm() * ref.norm()))
+        assert cos > 0.999 and abs(float(got.norm() / ref.norm()) - 1) < 0.02, (cos, float(got.norm() / ref.norm()))
+    finally:
+        models.cfg.skip_type, models.cfg.lstm, models.cfg.loss = old
