@@ -10,6 +10,7 @@
 #include "fsnet.cuh"
 #include "lstm_seq.cuh"
 #include "taps.cuh"
+#include "prof.cuh"
 
 static thread_local char g_err[1024] = "";
 
@@ -315,6 +316,7 @@ int sefd_bn_prelu_forward(const float* y, float* z, long long rows, int C, const
                           void* stream) {
     SEFD_REQUIRE(C >= 4 && C <= 512 && C % 4 == 0, "bn_prelu: C=%d unsupported", C);
     cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, ST);
+    sefd_absorb_stale_error();
     channel_stats_kernel<<<148 * 2, C > 256 ? 512 : 256, 0, ST>>>(y, rows, C, scratch);
     SEFD_TRY(sefd_check_launch("channel_stats"));
     BnPreluFwdParams b;

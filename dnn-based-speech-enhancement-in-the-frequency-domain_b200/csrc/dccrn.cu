@@ -416,6 +416,7 @@ int sefd_forward_impl(const sefd_plan* P, const float* prm, float* bnbuf, const 
         // ---- cfg.lstm = 'real': one 2-layer nn.LSTM on [T, B, 1024] + tranform (models.py:213-218) ----
         const RealLstmExt& R = *P->rl;
         const int tf = sefd_get_engine_internal() == 1;
+        sefd_absorb_stale_error();
         real_lstm_gather_kernel<<<148 * 4, 256, 0, st>>>(ws + P->enc[NL - 1].z, ws + R.x_tm, B, T, 0);
         SEFD_TRY(sefd_check_launch("real_lstm_gather"));
         SEFD_TRY(stack_forward(R.sc, R.st, ws, ws + R.x_tm, T, tf, nullptr, 0u, st));
@@ -714,6 +715,7 @@ int sefd_backward_impl(const sefd_plan* P, const float* prm, const float* dwav, 
             SEFD_TRY(sefd_permute3(ws + P->dbs, grads + R.b_tr, 1, RL_C, RL_D, 0, 1, RL_C, 0, st));    // dbs[d][c] -> grads[c * 4 + d]
         }
         SEFD_TRY(stack_backward(R.sc, R.st, ws, ws + R.x_tm, T, tf, nullptr, 0u, ws + R.dx_tm, grads, st));
+        sefd_absorb_stale_error();
         real_lstm_gather_kernel<<<148 * 4, 256, 0, st>>>(ws + (P->skip ? P->enc[NL - 1].dz2 : P->enc[NL - 1].dz), ws + R.dx_tm, B, T, 1);
         SEFD_TRY(sefd_check_launch("real_lstm_scatter"));
     }

@@ -597,12 +597,14 @@ int sefd_axpby_launch(float* y, const float* x, float a, float b, long long n, c
     if (n <= 0) return 0;
     long long g = (n + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
+    sefd_absorb_stale_error();
     axpby_kernel<<<(int)g, 256, 0, st>>>(y, x, a, b, n);
     return sefd_check_launch("axpby");
 }
 
 int sefd_counters_inc_launch(long long* const* ptrs, int n, long long inc, cudaStream_t st) {
     if (n <= 0) return 0;
+    sefd_absorb_stale_error();
     counters_inc_kernel<<<(n + 127) / 128, 128, 0, st>>>(ptrs, n, inc);
     return sefd_check_launch("counters_inc");
 }

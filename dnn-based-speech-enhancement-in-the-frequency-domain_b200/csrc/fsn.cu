@@ -240,12 +240,14 @@ int sefd_fsn_stft(const float* wav, int B, int L, float* spec, void* stream) {
 /* spec [n][2] -> mag [n], phase [n] (phase may be NULL) */
 int sefd_fsn_mag_phase(const float* spec, long long n, float* mag, float* phase, void* stream) {
     SEFD_REQUIRE(spec && mag && n > 0, "fsn_mag_phase: bad argument");
+    sefd_absorb_stale_error();
     fsn_mag_phase_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(spec), n, mag, phase);
     return sefd_check_launch("fsn_mag_phase");
 }
 /* noisy_spec, clean_spec [n][2] -> compressed complex ideal ratio mask [n][2] */
 int sefd_fsn_cirm(const float* noisy_spec, const float* clean_spec, long long n, float* cirm, void* stream) {
     SEFD_REQUIRE(noisy_spec && clean_spec && cirm && n > 0, "fsn_cirm: bad argument");
+    sefd_absorb_stale_error();
     fsn_cirm_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(noisy_spec),
                                                                     reinterpret_cast<const float2*>(clean_spec), n,
                                                                     reinterpret_cast<float2*>(cirm));
@@ -271,11 +273,13 @@ int sefd_fsn_istft(const float* spec_or_mag, const float* phase, int B, int T, i
 }
 int sefd_fsn_compress_cirm(const float* mask, long long n, float* out, void* stream) {
     SEFD_REQUIRE(mask && out && n > 0, "fsn_compress_cirm: bad argument");
+    sefd_absorb_stale_error();
     fsn_compress_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(mask, n, out);
     return sefd_check_launch("fsn_compress_cirm");
 }
 int sefd_fsn_decompress_cirm(const float* mask, long long n, float* out, void* stream) {
     SEFD_REQUIRE(mask && out && n > 0, "fsn_decompress_cirm: bad argument");
+    sefd_absorb_stale_error();
     fsn_decompress_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(mask, n, out);
     return sefd_check_launch("fsn_decompress_cirm");
 }

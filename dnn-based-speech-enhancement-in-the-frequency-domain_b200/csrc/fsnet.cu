@@ -414,6 +414,7 @@ int sefd_fsn_forward_impl(const sefd_plan* P, const float* prm, const float* noi
     // ---- packed operands ----
     SEFD_TRY(pack_stack(E.fb, prm, ws, tf, st));
     SEFD_TRY(pack_stack(E.sb, prm, ws, tf, st));
+    sefd_absorb_stale_error();
     pack_linear_kernel<<<148, 256, 0, st>>>(prm + E.fb.fc_w, prm + E.fb.fc_b, FBINS, FPAD, FB_H, ws + E.Wl_nk, ws + E.Wl_kn, ws + E.bl, tf);
     SEFD_TRY(sefd_check_launch("fsn_pack_linear"));
 

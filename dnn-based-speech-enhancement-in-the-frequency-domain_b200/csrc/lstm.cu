@@ -238,6 +238,7 @@ int launch_fwd(const LstmFwdParams& p, cudaStream_t st) {
         attr = true;
     }
     dim3 grid((p.rows + R - 1) / R, p.nl ? p.nl : 2);
+    sefd_absorb_stale_error();
     lstm_fwd_kernel<R, KR><<<grid, 512, smem, st>>>(p);
     return sefd_check_launch("lstm_fwd");
 }
@@ -250,6 +251,7 @@ int launch_bwd(const LstmBwdParams& p, cudaStream_t st) {
         attr = true;
     }
     dim3 grid((p.rows + R - 1) / R, p.nl ? p.nl : 2);
+    sefd_absorb_stale_error();
     lstm_bwd_kernel<R, KR><<<grid, 512, smem, st>>>(p);
     return sefd_check_launch("lstm_bwd");
 }

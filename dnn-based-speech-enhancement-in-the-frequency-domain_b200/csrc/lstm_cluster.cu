@@ -306,6 +306,7 @@ int launch_fwd(const LstmFwdParams& p, cudaStream_t st) {
         attr = true;
     }
     const int nl = p.nl ? p.nl : 2;
+    sefd_absorb_stale_error();
     lstm_cluster_fwd_kernel<R><<<nl * (p.rows / R) * CL, NT, smem, st>>>(p);
     return sefd_check_launch("lstm_cluster_fwd");
 }
@@ -318,6 +319,7 @@ int launch_bwd(const LstmBwdParams& p, cudaStream_t st) {
         attr = true;
     }
     const int nl = p.nl ? p.nl : 2;
+    sefd_absorb_stale_error();
     lstm_cluster_bwd_kernel<R><<<nl * (p.rows / R) * CL, NT, smem, st>>>(p);
     return sefd_check_launch("lstm_cluster_bwd");
 }
