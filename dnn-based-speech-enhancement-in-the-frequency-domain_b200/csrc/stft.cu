@@ -91,7 +91,7 @@ __device__ __forceinline__ float2 mask_bwd(int mode, float2 x, float2 m, float2 
 // ================================================================================================
 template <int NFFT>
 struct Geo {
-    static constexpr int N = NFFT, WIN = NFFT / 32 * 25, HOP = WIN / 4, NBIN = NFFT / 2 + 1, PAD = WIN - HOP, R1 = NFFT / 32;
+    static constexpr int WIN = NFFT / 32 * 25, HOP = WIN / 4, NBIN = NFFT / 2 + 1, PAD = WIN - HOP, R1 = NFFT / 32;
     static constexpr float INV_HALF = 2.0f / NFFT, INV_PARITY = 1.0f / (NFFT / 2 + WIN / 2);
 };
 constexpr int WF = 16;                  // frames per round of a CTA (8 warps x 2)
